@@ -20,6 +20,30 @@ class AcsConfig(ctypes.Structure):
                 ("fcs_dt", ctypes.c_double)]
 
 
+MAX_AGENTS, MAX_REWARDS, MAX_TERMS, INFO_DIM = 8, 12, 6, 4
+
+
+class AcsRewardSpec(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("potential", ctypes.c_int32), ("scale", ctypes.c_double), ("p0", ctypes.c_double),
+                ("p1", ctypes.c_double), ("p2", ctypes.c_double)]
+
+
+class AcsTaskConfig(ctypes.Structure):
+    _fields_ = [("n_envs", ctypes.c_int32), ("n_ego", ctypes.c_int32), ("n_enm", ctypes.c_int32), ("substeps", ctypes.c_int32),
+                ("max_steps", ctypes.c_int32), ("sim_dt", ctypes.c_double), ("fcs_dt", ctypes.c_double),
+                ("altitude_limit", ctypes.c_double), ("acc_limit", ctypes.c_double * 3), ("center", ctypes.c_double * 3),
+                ("obs_kind", ctypes.c_int32), ("obs_dim", ctypes.c_int32), ("act_kind", ctypes.c_int32), ("shoot_dim", ctypes.c_int32),
+                ("n_rewards", ctypes.c_int32), ("rewards", AcsRewardSpec * MAX_REWARDS), ("n_terms", ctypes.c_int32),
+                ("terms", ctypes.c_int32 * MAX_TERMS), ("dones_before_rewards", ctypes.c_int32), ("team_mean", ctypes.c_int32),
+                ("share_obs", ctypes.c_int32), ("reward_gate", ctypes.c_int32), ("launch_kind", ctypes.c_int32),
+                ("use_artillery", ctypes.c_int32), ("use_baseline", ctypes.c_int32), ("max_attack_angle", ctypes.c_double),
+                ("max_attack_distance", ctypes.c_double), ("min_attack_interval", ctypes.c_int32), ("lock_len", ctypes.c_int32),
+                ("num_missiles", ctypes.c_int32 * MAX_AGENTS), ("n_missile_slots", ctypes.c_int32),
+                ("init_state", (ctypes.c_double * 12) * MAX_AGENTS), ("heading_increments", ctypes.c_double * 3),
+                ("check_interval", ctypes.c_double), ("seed", ctypes.c_uint64), ("env_offset", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
 class AcsError(RuntimeError):
     pass
 
@@ -46,6 +70,22 @@ def lib():
         L.acs_get_state.argtypes = [vp, vp, vp]
         L.acs_set_state.argtypes = [vp, vp, vp]
         L.acs_get_outputs.argtypes = [vp, vp, vp]
+        L.acs_env_create.argtypes = [ctypes.POINTER(AcsTaskConfig), i, ctypes.POINTER(vp)]
+        L.acs_env_destroy.argtypes = [vp]
+        L.acs_env_set_init_states.argtypes = [vp, vp]
+        L.acs_env_set_seed.argtypes = [vp, ctypes.c_uint64, vp]
+        L.acs_env_reset.argtypes = [vp, vp, vp, vp, vp]
+        L.acs_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, vp]
+        L.acs_env_arena_info.argtypes = [vp, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
+        L.acs_env_arena_field_name.restype = cp
+        L.acs_env_arena_field_name.argtypes = [i, i]
+        L.acs_env_get_arena.argtypes = [vp, i, vp, vp]
+        L.acs_env_set_arena.argtypes = [vp, i, vp, vp]
+        L.acs_env_fdm.restype = vp
+        L.acs_env_fdm.argtypes = [vp]
+        L.acs_env_set_timing.argtypes = [vp, i]
+        L.acs_env_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i)]
+        L.acs_bench_fp64_peak.argtypes = [i, ctypes.POINTER(ctypes.c_double)]
         _LIB = L
     return _LIB
 
@@ -131,3 +171,144 @@ class FdmBatch:
         out = torch.empty((len(self.output_names), self.n_rows), dtype=torch.float64, device=self.device)
         _check(lib().acs_get_outputs(self._h, _ptr(out, torch.float64), _stream()))
         return out
+
+
+ARENAS = {"fdm": 0, "out": 1, "ac_d": 2, "ac_i": 3, "env_d": 4, "env_i": 5, "ms_d": 6, "ms_i": 7}
+
+
+def task_config(spec, n_envs: int, seed: int = 0, env_offset: int = 0) -> AcsTaskConfig:
+    """Pack a ``taskspec.TaskSpec`` into the C struct of include/acs.h."""
+    c = AcsTaskConfig()
+    c.n_envs, c.n_ego, c.n_enm, c.substeps, c.max_steps = n_envs, spec.n_ego, spec.n_enm, spec.substeps, spec.max_steps
+    c.sim_dt, c.fcs_dt, c.altitude_limit = spec.dt, spec.fcs_dt, spec.altitude_limit
+    for k in range(3):
+        c.acc_limit[k], c.center[k], c.heading_increments[k] = spec.acc_limit[k], spec.center[k], spec.heading_increments[k]
+    c.obs_kind, c.obs_dim, c.act_kind, c.shoot_dim = spec.obs_kind, spec.obs_dim, spec.act_kind, spec.shoot_dim
+    if len(spec.rewards) > MAX_REWARDS or len(spec.terminations) > MAX_TERMS or spec.n_agents > MAX_AGENTS:
+        raise AcsError("task exceeds ACS_MAX_REWARDS / ACS_MAX_TERMS / ACS_MAX_AGENTS")
+    c.n_rewards = len(spec.rewards)
+    for k, r in enumerate(spec.rewards):
+        c.rewards[k].kind, c.rewards[k].potential, c.rewards[k].scale = r.kind, int(r.potential), r.scale
+        c.rewards[k].p0, c.rewards[k].p1, c.rewards[k].p2 = r.p0, r.p1, r.p2
+    c.n_terms = len(spec.terminations)
+    for k, t in enumerate(spec.terminations):
+        c.terms[k] = t
+    c.dones_before_rewards, c.team_mean, c.share_obs = int(spec.dones_before_rewards), int(spec.team_mean), int(spec.share_obs)
+    c.reward_gate, c.launch_kind, c.use_artillery, c.use_baseline = spec.reward_gate, spec.launch_kind, int(spec.use_artillery), int(spec.use_baseline)
+    c.max_attack_angle = spec.max_attack_angle
+    c.max_attack_distance = spec.max_attack_distance
+    c.min_attack_interval, c.lock_len = spec.min_attack_interval, spec.lock_len
+    for k in range(spec.n_agents):
+        c.num_missiles[k] = spec.num_missiles[k] if spec.num_missiles else 0
+        for j in range(12):
+            c.init_state[k][j] = spec.init_states[k][j]
+    c.n_missile_slots = spec.n_missile_slots
+    c.check_interval = spec.check_interval
+    c.seed, c.env_offset = seed, env_offset
+    return c
+
+
+class EnvBatch:
+    """``n_envs`` environments of one task on one GPU -- the device-side counterpart of ``n_envs`` reference Env objects
+    (reference envs/JSBSim/envs/env_base.py).  Tensors in, tensors out; nothing here synchronises the stream."""
+
+    def __init__(self, spec, n_envs: int, seed: int = 0, device: int = 0, env_offset: int = 0):
+        if not torch.cuda.is_available():
+            raise AcsError("CUDA is not available; the simulator has no CPU fallback")
+        self.spec, self.n_envs, self.n_agents = spec, n_envs, spec.n_agents
+        self.device = torch.device("cuda", device)
+        self.cfg = task_config(spec, n_envs, seed, env_offset)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(lib().acs_env_create(ctypes.byref(self.cfg), device, ctypes.byref(h)))
+        self._h = h
+        B, A, D = n_envs, self.n_agents, spec.obs_dim
+        # every per-step output lives in ONE device buffer so the host-facing layer fetches a step with a single D2H copy
+        layout = [("obs", torch.float64, (B, A, D))]
+        if spec.share_obs:
+            layout.append(("share_obs", torch.float64, (B, A, A * D)))
+        layout += [("rewards", torch.float64, (B, A)), ("info", torch.int32, (B, A, INFO_DIM)), ("dones", torch.uint8, (B, A)),
+                   ("env_done", torch.uint8, (B,))]
+        self.out_layout, off = [], 0
+        for name, dt, shape in layout:
+            nbytes = int(torch.tensor([], dtype=dt).element_size()) * int(torch.Size(shape).numel())
+            self.out_layout.append((name, dt, shape, off, nbytes))
+            off += (nbytes + 15) // 16 * 16
+        self.out_buf = torch.zeros(off, dtype=torch.uint8, device=self.device)
+        self.share_obs = None
+        for name, dt, shape, o, nbytes in self.out_layout:
+            setattr(self, name, self.out_buf[o:o + nbytes].view(dt).view(shape))
+        self.act_dim = 4 + spec.shoot_dim
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().acs_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_init_states(self, init_states):
+        import numpy as np
+        arr = np.ascontiguousarray(init_states, dtype=np.float64)
+        assert arr.shape == (self.n_agents, 12)
+        _check(lib().acs_env_set_init_states(self._h, arr.ctypes.data_as(ctypes.c_void_p)))
+
+    def set_seed(self, seed: int):
+        _check(lib().acs_env_set_seed(self._h, ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), _stream()))
+
+    def host_views(self, host_buf: torch.Tensor):
+        """numpy views of a host copy of ``out_buf`` (same layout), keyed by output name."""
+        views = {}
+        for name, dt, shape, o, nbytes in self.out_layout:
+            views[name] = host_buf[o:o + nbytes].view(dt).view(shape).numpy()
+        return views
+
+    def reset(self, env_mask: torch.Tensor | None = None):
+        _check(lib().acs_env_reset(self._h, _ptr(env_mask, torch.uint8), _ptr(self.obs, torch.float64),
+                                   _ptr(self.share_obs, torch.float64), _stream()))
+        return self.obs, self.share_obs
+
+    def step(self, actions: torch.Tensor, auto_reset: bool = False):
+        """actions: int32 [n_envs, n_agents, 4 + shoot_dim] low-level discrete actions."""
+        assert actions.shape == (self.n_envs, self.n_agents, self.act_dim), actions.shape
+        _check(lib().acs_env_step(self._h, _ptr(actions, torch.int32), _ptr(self.obs, torch.float64),
+                                  _ptr(self.share_obs, torch.float64), _ptr(self.rewards, torch.float64),
+                                  _ptr(self.dones, torch.uint8), _ptr(self.info, torch.int32), _ptr(self.env_done, torch.uint8),
+                                  int(auto_reset), _stream()))
+        return self.obs, self.share_obs, self.rewards, self.dones, self.info
+
+    # ---- measurement
+    def set_timing(self, on: bool):
+        _check(lib().acs_env_set_timing(self._h, int(on)))
+
+    def get_timing(self):
+        """({'substeps': ms, 'post': ms, 'reset': ms}, n_steps) accumulated since the last call (synchronises)."""
+        ms, n = (ctypes.c_double * 3)(), ctypes.c_int()
+        _check(lib().acs_env_get_timing(self._h, ms, ctypes.byref(n)))
+        return {"substeps": ms[0], "post": ms[1], "reset": ms[2]}, n.value
+
+    # ---- introspection (parity tests, rendering)
+    def arena(self, name: str):
+        """Returns (field names, tensor [n_fields, n_per_field]) -- a copy."""
+        which = ARENAS[name]
+        nf, per, ii = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _check(lib().acs_env_arena_info(self._h, which, ctypes.byref(nf), ctypes.byref(per), ctypes.byref(ii)))
+        dt = torch.int32 if ii.value else torch.float64
+        t = torch.empty((nf.value, per.value), dtype=dt, device=self.device)
+        _check(lib().acs_env_get_arena(self._h, which, ctypes.c_void_p(t.data_ptr()), _stream()))
+        names = [lib().acs_env_arena_field_name(which, k).decode() for k in range(nf.value)]
+        return names, t
+
+    def set_arena(self, name: str, t: torch.Tensor):
+        assert t.is_cuda and t.is_contiguous()
+        _check(lib().acs_env_set_arena(self._h, ARENAS[name], ctypes.c_void_p(t.data_ptr()), _stream()))
+
+
+def fp64_peak_flops(device: int = 0) -> float:
+    out = ctypes.c_double()
+    _check(lib().acs_bench_fp64_peak(device, ctypes.byref(out)))
+    return out.value

@@ -1,0 +1,109 @@
+"""Batched low-level flight controller for the hierarchical tasks.
+
+The reference's hierarchical tasks turn a high-level action (delta altitude / heading / velocity class) into stick and
+throttle commands with a small recurrent policy, ``BaselineActor`` (reference envs/JSBSim/model/baseline_actor.py:88-110):
+MLP(12 -> 128 -> 128, ReLU + LayerNorm) -> one GRU layer (128) -> LayerNorm -> four categorical heads [41, 41, 41, 30],
+arg-max actions.  The reference evaluates it on the CPU with batch 1, once per agent per step, inside
+``normalize_action`` (reference envs/JSBSim/tasks/singlecombat_task.py:223-256).  Here it is ONE PyTorch call over all
+``n_envs * n_agents`` rows on the simulator's GPU, between "last step's observation" and "substeps" -- the policy side
+stays in PyTorch by design (BASELINE.json north_star); the physics kernels are the hand-written part.
+
+``load_reference_checkpoint`` reads the reference's ``baseline_model.pt`` state dict (key names of ``BaselineActor``).
+"""
+from __future__ import annotations
+
+import math
+import os
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+HIDDEN = 128
+HEAD_DIMS = (41, 41, 41, 30)
+
+# reference envs/JSBSim/tasks/singlecombat_task.py:216-218
+NORM_DELTA_ALTITUDE = (0.1, 0.0, -0.1)
+NORM_DELTA_HEADING = (-math.pi / 6, -math.pi / 12, 0.0, math.pi / 12, math.pi / 6)
+NORM_DELTA_VELOCITY = (0.05, 0.0, -0.05)
+
+
+class LowLevelController(nn.Module):
+    def __init__(self, input_dim: int = 12):
+        super().__init__()
+        self.fc1 = nn.Linear(input_dim, HIDDEN)
+        self.ln1 = nn.LayerNorm(HIDDEN)
+        self.fc2 = nn.Linear(HIDDEN, HIDDEN)
+        self.ln2 = nn.LayerNorm(HIDDEN)
+        self.gru = nn.GRUCell(HIDDEN, HIDDEN)      # one time step of the reference's 1-layer nn.GRU (same weight layout)
+        self.norm = nn.LayerNorm(HIDDEN)
+        self.heads = nn.Linear(HIDDEN, sum(HEAD_DIMS))   # the four logits_net layers stacked row-wise
+
+    @torch.no_grad()
+    def forward(self, obs12: torch.Tensor, h: torch.Tensor):
+        """obs12 [N, 12] float32, h [N, 128] float32 -> (actions [N, 4] int32, h' [N, 128])."""
+        x = self.ln1(F.relu(self.fc1(obs12)))
+        x = self.ln2(F.relu(self.fc2(x)))
+        h = self.gru(x, h)
+        logits = self.heads(self.norm(h))
+        acts, o = [], 0
+        for d in HEAD_DIMS:
+            acts.append(logits[:, o:o + d].argmax(dim=-1))     # Categorical(logits).probs.argmax == logits.argmax
+            o += d
+        return torch.stack(acts, dim=-1).to(torch.int32), h
+
+    def load_reference_state_dict(self, sd: dict):
+        """Maps ``BaselineActor.state_dict()`` keys (reference envs/JSBSim/model/baseline_actor.py) onto this module."""
+        m = {
+            "fc1.weight": sd["base.mlp.fc.0.weight"], "fc1.bias": sd["base.mlp.fc.0.bias"],
+            "ln1.weight": sd["base.mlp.fc.2.weight"], "ln1.bias": sd["base.mlp.fc.2.bias"],
+            "fc2.weight": sd["base.mlp.fc.3.weight"], "fc2.bias": sd["base.mlp.fc.3.bias"],
+            "ln2.weight": sd["base.mlp.fc.5.weight"], "ln2.bias": sd["base.mlp.fc.5.bias"],
+            "gru.weight_ih": sd["rnn.gru.weight_ih_l0"], "gru.weight_hh": sd["rnn.gru.weight_hh_l0"],
+            "gru.bias_ih": sd["rnn.gru.bias_ih_l0"], "gru.bias_hh": sd["rnn.gru.bias_hh_l0"],
+            "norm.weight": sd["rnn.norm.weight"], "norm.bias": sd["rnn.norm.bias"],
+            "heads.weight": torch.cat([sd[f"act.action_outs.{k}.logits_net.weight"] for k in range(4)], dim=0),
+            "heads.bias": torch.cat([sd[f"act.action_outs.{k}.logits_net.bias"] for k in range(4)], dim=0),
+        }
+        self.load_state_dict(m)
+
+
+def find_checkpoint(path=None):
+    """``baseline_model.pt`` lookup: explicit path, $ACS_BASELINE_MODEL, then ``<package>/model/baseline_model.pt``."""
+    cands = [path, os.environ.get("ACS_BASELINE_MODEL"), Path(__file__).resolve().parent / "model" / "baseline_model.pt"]
+    for c in cands:
+        if c and Path(c).exists():
+            return Path(c)
+    return None
+
+
+def make_controller(device, path=None, seed: int = 0) -> LowLevelController:
+    """The controller on ``device``.  Without a checkpoint the weights are a seeded random init of the same architecture
+    (benchmarks and shape tests; the flight behaviour then is of course not the trained one)."""
+    ck = find_checkpoint(path)
+    g = torch.Generator().manual_seed(seed)
+    ctl = LowLevelController()
+    if ck is not None:
+        ctl.load_reference_state_dict(torch.load(str(ck), map_location="cpu"))
+        ctl.checkpoint = str(ck)
+    else:
+        for p in ctl.parameters():
+            if p.dim() > 1:
+                p.data = torch.randn(p.shape, generator=g) / math.sqrt(p.shape[-1])
+        ctl.checkpoint = None
+    return ctl.to(device).eval()
+
+
+def hierarchical_input(high: torch.Tensor, obs: torch.Tensor, force_climb_below_m=None) -> torch.Tensor:
+    """input_obs of the reference (singlecombat_task.py:234-246 / multiplecombat_task.py:171-178).
+
+    high [N, 3] integer classes; obs [N, D] float64 current observations (obs[:, 0] = altitude / 5000).  The 1v1 task
+    forces the "climb" class below 3500 m (singlecombat_task.py:235-237)."""
+    dev = obs.device
+    da = torch.tensor(NORM_DELTA_ALTITUDE, dtype=torch.float64, device=dev)[high[:, 0].long()]
+    if force_climb_below_m is not None:
+        da = torch.where(obs[:, 0] * 5000.0 < force_climb_below_m, torch.full_like(da, NORM_DELTA_ALTITUDE[0]), da)
+    dh = torch.tensor(NORM_DELTA_HEADING, dtype=torch.float64, device=dev)[high[:, 1].long()]
+    dv = torch.tensor(NORM_DELTA_VELOCITY, dtype=torch.float64, device=dev)[high[:, 2].long()]
+    return torch.cat([torch.stack([da, dh, dv], dim=-1), obs[:, :9]], dim=-1).to(torch.float32)

@@ -3,9 +3,11 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 #include <cmath>
 #include "../../include/acs.h"
 #include "fdm_core.cuh"
+#include "env_core.cuh"
 
 // ----------------------------------------------------------------------------- device constants
 __constant__ AtmoConst g_atmo;
@@ -111,6 +113,8 @@ __global__ void k_set_controls(double* __restrict__ state, const double* __restr
     state[(size_t)(f_ail + k) * N + i] = v;
   }
 }
+
+#include "env_kernels.cuh"
 
 // ----------------------------------------------------------------------------- host side
 static void host_atmo(AtmoConst& c) {
@@ -233,6 +237,229 @@ int acs_set_state(AcsHandle* h, const double* src_dev, void* stream) {
 int acs_get_outputs(const AcsHandle* h, double* dst_dev, void* stream) {
   if (!h || !dst_dev) return fail("acs_get_outputs: null argument");
   CUDA_TRY(cudaMemcpyAsync(dst_dev, h->out, sizeof(double) * (size_t)FDM_N_OUT * h->n_rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+}  // extern "C"
+
+// ============================================================================= env layer host side
+struct AcsEnv {
+  AcsTaskConfig cfg;
+  AcsHandle* fdm;
+  EnvView v;
+  int G, lg;   // lanes per env (1, 2, 4 or 8) and its log2
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;   // 4 events per timed step: before substeps, after substeps, after post, after reset
+  size_t ev_used = 0;
+};
+
+static cudaEvent_t timing_event(AcsEnv* e, cudaStream_t st) {
+  if (e->ev_used == e->ev.size()) { cudaEvent_t x; cudaEventCreate(&x); e->ev.push_back(x); }
+  cudaEvent_t x = e->ev[e->ev_used++];
+  cudaEventRecord(x, st);
+  return x;
+}
+
+static int env_arena(const AcsEnv* e, int which, void** ptr, int* nf, int* per, int* is_int) {
+  const EnvView& v = e->v;
+  switch (which) {
+    case 0: *ptr = v.fdm; *nf = N_STATE; *per = v.rows; *is_int = 0; return 0;
+    case 1: *ptr = v.out; *nf = FDM_N_OUT; *per = v.rows; *is_int = 0; return 0;
+    case 2: *ptr = v.ad; *nf = N_AD; *per = v.rows; *is_int = 0; return 0;
+    case 3: *ptr = v.ai; *nf = N_AI; *per = v.rows; *is_int = 1; return 0;
+    case 4: *ptr = v.ed; *nf = N_ED; *per = v.B; *is_int = 0; return 0;
+    case 5: *ptr = v.ei; *nf = N_EI; *per = v.B; *is_int = 1; return 0;
+    case 6: *ptr = v.md; *nf = N_MD; *per = v.rows * v.S; *is_int = 0; return 0;
+    case 7: *ptr = v.mi; *nf = N_MI; *per = v.rows * v.S; *is_int = 1; return 0;
+  }
+  return fail("unknown arena id");
+}
+
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" {
+
+int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
+  if (!cfg || !out) return fail("acs_env_create: null argument");
+  const int A = cfg->n_ego + cfg->n_enm;
+  if (cfg->n_envs <= 0 || A <= 0 || A > ACS_MAX_AGENTS) return fail("acs_env_create: need 1..8 aircraft per env and n_envs > 0");
+  if (cfg->n_rewards < 0 || cfg->n_rewards > ACS_MAX_REWARDS || cfg->n_terms < 0 || cfg->n_terms > ACS_MAX_TERMS)
+    return fail("acs_env_create: too many rewards / terminations");
+  if (cfg->substeps <= 0 || cfg->obs_dim <= 0) return fail("acs_env_create: substeps and obs_dim must be positive");
+  if (cfg->shoot_dim != 0 && cfg->shoot_dim != 1 && cfg->shoot_dim != 4) return fail("acs_env_create: shoot_dim must be 0, 1 or 4");
+  if (cfg->lock_len > 64) return fail("acs_env_create: lock_len > 64 is not supported");
+  if (std::strcmp(STATE_NAMES[F_SIM_TIME], "sim_time") || std::strcmp(STATE_NAMES[F_CMD0], "fcs/aileron-cmd-norm") ||
+      std::strcmp(STATE_NAMES[F_CMD0 + 3], "fcs/throttle-cmd-norm"))
+    return fail("acs_env_create: FDM state layout changed (sim_time / control fields)");
+  AcsConfig fc;
+  fc.n_envs = cfg->n_envs; fc.n_agents = A; fc.sim_dt = cfg->sim_dt; fc.fcs_dt = cfg->fcs_dt;
+  AcsHandle* fh = nullptr;
+  if (acs_create(&fc, device, &fh)) return 1;
+  AcsEnv* e = new AcsEnv();
+  e->cfg = *cfg; e->fdm = fh;
+  e->lg = A <= 1 ? 0 : (A <= 2 ? 1 : (A <= 4 ? 2 : 3));
+  e->G = 1 << e->lg;
+  EnvView& v = e->v;
+  v.B = cfg->n_envs; v.A = A; v.S = cfg->n_missile_slots > 0 ? cfg->n_missile_slots : 1; v.rows = v.B * A;
+  v.fdm = fh->state; v.out = fh->out;
+  const size_t rows = v.rows, B = v.B, ms = rows * v.S;
+  CUDA_TRY(cudaMalloc(&v.ad, sizeof(double) * N_AD * rows)); CUDA_TRY(cudaMemset(v.ad, 0, sizeof(double) * N_AD * rows));
+  CUDA_TRY(cudaMalloc(&v.ai, sizeof(int) * N_AI * rows));    CUDA_TRY(cudaMemset(v.ai, 0, sizeof(int) * N_AI * rows));
+  CUDA_TRY(cudaMalloc(&v.ed, sizeof(double) * N_ED * B));    CUDA_TRY(cudaMemset(v.ed, 0, sizeof(double) * N_ED * B));
+  CUDA_TRY(cudaMalloc(&v.ei, sizeof(int) * N_EI * B));       CUDA_TRY(cudaMemset(v.ei, 0, sizeof(int) * N_EI * B));
+  CUDA_TRY(cudaMalloc(&v.md, sizeof(double) * N_MD * ms));   CUDA_TRY(cudaMemset(v.md, 0, sizeof(double) * N_MD * ms));
+  CUDA_TRY(cudaMalloc(&v.mi, sizeof(int) * N_MI * ms));      CUDA_TRY(cudaMemset(v.mi, 0, sizeof(int) * N_MI * ms));
+  // episode counters start at -1 so the first reset is episode 0
+  CUDA_TRY(cudaMemset(v.ei + (size_t)EI_EPISODE * B, 0xff, sizeof(int) * B));
+  *out = e;
+  return 0;
+}
+
+int acs_env_destroy(AcsEnv* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->fdm->device);
+  cudaFree(e->v.ad); cudaFree(e->v.ai); cudaFree(e->v.ed); cudaFree(e->v.ei); cudaFree(e->v.md); cudaFree(e->v.mi);
+  for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
+  acs_destroy(e->fdm);
+  delete e;
+  return 0;
+}
+
+int acs_env_set_init_states(AcsEnv* e, const double* init_host) {
+  if (!e || !init_host) return fail("acs_env_set_init_states: null argument");
+  std::memcpy(e->cfg.init_state, init_host, sizeof(double) * 12 * e->v.A);
+  return 0;
+}
+
+AcsHandle* acs_env_fdm(AcsEnv* e) { return e ? e->fdm : nullptr; }
+
+int acs_env_set_seed(AcsEnv* e, uint64_t seed, void* stream) {
+  if (!e) return fail("acs_env_set_seed: null handle");
+  e->cfg.seed = seed;
+  CUDA_TRY(cudaMemsetAsync(e->v.ei + (size_t)EI_EPISODE * e->v.B, 0xff, sizeof(int) * e->v.B, (cudaStream_t)stream));
+  return 0;
+}
+
+int acs_env_reset(AcsEnv* e, const uint8_t* env_mask_dev, double* obs_dev, double* share_obs_dev, void* stream) {
+  if (!e || !obs_dev) return fail("acs_env_reset: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = e->v.B * e->G;
+  k_env_reset_fdm<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, env_mask_dev);
+  CUDA_TRY(cudaGetLastError());
+  k_env_reset_task<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg, env_mask_dev, obs_dev, share_obs_dev);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double* share_obs_dev, double* rewards_dev,
+                 uint8_t* dones_dev, int32_t* info_dev, uint8_t* env_done_dev, int auto_reset, void* stream) {
+  if (!e || !actions_dev || !obs_dev || !rewards_dev || !dones_dev) return fail("acs_env_step: null argument");
+  if (auto_reset && !env_done_dev) return fail("acs_env_step: auto_reset needs env_done_dev");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int threads = e->v.B * e->G;
+  if (e->timing) timing_event(e, st);
+  k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
+  CUDA_TRY(cudaGetLastError());
+  if (e->timing) timing_event(e, st);
+  k_env_post<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg, obs_dev, share_obs_dev, rewards_dev, dones_dev, info_dev, env_done_dev);
+  CUDA_TRY(cudaGetLastError());
+  if (e->timing) timing_event(e, st);
+  int rc = 0;
+  if (auto_reset) rc = acs_env_reset(e, env_done_dev, obs_dev, share_obs_dev, stream);
+  if (e->timing) timing_event(e, st);
+  return rc;
+}
+
+int acs_env_set_timing(AcsEnv* e, int on) {
+  if (!e) return fail("acs_env_set_timing: null handle");
+  e->timing = on != 0;
+  e->ev_used = 0;
+  return 0;
+}
+
+int acs_env_get_timing(AcsEnv* e, double ms[3], int* n_steps) {
+  if (!e || !ms || !n_steps) return fail("acs_env_get_timing: null argument");
+  ms[0] = ms[1] = ms[2] = 0.0;
+  const size_t n = e->ev_used / 4;
+  for (size_t k = 0; k < n; k++) {
+    CUDA_TRY(cudaEventSynchronize(e->ev[4 * k + 3]));
+    for (int j = 0; j < 3; j++) {
+      float t = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&t, e->ev[4 * k + j], e->ev[4 * k + j + 1]));
+      ms[j] += t;
+    }
+  }
+  *n_steps = (int)n;
+  e->ev_used = 0;
+  return 0;
+}
+
+int acs_env_arena_info(const AcsEnv* e, int which, int* n_fields, int* n_per_field, int* is_int) {
+  if (!e) return fail("acs_env_arena_info: null handle");
+  void* p; int nf, per, ii;
+  if (env_arena(e, which, &p, &nf, &per, &ii)) return 1;
+  if (n_fields) *n_fields = nf; if (n_per_field) *n_per_field = per; if (is_int) *is_int = ii;
+  return 0;
+}
+const char* acs_env_arena_field_name(int which, int f) {
+  switch (which) {
+    case 0: return acs_state_field_name(f);
+    case 1: return acs_output_field_name(f);
+    case 2: return (f >= 0 && f < N_AD) ? AD_NAMES[f] : nullptr;
+    case 3: return (f >= 0 && f < N_AI) ? AI_NAMES[f] : nullptr;
+    case 4: return (f >= 0 && f < N_ED) ? ED_NAMES[f] : nullptr;
+    case 5: return (f >= 0 && f < N_EI) ? EI_NAMES[f] : nullptr;
+    case 6: return (f >= 0 && f < N_MD) ? MD_NAMES[f] : nullptr;
+    case 7: return (f >= 0 && f < N_MI) ? MI_NAMES[f] : nullptr;
+  }
+  return nullptr;
+}
+int acs_env_get_arena(const AcsEnv* e, int which, void* dst_dev, void* stream) {
+  if (!e || !dst_dev) return fail("acs_env_get_arena: null argument");
+  void* p; int nf, per, ii;
+  if (env_arena(e, which, &p, &nf, &per, &ii)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(dst_dev, p, (size_t)nf * per * (ii ? sizeof(int) : sizeof(double)), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int acs_env_set_arena(AcsEnv* e, int which, const void* src_dev, void* stream) {
+  if (!e || !src_dev) return fail("acs_env_set_arena: null argument");
+  void* p; int nf, per, ii;
+  if (env_arena(e, which, &p, &nf, &per, &ii)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(p, src_dev, (size_t)nf * per * (ii ? sizeof(int) : sizeof(double)), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int acs_bench_fp64_peak(int device, double* flops_out) {
+  if (!flops_out) return fail("acs_bench_fp64_peak: null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double* buf = nullptr;
+  CUDA_TRY(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  k_fp64_peak<<<blocks, threads>>>(buf, 1024);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CUDA_TRY(cudaEventRecord(e0));
+    k_fp64_peak<<<blocks, threads>>>(buf, iters);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  *flops_out = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
   return 0;
 }
 

@@ -1,0 +1,944 @@
+// env_kernels.cuh -- the three env-layer kernels (sm_100a), one thread per aircraft, the G = 1/2/4/8 lanes of one
+// environment adjacent inside a warp so cross-aircraft exchange is shared memory + __syncwarp on the group's lane mask:
+//
+//   k_env_substeps   actions -> controls, then the agent_interaction_steps substep loop with the FDM state in registers:
+//                    aircraft run(), missile run() (PN guidance + fused proximity fuze), chaff run(), chaff x missile test
+//                    (E/envs/env_base.py:131-154, E/core/simulatior.py:210-229,520-533)
+//   k_env_post       task.step (weapon launches), get_obs, get_reward, get_termination, packing
+//                    (E/envs/env_base.py:155-173, E/envs/multiplecombat_env.py:161-182)
+//   k_env_reset      masked per-env reset: sim.reload() for every aircraft, task.reset, reward resets, get_obs
+//                    (E/envs/env_base.py:98-113); with the mask = "all agents done" this is the VecEnv auto-reset
+//                    (R/envs/env_wrappers.py:191-204)
+#pragma once
+
+static constexpr int F_SIM_TIME = FDM_N_CORE - 1;  // "sim_time" is the last core field
+static constexpr int F_CMD0 = FDM_N_CORE;          // fcs/{aileron,elevator,rudder,throttle}-cmd-norm are the first carried fields
+
+struct Lane {
+  int tid, env, lane, row, gbase;
+  unsigned gmask;
+  bool valid;
+};
+// lg = log2 of the lanes per env (1, 2, 4 or 8 lanes)
+ENV_DEV Lane lane_setup(const EnvView& v, const int lg) {
+  Lane L;
+  const int G = 1 << lg;
+  L.tid = threadIdx.x;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  L.env = gid >> lg;
+  L.lane = gid & (G - 1);
+  L.gbase = L.tid - L.lane;
+  L.valid = (L.env < v.B) && (L.lane < v.A);
+  L.row = L.env * v.A + L.lane;
+  const unsigned wl = threadIdx.x & 31;
+  L.gmask = ((1u << G) - 1u) << (wl & ~(unsigned)(G - 1));
+  return L;
+}
+
+// what every aircraft publishes to the other lanes of its env
+struct PubAc {
+  Feat f;            // position (n, e, u) and velocity (vn, ve, vd), as AircraftSimulator.get_position / get_velocity
+  double h, u_mps, bloods;
+  int status;
+};
+struct PubChaff { double n, e, u; int state, count; };
+
+ENV_DEV bool same_team(const AcsTaskConfig& c, int a, int b) { return (a < c.n_ego) == (b < c.n_ego); }
+
+// derived catalog properties of an aircraft from the FDM outputs of its last frame (E/core/catalog.py:292-338: the
+// *_mps / h_sl_m properties are stored through set_property_value, hence clipped)
+ENV_DEV void derive_aircraft(const AcOut& o, const GeoOrigin& org, PubAc& p, double& v_mps, double& w_mps, double& vc_mps) {
+  p.h = env_clip(o.h_sl_ft * 0.3048, -500.0, 26000.0);
+  lla2neu(org, o.lon_deg, o.lat_geod_deg, p.h, p.f.n, p.f.e, p.f.u);
+  p.f.vn = env_clip(o.vn * 0.3048, -700.0, 700.0);
+  p.f.ve = env_clip(o.ve * 0.3048, -700.0, 700.0);
+  p.f.vd = env_clip(o.vd * 0.3048, -700.0, 700.0);
+  p.u_mps = env_clip(o.u * 0.3048, -700.0, 700.0);
+  v_mps = env_clip(o.v * 0.3048, -700.0, 700.0);
+  w_mps = env_clip(o.w * 0.3048, -700.0, 700.0);
+  vc_mps = env_clip(o.vc_fps * 0.3048, 0.0, 1400.0);
+}
+ENV_DEV void store_derived(const EnvView& v, int row, const PubAc& p, double v_mps, double w_mps, double vc_mps) {
+  AD(v, AD_POS_N, row) = p.f.n; AD(v, AD_POS_E, row) = p.f.e; AD(v, AD_POS_U, row) = p.f.u;
+  AD(v, AD_VEL_N, row) = p.f.vn; AD(v, AD_VEL_E, row) = p.f.ve; AD(v, AD_VEL_D, row) = p.f.vd;
+  AD(v, AD_H_SL_M, row) = p.h; AD(v, AD_U_MPS, row) = p.u_mps; AD(v, AD_V_MPS, row) = v_mps; AD(v, AD_W_MPS, row) = w_mps;
+  AD(v, AD_VC_MPS, row) = vc_mps;
+}
+ENV_DEV void load_pub(const EnvView& v, int row, PubAc& p) {
+  p.f.n = AD(v, AD_POS_N, row); p.f.e = AD(v, AD_POS_E, row); p.f.u = AD(v, AD_POS_U, row);
+  p.f.vn = AD(v, AD_VEL_N, row); p.f.ve = AD(v, AD_VEL_E, row); p.f.vd = AD(v, AD_VEL_D, row);
+  p.h = AD(v, AD_H_SL_M, row); p.u_mps = AD(v, AD_U_MPS, row); p.bloods = AD(v, AD_BLOODS, row);
+  p.status = AI(v, AI_STATUS, row);
+}
+
+// ============================================================================================== substep kernel
+// The missile phase of one substep for the lanes of one env (E/envs/env_base.py:141-154).  Reference order inside a
+// substep: every aircraft run(), then every missile run() in dict order, then every chaff run(), then the
+// chaff x missile test.  Missiles are processed in parallel by their shooter's lane; the only order-dependent outcome
+// -- two missiles inside the fuze radius of one target in the same substep, where the first in dict order scores the
+// HIT and later ones see a dead target and go MISS -- is resolved with a shared-memory atomicMin on the dict order.
+__device__ __noinline__ void missile_phase(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const GeoOrigin& org,
+                                           PubAc* sP, int* sWin, int* sShot, PubChaff* sCh, int substep_count) {
+  const double dt = cfg.sim_dt;
+  const int nl = L.valid ? AI(v, AI_N_LAUNCHED, L.row) : 0;
+  const int maxlen = (int)(5.0 / dt);
+  // ---- phase 1: who is inside its fuze radius (uses the state before this substep's missile moves)
+  for (int s = 0; s < nl; s++) {
+    const int mid = L.row * v.S + s;
+    if (MI(v, MI_DETACHED, mid)) continue;
+    Missile m;
+    missile_load(v, mid, m);
+    const MissileParams pr = missile_params(m.kind);
+    const double d = missile_distance(m, sP[L.gbase + m.target].f);
+    if (d < pr.Rc && m.status != MS_MISS) atomicMin(&sWin[L.gbase + m.target], MI(v, MI_ORDER, mid));
+  }
+  __syncwarp(L.gmask);
+  // ---- phase 2: MissileSimulator.run() (:520-533)
+  for (int s = 0; s < nl; s++) {
+    const int mid = L.row * v.S + s;
+    if (MI(v, MI_DETACHED, mid)) continue;
+    Missile m;
+    missile_load(v, mid, m);
+    const MissileParams pr = missile_params(m.kind);
+    const PubAc& tg = sP[L.gbase + m.target];
+    m.t += dt;
+    double ny, nz, dist;
+    missile_guidance(m, pr, tg.f, ny, nz, dist);
+    m.consec = (dist > m.d_prev) ? m.consec + 1 : 0;
+    m.d_prev = dist;
+    const int order = MI(v, MI_ORDER, mid);
+    const bool target_alive = (tg.status == ST_ALIVE) && !(sWin[L.gbase + m.target] < order);
+    if (dist < pr.Rc && target_alive && m.status != MS_MISS) {
+      m.status = MS_HIT;
+      sShot[L.gbase + m.target] = 1;
+    } else if (m.t > pr.t_max || sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu) < pr.v_min || m.consec >= maxlen || !target_alive) {
+      m.status = MS_MISS;
+    } else {
+      missile_state_trans(m, pr, org, ny, nz, dt);
+    }
+    missile_store(v, mid, m);
+  }
+  // ---- chaff run() (:377-381) and publication
+  {
+    PubChaff c;
+    c.state = CH_NONE; c.count = 0; c.n = c.e = c.u = 0.0;
+    if (L.valid) {
+      c.state = AI(v, AI_CH_STATE, L.row);
+      if (c.state != CH_NONE) {
+        const double t = AD(v, AD_CH_T, L.row) + dt;
+        AD(v, AD_CH_T, L.row) = t;
+        if (t > 20.0) c.state = CH_DONE;
+        AI(v, AI_CH_STATE, L.row) = c.state;
+        c.count = AI(v, AI_CH_COUNT, L.row);
+        c.n = AD(v, AD_CH_N, L.row); c.e = AD(v, AD_CH_E, L.row); c.u = AD(v, AD_CH_U, L.row);
+      }
+    }
+    sCh[L.tid] = c;
+  }
+  __syncwarp(L.gmask);
+  // ---- chaff x missile (E/envs/env_base.py:146-154): every live missile against every effective chaff
+  for (int s = 0; s < nl; s++) {
+    const int mid = L.row * v.S + s;
+    if (MI(v, MI_DETACHED, mid)) continue;
+    const int st = MI(v, MI_STATUS, mid);
+    if (st == MS_HIT || st == MS_MISS) continue;
+    const double pn = MD(v, MD_POS_N, mid), pe = MD(v, MD_POS_E, mid), pu = MD(v, MD_POS_U, mid);
+    const int keyn = MI(v, MI_KEYN, mid);
+    bool missed = false;
+    for (int j = 0; j < v.A; j++) {
+      const PubChaff& c = sCh[L.gbase + j];
+      if (c.state != CH_ACTIVE) continue;
+      const double dx = c.n - pn, dy = c.e - pe, dz = c.u - pu;
+      if (sqrt(dx * dx + dy * dy + dz * dz) <= 300.0) {
+        for (int q = 0; q < c.count; q++)
+          if (env_u01(cfg.seed, cfg.env_offset + L.env, RNG_CHAFF, substep_count, L.lane * 64 + keyn, j * 64 + q) < 0.85) missed = true;
+      }
+    }
+    if (missed) MI(v, MI_STATUS, mid) = MS_MISS;
+  }
+}
+
+__global__ void __launch_bounds__(FDM_BLOCK) k_env_substeps(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
+                                                           const int32_t* __restrict__ actions) {
+  __shared__ double sT[F16_NTAB];
+  __shared__ PubAc sP[FDM_BLOCK];
+  __shared__ int sWin[FDM_BLOCK];
+  __shared__ int sShot[FDM_BLOCK];
+  __shared__ PubChaff sCh[FDM_BLOCK];
+  stage_tables(sT);
+  const Lane L = lane_setup(v, lg);
+  const int N = v.rows, K = cfg.substeps;
+  const double dt = cfg.sim_dt, fcs_dt = cfg.fcs_dt;
+  const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
+
+  AcCore a; Props p; FcsState s; Frame f;
+  PubAc me;
+  double v_mps = 0, w_mps = 0, vc_mps = 0;
+  int status = ST_CRASH;
+  bool has_ms = false;
+  me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
+  if (L.valid) {
+    load_pub(v, L.row, me);
+    status = me.status;
+    has_ms = (AI(v, AI_N_LAUNCHED, L.row) > 0) || (AI(v, AI_CH_STATE, L.row) == CH_ACTIVE);
+    // ---- normalize_action + set_property_values(action_var) with the catalog clip (E/tasks/heading_task.py:102-110,
+    //      E/tasks/singlecombat_task.py:141-153, E/core/catalog.py:192-197); applied to dead aircraft too
+    const int adim = 4 + cfg.shoot_dim;
+    const int32_t* act = actions + (size_t)L.row * adim;
+    double u0, u1, u2, u3;
+    if (cfg.act_kind == ACS_ACT_HEADING) {
+      u0 = act[0] * 2. / (41 - 1.) - 1.; u1 = act[1] * 2. / (41 - 1.) - 1.; u2 = act[2] * 2. / (41 - 1.) - 1.; u3 = act[3] * 0.5 / (30 - 1.) + 0.4;
+    } else {
+      u0 = act[0] / 20. - 1.; u1 = act[1] / 20. - 1.; u2 = act[2] / 20. - 1.; u3 = act[3] / 58. + 0.4;
+    }
+    u0 = env_clip(u0, -1.0, 1.0); u1 = env_clip(u1, -1.0, 1.0); u2 = env_clip(u2, -1.0, 1.0); u3 = env_clip(u3, 0.0, 0.9);
+    int shoot = 0;
+    for (int k = 0; k < cfg.shoot_dim; k++) shoot |= (act[4 + k] != 0) << k;
+    if (cfg.shoot_dim > 0) AI(v, AI_SHOOT, L.row) = shoot;
+    if (status == ST_ALIVE) {
+      f16_props_init(p, s);
+      load_state(v.fdm, N, L.row, a, p, s);
+      p.fcs_aileron_cmd_norm = u0; p.fcs_elevator_cmd_norm = u1; p.fcs_rudder_cmd_norm = u2; p.fcs_throttle_cmd_norm = u3;
+    } else {
+      v.fdm[(size_t)(F_CMD0 + 0) * N + L.row] = u0; v.fdm[(size_t)(F_CMD0 + 1) * N + L.row] = u1;
+      v.fdm[(size_t)(F_CMD0 + 2) * N + L.row] = u2; v.fdm[(size_t)(F_CMD0 + 3) * N + L.row] = u3;
+    }
+  }
+  // an env needs the per-substep exchange only while it has missiles or chaff in the air
+  {
+    const unsigned b = __ballot_sync(L.gmask, has_ms);
+    has_ms = (b & L.gmask) != 0;
+  }
+  const bool was_alive = L.valid && status == ST_ALIVE;
+  const int sc0 = (L.env < v.B) ? EI(v, EI_SUBSTEP_COUNT, L.env) : 0;
+  AcOut o;
+  for (int k = 0; k < K; k++) {
+    bool ran = false;
+    if (L.valid && status == ST_ALIVE) {                     // AircraftSimulator.run (simulatior.py:210-229)
+      if (me.bloods <= 0) status = ST_SHOTDOWN;
+      fdm_frame(a, p, s, f, sT, g_atmo, dt, fcs_dt, false);
+      ran = true;
+    }
+    // _update_properties (simulatior.py:238-257): only materialised when somebody reads it -- missiles in the air,
+    // the end of the step, or the aircraft's last frame (bloods <= 0 flipped it to SHOTDOWN above)
+    if (ran && (has_ms || k == K - 1 || status != ST_ALIVE)) {
+      fdm_outputs(a, f, o);
+      derive_aircraft(o, org, me, v_mps, w_mps, vc_mps);
+    }
+    if (has_ms) {
+      me.status = status;
+      sP[L.tid] = me;
+      sWin[L.tid] = 0x7fffffff;
+      sShot[L.tid] = 0;
+      __syncwarp(L.gmask);
+      missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, sc0 + k);
+      __syncwarp(L.gmask);
+      if (sShot[L.tid]) status = ST_SHOTDOWN;                 // target_aircraft.shotdown() (simulatior.py:527)
+      __syncwarp(L.gmask);
+    }
+  }
+  if (L.valid) {
+    if (was_alive) {
+      store_state(v.fdm, N, L.row, a, p, s);
+      store_out(v.out, N, L.row, o);
+      store_derived(v, L.row, me, v_mps, w_mps, vc_mps);
+    }
+    AI(v, AI_STATUS, L.row) = status;
+    if (L.lane == 0) EI(v, EI_SUBSTEP_COUNT, L.env) = sc0 + K;
+  }
+}
+
+// ============================================================================================== per-step logic
+struct StepCtx {
+  const EnvView& v;
+  const AcsTaskConfig& cfg;
+  const Lane& L;
+  PubAc* sP;       // block-wide, index gbase + agent
+  int cs;          // env.current_step (already incremented)
+};
+
+// first live incoming missile in under_missiles (append order): AircraftSimulator.check_missile_warning (simulatior.py:321-325)
+ENV_DEV int missile_warning(const StepCtx& c, int agent) {
+  int best = -1, best_born = 0x7fffffff;
+  for (int j = 0; j < c.v.A; j++) {
+    if (same_team(c.cfg, agent, j)) continue;
+    const int row = c.L.env * c.v.A + j;
+    const int nl = AI(c.v, AI_N_LAUNCHED, row);
+    for (int s = 0; s < nl; s++) {
+      const int mid = row * c.v.S + s;
+      if (MI(c.v, MI_TARGET, mid) == agent && MI(c.v, MI_STATUS, mid) == MS_LAUNCHED) {
+        const int b = MI(c.v, MI_BORN, mid);
+        if (b < best_born) { best_born = b; best = mid; }
+      }
+    }
+  }
+  return best;
+}
+ENV_DEV void attack_geometry(const PubAc& ag, const PubAc& en, double& distance, double& ang_deg) {
+  const double tx = en.f.n - ag.f.n, ty = en.f.e - ag.f.e, tz = en.f.u - ag.f.u;
+  distance = sqrt(tx * tx + ty * ty + tz * tz);
+  const double hv = sqrt(ag.f.vn * ag.f.vn + ag.f.ve * ag.f.ve + ag.f.vd * ag.f.vd);
+  const double sum = tx * ag.f.vn + ty * ag.f.ve + tz * ag.f.vd;
+  ang_deg = acos(env_clip(sum / (distance * hv + 1e-8), -1.0, 1.0)) * (180.0 / 3.14159265358979323846);
+}
+// MissileSimulator.create -> launch + target (simulatior.py:497-518), env.add_temp_simulator (env_base.py:90-92)
+ENV_DEV int launch_missile(const StepCtx& c, int a, int target, int kind, int keyn) {
+  const EnvView& v = c.v;
+  const int row = c.L.env * v.A + a;
+  const int slot = AI(v, AI_N_LAUNCHED, row);
+  if (slot >= v.S) { EI(v, EI_FAULTS, c.L.env) += 1; return -1; }   // cannot happen: S = max launches per episode (taskspec.py)
+  AI(v, AI_N_LAUNCHED, row) = slot + 1;
+  const int mid = row * v.S + slot;
+  const PubAc& pa = c.sP[c.L.gbase + a];
+  const MissileParams pr = missile_params(kind);
+  MD(v, MD_POS_N, mid) = pa.f.n; MD(v, MD_POS_E, mid) = pa.f.e; MD(v, MD_POS_U, mid) = pa.f.u;
+  MD(v, MD_VEL_N, mid) = pa.f.vn; MD(v, MD_VEL_E, mid) = pa.f.ve; MD(v, MD_VEL_U, mid) = pa.f.vd;
+  MD(v, MD_THETA, mid) = OUTF(v, O_PITCH, row); MD(v, MD_PHI, mid) = OUTF(v, O_HEADING, row);
+  MD(v, MD_ALT, mid) = pa.h; MD(v, MD_T, mid) = 0.0; MD(v, MD_M, mid) = pr.m0; MD(v, MD_DTHETA, mid) = 0.0; MD(v, MD_DPHI, mid) = 0.0;
+  MD(v, MD_D_PREV, mid) = INFINITY;
+  MI(v, MI_STATUS, mid) = MS_LAUNCHED; MI(v, MI_KIND, mid) = kind; MI(v, MI_TARGET, mid) = target; MI(v, MI_CONSEC, mid) = 0;
+  MI(v, MI_KEYN, mid) = keyn; MI(v, MI_DETACHED, mid) = 0;
+  // dict semantics of env._tempsims[uid] = sim: a re-used uid keeps the old entry's position and drops the old object
+  int order = -1;
+  for (int s = 0; s < slot; s++) {
+    const int om = row * v.S + s;
+    if (!MI(v, MI_DETACHED, om) && MI(v, MI_KEYN, om) == keyn) { MI(v, MI_DETACHED, om) = 1; order = MI(v, MI_ORDER, om); }
+  }
+  if (order < 0) { order = EI(v, EI_ORDER_SEQ, c.L.env); EI(v, EI_ORDER_SEQ, c.L.env) = order + 1; }
+  MI(v, MI_ORDER, mid) = order;
+  const int born = EI(v, EI_BORN_SEQ, c.L.env);
+  EI(v, EI_BORN_SEQ, c.L.env) = born + 1;
+  MI(v, MI_BORN, mid) = born;
+  return slot;
+}
+ENV_DEV bool last_shot_free(const StepCtx& c, int row) {
+  const int ls = AI(c.v, AI_LAST_SHOT_SLOT, row);
+  if (ls < 0) return true;
+  const int st = MI(c.v, MI_STATUS, row * c.v.S + ls);
+  return st == MS_HIT || st == MS_MISS;
+}
+// scenario tasks: get_target = argmax distance (E/tasks/scenario2_task.py:150-156); a2a_launch_available (:116-148)
+ENV_DEV int scenario_target(const StepCtx& c, int a) {
+  const PubAc& ag = c.sP[c.L.gbase + a];
+  int best = -1; double bd = -1.0;
+  for (int j = 0; j < c.v.A; j++) {
+    if (same_team(c.cfg, a, j)) continue;
+    const PubAc& en = c.sP[c.L.gbase + j];
+    const double tx = en.f.n - ag.f.n, ty = en.f.e - ag.f.e, tz = en.f.u - ag.f.u;
+    const double d = sqrt(tx * tx + ty * ty + tz * tz);
+    if (d > bd) { bd = d; best = j; }   // np.argmax: first maximum
+  }
+  return best;
+}
+ENV_DEV void a2a_available(const StepCtx& c, int a, bool ret[3], int& enemy) {
+  ret[0] = ret[1] = ret[2] = false;
+  enemy = scenario_target(c, a);
+  const PubAc& en = c.sP[c.L.gbase + enemy];
+  if (en.status != ST_ALIVE) return;
+  double distance, ang;
+  attack_geometry(c.sP[c.L.gbase + a], en, distance, ang);
+  if (distance / 1000 < 3 && ang < 5) ret[0] = true;
+  if (distance / 1000 < 37 && ang < 90) ret[1] = true;
+  if (distance / 1000 < 7 && ang < 90) ret[2] = true;
+  if (c.cfg.use_baseline && a >= c.cfg.n_ego) {
+    ret[1] = false;
+    if (distance / 1000 < 37 && ang < 90 / 2) ret[1] = true;
+  }
+}
+
+// task.step for agent a (executed by lane a while the other lanes of the env wait)
+ENV_DEV void task_step_agent(const StepCtx& c, int a) {
+  const EnvView& v = c.v;
+  const AcsTaskConfig& cfg = c.cfg;
+  const int row = c.L.env * v.A + a;
+  PubAc* sP = c.sP + c.L.gbase;
+  const bool alive = sP[a].status == ST_ALIVE;
+  const int shoot = AI(v, AI_SHOOT, row);
+  if (cfg.launch_kind == ACS_L_RULE_LOCK) {          // E/tasks/singlecombat_with_missile_task.py:109-127
+    int e0 = -1;
+    for (int j = 0; j < v.A && e0 < 0; j++) if (!same_team(cfg, a, j)) e0 = j;
+    double distance, ang;
+    attack_geometry(sP[a], sP[e0], distance, ang);
+    // deque(maxlen = lock_len) of booleans, as a bit window
+    unsigned long long bits = ((unsigned long long)(unsigned)AI(v, AI_LOCK_HI, row) << 32) | (unsigned)AI(v, AI_LOCK_LO, row);
+    int n = AI(v, AI_LOCK_N, row);
+    bits = (bits << 1) | (ang < cfg.max_attack_angle ? 1ull : 0ull);
+    n = min(n + 1, cfg.lock_len);
+    const unsigned long long wmask = cfg.lock_len >= 64 ? ~0ull : ((1ull << cfg.lock_len) - 1ull);
+    bits &= wmask;
+    AI(v, AI_LOCK_LO, row) = (int)(unsigned)(bits & 0xffffffffull); AI(v, AI_LOCK_HI, row) = (int)(unsigned)(bits >> 32); AI(v, AI_LOCK_N, row) = n;
+    const int locked = __popcll(bits);
+    const int interval = c.cs - AI(v, AI_LAST_SHOOT_TIME, row);
+    const int rem = AI(v, AI_REM_MISSILES, row);
+    if (alive && locked >= cfg.lock_len && distance <= cfg.max_attack_distance && rem > 0 && interval >= cfg.min_attack_interval) {
+      launch_missile(c, a, e0, 0, rem);
+      AI(v, AI_REM_MISSILES, row) = rem - 1;
+      AI(v, AI_LAST_SHOOT_TIME, row) = c.cs;
+    }
+  } else if (cfg.launch_kind == ACS_L_RL_SINGLE) {   // E/tasks/singlecombat_with_missile_task.py:194-204
+    int e0 = -1;
+    for (int j = 0; j < v.A && e0 < 0; j++) if (!same_team(cfg, a, j)) e0 = j;
+    const int rem = AI(v, AI_REM_MISSILES, row);
+    if (alive && (shoot & 1) && rem > 0 && last_shot_free(c, row)) {
+      AI(v, AI_LAST_SHOT_SLOT, row) = launch_missile(c, a, e0, 0, rem);
+      AI(v, AI_REM_MISSILES, row) = rem - 1;
+    }
+  } else if (cfg.launch_kind == ACS_L_RL_NEAREST) {  // E/tasks/multiplecombat_task.py:278-299
+    int ti = -1; double bd = INFINITY;
+    for (int j = 0; j < v.A; j++) {
+      if (same_team(cfg, a, j)) continue;
+      const double tx = sP[j].f.n - sP[a].f.n, ty = sP[j].f.e - sP[a].f.e, tz = sP[j].f.u - sP[a].f.u;
+      const double d = sqrt(tx * tx + ty * ty + tz * tz);
+      if (d < bd) { bd = d; ti = j; }              // np.argmin: first minimum
+    }
+    double distance, ang;
+    attack_geometry(sP[a], sP[ti], distance, ang);
+    const int interval = c.cs - AI(v, AI_LAST_SHOOT_TIME, row);
+    const int rem = AI(v, AI_REM_MISSILES, row);
+    if (alive && (shoot & 1) && rem > 0 && ang <= cfg.max_attack_angle && distance <= cfg.max_attack_distance &&
+        interval >= cfg.min_attack_interval) {
+      launch_missile(c, a, ti, 0, rem);
+      AI(v, AI_REM_MISSILES, row) = rem - 1;
+      AI(v, AI_LAST_SHOOT_TIME, row) = c.cs;
+    }
+  } else if (cfg.launch_kind == ACS_L_SCENARIO) {    // E/tasks/scenario2_task.py:73-114
+    const bool f_gun = alive && (shoot & 1) && AI(v, AI_REM_GUN, row) > 0;
+    const bool f_9m = alive && (shoot & 2) && AI(v, AI_REM_9M, row) > 0;
+    const bool f_120 = alive && (shoot & 4) && AI(v, AI_REM_120B, row) > 0;
+    const bool f_chaff = alive && (shoot & 8) && AI(v, AI_REM_CHAFF, row) > 0;
+    bool av[3]; int enemy;
+    if (f_gun && last_shot_free(c, row)) {
+      a2a_available(c, a, av, enemy);
+      if (av[0]) { sP[enemy].bloods -= 5; AI(v, AI_REM_GUN, row) -= 1; }
+    }
+    if (f_120 && last_shot_free(c, row)) {
+      a2a_available(c, a, av, enemy);
+      if (av[1]) {
+        const int rem = AI(v, AI_REM_120B, row);
+        AI(v, AI_LAST_SHOT_SLOT, row) = launch_missile(c, a, scenario_target(c, a), 1, rem);
+        AI(v, AI_REM_120B, row) = rem - 1;
+      }
+    }
+    if (f_9m && last_shot_free(c, row)) {
+      a2a_available(c, a, av, enemy);
+      if (av[2]) {
+        const int rem = AI(v, AI_REM_9M, row);
+        AI(v, AI_LAST_SHOT_SLOT, row) = launch_missile(c, a, scenario_target(c, a), 1, rem);
+        AI(v, AI_REM_9M, row) = rem - 1;
+      }
+    }
+    if (f_chaff && AI(v, AI_CH_STATE, row) != CH_ACTIVE) {
+      // one chaff per missile (done ones included) within 1000 m that targets this aircraft (:105-111)
+      int cnt = 0;
+      for (int j = 0; j < v.A; j++) {
+        if (same_team(cfg, a, j)) continue;
+        const int jr = c.L.env * v.A + j;
+        const int nl = AI(v, AI_N_LAUNCHED, jr);
+        for (int s = 0; s < nl; s++) {
+          const int mid = jr * v.S + s;
+          if (MI(v, MI_DETACHED, mid) || MI(v, MI_TARGET, mid) != a) continue;
+          const double dx = sP[a].f.n - MD(v, MD_POS_N, mid), dy = sP[a].f.e - MD(v, MD_POS_E, mid), dz = sP[a].f.u - MD(v, MD_POS_U, mid);
+          if (sqrt(dx * dx + dy * dy + dz * dz) < 1000) cnt++;
+        }
+      }
+      if (cnt > 0) {
+        AD(v, AD_CH_N, row) = sP[a].f.n; AD(v, AD_CH_E, row) = sP[a].f.e; AD(v, AD_CH_U, row) = sP[a].f.u; AD(v, AD_CH_T, row) = 0.0;
+        AI(v, AI_CH_STATE, row) = CH_ACTIVE; AI(v, AI_CH_COUNT, row) = cnt;
+        AI(v, AI_REM_CHAFF, row) -= cnt;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- observations
+ENV_DEV void obs_ego9(const EnvView& v, int row, const PubAc& s, double* o) {
+  double sr, cr, sp, cp;
+  sincos(OUTF(v, O_ROLL, row), &sr, &cr);
+  sincos(OUTF(v, O_PITCH, row), &sp, &cp);
+  o[0] = s.h / 5000; o[1] = sr; o[2] = cr; o[3] = sp; o[4] = cp;
+  o[5] = s.u_mps / 340; o[6] = AD(v, AD_V_MPS, row) / 340; o[7] = AD(v, AD_W_MPS, row) / 340; o[8] = AD(v, AD_VC_MPS, row) / 340;
+}
+ENV_DEV void obs_rel6(const PubAc& ego, const PubAc& other, bool two_d, double* o) {
+  const AoTaR g = get_ao_ta_r(ego.f, other.f, two_d);
+  o[0] = (other.u_mps - ego.u_mps) / 340; o[1] = (other.h - ego.h) / 1000; o[2] = g.AO; o[3] = g.TA; o[4] = g.R / 10000; o[5] = g.side;
+}
+ENV_DEV bool obs_missile6(const StepCtx& c, int a, double* o) {
+  const int mid = missile_warning(c, a);
+  if (mid < 0) return false;
+  const EnvView& v = c.v;
+  const PubAc& ego = c.sP[c.L.gbase + a];
+  Feat mf;
+  mf.n = MD(v, MD_POS_N, mid); mf.e = MD(v, MD_POS_E, mid); mf.u = MD(v, MD_POS_U, mid);
+  mf.vn = MD(v, MD_VEL_N, mid); mf.ve = MD(v, MD_VEL_E, mid); mf.vd = MD(v, MD_VEL_U, mid);
+  const AoTaR g = get_ao_ta_r(ego.f, mf, false);
+  o[0] = (sqrt(mf.vn * mf.vn + mf.ve * mf.ve + mf.vd * mf.vd) - ego.u_mps) / 340; o[1] = (mf.u - ego.h) / 1000;
+  o[2] = g.AO; o[3] = g.TA; o[4] = g.R / 10000; o[5] = g.side;
+  return true;
+}
+// get_obs for agent a into o[obs_dim] (global memory); citations per branch in taskspec.py
+ENV_DEV void write_obs(const StepCtx& c, int a, double* __restrict__ o) {
+  const EnvView& v = c.v;
+  const AcsTaskConfig& cfg = c.cfg;
+  const int row = c.L.env * v.A + a;
+  const PubAc* sP = c.sP + c.L.gbase;
+  const PubAc& s = sP[a];
+  const int D = cfg.obs_dim, k = cfg.obs_kind;
+  double t[9];
+  for (int i = 0; i < D; i++) o[i] = 0.0;
+  if (k == ACS_OBS_HEADING) {                      // E/tasks/heading_task.py:67-100
+    const double psi_deg = OUTF(v, O_HEADING, row) * RADTODEG;
+    const double d_alt = env_clip((ED(v, ED_TGT_ALT, c.L.env) - OUTF(v, O_H_SL_FT, row)) * 0.3048, -40000.0, 40000.0);
+    const double d_head = delta_heading_deg(ED(v, ED_TGT_HEADING, c.L.env), psi_deg);
+    const double d_vel = env_clip(ED(v, ED_TGT_VEL, c.L.env) - s.u_mps, -1400.0, 1400.0);
+    o[0] = d_alt / 1000; o[1] = d_head / 180 * 3.14159265358979323846; o[2] = d_vel / 340;
+    obs_ego9(v, row, s, t);
+    for (int i = 0; i < 9; i++) o[3 + i] = t[i];
+    for (int i = 0; i < 12; i++) o[i] = env_clip(o[i], -10.0, 10.0);
+    return;
+  }
+  obs_ego9(v, row, s, t);
+  for (int i = 0; i < 9; i++) o[i] = t[i];
+  double r6[6];
+  if (k == ACS_OBS_1V1) {                          // E/tasks/singlecombat_task.py:88-139
+    int e0 = -1;
+    for (int j = 0; j < v.A && e0 < 0; j++) if (!same_team(cfg, a, j)) e0 = j;
+    obs_rel6(s, sP[e0], true, r6);
+    for (int i = 0; i < 6; i++) o[9 + i] = r6[i];
+    for (int i = 0; i < 15; i++) o[i] = env_clip(o[i], -10.0, 10.0);
+    return;
+  }
+  if (k == ACS_OBS_1V1_MISSILE || k == ACS_OBS_NV_MISSILE) {   // E/tasks/singlecombat_with_missile_task.py:31-99; multiplecombat_with_missile_task.py:32-117
+    const int ti = (k == ACS_OBS_1V1_MISSILE) ? 0 : (a < cfg.n_ego ? a : a - cfg.n_ego);
+    int cnt = 0, e = -1;
+    for (int j = 0; j < v.A; j++) if (!same_team(cfg, a, j)) { if (cnt == ti) e = j; cnt++; }
+    obs_rel6(s, sP[e], false, r6);
+    for (int i = 0; i < 6; i++) o[9 + i] = r6[i];
+    if (obs_missile6(c, a, r6)) for (int i = 0; i < 6; i++) o[15 + i] = r6[i];
+    return;
+  }
+  int off = 9;
+  if (k == ACS_OBS_MULTI || k == ACS_OBS_MULTI_MISSILE || k == ACS_OBS_NVN) {   // E/tasks/multiplecombat_task.py:105-135,232-267; scenario2_task.py:256-316
+    for (int pass = 0; pass < 2; pass++)
+      for (int j = 0; j < v.A; j++) {
+        if (j == a || same_team(cfg, a, j) != (pass == 0)) continue;
+        obs_rel6(s, sP[j], false, r6);
+        for (int i = 0; i < 6; i++) o[off + i] = r6[i];
+        off += 6;
+      }
+    if (k != ACS_OBS_NVN) for (int i = 0; i < off; i++) o[i] = env_clip(o[i], -10.0, 10.0);
+    if (k != ACS_OBS_MULTI && obs_missile6(c, a, r6)) for (int i = 0; i < 6; i++) o[off + i] = r6[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- rewards
+ENV_DEV double reward_process(const StepCtx& c, int ri, int row, double new_reward) {   // BaseRewardFunction._process
+  const AcsRewardSpec& r = c.cfg.rewards[ri];
+  double reward = new_reward * r.scale;
+  if (r.potential) {
+    const double pre = AD(c.v, AD_PRE_REWARD0 + ri, row);
+    AD(c.v, AD_PRE_REWARD0 + ri, row) = reward;
+    reward = reward - pre;
+  }
+  return reward;
+}
+ENV_DEV double reward_one(const StepCtx& c, int ri, int a) {
+  const EnvView& v = c.v;
+  const AcsTaskConfig& cfg = c.cfg;
+  const AcsRewardSpec& r = cfg.rewards[ri];
+  const int env = c.L.env, row = env * v.A + a;
+  const PubAc* sP = c.sP + c.L.gbase;
+  const PubAc& s = sP[a];
+  const double FT = 1 / 3.28084, PI = 3.14159265358979323846;
+  switch (r.kind) {
+    case ACS_R_ALTITUDE: {            // altitude_reward.py:20-40
+      const double ego_z = s.f.u / 1000, ego_vz = s.f.vd / 340;
+      double Pv = 0., PH = 0.;
+      if (ego_z <= r.p0) Pv = -env_clip(ego_vz / r.p2 * (r.p0 - ego_z) / r.p0, 0., 1.);
+      if (ego_z <= r.p1) PH = env_clip(ego_z / r.p1, 0., 1.) - 1. - 1.;
+      return reward_process(c, ri, row, Pv + PH);
+    }
+    case ACS_R_POSTURE: {             // posture_reward.py:26-75
+      double nr = 0;
+      for (int j = 0; j < v.A; j++) {
+        if (same_team(cfg, a, j)) continue;
+        const AoTaR g = get_ao_ta_r(s.f, sP[j].f, false);
+        nr += posture_orientation((int)r.p0, g.AO, g.TA) * posture_range((int)r.p1, g.R / 1000, r.p2);
+      }
+      return reward_process(c, ri, row, nr);
+    }
+    case ACS_R_EVENT: {               // event_driven_reward.py:15-34
+      double rew = 0;
+      if (s.status == ST_SHOTDOWN) rew -= 200; else if (s.status == ST_CRASH) rew -= 200;
+      const int nl = AI(v, AI_N_LAUNCHED, row);
+      for (int q = 0; q < nl; q++) if (MI(v, MI_STATUS, row * v.S + q) == MS_HIT) rew += 200;
+      return reward_process(c, ri, row, rew);
+    }
+    case ACS_R_MISSILE_POSTURE: {     // missile_posture_reward.py:18-46 (bypasses _process; previous_missile_v aliases a live array)
+      double rew = 0;
+      const int mid = missile_warning(c, a);
+      if (mid >= 0) {
+        int ref = EI(v, EI_PMV_REF, env);
+        if (ref < 0) { ref = mid; EI(v, EI_PMV_REF, env) = ref; }
+        const double mvx = MD(v, MD_VEL_N, mid), mvy = MD(v, MD_VEL_E, mid), mvz = MD(v, MD_VEL_U, mid);
+        const double pvx = MD(v, MD_VEL_N, ref), pvy = MD(v, MD_VEL_E, ref), pvz = MD(v, MD_VEL_U, ref);
+        const double nm = sqrt(mvx * mvx + mvy * mvy + mvz * mvz), np_ = sqrt(pvx * pvx + pvy * pvy + pvz * pvz);
+        const double na = sqrt(s.f.vn * s.f.vn + s.f.ve * s.f.ve + s.f.vd * s.f.vd);
+        const double v_dec = (np_ - nm) / 340 * r.scale;
+        const double ang = (mvx * s.f.vn + mvy * s.f.ve + mvz * s.f.vd) / (nm * na);
+        rew = ang < 0 ? ang / (fmax(v_dec, 0.0) + 1) : ang * fmax(v_dec, 0.0);
+      } else {
+        EI(v, EI_PMV_REF, env) = -1;
+      }
+      return rew;
+    }
+    case ACS_R_SHOOT_PENALTY: {       // shoot_penalty_reward.py:17-32
+      double rew = 0;
+      const int rem = AI(v, AI_REM_MISSILES, row);
+      if (rem == AI(v, AI_PRE_REMAINING, row) - 1) rew -= 30;
+      AI(v, AI_PRE_REMAINING, row) = rem;
+      return reward_process(c, ri, row, rew);
+    }
+    case ACS_R_HEADING: {             // heading_reward.py:18-71
+      const double roll = OUTF(v, O_ROLL, row), p = OUTF(v, O_P, row), q = OUTF(v, O_Q, row);
+      const double psi_deg = OUTF(v, O_HEADING, row) * RADTODEG;
+      const double d_head = delta_heading_deg(ED(v, ED_TGT_HEADING, env), psi_deg);
+      const double d_alt = env_clip((ED(v, ED_TGT_ALT, env) - OUTF(v, O_H_SL_FT, row)) * 0.3048, -40000.0, 40000.0);
+      const double d_vel = env_clip(ED(v, ED_TGT_VEL, env) - s.u_mps, -1400.0, 1400.0);
+      const double heading_r = exp(-((d_head / 5.0) * (d_head / 5.0)));
+      const double alt_r = exp(-((d_alt / 15.24) * (d_alt / 15.24)));
+      const double roll_r = exp(-((roll / 0.35) * (roll / 0.35)));
+      const double speed_r = exp(-((d_vel / 24) * (d_vel / 24)));
+      double rew = pow(heading_r * alt_r * roll_r * speed_r, 1 / 4.0);
+      if (c.cs > 1) rew = rew + (-fabs(p - AD(v, AD_HR_P, row)) * 1.0) + (-fabs(q - AD(v, AD_HR_Q, row)) * 1.0);
+      AD(v, AD_HR_ROLL, row) = roll; AD(v, AD_HR_P, row) = p; AD(v, AD_HR_Q, row) = q;
+      return reward_process(c, ri, row, rew);
+    }
+    case ACS_R_RELATIVE_ALTITUDE: {   // relative_altitude_reward.py:18-32
+      int e0 = -1;
+      for (int j = 0; j < v.A && e0 < 0; j++) if (!same_team(cfg, a, j)) e0 = j;
+      const double ego_z = s.f.u / 1000, enm_z = sP[e0].f.u / 1000;
+      return reward_process(c, ri, row, fmin(r.p0 - fabs(ego_z - enm_z), 0.0));
+    }
+    default: break;
+  }
+  // per-enemy geometry rewards share the (AO, TA, R) list
+  AoTaR geo[ACS_MAX_AGENTS];
+  int n = 0;
+  for (int j = 0; j < v.A; j++) if (!same_team(cfg, a, j)) geo[n++] = get_ao_ta_r(s.f, sP[j].f, false);
+  double nr = 0;
+  if (r.kind == ACS_R_COMBAT_GEOMETRY) {          // combat_geometry_reward.py:28-68 (index never advances; prev list only grows)
+    if (!EI(v, EI_CG_VALID, env)) { ED(v, ED_CG_PREV0, env) = geo[0].AO; ED(v, ED_CG_PREV1, env) = geo[0].TA; EI(v, EI_CG_VALID, env) = 1; }
+    const double p0 = ED(v, ED_CG_PREV0, env), p1 = ED(v, ED_CG_PREV1, env);
+    for (int i = 0; i < n; i++) nr += -(geo[0].AO - p0) - (geo[0].TA - p1);
+  } else if (r.kind == ACS_R_GUN_BEHIT) {         // gun_behit_reward.py:27-54
+    for (int i = 0; i < n; i++) if (geo[i].R >= 500 * FT && geo[i].R <= 3000 * FT && geo[i].AO >= 179 * PI / 180) nr += -5;
+  } else if (r.kind == ACS_R_GUN_WEZ) {           // gun_WEZ_reward.py:28-55
+    for (int i = 0; i < n; i++)
+      if (geo[i].R >= 500 * FT && geo[i].R <= 3000 * FT && geo[i].AO <= 1 * PI / 180) nr += 5 + 5 * (3000 * FT - geo[i].R) / (2500 * FT);
+  } else if (r.kind == ACS_R_GUN_TARGETTAIL || r.kind == ACS_R_GUN_WEZDOT) {   // gun_targettail_reward.py:28-78; gun_WEZDOT_reward.py:29-77
+    const bool tt = r.kind == ACS_R_GUN_TARGETTAIL;
+    double d[ACS_MAX_AGENTS];
+    for (int i = 0; i < n; i++) {
+      const double R = geo[i].R;
+      if (tt) {
+        if (R >= 3000 * FT && R <= 5000 * FT) d[i] = R * sin(geo[i].TA);
+        else if (R <= 3000 * FT) d[i] = sqrt(R * R + (3000 * FT) * (3000 * FT) - 2 * R * (3000 * FT) * cos(geo[i].TA));
+        else d[i] = sqrt(R * R + (5000 * FT) * (5000 * FT) - 2 * R * (5000 * FT) * cos(geo[i].TA));
+      } else {
+        if (R >= 500 * FT && R <= 3000 * FT) d[i] = R * sin(geo[i].AO);
+        else d[i] = sqrt(R * R + (3000 * FT) * (3000 * FT) - 2 * R * (3000 * FT) * cos(geo[i].AO));
+      }
+    }
+    const int fvalid = tt ? EI_TT_VALID : EI_WD_VALID, fprev = tt ? ED_TT_PREV0 : ED_WD_PREV0;
+    if (!EI(v, fvalid, env)) {     // the first evaluation after reset records prev = [d0, d0, d1, ...]
+      ED(v, fprev, env) = d[0];
+      for (int i = 1; i < n; i++) ED(v, fprev + i, env) = d[i - 1];
+      EI(v, fvalid, env) = 1;
+    }
+    for (int i = 0; i < n; i++) nr += -1 / 60.0 * tanh((d[i] - ED(v, fprev + i, env)) / sqrt(geo[i].R));
+  }
+  return reward_process(c, ri, row, nr);
+}
+// task.get_reward for agent a (gating per E/tasks/singlecombat_task.py:190-195, multiplecombat_task.py:147-151)
+ENV_DEV double agent_reward(const StepCtx& c, int a) {
+  const int row = c.L.env * c.v.A + a;
+  const PubAc& s = c.sP[c.L.gbase + a];
+  if (c.cfg.reward_gate == ACS_G_DIE_FLAG) {
+    if (AI(c.v, AI_DIE_FLAG, row)) return 0.0;
+    AI(c.v, AI_DIE_FLAG, row) = (s.status != ST_ALIVE);
+  } else if (c.cfg.reward_gate == ACS_G_ALIVE) {
+    if (s.status != ST_ALIVE) return 0.0;
+  }
+  double tot = 0.0;
+  for (int ri = 0; ri < c.cfg.n_rewards; ri++) tot += reward_one(c, ri, a);
+  return tot;
+}
+
+// ---------------------------------------------------------------------------------------------- terminations
+// task.get_termination for agent a: conditions in order, first done short-circuits (E/tasks/task_base.py:90-112).
+// Returns the cause (ACS_T_*) or -1.  crash() side effects go to sP[a].status.
+ENV_DEV int agent_termination(const StepCtx& c, int a) {
+  const EnvView& v = c.v;
+  const AcsTaskConfig& cfg = c.cfg;
+  const int env = c.L.env, row = env * v.A + a;
+  PubAc* sP = c.sP + c.L.gbase;
+  for (int ti = 0; ti < cfg.n_terms; ti++) {
+    const int t = cfg.terms[ti];
+    bool done = false;
+    if (t == ACS_T_UNREACH_HEADING) {              // unreach_heading.py:22-65
+      const double sim_time = v.fdm[(size_t)F_SIM_TIME * v.rows + row];
+      const double check_time = ED(v, ED_CHECK_TIME, env);
+      if (sim_time >= check_time) {
+        const double d_head = delta_heading_deg(ED(v, ED_TGT_HEADING, env), OUTF(v, O_HEADING, row) * RADTODEG);
+        if (fabs(d_head) > 10) done = true;
+        else {
+          const int tc = EI(v, EI_TURN_COUNTS, env);
+          const double inc_tab[5] = {0.2, 0.4, 0.6, 0.8, 1.0};
+          const double inc = inc_tab[tc < 4 ? tc : 4];
+          const int ep = EI(v, EI_EPISODE, env);
+          const double d0 = env_u01(cfg.seed, cfg.env_offset + env, RNG_HEADING, ep, tc, 0);
+          const double d1 = env_u01(cfg.seed, cfg.env_offset + env, RNG_HEADING, ep, tc, 1);
+          const double d2 = env_u01(cfg.seed, cfg.env_offset + env, RNG_HEADING, ep, tc, 2);
+          const double dh = (-inc + 2 * inc * d0) * cfg.heading_increments[0];
+          const double da = (-inc + 2 * inc * d1) * cfg.heading_increments[1];
+          const double dv = (-inc + 2 * inc * d2) * cfg.heading_increments[2];
+          double nh = fmod(ED(v, ED_TGT_HEADING, env) + dh + 360, 360.0);
+          if (nh < 0) nh += 360.0;
+          ED(v, ED_TGT_HEADING, env) = env_clip(nh, 0.0, 360.0);
+          ED(v, ED_TGT_ALT, env) = env_clip(ED(v, ED_TGT_ALT, env) + da, -1400.0, 85000.0);
+          ED(v, ED_TGT_VEL, env) = env_clip(ED(v, ED_TGT_VEL, env) + dv, -700.0, 700.0);
+          ED(v, ED_CHECK_TIME, env) = env_clip(check_time + cfg.check_interval, 0.0, 1000000.0);
+          EI(v, EI_TURN_COUNTS, env) = tc + 1;
+        }
+      }
+    } else if (t == ACS_T_EXTREME_STATE) {         // extreme_state.py:14-33 + catalog.py:386-416
+      const double pp = OUTF(v, O_P, row), qq = OUTF(v, O_Q, row), rr = OUTF(v, O_R, row);
+      const bool ev = OUTF(v, O_ECI_VMAG, row) >= 1e10;
+      const bool er = sqrt(pp * pp + qq * qq + rr * rr) >= 1000;
+      const bool ea = OUTF(v, O_H_SL_FT, row) >= 1e10;
+      const bool eacc = fmax(fmax(fabs(OUTF(v, O_NPX, row)), fabs(OUTF(v, O_NPY, row))), fabs(OUTF(v, O_NPZ, row))) > 1e1;
+      done = ea || er || ev || eacc;
+      if (done) sP[a].status = ST_CRASH;
+    } else if (t == ACS_T_OVERLOAD) {              // overload.py:18-46
+      const double sim_time = v.fdm[(size_t)F_SIM_TIME * v.rows + row];
+      if (sim_time > 10)
+        if (fabs(OUTF(v, O_NPX, row)) > cfg.acc_limit[0] || fabs(OUTF(v, O_NPY, row)) > cfg.acc_limit[1] ||
+            fabs(OUTF(v, O_NPZ, row) + 1) > cfg.acc_limit[2]) done = true;
+      if (done) sP[a].status = ST_CRASH;
+    } else if (t == ACS_T_LOW_ALTITUDE) {          // low_altitude.py:15-34
+      done = sP[a].h <= cfg.altitude_limit;
+      if (done) sP[a].status = ST_CRASH;
+    } else if (t == ACS_T_TIMEOUT) {               // timeout.py:14-32
+      done = c.cs >= cfg.max_steps;
+    } else if (t == ACS_T_SAFE_RETURN) {           // safe_return.py:15-50
+      if (sP[a].status == ST_SHOTDOWN || sP[a].status == ST_CRASH) done = true;
+      else {
+        bool all_dead = true;
+        for (int j = 0; j < v.A; j++) if (!same_team(cfg, a, j) && sP[j].status == ST_ALIVE) all_dead = false;
+        if (all_dead && missile_warning(c, a) < 0) done = true;
+      }
+    }
+    if (done) return t;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(128) k_env_post(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg, double* __restrict__ obs,
+                                                  double* __restrict__ share_obs, double* __restrict__ rewards,
+                                                  uint8_t* __restrict__ dones, int32_t* __restrict__ info, uint8_t* __restrict__ env_done) {
+  __shared__ PubAc sP[128];
+  __shared__ double sRew[128];
+  __shared__ int sDone[128];
+  const Lane L = lane_setup(v, lg);
+  const int A = v.A;
+  PubAc me;
+  me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
+  if (L.valid) load_pub(v, L.row, me);
+  sP[L.tid] = me;
+  sRew[L.tid] = 0.0;
+  sDone[L.tid] = 1;
+  const int cs = (L.env < v.B) ? EI(v, EI_CURRENT_STEP, L.env) + 1 : 0;
+  __syncwarp(L.gmask);
+  const StepCtx c{v, cfg, L, sP, cs};
+  // ---- task.step: artillery (E/tasks/singlecombat_task.py:163-188), then the launch rules, agents in dict order
+  if (cfg.use_artillery) {
+    for (int a = 0; a < A; a++) {
+      if (L.valid && L.lane == a) {
+        for (int j = 0; j < A; j++) {
+          if (same_team(cfg, a, j) || sP[L.gbase + j].status != ST_ALIVE) continue;
+          const AoTaR g = get_ao_ta_r(sP[L.gbase + a].f, sP[L.gbase + j].f, false);
+          double of = 0.0;
+          if (g.AO >= 0 && g.AO <= 0.5236) of = 1 - g.AO / 0.5236; else if (g.AO >= -0.5236 && g.AO <= 0) of = 1 + g.AO / 0.5236;
+          const double Rk = g.R / 1000;
+          const double df = Rk <= 1 ? 1.0 : (Rk <= 3 ? (3 - Rk) / 2. : 0.0);
+          sP[L.gbase + j].bloods -= of * df;
+        }
+      }
+      __syncwarp(L.gmask);
+    }
+  }
+  if (cfg.launch_kind != ACS_L_NONE) {
+    for (int a = 0; a < A; a++) {
+      if (L.valid && L.lane == a) task_step_agent(c, a);
+      __syncwarp(L.gmask);
+    }
+  }
+  // ---- get_obs (every agent, before terminations / rewards)
+  if (L.valid) write_obs(c, L.lane, obs + ((size_t)L.env * A + L.lane) * cfg.obs_dim);
+  __syncwarp(L.gmask);
+  // ---- dones and rewards in the reference's order
+  int cause = -1;
+  if (cfg.dones_before_rewards) {
+    for (int a = 0; a < A; a++) {
+      if (L.valid && L.lane == a) cause = agent_termination(c, a);
+      __syncwarp(L.gmask);
+    }
+    for (int a = 0; a < A; a++) {
+      if (L.valid && L.lane == a) sRew[L.tid] = agent_reward(c, a);
+      __syncwarp(L.gmask);
+    }
+  } else {
+    for (int a = 0; a < A; a++) {
+      if (L.valid && L.lane == a) sRew[L.tid] = agent_reward(c, a);
+      __syncwarp(L.gmask);
+    }
+    if (cfg.team_mean) {                            // E/envs/multiplecombat_env.py:170-175
+      double ego = 0.0, enm = 0.0;
+      for (int j = 0; j < cfg.n_ego; j++) ego += sRew[L.gbase + j];
+      for (int j = cfg.n_ego; j < A; j++) enm += sRew[L.gbase + j];
+      ego /= cfg.n_ego; if (cfg.n_enm > 0) enm /= cfg.n_enm;
+      __syncwarp(L.gmask);
+      sRew[L.tid] = L.lane < cfg.n_ego ? ego : enm;
+    }
+    for (int a = 0; a < A; a++) {
+      if (L.valid && L.lane == a) cause = agent_termination(c, a);
+      __syncwarp(L.gmask);
+    }
+  }
+  if (L.valid) sDone[L.tid] = cause >= 0;
+  __syncwarp(L.gmask);
+  if (L.valid) {
+    const size_t oa = (size_t)L.env * A + L.lane;
+    rewards[oa] = sRew[L.tid];
+    dones[oa] = cause >= 0;
+    AI(v, AI_STATUS, L.row) = sP[L.tid].status;
+    AD(v, AD_BLOODS, L.row) = sP[L.tid].bloods;
+    if (info) {
+      info[oa * ACS_INFO_DIM + 0] = cause; info[oa * ACS_INFO_DIM + 1] = sP[L.tid].status;
+      info[oa * ACS_INFO_DIM + 2] = cs; info[oa * ACS_INFO_DIM + 3] = EI(v, EI_TURN_COUNTS, L.env);
+    }
+    if (share_obs) {                                 // get_state: hstack of every agent's obs (E/envs/env_base.py:183-189)
+      const int D = cfg.obs_dim;
+      double* so = share_obs + oa * (size_t)(A * D);
+      const double* src = obs + (size_t)L.env * A * D;
+      for (int i = 0; i < A * D; i++) so[i] = src[i];
+    }
+    if (L.lane == 0) {
+      bool all = true;
+      for (int j = 0; j < A; j++) all = all && sDone[L.gbase + j];
+      if (env_done) env_done[L.env] = all;
+      EI(v, EI_CURRENT_STEP, L.env) = cs;
+    }
+  }
+}
+
+// ============================================================================================== reset
+// Stage 1: per aircraft FDM reload (AircraftSimulator.reload, simulatior.py:152-190) for masked envs.
+__global__ void __launch_bounds__(FDM_BLOCK) k_env_reset_fdm(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
+                                                            const uint8_t* __restrict__ env_mask) {
+  __shared__ double sT[F16_NTAB];
+  stage_tables(sT);
+  const Lane L = lane_setup(v, lg);
+  if (!L.valid) return;
+  if (env_mask != nullptr && !env_mask[L.env]) return;
+  const int N = v.rows;
+  const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
+  IcParams c;
+  const double* r = cfg.init_state[L.lane];
+  c.lon_deg = r[0]; c.lat_geod_deg = r[1]; c.h_sl_ft = r[2]; c.psi_deg = r[3]; c.u = r[4]; c.v = r[5]; c.w = r[6];
+  c.p = r[7]; c.q = r[8]; c.r = r[9]; c.phi_deg = r[10]; c.theta_deg = r[11];
+  const int episode = EI(v, EI_EPISODE, L.env) + 1;    // the task stage stores it
+  if (cfg.obs_kind == ACS_OBS_HEADING) {               // E/envs/singlecontrol_env.py:32-49
+    const int64_t e = cfg.env_offset + L.env;
+    c.psi_deg = 0.0 + 180.0 * env_u01(cfg.seed, e, RNG_RESET, episode, 0, 0);
+    c.h_sl_ft = 14000.0 + 16000.0 * env_u01(cfg.seed, e, RNG_RESET, episode, 1, 0);
+    c.u = 400.0 + 800.0 * env_u01(cfg.seed, e, RNG_RESET, episode, 2, 0);
+    ED(v, ED_TGT_HEADING, L.env) = env_clip(c.psi_deg, 0.0, 360.0);
+    ED(v, ED_TGT_ALT, L.env) = env_clip(c.h_sl_ft, -1400.0, 85000.0);
+    ED(v, ED_TGT_VEL, L.env) = env_clip(c.u * 0.3048, -700.0, 700.0);
+    ED(v, ED_CHECK_TIME, L.env) = 0.0;
+    EI(v, EI_TURN_COUNTS, L.env) = 0;
+  }
+  AcCore a; Props p; FcsState s; Frame f;
+  fdm_reset(a, p, s, f, sT, g_atmo, c, cfg.fcs_dt);
+  store_state(v.fdm, N, L.row, a, p, s);
+  AcOut o;
+  fdm_outputs(a, f, o);
+  store_out(v.out, N, L.row, o);
+  PubAc me;
+  double v_mps, w_mps, vc_mps;
+  derive_aircraft(o, org, me, v_mps, w_mps, vc_mps);
+  store_derived(v, L.row, me, v_mps, w_mps, vc_mps);
+  AD(v, AD_BLOODS, L.row) = 100.0;
+  AI(v, AI_STATUS, L.row) = ST_ALIVE;
+}
+// Stage 2: task.reset + reward-function resets + get_obs for masked envs.
+__global__ void __launch_bounds__(128) k_env_reset_task(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
+                                                        const uint8_t* __restrict__ env_mask, double* __restrict__ obs,
+                                                        double* __restrict__ share_obs) {
+  __shared__ PubAc sP[128];
+  const Lane L = lane_setup(v, lg);
+  const int A = v.A;
+  const bool on = L.valid && (env_mask == nullptr || env_mask[L.env]);
+  PubAc me;
+  me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
+  if (on) {
+    const int row = L.row;
+    const int nm = cfg.num_missiles[L.lane];
+    AI(v, AI_DIE_FLAG, row) = 0;
+    AI(v, AI_REM_MISSILES, row) = nm; AI(v, AI_REM_9M, row) = nm; AI(v, AI_REM_120B, row) = nm; AI(v, AI_REM_GUN, row) = nm;
+    AI(v, AI_REM_CHAFF, row) = nm;
+    AI(v, AI_LAST_SHOOT_TIME, row) = -cfg.min_attack_interval;
+    AI(v, AI_LAST_SHOT_SLOT, row) = -1; AI(v, AI_N_LAUNCHED, row) = 0;
+    AI(v, AI_LOCK_LO, row) = 0; AI(v, AI_LOCK_HI, row) = 0; AI(v, AI_LOCK_N, row) = 0;
+    AI(v, AI_PRE_REMAINING, row) = nm; AI(v, AI_SHOOT, row) = 0; AI(v, AI_CH_STATE, row) = CH_NONE; AI(v, AI_CH_COUNT, row) = 0;
+    AD(v, AD_HR_ROLL, row) = 0; AD(v, AD_HR_P, row) = 0; AD(v, AD_HR_Q, row) = 0;
+    AD(v, AD_CH_N, row) = 0; AD(v, AD_CH_E, row) = 0; AD(v, AD_CH_U, row) = 0; AD(v, AD_CH_T, row) = 0;
+    for (int ri = 0; ri < ACS_MAX_REWARDS; ri++) AD(v, AD_PRE_REWARD0 + ri, row) = 0.0;
+    for (int s = 0; s < v.S; s++) {
+      const int mid = row * v.S + s;
+      MI(v, MI_STATUS, mid) = MS_INACTIVE; MI(v, MI_DETACHED, mid) = 0; MI(v, MI_KEYN, mid) = -1; MI(v, MI_TARGET, mid) = 0;
+      MI(v, MI_KIND, mid) = 0; MI(v, MI_CONSEC, mid) = 0; MI(v, MI_ORDER, mid) = 0; MI(v, MI_BORN, mid) = 0;
+    }
+    if (L.lane == 0) {
+      const int env = L.env;
+      EI(v, EI_CURRENT_STEP, env) = 0; EI(v, EI_EPISODE, env) = EI(v, EI_EPISODE, env) + 1; EI(v, EI_SUBSTEP_COUNT, env) = 0;
+      EI(v, EI_PMV_REF, env) = -1; EI(v, EI_CG_VALID, env) = 0; EI(v, EI_TT_VALID, env) = 0; EI(v, EI_WD_VALID, env) = 0;
+      EI(v, EI_ORDER_SEQ, env) = 0; EI(v, EI_BORN_SEQ, env) = 0;
+      if (cfg.obs_kind != ACS_OBS_HEADING) EI(v, EI_TURN_COUNTS, env) = 0;
+    }
+    load_pub(v, row, me);
+  }
+  sP[L.tid] = me;
+  __syncwarp(L.gmask);
+  const StepCtx c{v, cfg, L, sP, 0};
+  // reward_function.reset (E/reward_functions/reward_function_base.py:20-32): potential rewards seed pre_rewards
+  for (int ri = 0; ri < cfg.n_rewards; ri++) {
+    if (!cfg.rewards[ri].potential) continue;
+    for (int a = 0; a < A; a++) {
+      if (on && L.lane == a) {
+        const double r0 = reward_one(c, ri, a);
+        AD(v, AD_PRE_REWARD0 + ri, L.row) = r0;
+      }
+      __syncwarp(L.gmask);
+    }
+  }
+  if (on) write_obs(c, L.lane, obs + ((size_t)L.env * A + L.lane) * cfg.obs_dim);
+  __syncwarp(L.gmask);
+  if (on && share_obs) {
+    const int D = cfg.obs_dim;
+    double* so = share_obs + ((size_t)L.env * A + L.lane) * (size_t)(A * D);
+    const double* src = obs + (size_t)L.env * A * D;
+    for (int i = 0; i < A * D; i++) so[i] = src[i];
+  }
+}

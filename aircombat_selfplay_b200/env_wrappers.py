@@ -1,0 +1,204 @@
+"""The VecEnv contract of the reference (reference envs/env_wrappers.py:48-462) over the batched device simulator.
+
+The reference runs N environments as N OS processes (``SubprocVecEnv`` / ``ShareSubprocVecEnv``) or N Python objects
+(``DummyVecEnv`` / ``ShareDummyVecEnv``) and stacks their numpy results.  Here the N environments ARE one device batch:
+
+    reset() -> obs [N, A, D]                                   (Share*: (obs, share_obs [N, A, A*D]))
+    step(actions [N, A, act]) -> obs, rewards [N, A, 1], dones [N, A, 1], infos [N] of dict
+                                                               (Share*: obs, share_obs, rewards, dones, infos)
+    auto-reset of an env whose agents are all done, the reset observation returned in place
+    (reference envs/env_wrappers.py:191-204,380-393) -- done on the device, inside the step call.
+
+The four reference class names are kept, constructor signature included (a list of env factories): the first factory
+is called once to learn the scenario (it must return one of this package's env classes), the rest only contribute
+their count.  ``BatchedVecEnv`` / ``ShareBatchedVecEnv`` are the direct constructors.  One step moves the action array
+host->device and one packed output buffer device->host (pinned memory, one copy each way).
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import taskspec as ts
+from .envs import BatchedEnv, LazyInfo, _SingleEnvBase
+
+
+class VecEnv(ABC):
+    """reference envs/env_wrappers.py:48-121"""
+    closed = False
+
+    def __init__(self, num_envs, observation_space, action_space):
+        self.num_envs = num_envs
+        self.observation_space = observation_space
+        self.action_space = action_space
+
+    @abstractmethod
+    def reset(self):
+        pass
+
+    @abstractmethod
+    def step_async(self, actions):
+        pass
+
+    @abstractmethod
+    def step_wait(self):
+        pass
+
+    def close_extras(self):
+        pass
+
+    def close(self):
+        if self.closed:
+            return
+        self.close_extras()
+        self.closed = True
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+
+class ShareVecEnv(VecEnv):
+    """reference envs/env_wrappers.py:325-336"""
+
+    def __init__(self, num_envs, observation_space, share_observation_space, action_space):
+        super().__init__(num_envs, observation_space, action_space)
+        self.share_observation_space = share_observation_space
+
+
+class BatchedVecEnv(VecEnv):
+    """N environments of one scenario on one GPU behind the reference's VecEnv contract."""
+    share = False
+
+    def __init__(self, config_name: str, num_envs: int, device: int = 0, seed: int = 0, env_offset: int = 0,
+                 config_dir: Optional[str] = None, substeps: Optional[int] = None, controller_path: Optional[str] = None,
+                 copy: bool = True):
+        self.core = BatchedEnv(config_name, num_envs, device=device, seed=seed, env_offset=env_offset, config_dir=config_dir,
+                               substeps=substeps, controller_path=controller_path, auto_reset=True)
+        if self.share:
+            ShareVecEnv.__init__(self, num_envs, self.core.observation_space, self.core.share_observation_space,
+                                 self.core.action_space)
+        else:
+            VecEnv.__init__(self, num_envs, self.core.observation_space, self.core.action_space)
+        self.num_agents = self.core.num_agents
+        self.copy = copy
+        b = self.core.batch
+        with torch.cuda.device(self.core.device):
+            self._host = torch.empty(b.out_buf.shape, dtype=torch.uint8).pin_memory()
+            self._views = b.host_views(self._host)
+            self._act_host = torch.empty((num_envs, self.num_agents, self.core.act_dim), dtype=torch.int32).pin_memory()
+            self._act_np = self._act_host.numpy()
+            self._act_dev = torch.empty_like(self._act_host, device=self.core.device)
+        src = {"info": self._views["info"], "heading": self.core.spec.obs_kind == ts.OBS_HEADING}
+        self._infos = np.empty(num_envs, dtype=object)
+        for i in range(num_envs):
+            self._infos[i] = LazyInfo(src, i)
+        self._pending = False
+        self.h2d_bytes_per_step = self._act_host.numel() * 4
+        self.d2h_bytes_per_step = self._host.numel()
+
+    # ------------------------------------------------------------------ helpers
+    def _fetch(self):
+        self._host.copy_(self.core.batch.out_buf, non_blocking=True)
+        torch.cuda.current_stream(self.core.device).synchronize()
+
+    def _arr(self, name):
+        a = self._views[name]
+        return a.copy() if self.copy else a
+
+    def _put_actions(self, actions):
+        a = self._act_np
+        if isinstance(actions, np.ndarray) and actions.shape == a.shape:
+            np.copyto(a, actions, casting="unsafe")
+        else:   # nested lists of per-agent actions, Tuple-space samples included (reference tests pass these)
+            for i, env_act in enumerate(actions):
+                for j, x in enumerate(env_act):
+                    if isinstance(x, (tuple, list)):
+                        x = np.concatenate([np.atleast_1d(np.asarray(y)).ravel() for y in x])
+                    a[i, j, :] = np.asarray(x).ravel()
+        self._act_dev.copy_(self._act_host, non_blocking=True)
+
+    # ------------------------------------------------------------------ VecEnv
+    def reset(self):
+        with torch.cuda.device(self.core.device):
+            self.core.reset()
+            self._fetch()
+        if self.share:
+            return self._arr("obs"), self._arr("share_obs")
+        return self._arr("obs")
+
+    def step_async(self, actions):
+        with torch.cuda.device(self.core.device):
+            self._put_actions(actions)
+            self.core.step(self._act_dev)
+        self._pending = True
+
+    def step_wait(self):
+        assert self._pending, "step_wait() without step_async()"
+        with torch.cuda.device(self.core.device):
+            self._fetch()
+        self._pending = False
+        N, A = self.num_envs, self.num_agents
+        obs = self._arr("obs")
+        rewards = self._arr("rewards").reshape(N, A, 1)
+        dones = self._views["dones"].astype(bool).reshape(N, A, 1)
+        if self.share:
+            return obs, self._arr("share_obs"), rewards, dones, self._infos
+        return obs, rewards, dones, self._infos
+
+    def render(self, mode, filepath):
+        raise NotImplementedError("TacView rendering is outside the env-step hot path (DESIGN.md, out of scope)")
+
+    def close_extras(self):
+        self.core.close()
+
+
+class ShareBatchedVecEnv(BatchedVecEnv, ShareVecEnv):
+    share = True
+
+
+def _from_env_fns(cls, env_fns, **kw):
+    env_fns = list(env_fns)
+    assert len(env_fns) > 0
+    template = env_fns[0]()
+    if not isinstance(template, _SingleEnvBase):
+        raise TypeError("env factories must return aircombat_selfplay_b200 env classes (SingleControlEnv, SingleCombatEnv, "
+                        "MultipleCombatEnv)")
+    core = template.core
+    args = dict(config_name=core.config_name, num_envs=len(env_fns), device=core.device.index or 0,
+                seed=core.seed_value, substeps=core.spec.substeps)
+    args.update(kw)
+    template.close()
+    return cls(**args)
+
+
+class DummyVecEnv(BatchedVecEnv):
+    """reference envs/env_wrappers.py:123-181 -- same constructor: ``DummyVecEnv([env_fn, ...])``"""
+
+    def __new__(cls, env_fns, **kw):
+        return _from_env_fns(BatchedVecEnv, env_fns, **kw)
+
+
+class SubprocVecEnv(BatchedVecEnv):
+    """reference envs/env_wrappers.py:231-322 -- ``SubprocVecEnv([env_fn, ...], context='spawn', in_series=1)``; the
+    process arguments are accepted and ignored: there are no worker processes."""
+
+    def __new__(cls, env_fns, context="spawn", in_series=1, **kw):
+        return _from_env_fns(BatchedVecEnv, env_fns, **kw)
+
+
+class ShareDummyVecEnv(ShareBatchedVecEnv):
+    """reference envs/env_wrappers.py:339-372"""
+
+    def __new__(cls, env_fns, **kw):
+        return _from_env_fns(ShareBatchedVecEnv, env_fns, **kw)
+
+
+class ShareSubprocVecEnv(ShareBatchedVecEnv):
+    """reference envs/env_wrappers.py:414-462"""
+
+    def __new__(cls, env_fns, context="spawn", in_series=1, **kw):
+        return _from_env_fns(ShareBatchedVecEnv, env_fns, **kw)

@@ -1,0 +1,374 @@
+"""Host-side mirror of the reference's environment classes over the batched device simulator.
+
+``BatchedEnv``        n_envs environments of one scenario on one GPU; torch tensors in / out; auto-reset on device.
+``SingleControlEnv`` / ``SingleCombatEnv`` / ``MultipleCombatEnv``
+                      the reference's per-env classes (reference envs/JSBSim/envs/*.py): same constructor argument
+                      (yaml config name), same gym-style ``reset``/``step`` shapes, ``seed``, ``agents``, ``ego_ids`` /
+                      ``enm_ids``, ``num_agents``, ``observation_space`` / ``action_space`` (/ ``share_observation_space``),
+                      ``time_interval``, ``current_step`` -- each is a batch of ONE env on the GPU.
+The vectorised contract the runners consume lives in ``env_wrappers.py``.
+
+There is no CPU fallback: constructing any of these without a CUDA device or without the built ``libacs.so`` raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import spaces
+from . import taskspec as ts
+from .capi import INFO_DIM, AcsError, EnvBatch
+from .controller import hierarchical_input, make_controller
+from .tasks import TASKS, load_spec, parse_config
+
+# done_condition strings of the reference's termination classes (without colorama codes), by ACS_T_* id
+DONE_CONDITIONS = {
+    ts.T_UNREACH_HEADING: "unreach_heading", ts.T_EXTREME_STATE: "extreme_state", ts.T_OVERLOAD: "overload",
+    ts.T_LOW_ALTITUDE: "low_altitude", ts.T_TIMEOUT: "timeout", ts.T_SAFE_RETURN: "safe_return",
+}
+
+
+def action_space_for(task_name: str):
+    """reference load_action_space of each Task class (E/tasks/*.py)."""
+    t = TASKS[task_name]
+    low = spaces.MultiDiscrete([3, 5, 3]) if t["hier"] else spaces.MultiDiscrete([41, 41, 41, 30])
+    if t["shoot"] == 0:
+        return low
+    if t["shoot"] == 1:
+        return spaces.Tuple([low, spaces.Discrete(2)])
+    return spaces.Tuple([low, spaces.MultiDiscrete([2, 2, 2, 2])])
+
+
+class BatchedEnv:
+    """``n_envs`` environments of one yaml scenario on one GPU.
+
+    ``step(actions)`` takes the task's own action layout -- int tensor ``[n_envs, n_agents, act_dim]`` where ``act_dim``
+    is 4 (direct stick/throttle classes) or 3 (hierarchical classes) plus the shoot entries -- runs the batched low-level
+    controller for hierarchical tasks, then the device step with auto-reset.  Outputs are views of one device buffer
+    (``self.batch.out_buf``) that the next step overwrites.
+    """
+
+    def __init__(self, config_name: str, n_envs: int, device: int = 0, seed: int = 0, env_offset: int = 0,
+                 config_dir: Optional[str] = None, substeps: Optional[int] = None, controller_path: Optional[str] = None,
+                 auto_reset: bool = True):
+        if not torch.cuda.is_available():
+            raise AcsError("CUDA is not available; the simulator has no CPU fallback")
+        self.config_name = config_name
+        self.config = parse_config(config_name, config_dir)
+        self.spec = load_spec(config_name, config_dir, substeps)
+        self.task_name = self.spec.name
+        self.task = TASKS[self.task_name]
+        if self.spec.use_baseline:
+            raise NotImplementedError("use_baseline scenarios (rule-based opponents) are not part of this build yet; "
+                                      "use the Selfplay configs")
+        self.n_envs, self.n_agents = n_envs, self.spec.n_agents
+        self.device = torch.device("cuda", device)
+        self.auto_reset = auto_reset
+        self.seed_value = int(seed)
+        with torch.cuda.device(self.device):
+            self.batch = EnvBatch(self.spec, n_envs, seed=seed, device=device, env_offset=env_offset)
+        self.hier = bool(self.task["hier"])
+        self.high_dim = 3 if self.hier else 4
+        self.act_dim = self.high_dim + self.spec.shoot_dim
+        self.observation_space = spaces.Box(low=-10, high=10.0, shape=(self.spec.obs_dim,))
+        self.share_observation_space = spaces.Box(low=-10, high=10.0, shape=(self.n_agents * self.spec.obs_dim,))
+        self.action_space = action_space_for(self.task_name)
+        uids = list(self.config["aircraft_configs"].keys())
+        self.ego_ids = [u for u in uids if u[0] == uids[0][0]]
+        self.enm_ids = [u for u in uids if u[0] != uids[0][0]]
+        self._low = torch.zeros((n_envs, self.n_agents, 4 + self.spec.shoot_dim), dtype=torch.int32, device=self.device)
+        if self.hier:
+            self.controller = make_controller(self.device, controller_path)
+            self.rnn = torch.zeros((n_envs * self.n_agents, 128), dtype=torch.float32, device=self.device)
+            # 1v1 hierarchical tasks force a climb below 3500 m (E/tasks/singlecombat_task.py:235-237)
+            self._climb_below = 3500.0 if self.task["env"] == "1v1" else None
+        self._was_reset = False
+
+    # ------------------------------------------------------------------ reference-shaped properties
+    @property
+    def num_agents(self) -> int:
+        return self.n_agents
+
+    @property
+    def time_interval(self) -> float:
+        return self.spec.substeps / self.spec.sim_freq
+
+    @property
+    def max_steps(self) -> int:
+        return self.spec.max_steps
+
+    def seed(self, seed: int = 0):
+        self.seed_value = int(seed or 0)
+        self.batch.set_seed(self.seed_value)
+        return [seed]
+
+    def close(self):
+        self.batch.close()
+
+    # ------------------------------------------------------------------ device API
+    def reset(self, env_mask: Optional[torch.Tensor] = None):
+        with torch.cuda.device(self.device):
+            if self.hier:
+                if env_mask is None:
+                    self.rnn.zero_()
+                else:
+                    self.rnn.view(self.n_envs, self.n_agents, 128)[env_mask.bool()] = 0
+            self._was_reset = True
+            return self.batch.reset(env_mask)
+
+    def low_level_actions(self, actions: torch.Tensor) -> torch.Tensor:
+        """normalize_action's discrete half: the task's action rows -> low-level rows [n_envs, A, 4 + shoot_dim]."""
+        B, A = self.n_envs, self.n_agents
+        if not self.hier:
+            return actions if actions.dtype == torch.int32 else actions.to(torch.int32)
+        high = actions[..., :3].reshape(B * A, 3)
+        obs = self.batch.obs.view(B * A, -1)
+        x = hierarchical_input(high, obs, self._climb_below)
+        low, self.rnn = self.controller(x, self.rnn)
+        self._low[..., :4] = low.view(B, A, 4)
+        if self.spec.shoot_dim:
+            self._low[..., 4:] = actions[..., 3:].to(torch.int32)
+        return self._low
+
+    def step(self, actions: torch.Tensor):
+        """actions: integer tensor [n_envs, n_agents, act_dim] on this env's device."""
+        if not self._was_reset:
+            raise AcsError("step() called before reset()")
+        assert actions.shape == (self.n_envs, self.n_agents, self.act_dim), (tuple(actions.shape), self.act_dim)
+        with torch.cuda.device(self.device):
+            low = self.low_level_actions(actions)
+            out = self.batch.step(low.contiguous(), auto_reset=self.auto_reset)
+            if self.hier and self.auto_reset:
+                # task.reset re-zeroes the controller's recurrent state of the envs that were just reset
+                self.rnn.view(self.n_envs, self.n_agents, 128).mul_((1 - self.batch.env_done.view(-1, 1, 1)).to(torch.float32))
+        return out
+
+
+class LazyInfo(dict):
+    """``infos[i]`` of the VecEnv contract: a dict view over the step's info arrays, materialised on access, so that
+    building ``n_envs`` Python dicts is not on the step path.  Keys as the reference: ``current_step`` always,
+    ``done_condition`` when an agent terminated this step, ``heading_turn_counts`` for the heading task
+    (reference envs/JSBSim/envs/env_base.py:132, termination_conditions/*.py, unreach_heading.py:62)."""
+    __slots__ = ("_src", "_i")
+
+    def __init__(self, src, i):
+        super().__init__()
+        self._src, self._i = src, i
+
+    def _materialise(self):
+        s, i = self._src, self._i
+        info = s["info"][i]
+        d = {"current_step": int(info[0, 2])}
+        causes = [int(c) for c in info[:, 0]]
+        if any(c >= 0 for c in causes):
+            d["done_condition"] = [DONE_CONDITIONS.get(c, "") for c in causes]
+        if s["heading"]:
+            d["heading_turn_counts"] = int(info[0, 3])
+        return d
+
+    def __getitem__(self, k):
+        return self._materialise()[k]
+
+    def __contains__(self, k):
+        return k in self._materialise()
+
+    def get(self, k, default=None):
+        return self._materialise().get(k, default)
+
+    def keys(self):
+        return self._materialise().keys()
+
+    def items(self):
+        return self._materialise().items()
+
+    def values(self):
+        return self._materialise().values()
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+    def __len__(self):
+        return len(self._materialise())
+
+    def __repr__(self):
+        return repr(self._materialise())
+
+    def __eq__(self, other):
+        return self._materialise() == other
+
+
+class AircraftView:
+    """Read/poke access to one aircraft of env 0 -- the slice of ``AircraftSimulator`` (reference
+    envs/JSBSim/core/simulatior.py:89-325) the reference's tests and render scripts touch.  Off the hot path: every
+    access copies an arena from the device."""
+
+    def __init__(self, env: "_SingleEnvBase", uid: str, index: int):
+        self._env, self.uid, self.index = env, uid, index
+        self.partners: List["AircraftView"] = []
+        self.enemies: List["AircraftView"] = []
+        cfg = env.core.config["aircraft_configs"][uid]
+        self.color = cfg.get("color", "Red")
+        self.model = cfg.get("model", "f16")
+        self.num_missiles = int(cfg.get("missile", 0))
+
+    def _field(self, arena, name):
+        names, t = self._env.core.batch.arena(arena)
+        return t[names.index(name), self.index]
+
+    def _set_field(self, arena, name, value):
+        b = self._env.core.batch
+        names, t = b.arena(arena)
+        t[names.index(name), self.index] = value
+        b.set_arena(arena, t)
+
+    @property
+    def status(self) -> int:
+        return int(self._field("ac_i", "status"))
+
+    is_alive = property(lambda s: s.status == 0)
+    is_crash = property(lambda s: s.status == 1)
+    is_shotdown = property(lambda s: s.status == 2)
+
+    def crash(self):
+        self._set_field("ac_i", "status", 1)
+
+    def shotdown(self):
+        self._set_field("ac_i", "status", 2)
+
+    @property
+    def bloods(self) -> float:
+        return float(self._field("ac_d", "bloods"))
+
+    def get_position(self):
+        return np.array([float(self._field("ac_d", k)) for k in ("pos_n", "pos_e", "pos_u")])
+
+    def get_velocity(self):
+        return np.array([float(self._field("ac_d", k)) for k in ("vel_n", "vel_e", "vel_d")])
+
+    def get_geodetic(self):
+        return np.array([float(self._field("out", "lon_deg")), float(self._field("out", "lat_geod_deg")),
+                         float(self._field("ac_d", "h_sl_m"))])
+
+    def get_rpy(self):
+        return np.array([float(self._field("out", k)) for k in ("roll_rad", "pitch_rad", "heading_rad")])
+
+    def get_sim_time(self):
+        return float(self._field("fdm", "sim_time"))
+
+    def get_property_value(self, name: str):
+        """FDM outputs / state by this package's field names (``acs_output_field_name`` / ``acs_state_field_name``)."""
+        b = self._env.core.batch
+        for arena in ("out", "fdm", "ac_d"):
+            names, t = b.arena(arena)
+            if name in names:
+                return float(t[names.index(name), self.index])
+        raise KeyError(name)
+
+
+class _SingleEnvBase:
+    """One environment (a device batch of 1) with the reference's numpy-facing gym-style API."""
+    ENV_KIND = None
+
+    def __init__(self, config_name: str, device: int = 0, config_dir: Optional[str] = None, substeps: Optional[int] = None,
+                 controller_path: Optional[str] = None):
+        self.core = BatchedEnv(config_name, 1, device=device, config_dir=config_dir, substeps=substeps,
+                               controller_path=controller_path, auto_reset=False)
+        kind = self.core.task["env"]
+        if self.ENV_KIND is not None and kind != self.ENV_KIND:
+            raise NotImplementedError(f"Unknown taskname: {self.core.task_name}")   # load_task of the reference env classes
+        self.config_name = config_name
+        self.config = self.core.config
+        self.current_step = 0
+        self._jsbsims: Dict[str, AircraftView] = {}
+        for k, uid in enumerate(self.core.ego_ids + self.core.enm_ids):
+            self._jsbsims[uid] = AircraftView(self, uid, k)
+        for u, a in self._jsbsims.items():
+            for w, b in self._jsbsims.items():
+                if u == w:
+                    continue
+                (a.partners if u[0] == w[0] else a.enemies).append(b)
+
+    # reference-shaped attributes
+    agents = property(lambda s: s._jsbsims)
+    ego_ids = property(lambda s: s.core.ego_ids)
+    enm_ids = property(lambda s: s.core.enm_ids)
+    num_agents = property(lambda s: s.core.num_agents)
+    observation_space = property(lambda s: s.core.observation_space)
+    share_observation_space = property(lambda s: s.core.share_observation_space)
+    action_space = property(lambda s: s.core.action_space)
+    time_interval = property(lambda s: s.core.time_interval)
+    max_steps = property(lambda s: s.core.max_steps)
+    sim_freq = property(lambda s: s.core.spec.sim_freq)
+    agent_interaction_steps = property(lambda s: s.core.spec.substeps)
+
+    def seed(self, seed=None):
+        return self.core.seed(seed)
+
+    def close(self):
+        self.core.close()
+
+    def _actions(self, action):
+        """Legal inputs as in the reference: list / tuple / ndarray of per-agent actions, Tuple-space samples included."""
+        rows = []
+        for a in action:
+            if isinstance(a, (tuple, list)):
+                rows.append(np.concatenate([np.atleast_1d(np.asarray(x)).ravel() for x in a]))
+            else:
+                rows.append(np.asarray(a).ravel())
+        arr = np.stack(rows).astype(np.int32)
+        assert arr.shape == (self.num_agents, self.core.act_dim), (arr.shape, self.core.act_dim)
+        return torch.from_numpy(arr).to(self.core.device).unsqueeze(0)
+
+    def _info(self, info_t):
+        info = info_t[0].cpu().numpy()
+        d = {"current_step": int(info[0, 2])}
+        causes = [int(c) for c in info[:, 0]]
+        if any(c >= 0 for c in causes):
+            d["done_condition"] = [DONE_CONDITIONS.get(c, "") for c in causes]
+        if self.core.spec.obs_kind == ts.OBS_HEADING:
+            d["heading_turn_counts"] = int(info[0, 3])
+        return d
+
+
+class _PlainEnv(_SingleEnvBase):
+    """BaseEnv.reset/step (reference envs/JSBSim/envs/env_base.py:98-173): obs [A, D]; rewards, dones [A, 1]; info."""
+
+    def reset(self) -> np.ndarray:
+        self.current_step = 0
+        obs, _ = self.core.reset()
+        return obs[0].cpu().numpy()
+
+    def step(self, action):
+        obs, _, rew, done, info = self.core.step(self._actions(action))
+        self.current_step += 1
+        return (obs[0].cpu().numpy(), rew[0].cpu().numpy().reshape(-1, 1), done[0].cpu().numpy().astype(bool).reshape(-1, 1),
+                self._info(info))
+
+
+class SingleControlEnv(_PlainEnv):
+    """reference envs/JSBSim/envs/singlecontrol_env.py"""
+    ENV_KIND = "control"
+
+
+class SingleCombatEnv(_PlainEnv):
+    """reference envs/JSBSim/envs/singlecombat_env.py"""
+    ENV_KIND = "1v1"
+
+
+class MultipleCombatEnv(_SingleEnvBase):
+    """reference envs/JSBSim/envs/multiplecombat_env.py: reset -> (obs, share_obs); step -> (obs, share_obs, rewards,
+    dones, info)."""
+    ENV_KIND = "nvn"
+
+    def reset(self):
+        self.current_step = 0
+        obs, share = self.core.reset()
+        return obs[0].cpu().numpy(), share[0].cpu().numpy()
+
+    def step(self, action):
+        obs, share, rew, done, info = self.core.step(self._actions(action))
+        self.current_step += 1
+        return (obs[0].cpu().numpy(), share[0].cpu().numpy(), rew[0].cpu().numpy().reshape(-1, 1),
+                done[0].cpu().numpy().astype(bool).reshape(-1, 1), self._info(info))

@@ -115,4 +115,9 @@ class TaskSpec:
 
     @property
     def n_missile_slots(self):
-        return max([0] + list(self.num_missiles)) if self.launch_kind != L_NONE else 0
+        """Missile slots per aircraft = the most launches one aircraft can make in an episode.  Scenario tasks keep
+        separate AIM-9M and AIM-120B counters, each initialised to ``num_missiles`` (scenario2_task.py:66-69)."""
+        if self.launch_kind == L_NONE:
+            return 0
+        n = max([0] + list(self.num_missiles))
+        return 2 * n if self.launch_kind == L_SCENARIO else n

@@ -2,12 +2,14 @@
 """bench.py -- agent-steps/s of the env-step hot path (60 Hz sim, 12 substeps per step) on N B200s.
 
 Contract: `python bench.py --gpus N --steps K --warmup W` (under torchrun for N > 1) prints ONE JSON line on rank 0.
-  value         whole-job agent-steps/s with inputs resident in HBM (device-timed, CUDA events, max over ranks)
-  e2e           the same metric through the reference-facing VecEnv API with HOST numpy actions in / obs,reward,done out
+  value         whole-job agent-steps/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e           the same metric through the reference-facing VecEnv API: HOST numpy actions in, host obs / rewards /
+                dones out, both copies inside the timed region
   roofline      the dominant kernel (k_env_substeps) against the measured HBM peak, plus the fp64-pipe view
   cpu_baseline  the CPU oracle port of the same workload on the host cores (rank 0, N=1 only; bounded sample)
-`--impl reference` times the reference-shaped CPU path instead (the oracle port: Python env layer over the C++ FDM,
-one env per worker process on all host cores) -- see DESIGN.md section 6 for why the real JSBSim cannot run here.
+`--impl reference` times the reference-shaped CPU path instead: the restated Python env layer over the restated C++
+FDM, one worker process per host core -- DESIGN.md section 3 explains why the real JSBSim cannot run here.
+Envs shard across GPUs as contiguous slices with no data-path collective ("scaling": "weak").
 """
 from __future__ import annotations
 
@@ -25,6 +27,16 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "agent-steps/sec (60 Hz sim, 12 substeps/step)"
 UNIT = "agent-steps/s"
+SUBSTEPS = 12
+
+# name -> (yaml config, envs per GPU, what BASELINE.json calls it)
+WORKLOADS = {
+    "1v1_noweapon": ("1v1/NoWeapon/Selfplay", 4096, "SingleCombat 1v1/NoWeapon/Selfplay, 4096 envs on 1xB200 (BASELINE.json configs[1])"),
+    "1v1_shoot": ("1v1/ShootMissile/Selfplay", 16384, "SingleCombat 1v1/ShootMissile/Selfplay, 16384 envs (configs[2])"),
+    "2v2_shoot": ("2v2/ShootMissile/HierarchySelfplay", 8192, "MultipleCombat 2v2/ShootMissile, 65536 envs over 8 GPUs = 8192 per GPU (configs[3])"),
+    "4v4": ("scenario3/scenario3", 4096, "MultipleCombat 4v4 with missiles, 8 agents/env (configs[4])"),
+    "heading": ("singlecontrol/heading", 32, "SingleControl heading, 32 envs (configs[0])"),
+}
 
 
 def _peaks():
@@ -78,16 +90,14 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-
-def _dist_init(args):
-    import torch
+def _dist_init(backend):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl" if (args.impl == "b200") else "gloo", rank=rank, world_size=world)
+        dist.init_process_group(backend, rank=rank, world_size=world)
     return world, rank, local
 
 
@@ -107,134 +117,173 @@ def _max_over_ranks(x: float, world, device) -> float:
     return float(t.item())
 
 
-# ----------------------------------------------------------------------------- workloads
-WORKLOADS = {
-    # name: (description, envs per GPU, agents per env)
-    "fdm_only": ("F-16 FDM substep loop only (no task layer) -- bring-up workload, NOT the headline metric", 4096, 2),
-}
-
-
-def cpu_fdm_baseline(n_aircraft: int, steps: int, substeps: int, seconds_budget: float = 15.0):
-    """CPU oracle port on all host cores: one OracleFdm per aircraft, threads release the GIL inside the C call."""
-    from concurrent.futures import ThreadPoolExecutor
+def synthetic_actions(rng, spec, high_dim, n_envs, n_steps):
+    """i.i.d. uniform ints over each MultiDiscrete dim, shoot bits Bernoulli(0.05)."""
     import numpy as np
-    from oracle.fdm import OracleFdm
+    A = spec.n_agents
+    a = np.zeros((n_steps, n_envs, A, high_dim + spec.shoot_dim), dtype=np.int32)
+    nvec = [41, 41, 41, 30] if high_dim == 4 else [3, 5, 3]
+    for k, n in enumerate(nvec):
+        a[..., k] = rng.integers(0, n, (n_steps, n_envs, A))
+    if spec.shoot_dim:
+        a[..., high_dim:] = rng.random((n_steps, n_envs, A, spec.shoot_dim)) < 0.05
+    return a
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def _cpu_worker(args):
+    config, n_envs, warm_rounds, n_rounds, seed, budget_s = args
+    import numpy as np
+    from aircombat_selfplay_b200.tasks import load_spec
+    from oracle.env_oracle import OracleEnv
+    spec = load_spec(config, substeps_override=SUBSTEPS)
+    envs = [OracleEnv(spec, seed=seed, env_index=i) for i in range(n_envs)]
+    for e in envs:
+        e.reset()
+    rng = np.random.default_rng(seed)
+    acts = synthetic_actions(rng, spec, 4, n_envs, 64)    # low-level rows: the oracle sits below the GRU controller
+
+    def one_round(t):
+        for i, e in enumerate(envs):
+            _, _, _, d, _ = e.step(acts[t % 64, i])
+            if d.all():
+                e.reset()
+    for t in range(warm_rounds):
+        one_round(t)
+    t0 = time.perf_counter()
+    done = 0
+    for t in range(n_rounds):
+        one_round(warm_rounds + t)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return n_envs * spec.n_agents * done, time.perf_counter() - t0
+
+
+def cpu_env_baseline(config: str, rounds: int, warm_rounds: int = 2, budget_s: float = 20.0, envs_per_core: int = 2):
+    """The oracle port of the same workload on every host core: one process per core, ``envs_per_core`` envs each (the
+    reference's SubprocVecEnv layout), synthetic actions of the same distribution, K = 12.  Each worker times its own
+    step loop (env construction and the first reset are outside); the rate is total agent-steps / slowest worker."""
+    import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n = min(n_aircraft, 8 * cores)
-    fdms = [OracleFdm() for _ in range(n)]
-    rng = np.random.default_rng(0)
-    for f in fdms:
-        f.reset(psi_deg=float(rng.uniform(0, 360)), h_sl_ft=float(rng.uniform(15000, 28000)))
-        f.set_controls(0.1, -0.1, 0.0, 0.7)
-    chunks = [fdms[k::cores] for k in range(cores)]
-
-    def work(chunk):
-        for f in chunk:
-            f.run(substeps)
-    done, t0 = 0, time.perf_counter()
-    with ThreadPoolExecutor(cores) as ex:
-        while True:
-            list(ex.map(work, chunks))
-            done += 1
-            el = time.perf_counter() - t0
-            if done >= steps or el > seconds_budget:
-                break
-    return {"value": n * done / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} aircraft x {done} steps x {substeps} substeps, CPU oracle FDM (restated JSBSim F-16 path), {cores} threads"}
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(config, envs_per_core, warm_rounds, rounds, 100 + k, budget_s) for k in range(cores)])
+    agent_steps = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return {"value": agent_steps / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{cores} worker processes x {envs_per_core} envs of {config}, {agent_steps} agent-steps in {wall:.1f} s, K={SUBSTEPS}; "
+                      "restated Python env layer over the restated C++ F-16 FDM (not JSBSim itself, which cannot run here)"}
 
 
+# ----------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     import numpy as np
     import torch
-    world, rank, local = _dist_init(args)
+    world, rank, local = _dist_init("nccl")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the simulator has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    from aircombat_selfplay_b200.capi import FdmBatch
-    desc, n_envs, n_agents = WORKLOADS[args.workload]
+    from aircombat_selfplay_b200 import capi
+    from aircombat_selfplay_b200.env_wrappers import BatchedVecEnv, ShareBatchedVecEnv
+    config, n_envs, desc = WORKLOADS[args.workload]
     if args.envs:
         n_envs = args.envs
-    K = 12
-    rows = n_envs * n_agents
-    rng = np.random.default_rng(rank)
-    ic = np.zeros((rows, 12))
-    ic[:, 0] = 120.0; ic[:, 1] = 60.0 + 0.1 * (np.arange(rows) % 2)
-    ic[:, 2] = 20000.0; ic[:, 3] = 180.0 * (np.arange(rows) % 2); ic[:, 4] = 800.0
-    fb = FdmBatch(n_envs, n_agents, device=local)
-    fb.reset(torch.tensor(ic, device=dev))
+    from aircombat_selfplay_b200.tasks import load_spec
+    cls = ShareBatchedVecEnv if load_spec(config).share_obs else BatchedVecEnv
+    # one env slice per GPU: rank r owns envs [r*n_envs, (r+1)*n_envs) of the job (RNG streams keyed by global env index)
+    ve = cls(config, n_envs, device=local, seed=args.seed, env_offset=rank * n_envs, substeps=SUBSTEPS, copy=False)
+    core, batch, spec = ve.core, ve.core.batch, ve.core.spec
+    A = spec.n_agents
+    rng = np.random.default_rng(args.seed + rank)
     total = args.warmup + args.steps
-    acts_host = np.column_stack([rng.integers(0, 41, (total * rows, 3)) / 20.0 - 1.0, rng.integers(0, 30, total * rows) / 58.0 + 0.4]) \
-        .reshape(total, rows, 4)
-    acts_dev = torch.tensor(acts_host, device=dev)
+    acts_host = synthetic_actions(rng, spec, core.high_dim, n_envs, total)
+    acts_dev = torch.from_numpy(acts_host).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step_dev(t):
-        fb.set_controls(acts_dev[t])
-        fb.run(K)
-
+    # ---- device-resident arm
+    core.reset()
     for t in range(args.warmup):
-        step_dev(t)
+        core.step(acts_dev[t])
     torch.cuda.synchronize(); _barrier(world)
+    batch.set_timing(True)
     sampler = ClockSampler(local); sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    done_envs = 0
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
-        ev[k][0].record(); step_dev(args.warmup + k); ev[k][1].record()
+        ev[k][0].record(); core.step(acts_dev[args.warmup + k]); ev[k][1].record()
     torch.cuda.synchronize(); _barrier(world)
     clocks = sampler.stop()
+    kms, ksteps = batch.get_timing()
+    batch.set_timing(False)
     ms = sum(a.elapsed_time(b) for a, b in ev)
     ms = _max_over_ranks(ms, world, dev)
-    value = world * rows * args.steps / (ms * 1e-3)
+    value = world * n_envs * A * args.steps / (ms * 1e-3)
 
-    # e2e: host numpy actions in, host outputs out, through the public host API
-    pin_in = torch.empty((rows, 4), dtype=torch.float64).pin_memory()
-    n_out = len(fb.output_names)
-    pin_out = torch.empty((n_out, rows), dtype=torch.float64).pin_memory()
-    u_dev = torch.empty((rows, 4), dtype=torch.float64, device=dev)
+    # ---- end to end through the VecEnv contract (host numpy in / out)
+    ve.reset()
+    for t in range(args.warmup):
+        ve.step(acts_host[t])
     torch.cuda.synchronize(); _barrier(world)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        pin_in.copy_(torch.from_numpy(acts_host[args.warmup + k]))
-        u_dev.copy_(pin_in, non_blocking=True)
-        fb.set_controls(u_dev); fb.run(K)
-        pin_out.copy_(fb.get_outputs(), non_blocking=True)
-        torch.cuda.synchronize()
+        out = ve.step(acts_host[args.warmup + k])
+        done_envs += int(out[-2].all(axis=1).sum())
     _barrier(world)
     e2e_s = _max_over_ranks(time.perf_counter() - t0, world, dev)
-    e2e = {"value": world * rows * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": rows * 4 * 8, "d2h_bytes_per_step": n_out * rows * 8}
+    e2e = {"value": world * n_envs * A * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ve.h2d_bytes_per_step,
+           "d2h_bytes_per_step": ve.d2h_bytes_per_step, "ms_per_step": e2e_s / args.steps * 1e3}
 
+    # ---- roofline of the dominant kernel (k_env_substeps): algorithmic bytes per agent-step (DESIGN.md section 5)
     peak, peak_src = _peaks()
-    n_state = len(fb.state_names)
-    bytes_per_agent_step = (2 * n_state + n_out) * 8 + 4 * 8
-    kernel_ms = ms / args.steps
-    ach = rows * bytes_per_agent_step / (kernel_ms * 1e-3) / 1e9
+    n_state, n_out = len(capi.state_field_names()), len(capi.output_field_names())
+    bytes_per_agent_step = (2 * n_state + n_out + 11 + 11) * 8 + 2 * 4 + (4 + spec.shoot_dim) * 4
+    k_ms = kms["substeps"] / max(ksteps, 1)
+    ach = n_envs * A * bytes_per_agent_step / (k_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_env_substeps", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_agent_step": bytes_per_agent_step,
+            "kernel_ms": k_ms, "kernel_share_of_step": kms["substeps"] / max(sum(kms.values()), 1e-12),
+            "post_ms": kms["post"] / max(ksteps, 1), "reset_ms": kms["reset"] / max(ksteps, 1),
+            "note": "the fused K-substep kernel is fp64-pipe/latency bound, not HBM bound (DESIGN.md section 5); fp64 view below"}
+    if rank == 0 and not args.no_fp64_peak:
+        try:
+            fp64_peak = capi.fp64_peak_flops(local)
+            flops_per_agent_step = args.flops_per_substep * SUBSTEPS
+            roof["fp64"] = {"achieved_tflops": n_envs * A * flops_per_agent_step / (k_ms * 1e-3) / 1e12,
+                            "peak_tflops": fp64_peak / 1e12, "peak_source": "measured live (acs_bench_fp64_peak: dependent-free DFMA loop)",
+                            "flops_per_agent_step": flops_per_agent_step}
+            roof["fp64"]["frac"] = roof["fp64"]["achieved_tflops"] / roof["fp64"]["peak_tflops"]
+        except Exception as exc:   # measurement helper only
+            roof["fp64"] = {"error": str(exc)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": desc, "envs_per_gpu": n_envs, "agents_per_env": n_agents, "substeps": K, "sim_freq": 60,
-                       "l2": "flushed between timed steps (256 MB fill)"},
-            "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_agent_step": bytes_per_agent_step,
-                         "note": "fp64-pipe/latency bound, see DESIGN.md"}}
+            "config": {"workload": desc, "scenario": config, "envs_per_gpu": n_envs, "agents_per_env": A, "substeps": SUBSTEPS,
+                       "sim_freq": 60, "auto_reset": True, "l2": "flushed between timed steps (256 MB fill)",
+                       "controller": ("batched GRU low-level controller in PyTorch" if core.hier else "none (direct stick/throttle classes)")},
+            "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks, "roofline": roof,
+            "episodes_finished_in_e2e": done_envs}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_fdm_baseline(rows, 5, K)
+            line["cpu_baseline"] = cpu_env_baseline(config, rounds=10 ** 9, budget_s=args.cpu_seconds)
         print(json.dumps(line), flush=True)
+    ve.close()
 
 
 def run_reference(args):
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    desc, n_envs, n_agents = WORKLOADS[args.workload]
-    K = 12
-    t0 = time.perf_counter()
-    b = cpu_fdm_baseline(n_envs * n_agents, args.steps + args.warmup, K, seconds_budget=60.0)
+    config, n_envs, desc = WORKLOADS[args.workload]
+    # every "step" of this arm is a bounded sample of the workload: `ref_rounds` env-steps of (host cores x 2) envs;
+    # W warm-up steps untimed, K steps timed, the whole run capped at 150 s of wall clock
+    b = cpu_env_baseline(config, rounds=args.steps * args.ref_rounds, warm_rounds=args.warmup * args.ref_rounds, budget_s=150.0)
     line = {"impl": "reference", "metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": desc, "substeps": K, "sim_freq": 60},
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "scenario": config, "substeps": SUBSTEPS, "sim_freq": 60},
             "cpu_baseline": b, "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -246,8 +295,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's own size)")
-    ap.add_argument("--workload", default="fdm_only")
+    ap.add_argument("--workload", default="1v1_noweapon", choices=sorted(WORKLOADS))
+    ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp64-peak", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="wall budget of the CPU baseline sample")
+    ap.add_argument("--ref-rounds", type=int, default=10, help="--impl reference: env-steps per bench step")
+    ap.add_argument("--flops-per-substep", type=float, default=5200.0,
+                    help="fp64 FLOPs per aircraft per substep (counted from the ncu instruction mix, DESIGN.md section 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -64,6 +64,107 @@ int acs_get_state(const AcsHandle* h, double* dst_dev, void* stream);    /* [n_s
 int acs_set_state(AcsHandle* h, const double* src_dev, void* stream);
 int acs_get_outputs(const AcsHandle* h, double* dst_dev, void* stream);  /* [n_output_fields][n_rows] */
 
+
+/* ======================================================================================================
+ * Environment layer: the gym-style reset/step of SingleControlEnv / SingleCombatEnv / MultipleCombatEnv
+ * (E/envs/env_base.py:98-173, E/envs/multiplecombat_env.py:66-182) for n_envs environments at once.
+ * AcsTaskConfig is what a reference Task class + yaml config boils down to once Python class composition
+ * is resolved (E/tasks/*.py, E/reward_functions/*.py, E/termination_conditions/*.py); the host layer
+ * (aircombat_selfplay_b200/taskspec.py) builds it from the same yaml files the reference parses.
+ * ====================================================================================================== */
+#define ACS_MAX_AGENTS 8
+#define ACS_MAX_REWARDS 12
+#define ACS_MAX_TERMS 6
+#define ACS_INFO_DIM 4   /* per agent: done cause (-1 none, else ACS_T_*), status (0 alive,1 crash,2 shotdown), spare, spare */
+
+enum { ACS_OBS_HEADING = 0, ACS_OBS_1V1 = 1, ACS_OBS_1V1_MISSILE = 2, ACS_OBS_NV_MISSILE = 3, ACS_OBS_MULTI = 4,
+       ACS_OBS_MULTI_MISSILE = 5, ACS_OBS_NVN = 6 };
+enum { ACS_ACT_HEADING = 0, ACS_ACT_COMBAT = 1 };
+enum { ACS_R_ALTITUDE = 0, ACS_R_POSTURE, ACS_R_EVENT, ACS_R_MISSILE_POSTURE, ACS_R_SHOOT_PENALTY, ACS_R_HEADING,
+       ACS_R_RELATIVE_ALTITUDE, ACS_R_COMBAT_GEOMETRY, ACS_R_GUN_BEHIT, ACS_R_GUN_TARGETTAIL, ACS_R_GUN_WEZ, ACS_R_GUN_WEZDOT };
+enum { ACS_T_UNREACH_HEADING = 0, ACS_T_EXTREME_STATE, ACS_T_OVERLOAD, ACS_T_LOW_ALTITUDE, ACS_T_TIMEOUT, ACS_T_SAFE_RETURN };
+enum { ACS_L_NONE = 0, ACS_L_RULE_LOCK, ACS_L_RL_SINGLE, ACS_L_RL_NEAREST, ACS_L_SCENARIO };
+enum { ACS_G_NONE = 0, ACS_G_DIE_FLAG, ACS_G_ALIVE };
+
+typedef struct AcsRewardSpec {
+  int32_t kind;       /* ACS_R_* */
+  int32_t potential;  /* BaseRewardFunction.is_potential (E/reward_functions/reward_function_base.py:15) */
+  double scale;       /* reward_scale */
+  double p0, p1, p2;  /* Altitude: safe_altitude, danger_altitude, Kv | Posture: orientation version, range version, target_dist | RelativeAltitude: KH */
+} AcsRewardSpec;
+
+typedef struct AcsTaskConfig {
+  int32_t n_envs, n_ego, n_enm;
+  int32_t substeps;                 /* agent_interaction_steps (E/envs/env_base.py:27) */
+  int32_t max_steps;
+  double sim_dt, fcs_dt;
+  double altitude_limit, acc_limit[3], center[3];   /* center = battle_field_center (lon, lat, alt) */
+  int32_t obs_kind, obs_dim, act_kind, shoot_dim;   /* action row = 4 low-level ints + shoot_dim shoot bits */
+  int32_t n_rewards;
+  AcsRewardSpec rewards[ACS_MAX_REWARDS];
+  int32_t n_terms;
+  int32_t terms[ACS_MAX_TERMS];     /* evaluated in this order, first done short-circuits (E/tasks/task_base.py:90-112) */
+  int32_t dones_before_rewards;     /* BaseEnv.step order (env_base.py:159-171) vs MultipleCombatEnv.step (:163-180) */
+  int32_t team_mean, share_obs, reward_gate, launch_kind, use_artillery, use_baseline;
+  double max_attack_angle, max_attack_distance;
+  int32_t min_attack_interval, lock_len;
+  int32_t num_missiles[ACS_MAX_AGENTS];
+  int32_t n_missile_slots;          /* per aircraft */
+  double init_state[ACS_MAX_AGENTS][12];  /* per aircraft, layout of acs_fdm_reset's ic rows */
+  double heading_increments[3];     /* UnreachHeading increment sizes (heading deg, altitude ft, velocity m/s) */
+  double check_interval;
+  uint64_t seed;                    /* keyed counter RNG seed (replaces np.random / gymnasium np_random draws) */
+  int32_t env_offset;               /* global index of this handle's first env (multi-GPU sharding keeps RNG streams per env) */
+  int32_t reserved;
+} AcsTaskConfig;
+
+typedef struct AcsEnv AcsEnv;
+
+/* replaces: constructing n_envs Env objects (BaseEnv.__init__ -> load_task, load_simulator; E/envs/env_base.py:24-87) */
+int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out);
+int acs_env_destroy(AcsEnv* e);
+/* replaces: env.reload-time changes of init_state (reset_simulators / curriculum resets, E/envs/singlecombat_env.py:45-122) */
+int acs_env_set_init_states(AcsEnv* e, const double* init_host /* [n_agents][12], HOST memory */);
+
+/* replaces: env.seed(seed) (E/envs/env_base.py:251-266): re-keys the counter RNG and restarts the per-env episode counters, so
+ * seed(s); reset(); ... replays the same draws (the reference's determinism test, R/tests/test_jsbsim.py:55-64). */
+int acs_env_set_seed(AcsEnv* e, uint64_t seed, void* stream);
+
+/* replaces: BaseEnv.reset() for every env with env_mask_dev[env] != 0 (NULL = all): sim.reload() for every aircraft,
+ * task.reset (reward-function resets included), get_obs (E/envs/env_base.py:98-113).
+ * obs_dev [n_envs][n_agents][obs_dim] doubles; share_obs_dev [n_envs][n_agents][n_agents*obs_dim] or NULL.  Rows of
+ * unmasked envs are left untouched. */
+int acs_env_reset(AcsEnv* e, const uint8_t* env_mask_dev, double* obs_dev, double* share_obs_dev, void* stream);
+
+/* replaces: BaseEnv.step(action) / MultipleCombatEnv.step(action) for all envs, plus -- when auto_reset != 0 -- the
+ * VecEnv worker's `if all(done): obs = env.reset()` (R/envs/env_wrappers.py:191-204,380-393).
+ * actions_dev [n_envs][n_agents][4+shoot_dim] int32 LOW-LEVEL discrete actions (hierarchical tasks run their GRU
+ * controller above this boundary); rewards_dev [n_envs][n_agents] doubles; dones_dev [n_envs][n_agents] bytes;
+ * info_dev [n_envs][n_agents][ACS_INFO_DIM] int32 or NULL; env_done_dev [n_envs] bytes (all agents done) or NULL. */
+int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double* share_obs_dev, double* rewards_dev,
+                 uint8_t* dones_dev, int32_t* info_dev, uint8_t* env_done_dev, int auto_reset, void* stream);
+
+/* Introspection for parity tests: named SoA arenas.  which: 0 FDM state [n_state_fields][rows] doubles, 1 FDM outputs,
+ * 2 per-aircraft doubles, 3 per-aircraft ints, 4 per-env doubles, 5 per-env ints, 6 missile doubles [f][rows*slots],
+ * 7 missile ints.  acs_env_arena_size returns the number of fields of an arena (elements per field via its own
+ * second output).  Copies are device-to-device on `stream`. */
+int acs_env_arena_info(const AcsEnv* e, int which, int* n_fields, int* n_per_field, int* is_int);
+const char* acs_env_arena_field_name(int which, int field);
+int acs_env_get_arena(const AcsEnv* e, int which, void* dst_dev, void* stream);
+int acs_env_set_arena(AcsEnv* e, int which, const void* src_dev, void* stream);
+/* the FDM batch inside an env handle (for acs_fdm_* / acs_get_state on the same aircraft rows) */
+AcsHandle* acs_env_fdm(AcsEnv* e);
+
+/* Measurement (no reference counterpart): with timing on, acs_env_step brackets each of its kernels with CUDA events on the
+ * caller's stream; acs_env_get_timing synchronises those events and returns the accumulated milliseconds per kernel since
+ * the last call -- ms[0] k_env_substeps, ms[1] k_env_post, ms[2] the two reset kernels -- and the number of steps covered. */
+int acs_env_set_timing(AcsEnv* e, int on);
+int acs_env_get_timing(AcsEnv* e, double ms[3], int* n_steps);
+
+/* Measurement helper (no reference counterpart): runs a dependent-free fp64 FMA loop on every SM and returns the
+ * achieved FLOP/s in *flops_out; used by bench.py to put an fp64-pipe roof beside the HBM roof. */
+int acs_bench_fp64_peak(int device, double* flops_out);
+
 #ifdef __cplusplus
 }
 #endif

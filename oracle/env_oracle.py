@@ -119,7 +119,7 @@ def get_AO_TA_R(ego, enm, two_d=False):
     AO = math.acos(min(1.0, max(-1.0, p1 / (R * ego_v + 1e-8))))
     TA = math.acos(min(1.0, max(-1.0, p2 / (R * enm_v + 1e-8))))
     cr = evx * dy - evy * dx
-    side = (cr > 0) - (cr < 0)
+    side = int(cr > 0) - int(cr < 0)
     return AO, TA, R, float(side)
 
 
@@ -874,6 +874,6 @@ def posture_range(version, R, target_dist):  # posture_reward.py:65-75
     if version == 1:
         return _clip(1.2 * min(math.exp(-(R - target_dist) * 0.21), 1) / (1. + math.exp(-(R - target_dist + 1) * 0.8)), 0.3, 1)
     if version == 2:
-        sg = (7 - R > 0) - (7 - R < 0)
+        sg = int(7 - R > 0) - int(7 - R < 0)
         return max(_clip(1.2 * min(math.exp(-(R - target_dist) * 0.21), 1) / (1. + math.exp(-(R - target_dist + 1) * 0.8)), 0.3, 1), sg)
     return 1 * (R < 5) + (R >= 5) * _clip(-0.032 * R ** 2 + 0.284 * R + 0.38, 0, 1) + _clip(math.exp(-0.16 * R), 0, 0.2)

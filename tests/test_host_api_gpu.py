@@ -1,0 +1,200 @@
+"""GPU tests of the reference-facing Python API, modelled on the reference's own tests (reference tests/test_jsbsim.py):
+env classes (shapes, same seed => same trajectory, crash semantics) and the VecEnv contract (shapes, infos, auto reset)."""
+import numpy as np
+import pytest
+import torch
+
+from aircombat_selfplay_b200.env_wrappers import (BatchedVecEnv, DummyVecEnv, ShareBatchedVecEnv, ShareDummyVecEnv,
+                                                  ShareSubprocVecEnv, SubprocVecEnv)
+from aircombat_selfplay_b200.envs import BatchedEnv, MultipleCombatEnv, SingleCombatEnv, SingleControlEnv
+
+pytestmark = pytest.mark.gpu
+
+
+def _sample(env, n=None):
+    return [env.action_space.sample() for _ in range(n or env.num_agents)]
+
+
+class TestSingleControlEnv:
+    def test_env(self):                                   # reference tests/test_jsbsim.py:18-64
+        env = SingleControlEnv("singlecontrol/heading")
+        assert env.num_agents == 1
+        for agent in env.agents.values():
+            assert len(agent.partners) == 0 and len(agent.enemies) == 0
+        obs_shape = (env.num_agents, *env.observation_space.shape)
+        env.seed(0)
+        env.action_space.seed(0)
+        obs = env.reset()
+        assert obs.shape == obs_shape
+        obs_buf, act_buf, rew_buf, done_buf = [obs], [], [], []
+        for _ in range(40):
+            actions = np.array(_sample(env))
+            obs, reward, done, info = env.step(actions)
+            assert obs.shape == obs_shape and reward.shape == (1, 1) and done.shape == (1, 1)
+            assert info["current_step"] == env.current_step and "heading_turn_counts" in info
+            act_buf.append(actions); obs_buf.append(obs); rew_buf.append(reward); done_buf.append(done)
+            if done:
+                assert env.current_step <= env.max_steps
+                break
+        env.seed(0)                                        # repetition: same seed => same data
+        obs = env.reset()
+        assert np.linalg.norm(obs - obs_buf[0]) < 1e-8
+        for t in range(len(done_buf)):
+            obs, reward, done, info = env.step(act_buf[t])
+            assert np.linalg.norm(obs - obs_buf[t + 1]) < 1e-8 and np.all(reward == rew_buf[t]) and np.all(done == done_buf[t])
+
+    @pytest.mark.parametrize("vecenv", [DummyVecEnv, SubprocVecEnv])
+    def test_vec_env(self, vecenv):                       # reference tests/test_jsbsim.py:66-89
+        n = 4
+        envs = vecenv([lambda: SingleControlEnv("singlecontrol/heading") for _ in range(n)])
+        obs_shape = (n, envs.num_agents, *envs.observation_space.shape)
+        obss = envs.reset()
+        assert obss.shape == obs_shape
+        actions = np.array([[envs.action_space.sample() for _ in range(envs.num_agents)] for _ in range(n)])
+        for _ in range(200):
+            obss, rewards, dones, infos = envs.step(actions)
+            assert obss.shape == obs_shape and rewards.shape == (n, 1, 1) and dones.shape == (n, 1, 1) \
+                and infos.shape[0] == n and isinstance(infos[0], dict) and "current_step" in infos[0]
+            if np.any(dones):
+                break
+        assert np.any(dones)
+        envs.close()
+
+
+class TestSingleCombatEnv:
+    @pytest.mark.parametrize("config", ["1v1/NoWeapon/Selfplay", "1v1/DodgeMissile/Selfplay", "1v1/ShootMissile/Selfplay",
+                                        "1v1/NoWeapon/HierarchySelfplay", "scenario1/scenario1"])
+    def test_env(self, config):                           # reference tests/test_jsbsim.py:94-145
+        env = SingleCombatEnv(config)
+        for agent in env.agents.values():
+            assert len(agent.partners) == 0 and len(agent.enemies) == 1
+        obs_shape = (env.num_agents, *env.observation_space.shape)
+        env.seed(0)
+        env.action_space.seed(0)
+        obs = env.reset()
+        assert obs.shape == obs_shape
+        obs_buf, act_buf, rew_buf, done_buf = [obs], [], [], []
+        for _ in range(30):
+            actions = _sample(env) if env.current_step % 2 == 0 else np.array(
+                [np.concatenate([np.atleast_1d(x).ravel() for x in a]) if isinstance(a, tuple) else a for a in _sample(env)])
+            obs, rewards, dones, info = env.step(actions)
+            assert obs.shape == obs_shape and rewards.shape == (2, 1) and dones.shape == (2, 1)
+            act_buf.append(actions); obs_buf.append(obs); rew_buf.append(rewards); done_buf.append(dones)
+            if np.all(dones):
+                break
+        env.seed(0)
+        obs = env.reset()
+        assert np.linalg.norm(obs - obs_buf[0]) < 1e-8
+        for t in range(len(done_buf)):
+            obs, rewards, dones, info = env.step(act_buf[t])
+            assert np.linalg.norm(obs - obs_buf[t + 1]) < 1e-8 and np.all(rewards == rew_buf[t]) and np.all(dones == done_buf[t])
+
+    def test_agent_crash(self):                           # reference tests/test_jsbsim.py:147-157
+        env = SingleCombatEnv("1v1/NoWeapon/Selfplay")
+        env.seed(0)
+        env.reset()
+        env.agents[env.ego_ids[0]].crash()
+        obs, rewards, dones, info = env.step(np.array(_sample(env)))
+        assert np.min(rewards) < -100      # crash reward
+        assert np.all(dones)               # no weapons: once one side is gone, the env terminates
+        assert "done_condition" in info
+
+    def test_wrong_env_class(self):
+        with pytest.raises(NotImplementedError):
+            SingleCombatEnv("scenario2/scenario2")
+
+
+class TestMultipleCombatEnv:
+    @pytest.mark.parametrize("config", ["2v2/NoWeapon/Selfplay", "2v2/ShootMissile/HierarchySelfplay", "scenario2/scenario2",
+                                        "scenario3/scenario3_nvn"])
+    def test_env(self, config):                           # reference tests/test_jsbsim.py:279-330
+        env = MultipleCombatEnv(config)
+        A = env.num_agents
+        assert A == len(env.agents)
+        for agent in env.agents.values():
+            assert len(agent.partners) == A // 2 - 1 and len(agent.enemies) == A // 2
+        obs_shape = (A, *env.observation_space.shape)
+        share_shape = (A, *env.share_observation_space.shape)
+        env.seed(0)
+        env.action_space.seed(0)
+        obs, share = env.reset()
+        assert obs.shape == obs_shape and share.shape == share_shape
+        assert np.array_equal(share[0], obs.reshape(-1))
+        bufs = []
+        for _ in range(20):
+            actions = _sample(env)
+            obs, share, rewards, dones, info = env.step(actions)
+            assert obs.shape == obs_shape and share.shape == share_shape and rewards.shape == (A, 1) and dones.shape == (A, 1)
+            # team reward: every member of a team gets the team mean (reference multiplecombat_env.py:170-175)
+            assert np.all(rewards[:A // 2] == rewards[0]) and np.all(rewards[A // 2:] == rewards[A // 2])
+            bufs.append((actions, obs, rewards, dones))
+        env.seed(0)
+        env.reset()
+        for actions, o, r, d in bufs:
+            obs, share, rewards, dones, info = env.step(actions)
+            assert np.linalg.norm(obs - o) < 1e-8 and np.all(rewards == r) and np.all(dones == d)
+
+    def test_dead_agent_semantics(self):                  # reference tests/test_jsbsim.py:332-382
+        env = MultipleCombatEnv("2v2/NoWeapon/Selfplay")
+        env.seed(0)
+        env.reset()
+        env.agents[env.ego_ids[0]].crash()
+        straight = np.array([[20, 19, 20, 0]] * 4)
+        obs, share, rewards, dones, info = env.step(straight)
+        assert dones[0][0] and not dones[1][0] and not np.all(dones)
+        frozen = obs[0, :9].copy()
+        for _ in range(3):
+            obs, share, rewards, dones, info = env.step(straight)
+            assert dones[0][0] and np.linalg.norm(obs[0, :9] - frozen) < 1e-8     # a dead aircraft's own state is frozen
+
+    @pytest.mark.parametrize("vecenv", [ShareDummyVecEnv, ShareSubprocVecEnv])
+    def test_vec_env(self, vecenv):                       # reference tests/test_jsbsim.py:384-404
+        n = 4
+        envs = vecenv([lambda: MultipleCombatEnv("scenario2/scenario2") for _ in range(n)])
+        A = envs.num_agents
+        obs_shape = (n, A, *envs.observation_space.shape)
+        share_shape = (n, A, *envs.share_observation_space.shape)
+        obss, share = envs.reset()
+        assert obss.shape == obs_shape and share.shape == share_shape
+        actions = [[envs.action_space.sample() for _ in range(A)] for _ in range(n)]
+        for _ in range(10):
+            obss, share, rewards, dones, infos = envs.step(actions)
+            assert obss.shape == obs_shape and share.shape == share_shape and rewards.shape == (n, A, 1) \
+                and dones.shape == (n, A, 1) and infos.shape[0] == n and isinstance(infos[0], dict)
+            assert infos[0]["current_step"] >= 1
+        envs.close()
+
+
+def test_vecenv_matches_device_api_and_auto_resets():
+    """The numpy-facing VecEnv returns exactly what the device API computes, and an env whose agents are all done
+    restarts inside the same call (reset obs in place, terminal rewards/dones kept)."""
+    n = 16
+    ve = BatchedVecEnv("1v1/NoWeapon/Selfplay", n, seed=3)
+    ve.core.spec.max_steps  # noqa: B018
+    ref = BatchedEnv("1v1/NoWeapon/Selfplay", n, seed=3)
+    o_ve = ve.reset()
+    o_ref = ref.reset()[0]
+    assert np.array_equal(o_ve, o_ref.cpu().numpy())
+    rng = np.random.default_rng(0)
+    for t in range(5):
+        a = rng.integers(0, 30, (n, 2, 4))
+        obs, rew, done, infos = ve.step(a)
+        o2, _, r2, d2, i2 = ref.step(torch.tensor(a, dtype=torch.int32, device="cuda"))
+        assert np.array_equal(obs, o2.cpu().numpy()) and np.array_equal(rew[..., 0], r2.cpu().numpy())
+        assert np.array_equal(done[..., 0], d2.cpu().numpy().astype(bool))
+        assert infos[3]["current_step"] == t + 1
+    ve.close(); ref.close()
+
+
+def test_hierarchical_controller_runs_batched_on_device():
+    ve = ShareBatchedVecEnv("scenario2/scenario2", 32, seed=1)
+    assert ve.action_space.__class__.__name__ == "Tuple" and ve.core.act_dim == 7
+    obs, share = ve.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        a = np.concatenate([rng.integers(0, 3, (32, 4, 1)), rng.integers(0, 5, (32, 4, 1)), rng.integers(0, 3, (32, 4, 1)),
+                            rng.integers(0, 2, (32, 4, 4))], axis=-1)
+        obs, share, rew, done, infos = ve.step(a)
+        assert np.isfinite(obs).all() and np.isfinite(rew).all()
+    assert ve.core.rnn.abs().sum() > 0
+    ve.close()
