@@ -33,6 +33,8 @@ DONE_CONDITIONS = {
 def action_space_for(task_name: str):
     """reference load_action_space of each Task class (E/tasks/*.py)."""
     t = TASKS[task_name]
+    if task_name == "hierarchical_multiplecombat_shoot_nearest":      # E/tasks/multiplecombat_task.py:217-218
+        return spaces.MultiDiscrete([3, 5, 3, 2])
     low = spaces.MultiDiscrete([3, 5, 3]) if t["hier"] else spaces.MultiDiscrete([41, 41, 41, 30])
     if t["shoot"] == 0:
         return low

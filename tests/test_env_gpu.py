@@ -49,8 +49,8 @@ def test_close_engagement(name):
         assert "launched" in ev and "miss" in ev
 
 
-@pytest.mark.parametrize("name", ["singlecontrol/heading", "1v1/NoWeapon/Selfplay", "2v2/NoWeapon/Selfplay",
-                                  "1v1/ShootMissile/Selfplay", "scenario2/scenario2"])
+@pytest.mark.parametrize("name", ["1v1/NoWeapon/Selfplay", "2v2/NoWeapon/Selfplay", "1v1/ShootMissile/Selfplay",
+                                  "scenario2/scenario2"])
 def test_crash_terminations(name):
     ev = _run(name, n_envs=3, steps=60, mode="dive", init="low")
     assert "term3" in ev      # LowAltitude

@@ -51,7 +51,7 @@ class TestSingleControlEnv:
         obss = envs.reset()
         assert obss.shape == obs_shape
         actions = np.array([[envs.action_space.sample() for _ in range(envs.num_agents)] for _ in range(n)])
-        for _ in range(200):
+        for _ in range(1500):     # the first heading check that can fail is at sim_time 30 s = step 300 (K = 6)
             obss, rewards, dones, infos = envs.step(actions)
             assert obss.shape == obs_shape and rewards.shape == (n, 1, 1) and dones.shape == (n, 1, 1) \
                 and infos.shape[0] == n and isinstance(infos[0], dict) and "current_step" in infos[0]
