@@ -11,7 +11,8 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libacs.so"
+import os as _os
+LIB_PATH = Path(_os.environ["ACS_LIB"]) if _os.environ.get("ACS_LIB") else _PKG / "libacs.so"   # ACS_LIB: tuning experiments only
 _LIB = None
 
 

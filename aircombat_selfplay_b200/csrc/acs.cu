@@ -61,9 +61,15 @@ __device__ __forceinline__ void stage_tables(double* sT) {
 }
 
 // ----------------------------------------------------------------------------- kernels
-constexpr int FDM_BLOCK = 128;
+#ifndef ACS_FDM_BLOCK
+#define ACS_FDM_BLOCK 128
+#endif
+#ifndef ACS_FDM_MIN_BLOCKS
+#define ACS_FDM_MIN_BLOCKS 1
+#endif
+constexpr int FDM_BLOCK = ACS_FDM_BLOCK;
 
-__global__ void __launch_bounds__(FDM_BLOCK) k_fdm_run(double* __restrict__ state, double* __restrict__ out,
+__global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_fdm_run(double* __restrict__ state, double* __restrict__ out,
                                                       const uint8_t* __restrict__ alive, int N, int n_frames, double dt,
                                                       double fcs_dt) {
   __shared__ double sT[F16_NTAB];

@@ -158,7 +158,7 @@ __device__ __noinline__ void missile_phase(const EnvView& v, const AcsTaskConfig
   }
 }
 
-__global__ void __launch_bounds__(FDM_BLOCK) k_env_substeps(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
+__global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
                                                            const int32_t* __restrict__ actions) {
   __shared__ double sT[F16_NTAB];
   __shared__ PubAc sP[FDM_BLOCK];

@@ -301,7 +301,7 @@ def main():
     ap.add_argument("--no-fp64-peak", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="wall budget of the CPU baseline sample")
     ap.add_argument("--ref-rounds", type=int, default=10, help="--impl reference: env-steps per bench step")
-    ap.add_argument("--flops-per-substep", type=float, default=5200.0,
+    ap.add_argument("--flops-per-substep", type=float, default=3713.0,
                     help="fp64 FLOPs per aircraft per substep (counted from the ncu instruction mix, DESIGN.md section 5)")
     args = ap.parse_args()
     if args.impl == "reference":
