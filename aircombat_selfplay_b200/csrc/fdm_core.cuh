@@ -13,6 +13,12 @@
 #include <cmath>
 
 #define FDM_DEV __device__ __forceinline__
+// helpers instantiated many times per frame; ACS_NOINLINE_HELPERS trades call overhead for instruction-cache footprint
+#ifdef ACS_NOINLINE_HELPERS
+#define FDM_HELPER __device__ __noinline__
+#else
+#define FDM_HELPER __device__ __forceinline__
+#endif
 
 static constexpr double RADTODEG = 180.0 / 3.14159265358979323846;
 static constexpr double DEGTORAD = 3.14159265358979323846 / 180.0;
@@ -68,24 +74,28 @@ FDM_DEV M33 mulABt(const M33& a, const M33& b) {  // a * b^T
 FDM_DEV double f16_constrain(double lo, double v, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ------------------------------------------------------------------ table lookups (J/math/FGTable.cpp:443-517)
-// Stateless bracket rule shared with the oracle: first upper row r>=1 (0-based) whose key >= lookup key.
-struct Bracket { int r; double f; int below, above; };
-FDM_DEV Bracket f16_bracket(const double* __restrict__ k, int n, double key) {
+// Stateless bracket rule shared with the oracle: first upper row r>=1 (0-based) whose key >= lookup key.  The
+// breakpoints ascend, so that row is 1 + #{1 <= i <= n-2 : k[i] < key}: a branch-free count (n is a literal at every
+// call site, the loop unrolls into independent shared-memory loads).  The model compiler stores the reciprocal
+// breakpoint spacings behind the keys (k[n + r] = 1 / (k[r] - k[r-1])), so the interpolation factor is a multiply.
+struct Bracket { int r; double f; bool above; };
+FDM_HELPER Bracket f16_bracket(const double* __restrict__ k, const int n, const double key) {
   Bracket b;
   int r = 1;
-  while (r < n - 1 && k[r] < key) r++;
-  const double lo = k[r - 1], hi = k[r];
-  double f = (key - lo) / (hi - lo);
+#pragma unroll
+  for (int i = 1; i < n - 1; i++) r += (k[i] < key) ? 1 : 0;
+  double f = (key - k[r - 1]) * k[n + r];
   f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f);
-  b.r = r; b.f = f; b.below = key <= k[0]; b.above = key >= k[n - 1];
+  b.r = r; b.f = f; b.above = key >= k[n - 1];
   return b;
 }
-FDM_DEV double f16_tab1(const double* __restrict__ v, int n, const Bracket& b) {
-  if (b.below) return v[0];
-  if (b.above) return v[n - 1];
-  return b.f * (v[b.r] - v[b.r - 1]) + v[b.r - 1];
+// 1-D: clamp, no extrapolation.  Below the first key r = 1 and f = 0, which already yields v[0] exactly.
+FDM_DEV double f16_tab1(const double* __restrict__ v, const int n, const Bracket& b) {
+  const double lo = v[b.r - 1];
+  const double y = b.f * (v[b.r] - lo) + lo;
+  return b.above ? v[n - 1] : y;
 }
-FDM_DEV double f16_tab2(const double* __restrict__ v, int nc, const Bracket& rb, const Bracket& cb) {
+FDM_DEV double f16_tab2(const double* __restrict__ v, const int nc, const Bracket& rb, const Bracket& cb) {
   const double* r0 = v + (rb.r - 1) * nc;
   const double* r1 = v + rb.r * nc;
   const double col1 = rb.f * (r1[cb.r - 1] - r0[cb.r - 1]) + r0[cb.r - 1];
@@ -98,7 +108,7 @@ FDM_DEV double f16_tab2(const double* __restrict__ v, int nc, const Bracket& rb,
 FDM_DEV double f16_pid(double Input, double test, double kp, double ki, double kd, int int_type, double dt,
                        double& prev, double& prev2, double& itot) {
   double I_out_delta = 0.0;
-  const double Dval = (Input - prev) / dt;
+  const double Dval = (Input - prev) / dt;   // dt is a kernel-uniform value: one reciprocal, hoisted by the compiler
   if (fabs(test) < 0.000001) {
     switch (int_type) {
       case 1: I_out_delta = Input; break;
@@ -136,6 +146,22 @@ FDM_DEV double f16_kinemat(const double* __restrict__ det, const double* __restr
   return Output;
 }
 
+// Two-detent kinematic (every F-16 actuator except the flaps): the traverse loop above runs exactly once, so the
+// component collapses to one rate-limited move.  d0, d1, t1 are literals of the generated call site.
+FDM_HELPER double f16_kinemat2(const double d0, const double d1, const double t1, double Input, double Output, const double dt) {
+  Input = f16_constrain(d0, Input, d1);
+  if (dt > 0.0 && !f16_equal_to_roundoff(Input, Output)) {
+    if (t1 <= 0.0) return Input;
+    const double Rate = (d1 - d0) / t1;
+    const double ThisDt = fabs((Input - Output) / Rate);
+    if (dt < ThisDt) { if (Output < Input) Output += dt * Rate; else Output -= dt * Rate; }
+    else Output = Input;
+  }
+  return Output;
+}
+// x^y for x > 0 as exp(y ln x): 2-3 ulp instead of pow()'s < 1 ulp at a quarter of its instruction count
+FDM_HELPER double f16_powpos(const double x, const double y) { return exp(y * log(x)); }
+
 #include "gen/f16_gen.cuh"
 
 // ------------------------------------------------------------------ ISA-1976 (J/models/atmosphere/FGStandardAtmosphere.cpp)
@@ -168,7 +194,7 @@ FDM_DEV void atmosphere_calculate(const AtmoConst& c, double altitude, Atmo& o) 
   for (; b < 7; ++b) { const double testAlt = c.H[b + 1]; if (G < testAlt) break; BaseAlt = testAlt; }
   const double Tmb = c.Tmb[b], deltaH = G - BaseAlt, Lmb = c.Lapse[b];
   double Pm;
-  if (Lmb != 0.0) Pm = c.PB[b] * pow(Tmb / (Tmb + Lmb * deltaH), c.g0 / (c.Reng * Lmb));
+  if (Lmb != 0.0) Pm = c.PB[b] * f16_powpos(Tmb / (Tmb + Lmb * deltaH), c.g0 / (c.Reng * Lmb));
   else Pm = c.PB[b] * exp(-c.g0 * deltaH / (c.Reng * Tmb));
   o.T = Tm; o.P = Pm; o.rho = Pm / (c.Reng * Tm);
   o.a = sqrt(1.4 * c.Reng * Tm);
@@ -177,7 +203,7 @@ FDM_DEV void atmosphere_calculate(const AtmoConst& c, double altitude, Atmo& o) 
   for (; d < 7; d++) if (o.rho >= c.DB[d + 1]) break;
   const double Ld = c.Lapse[d];
   double da;
-  if (Ld != 0.0) da = c.H[d] + (c.Tt[d] / Ld) * (pow(o.rho / c.DB[d], -1.0 / (1.0 + c.g0 / (c.Reng * Ld))) - 1);
+  if (Ld != 0.0) da = c.H[d] + (c.Tt[d] / Ld) * (f16_powpos(o.rho / c.DB[d], -1.0 / (1.0 + c.g0 / (c.Reng * Ld))) - 1);
   else da = c.H[d] + (-c.Reng * c.Tt[d] / c.g0) * log(o.rho / c.DB[d]);
   o.density_altitude = atmo_geomet(c, da);
 }
@@ -185,14 +211,15 @@ FDM_DEV void atmosphere_calculate(const AtmoConst& c, double altitude, Atmo& o) 
 // J/FGJSBBase.cpp:245-296
 FDM_DEV double pitot_total_pressure(double mach, double p) {
   if (mach < 0) return p;
-  if (mach < 1) return p * pow((1 + 0.2 * mach * mach), 3.5);
-  return p * 166.92158009316827 * pow(mach, 7.0) / pow(7 * mach * mach - 1, 2.5);
+  if (mach < 1) { const double t = 1 + 0.2 * mach * mach; return p * ((t * t) * t * sqrt(t)); }       // t^3.5
+  const double m2 = mach * mach, m7 = (m2 * m2) * (m2 * mach), x = 7 * m2 - 1;
+  return p * 166.92158009316827 * m7 / ((x * x) * sqrt(x));                                          // M^7 / x^2.5
 }
 FDM_DEV double mach_from_impact_pressure(double qc, double p) {
   const double A = qc / p + 1;
-  double M = sqrt(5.0 * (pow(A, 1. / 3.5) - 1));
+  double M = sqrt(5.0 * (f16_powpos(A, 1. / 3.5) - 1));
   if (M > 1.0)
-    for (int i = 0; i < 10; i++) M = 0.8812848543473311 * sqrt(A * pow(1 - 1.0 / (7.0 * M * M), 2.5));
+    for (int i = 0; i < 10; i++) { const double y = 1 - 1.0 / (7.0 * M * M); M = 0.8812848543473311 * sqrt(A * ((y * y) * sqrt(y))); }
   return M;
 }
 
@@ -245,14 +272,13 @@ struct AcOut {
 
 // ------------------------------------------------------------------ per-frame scratch shared between the model stages
 struct Frame {
-  M33 Ti2b, Tl2b, Tec2b;   // body matrices of this frame
+  M33 Ti2b, Tl2b;          // body matrices of this frame
   double sin_epa, cos_epa;
   V3 ecef;                 // vLocation
-  double radius, rxy, geodAlt, sinLatGd, cosLatGd, sinLon, cosLon, latGc, gd_s1, gd_cc;
+  double radius, rxy, geodAlt, sinLatGd, cosLatGd, sinLon, cosLon, cosLatGc, h_asl, gd_s1, gd_cc;
   V3 uvw, pqr, vel;        // body velocity, body rates (wrt ECEF), NED velocity
   V3 grav;                 // ECEF gravity
   Atmo atm;
-  double roll, pitch, psi;
   double alpha, beta, Vt, qbar, mach, vcas;
   V3 pilotN;
   double Mass; V3 cg; M33 J, Jinv;
@@ -312,13 +338,15 @@ FDM_DEV void add_pointmass_inertia(M33& J, const V3& cg, double mass_sl, double 
 // ---- location-dependent part of Propagate: ECEF -> geodetic quantities and Tec2l (J/math/FGLocation.cpp:283-370)
 FDM_DEV void location_derived(Frame& f, M33& Tec2l) {
   const double x = f.ecef.x, y = f.ecef.y, z = f.ecef.z;
-  f.radius = sqrt(x * x + y * y + z * z);
-  const double rxy = sqrt(x * x + y * y);
+  const double rxy2 = x * x + y * y;
+  f.radius = sqrt(rxy2 + z * z);
+  const double rxy = sqrt(rxy2);
   f.rxy = rxy;
   double sinLon, cosLon;
-  if (rxy == 0.0) { sinLon = 0.0; cosLon = 1.0; } else { sinLon = y / rxy; cosLon = x / rxy; }
+  if (rxy == 0.0) { sinLon = 0.0; cosLon = 1.0; } else { const double ir = 1.0 / rxy; sinLon = y * ir; cosLon = x * ir; }
   f.sinLon = sinLon; f.cosLon = cosLon;
-  f.latGc = atan2(z, rxy);
+  // geocentric latitude only enters through its sine and cosine (J2 gravity, sea-level radius): z/r and rxy/r
+  f.cosLatGc = rxy / f.radius;
   const double ec = EARTH_B / EARTH_A, ec2 = ec * ec, e2 = 1.0 - ec2, c = EARTH_A * e2;
   const double s0 = fabs(z), zc = ec * s0, c0 = ec * rxy, c02 = c0 * c0, s02 = s0 * s0, a02 = c02 + s02;
   const double a0 = sqrt(a02), a03 = a02 * a0;
@@ -327,11 +355,11 @@ FDM_DEV void location_derived(Frame& f, M33& Tec2l) {
   const double b0 = 1.5 * cs0c0 * ((rxy * s0 - zc * c0) * a0 - cs0c0);
   s1 = s1 * a03 - b0 * s0;
   const double cc = ec * (c1 * a03 - b0 * c0);
-  const double s12 = s1 * s1, cc2 = cc * cc, norm = sqrt(s12 + cc2);
+  const double s12 = s1 * s1, cc2 = cc * cc, inorm = 1.0 / sqrt(s12 + cc2);
   const double sgn = z < 0.0 ? -1.0 : 1.0;
-  const double cosLat = cc / norm, sinLat = sgn * s1 / norm;
+  const double cosLat = cc * inorm, sinLat = sgn * s1 * inorm;
   f.cosLatGd = cosLat; f.sinLatGd = sinLat; f.gd_s1 = s1; f.gd_cc = cc;
-  f.geodAlt = (rxy * cc + s0 * s1 - EARTH_A * sqrt(ec2 * s12 + cc2)) / norm;
+  f.geodAlt = (rxy * cc + s0 * s1 - EARTH_A * sqrt(ec2 * s12 + cc2)) * inorm;
   Tec2l.m[0][0] = -cosLon * sinLat; Tec2l.m[0][1] = -sinLon * sinLat; Tec2l.m[0][2] = cosLat;
   Tec2l.m[1][0] = -sinLon; Tec2l.m[1][1] = cosLon; Tec2l.m[1][2] = 0.0;
   Tec2l.m[2][0] = -cosLon * cosLat; Tec2l.m[2][1] = -sinLon * cosLat; Tec2l.m[2][2] = -sinLat;
@@ -341,7 +369,6 @@ FDM_DEV void location_derived(Frame& f, M33& Tec2l) {
 // integrate=false reproduces the suspended-integration passes of FGFDMExec::RunIC (dt = 0).
 FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double* __restrict__ T, const AtmoConst& ac,
                        const double dt, const double fcs_dt, const bool trim_fuel_freeze) {
-  const V3 Omega = v3(0.0, 0.0, EARTH_OMEGA);
   // ---------------- Propagate (J/models/FGPropagate.cpp:218-297)
   if (dt != 0.0) {
     a.sim_time += dt;  // FGFDMExec::IncrTime
@@ -373,41 +400,36 @@ FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
   f.ecef = v3(f.cos_epa * a.ri.x + f.sin_epa * a.ri.y, -f.sin_epa * a.ri.x + f.cos_epa * a.ri.y, a.ri.z);
   M33 Tec2l;
   location_derived(f, Tec2l);
-  M33 Ti2ec;
-  Ti2ec.m[0][0] = f.cos_epa; Ti2ec.m[0][1] = f.sin_epa; Ti2ec.m[0][2] = 0.0;
-  Ti2ec.m[1][0] = -f.sin_epa; Ti2ec.m[1][1] = f.cos_epa; Ti2ec.m[1][2] = 0.0;
-  Ti2ec.m[2][0] = 0.0; Ti2ec.m[2][1] = 0.0; Ti2ec.m[2][2] = 1.0;
-  const M33 Ti2l = mul(Tec2l, Ti2ec);
+  // Ti2l = Tec2l * Ti2ec with Ti2ec = Rz(epa): only the first two columns mix (J/models/FGPropagate.cpp:475-496)
+  M33 Ti2l;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    Ti2l.m[i][0] = Tec2l.m[i][0] * f.cos_epa - Tec2l.m[i][1] * f.sin_epa;
+    Ti2l.m[i][1] = Tec2l.m[i][0] * f.sin_epa + Tec2l.m[i][1] * f.cos_epa;
+    Ti2l.m[i][2] = Tec2l.m[i][2];
+  }
   f.Ti2b = quat_T(a.q0, a.q1, a.q2, a.q3);
   f.Tl2b = mulABt(f.Ti2b, Ti2l);        // Ti2b * Tl2i
-  f.Tec2b = mulABt(f.Ti2b, Ti2ec);      // Ti2b * Tec2i
-  const V3 OmegaXr = cross(Omega, a.ri);
-  f.uvw = mul(f.Ti2b, a.vi - OmegaXr);
-  const V3 OmegaB = mul(f.Ti2b, Omega);
-  f.pqr = a.wi - OmegaB;
+  // Omega = (0, 0, w): Omega x r = (-w y, w x, 0); Ti2b * Omega = w * third column of Ti2b
+  f.uvw = mul(f.Ti2b, v3(a.vi.x + EARTH_OMEGA * a.ri.y, a.vi.y - EARTH_OMEGA * a.ri.x, a.vi.z));
+  f.pqr = v3(a.wi.x - EARTH_OMEGA * f.Ti2b.m[0][2], a.wi.y - EARTH_OMEGA * f.Ti2b.m[1][2], a.wi.z - EARTH_OMEGA * f.Ti2b.m[2][2]);
   f.vel = mulT(f.Tl2b, f.uvw);
-  // Euler angles through the local quaternion, as FGPropagate::GetEuler does (qAttitudeLocal = Tl2b.GetQuaternion())
-  {
-    double ql[4];
-    mat_quat(f.Tl2b, ql);
-    const M33 mT = quat_T(ql[0], ql[1], ql[2], ql[3]);
-    mat_euler(mT, f.roll, f.pitch, f.psi);
-  }
-  p.attitude_pitch_rad = f.pitch; p.attitude_roll_rad = f.roll; p.velocities_u_fps = f.uvw.x; p.velocities_v_fps = f.uvw.y;
+  // The FCS reads the Euler angles only as cos(pitch) * cos(roll) (fcs/n-pilot-z-correction), which is Tl2b(3,3); the
+  // angles themselves are extracted once per interaction step in fdm_outputs.
+  p.attitude_cos_pitch_cos_roll = f.Tl2b.m[2][2]; p.velocities_u_fps = f.uvw.x; p.velocities_v_fps = f.uvw.y;
   // ---------------- Inertial: J2 gravity in ECEF (J/models/FGInertial.cpp:193-211)
   {
-    const double r = f.radius, sinLat = sin(f.latGc), adivr = EARTH_A / r, preCommon = 1.5 * EARTH_J2 * adivr * adivr;
-    const double xy = 1.0 - 5.0 * (sinLat * sinLat), z = 3.0 - 5.0 * (sinLat * sinLat), GMOverr2 = EARTH_GM / (r * r);
-    f.grav.x = -GMOverr2 * ((1.0 + (preCommon * xy)) * f.ecef.x / r);
-    f.grav.y = -GMOverr2 * ((1.0 + (preCommon * xy)) * f.ecef.y / r);
-    f.grav.z = -GMOverr2 * ((1.0 + (preCommon * z)) * f.ecef.z / r);
+    const double ir = 1.0 / f.radius, sinLat = f.ecef.z * ir, adivr = EARTH_A * ir, preCommon = 1.5 * EARTH_J2 * adivr * adivr;
+    const double xy = 1.0 - 5.0 * (sinLat * sinLat), z = 3.0 - 5.0 * (sinLat * sinLat), GMOverr2 = EARTH_GM * (ir * ir);
+    f.grav.x = -GMOverr2 * ((1.0 + (preCommon * xy)) * f.ecef.x * ir);
+    f.grav.y = -GMOverr2 * ((1.0 + (preCommon * xy)) * f.ecef.y * ir);
+    f.grav.z = -GMOverr2 * ((1.0 + (preCommon * z)) * f.ecef.z * ir);
   }
   // ---------------- Atmosphere at h = |r| - sea-level radius (J/models/FGPropagate.cpp:573-576, FGLocation.cpp:273-279)
-  const double cosLatGc = cos(f.latGc);
   const double ecr = EARTH_B / EARTH_A;
-  const double slr = EARTH_A * ecr / sqrt(1.0 - (1.0 - ecr * ecr) * cosLatGc * cosLatGc);
-  const double h_asl = f.radius - slr;
-  atmosphere_calculate(ac, h_asl, f.atm);
+  const double slr = EARTH_A * ecr / sqrt(1.0 - (1.0 - ecr * ecr) * f.cosLatGc * f.cosLatGc);
+  f.h_asl = f.radius - slr;
+  atmosphere_calculate(ac, f.h_asl, f.atm);
   p.atmosphere_density_altitude = f.atm.density_altitude;
   // ---------------- FCS (generated)
   f16_fcs(p, s, T, fcs_dt);
@@ -476,9 +498,13 @@ FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
     const double AeroU2 = U * U, AeroV2 = V * V, AeroW2 = W * W, mUW = AeroU2 + AeroW2, Vt2 = mUW + AeroV2;
     f.Vt = sqrt(Vt2);
     f.alpha = 0.0; f.beta = 0.0;
-    if (f.Vt > 0.001) { f.beta = atan2(V, sqrt(mUW)); if (mUW >= 1E-6) f.alpha = atan2(W, U); }
-    sincos(f.alpha, &sa, &ca);
-    sincos(f.beta, &sb, &cb);
+    sa = 0.0; ca = 1.0; sb = 0.0; cb = 1.0;
+    if (f.Vt > 0.001) {
+      // the wind->body matrix needs only sines and cosines of alpha and beta: ratios of the velocity components
+      const double sUW = sqrt(mUW), iVt = 1.0 / f.Vt;
+      f.beta = atan2(V, sUW); sb = V * iVt; cb = sUW * iVt;
+      if (mUW >= 1E-6) { const double iUW = 1.0 / sUW; f.alpha = atan2(W, U); sa = W * iUW; ca = U * iUW; }
+    }
     f.qbar = (0.5 * f.atm.rho) * Vt2;
     f.mach = f.Vt / f.atm.a;
     const double Vground = sqrt(f.vel.x * f.vel.x + f.vel.y * f.vel.y);
@@ -540,8 +566,7 @@ FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
       if (!augmentation) {
         const double tsfc = K_ENG_tsfc * sqrt(f.atm.T / 389.7) * (0.84 + (1 - a.N2norm) * (1 - a.N2norm));
         a.FF = seek(a.FF, thrust * tsfc, 1000.0, 10000.0);
-        const double IdleFF = pow(K_ENG_milthrust, 0.2) * 107.0;
-        if (a.FF < IdleFF) a.FF = IdleFF;
+        if (a.FF < K_ENG_idleff) a.FF = K_ENG_idleff;
       }
       if (AugmentCmd > 0.0) {
         augmentation = true;
@@ -596,10 +621,13 @@ FDM_DEV void fdm_outputs(const AcCore& a, const Frame& f, AcOut& o) {
   o.lon_deg = lon * RADTODEG;
   const double sgn = f.ecef.z < 0.0 ? -1.0 : 1.0;
   o.lat_geod_deg = (sgn * atan(f.gd_s1 / f.gd_cc)) * RADTODEG;
-  const double cosLatGc = cos(f.latGc);
-  const double ecr = EARTH_B / EARTH_A;
-  o.h_sl_ft = f.radius - EARTH_A * ecr / sqrt(1.0 - (1.0 - ecr * ecr) * cosLatGc * cosLatGc);
-  o.roll = f.roll; o.pitch = f.pitch; o.heading = f.psi;
+  o.h_sl_ft = f.h_asl;
+  {  // Euler angles through the local quaternion, as FGPropagate::GetEuler does (qAttitudeLocal = Tl2b.GetQuaternion())
+    double ql[4];
+    mat_quat(f.Tl2b, ql);
+    const M33 mT = quat_T(ql[0], ql[1], ql[2], ql[3]);
+    mat_euler(mT, o.roll, o.pitch, o.heading);
+  }
   o.vn = f.vel.x; o.ve = f.vel.y; o.vd = f.vel.z; o.u = f.uvw.x; o.v = f.uvw.y; o.w = f.uvw.z;
   o.vc_fps = f.vcas; o.npx = f.pilotN.x; o.npy = f.pilotN.y; o.npz = f.pilotN.z;
   o.p = f.pqr.x; o.q = f.pqr.y; o.r = f.pqr.z; o.eci_vmag = mag(a.vi);
@@ -711,7 +739,7 @@ FDM_DEV void fdm_reset(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
     const double N1_factor = K_ENG_maxn1 - K_ENG_idlen1, N2_factor = K_ENG_maxn2 - K_ENG_idlen2;
     const double idlethrust = K_ENG_milthrust * idleT, milthrust = (K_ENG_milthrust - idlethrust) * milT;
     const double sigma = f.atm.rho / ac.SLdensity, dbase = 90.0 / (K_ENG_bypassratio + 3.0);
-    const double IdleFF = pow(K_ENG_milthrust, 0.2) * 107.0;
+    const double IdleFF = K_ENG_idleff;
     bool augmentation = false;
     double currentThrust = 0, lastThrust = -1;
     int steady_count = 0, j = 0;

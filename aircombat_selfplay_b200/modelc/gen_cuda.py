@@ -26,7 +26,8 @@ AXES = ["DRAG", "SIDE", "LIFT", "ROLL", "PITCH", "YAW"]
 INPUT_PROPS = ["fcs/aileron-cmd-norm", "fcs/elevator-cmd-norm", "fcs/rudder-cmd-norm", "fcs/throttle-cmd-norm"]
 # published by the hand-written core models, in frame order (stage name -> props)
 CORE_PUBLISH = [
-    ("propagate", ["attitude/pitch-rad", "attitude/roll-rad", "velocities/u-fps", "velocities/v-fps"]),
+    ("propagate", ["attitude/pitch-rad", "attitude/roll-rad", "attitude/cos-pitch-cos-roll", "velocities/u-fps",
+                   "velocities/v-fps"]),
     ("atmosphere", ["atmosphere/density-altitude"]),
     ("fcs", None),
     ("auxiliary", ["aero/alpha-rad", "aero/alpha-deg", "aero/beta-rad", "aero/qbar-psf", "velocities/mach",
@@ -71,9 +72,11 @@ class CudaGen:
         return off
 
     def keys_off(self, keys):
-        k = tuple(keys)
+        """Breakpoint vector followed by its reciprocal spacings: k[n + r] = 1 / (k[r] - k[r-1]), k[n] unused."""
+        k = tuple(float(x) for x in keys)
         if k not in self.keyarrays:
-            self.keyarrays[k] = self.pack(k)
+            inv = [0.0] + [1.0 / (k[r] - k[r - 1]) for r in range(1, len(k))]
+            self.keyarrays[k] = self.pack(list(k) + inv)
         return self.keyarrays[k]
 
     # ------------------------------------------------------------------ dataflow
@@ -207,6 +210,12 @@ class CudaGen:
 
     def product(self, fs, scope):
         terms = []
+        fs = list(fs)
+        # cos(pitch) * cos(roll) is element (3,3) of the local-to-body matrix the core already holds: no trig, and the
+        # Euler angles need not be extracted every frame
+        cp, cr = ("cos", "attitude/pitch-rad"), ("cos", "attitude/roll-rad")
+        if any(tuple(f[:2]) == cp for f in fs) and any(tuple(f[:2]) == cr for f in fs):
+            fs = [f for f in fs if tuple(f[:2]) not in (cp, cr)] + [("prop", "attitude/cos-pitch-cos-roll")]
         for f in fs:
             if f[0] == "prop":
                 terms.append(self.pexpr(f[1]))
@@ -268,11 +277,15 @@ class CudaGen:
                 code.append(f"    out = f16_pid({ins[0]}, {trig}, {lit(c['kp'])}, {lit(c['ki'])}, {lit(c['kd'])}, {itype}, fcs_dt, "
                             f"s.pid_{n}_prev, s.pid_{n}_prev2, s.pid_{n}_itot);")
             elif t == "kinematic":
-                doff = self.pack(c["detents"])
-                toff = self.pack(c["times"])
                 scale = "" if c["noscale"] else f" * {lit(c['detents'][-1])}"
-                code.append(f"    out = f16_kinemat(T + {doff}, T + {toff}, {len(c['detents'])}, {ins[0]}{scale}, "
-                            f"{self.pexpr(c['outputs'][0])}, fcs_dt);")
+                if len(c["detents"]) == 2:
+                    code.append(f"    out = f16_kinemat2({lit(c['detents'][0])}, {lit(c['detents'][1])}, {lit(c['times'][1])}, "
+                                f"{ins[0]}{scale}, {self.pexpr(c['outputs'][0])}, fcs_dt);")
+                else:
+                    doff = self.pack(c["detents"])
+                    toff = self.pack(c["times"])
+                    code.append(f"    out = f16_kinemat(T + {doff}, T + {toff}, {len(c['detents'])}, {ins[0]}{scale}, "
+                                f"{self.pexpr(c['outputs'][0])}, fcs_dt);")
             elif t == "fcs_function":
                 code.append(f"    out = {self.product(c['factors'], scope)};")
                 if ins:
@@ -347,11 +360,16 @@ class CudaGen:
         assert len(mass["pointmasses"]) == 2 and len(ir["tanks"]) == 4, "fdm_core.cuh is written for 2 point masses / 4 tanks"
         for k in ("milthrust", "maxthrust", "bypassratio", "tsfc", "atsfc", "idlen1", "idlen2", "maxn1", "maxn2"):
             o.append(f"static constexpr double K_ENG_{k} = {lit(e[k])};")
+        o.append(f"static constexpr double K_ENG_idleff = {lit(e['milthrust'] ** 0.2 * 107.0)};  // pow(MilThrust, 0.2) * 107 (FGTurbine.cpp:231)")
         o.append(f"static constexpr int K_ENG_augmented = {e['augmented']}, K_ENG_augmethod = {e['augmethod']};")
         o.append(f"static constexpr double K_THRUSTER_X = {lit(e['thruster_loc'][0])}, K_THRUSTER_Y = {lit(e['thruster_loc'][1])}, "
                  f"K_THRUSTER_Z = {lit(e['thruster_loc'][2])};")
         # props struct: everything that is not a folded constant
         members = [p for p in self.props if p not in self.consts]
+        for stage, pubs in CORE_PUBLISH:          # core-published helpers that are not JSBSim properties
+            for p in pubs or []:
+                if p not in members and p not in self.consts:
+                    members.append(p)
         o.append("struct Props {")
         for p in members:
             o.append(f"  double {cid(p)};  // {p}")
