@@ -85,7 +85,7 @@ def lib():
         L.acs_env_fdm.restype = vp
         L.acs_env_fdm.argtypes = [vp]
         L.acs_env_set_timing.argtypes = [vp, i]
-        L.acs_env_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i)]
+        L.acs_env_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i), i]
         L.acs_bench_fp64_peak.argtypes = [i, ctypes.POINTER(ctypes.c_double)]
         _LIB = L
     return _LIB
@@ -213,7 +213,10 @@ class EnvBatch:
     """``n_envs`` environments of one task on one GPU -- the device-side counterpart of ``n_envs`` reference Env objects
     (reference envs/JSBSim/envs/env_base.py).  Tensors in, tensors out; nothing here synchronises the stream."""
 
-    def __init__(self, spec, n_envs: int, seed: int = 0, device: int = 0, env_offset: int = 0):
+    def __init__(self, spec, n_envs: int, seed: int = 0, device: int = 0, env_offset: int = 0, device_share_obs: bool = False):
+        """``device_share_obs``: also materialise share_obs [B, A, A*D] in HBM (the kernel writes it).  The default leaves
+        it as what it is -- every agent's row is the same concatenation of all observations (reference
+        envs/JSBSim/envs/env_base.py:183-189) -- and exposes it as a stride-0 view of ``obs``."""
         if not torch.cuda.is_available():
             raise AcsError("CUDA is not available; the simulator has no CPU fallback")
         self.spec, self.n_envs, self.n_agents = spec, n_envs, spec.n_agents
@@ -226,7 +229,8 @@ class EnvBatch:
         B, A, D = n_envs, self.n_agents, spec.obs_dim
         # every per-step output lives in ONE device buffer so the host-facing layer fetches a step with a single D2H copy
         layout = [("obs", torch.float64, (B, A, D))]
-        if spec.share_obs:
+        self.device_share_obs = bool(device_share_obs and spec.share_obs)
+        if self.device_share_obs:
             layout.append(("share_obs", torch.float64, (B, A, A * D)))
         layout += [("rewards", torch.float64, (B, A)), ("info", torch.int32, (B, A, INFO_DIM)), ("dones", torch.uint8, (B, A)),
                    ("env_done", torch.uint8, (B,))]
@@ -236,9 +240,9 @@ class EnvBatch:
             self.out_layout.append((name, dt, shape, off, nbytes))
             off += (nbytes + 15) // 16 * 16
         self.out_buf = torch.zeros(off, dtype=torch.uint8, device=self.device)
-        self.share_obs = None
+        self._share_dev = None
         for name, dt, shape, o, nbytes in self.out_layout:
-            setattr(self, name, self.out_buf[o:o + nbytes].view(dt).view(shape))
+            setattr(self, "_share_dev" if name == "share_obs" else name, self.out_buf[o:o + nbytes].view(dt).view(shape))
         self.act_dim = 4 + spec.shoot_dim
 
     def close(self):
@@ -258,6 +262,15 @@ class EnvBatch:
         assert arr.shape == (self.n_agents, 12)
         _check(lib().acs_env_set_init_states(self._h, arr.ctypes.data_as(ctypes.c_void_p)))
 
+    @property
+    def share_obs(self):
+        if not self.spec.share_obs:
+            return None
+        if self._share_dev is not None:
+            return self._share_dev
+        B, A, D = self.obs.shape
+        return self.obs.view(B, 1, A * D).expand(B, A, A * D)
+
     def set_seed(self, seed: int):
         _check(lib().acs_env_set_seed(self._h, ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), _stream()))
 
@@ -270,14 +283,14 @@ class EnvBatch:
 
     def reset(self, env_mask: torch.Tensor | None = None):
         _check(lib().acs_env_reset(self._h, _ptr(env_mask, torch.uint8), _ptr(self.obs, torch.float64),
-                                   _ptr(self.share_obs, torch.float64), _stream()))
+                                   _ptr(self._share_dev, torch.float64), _stream()))
         return self.obs, self.share_obs
 
     def step(self, actions: torch.Tensor, auto_reset: bool = False):
         """actions: int32 [n_envs, n_agents, 4 + shoot_dim] low-level discrete actions."""
         assert actions.shape == (self.n_envs, self.n_agents, self.act_dim), actions.shape
         _check(lib().acs_env_step(self._h, _ptr(actions, torch.int32), _ptr(self.obs, torch.float64),
-                                  _ptr(self.share_obs, torch.float64), _ptr(self.rewards, torch.float64),
+                                  _ptr(self._share_dev, torch.float64), _ptr(self.rewards, torch.float64),
                                   _ptr(self.dones, torch.uint8), _ptr(self.info, torch.int32), _ptr(self.env_done, torch.uint8),
                                   int(auto_reset), _stream()))
         return self.obs, self.share_obs, self.rewards, self.dones, self.info
@@ -286,10 +299,10 @@ class EnvBatch:
     def set_timing(self, on: bool):
         _check(lib().acs_env_set_timing(self._h, int(on)))
 
-    def get_timing(self):
-        """({'substeps': ms, 'post': ms, 'reset': ms}, n_steps) accumulated since the last call (synchronises)."""
+    def get_timing(self, reset: bool = True):
+        """({'substeps': ms, 'post': ms, 'reset': ms}, n_steps) of the recorded steps (synchronises)."""
         ms, n = (ctypes.c_double * 3)(), ctypes.c_int()
-        _check(lib().acs_env_get_timing(self._h, ms, ctypes.byref(n)))
+        _check(lib().acs_env_get_timing(self._h, ms, ctypes.byref(n), int(reset)))
         return {"substeps": ms[0], "post": ms[1], "reset": ms[2]}, n.value
 
     # ---- introspection (parity tests, rendering)

@@ -95,15 +95,22 @@ def make_controller(device, path=None, seed: int = 0) -> LowLevelController:
     return ctl.to(device).eval()
 
 
-def hierarchical_input(high: torch.Tensor, obs: torch.Tensor, force_climb_below_m=None) -> torch.Tensor:
+def hierarchical_luts(device):
+    """The three class -> delta lookup tables as device tensors (created once: building them inside a step would be a
+    pageable H2D copy, which a CUDA-graph capture forbids)."""
+    kw = dict(dtype=torch.float64, device=device)
+    return (torch.tensor(NORM_DELTA_ALTITUDE, **kw), torch.tensor(NORM_DELTA_HEADING, **kw), torch.tensor(NORM_DELTA_VELOCITY, **kw))
+
+
+def hierarchical_input(high: torch.Tensor, obs: torch.Tensor, force_climb_below_m=None, luts=None) -> torch.Tensor:
     """input_obs of the reference (singlecombat_task.py:234-246 / multiplecombat_task.py:171-178).
 
     high [N, 3] integer classes; obs [N, D] float64 current observations (obs[:, 0] = altitude / 5000).  The 1v1 task
     forces the "climb" class below 3500 m (singlecombat_task.py:235-237)."""
-    dev = obs.device
-    da = torch.tensor(NORM_DELTA_ALTITUDE, dtype=torch.float64, device=dev)[high[:, 0].long()]
+    lut_a, lut_h, lut_v = luts if luts is not None else hierarchical_luts(obs.device)
+    da = lut_a[high[:, 0].long()]
     if force_climb_below_m is not None:
-        da = torch.where(obs[:, 0] * 5000.0 < force_climb_below_m, torch.full_like(da, NORM_DELTA_ALTITUDE[0]), da)
-    dh = torch.tensor(NORM_DELTA_HEADING, dtype=torch.float64, device=dev)[high[:, 1].long()]
-    dv = torch.tensor(NORM_DELTA_VELOCITY, dtype=torch.float64, device=dev)[high[:, 2].long()]
+        da = torch.where(obs[:, 0] * 5000.0 < force_climb_below_m, lut_a[0], da)
+    dh = lut_h[high[:, 1].long()]
+    dv = lut_v[high[:, 2].long()]
     return torch.cat([torch.stack([da, dh, dv], dim=-1), obs[:, :9]], dim=-1).to(torch.float32)

@@ -391,7 +391,7 @@ int acs_env_set_timing(AcsEnv* e, int on) {
   return 0;
 }
 
-int acs_env_get_timing(AcsEnv* e, double ms[3], int* n_steps) {
+int acs_env_get_timing(AcsEnv* e, double ms[3], int* n_steps, int reset) {
   if (!e || !ms || !n_steps) return fail("acs_env_get_timing: null argument");
   ms[0] = ms[1] = ms[2] = 0.0;
   const size_t n = e->ev_used / 4;
@@ -404,7 +404,7 @@ int acs_env_get_timing(AcsEnv* e, double ms[3], int* n_steps) {
     }
   }
   *n_steps = (int)n;
-  e->ev_used = 0;
+  if (reset) e->ev_used = 0;
   return 0;
 }
 

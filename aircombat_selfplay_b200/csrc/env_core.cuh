@@ -39,7 +39,7 @@ enum { EI_CURRENT_STEP, EI_EPISODE, EI_SUBSTEP_COUNT, EI_TURN_COUNTS, EI_PMV_REF
        EI_ORDER_SEQ, EI_BORN_SEQ, EI_FAULTS, N_EI };
 // per missile slot doubles / ints
 enum { MD_POS_N, MD_POS_E, MD_POS_U, MD_VEL_N, MD_VEL_E, MD_VEL_U, MD_THETA, MD_PHI, MD_ALT, MD_T, MD_M, MD_DTHETA,
-       MD_DPHI, MD_D_PREV, N_MD };
+       MD_DPHI, MD_D_PREV, MD_SIN_THETA, MD_COS_THETA, N_MD };
 enum { MI_STATUS, MI_KIND, MI_TARGET, MI_CONSEC, MI_ORDER, MI_BORN, MI_KEYN, MI_DETACHED, N_MI };
 
 static const char* const AD_NAMES[] = {"pos_n", "pos_e", "pos_u", "vel_n", "vel_e", "vel_d", "h_sl_m", "u_mps", "v_mps", "w_mps",
@@ -55,7 +55,7 @@ static const char* const ED_NAMES[] = {"tgt_heading_deg", "tgt_altitude_ft", "tg
 static const char* const EI_NAMES[] = {"current_step", "episode", "substep_count", "turn_counts", "pmv_ref", "cg_valid", "tt_valid",
   "wd_valid", "order_seq", "born_seq", "faults"};
 static const char* const MD_NAMES[] = {"pos_n", "pos_e", "pos_u", "vel_n", "vel_e", "vel_u", "theta", "phi", "alt", "t", "m",
-  "dtheta", "dphi", "d_prev"};
+  "dtheta", "dphi", "d_prev", "sin_theta", "cos_theta"};
 static const char* const MI_NAMES[] = {"status", "kind", "target", "consec", "order", "born", "keyn", "detached"};
 static_assert(sizeof(AD_NAMES) / sizeof(AD_NAMES[0]) == N_AD, "AD names");
 static_assert(sizeof(AI_NAMES) / sizeof(AI_NAMES[0]) == N_AI, "AI names");
@@ -145,28 +145,27 @@ ENV_DEV void lla2neu(const GeoOrigin& o, double lon, double lat, double alt, dou
   up = o.cla * t + o.sla * w;
   north = -o.sla * t + o.cla * w;
 }
-// altitude component of NEU2LLA (E/utils/utils.py:44-55): enu2ecef, ecef2geodetic (You 2000)
+// altitude component of NEU2LLA (E/utils/utils.py:44-55, pymap3d.ned2geodetic): enu2ecef, then the geodetic height.
+// Only the height is consumed on the hot path (missile air density, rho = 1.225 exp(-h / 9300)); it is computed with
+// Fukushima's (2006) trig-free Halley step -- the same closed form JSBSim's FGLocation uses -- which agrees with the
+// iteration pymap3d uses (You 2000, restated in the oracle) to < 1e-8 m at flight altitudes.
 ENV_DEV double neu2alt(const GeoOrigin& o, double n, double e, double u) {
   const double t = o.cla * u - o.sla * n;
   const double w = o.sla * u + o.cla * n;
   const double uu = o.clo * t - o.slo * e;
   const double vv = o.slo * t + o.clo * e;
   const double x = o.x0 + uu, y = o.y0 + vv, z = o.z0 + w;
-  const double a = WGS84_A, b = WGS84_B;
-  const double r = sqrt(x * x + y * y + z * z);
-  const double E = sqrt(a * a - b * b);
-  const double uq = sqrt(0.5 * (r * r - E * E) + 0.5 * hypot(r * r - E * E, 2 * E * z));
-  const double Q = hypot(x, y);
-  const double huE = hypot(uq, E);
-  double beta = atan(huE / uq * z / Q);
-  double sb, cb;
-  sincos(beta, &sb, &cb);
-  const double dbeta = ((b * uq - a * huE + E * E) * sb) / (a * huE / cb - E * E * cb);
-  beta += dbeta;
-  sincos(beta, &sb, &cb);
-  const double alt = hypot(z - b * sb, Q - a * cb);
-  const bool inside = x * x / (a * a) + y * y / (a * a) + z * z / (b * b) < 1.0;
-  return inside ? -alt : alt;
+  const double a = WGS84_A, ec = WGS84_B / WGS84_A, ec2 = ec * ec, e2 = 1.0 - ec2, c = a * e2;
+  const double rxy = sqrt(x * x + y * y);
+  const double s0 = fabs(z), zc = ec * s0, c0 = ec * rxy, c02 = c0 * c0, s02 = s0 * s0, a02 = c02 + s02;
+  const double a0 = sqrt(a02), a03 = a02 * a0;
+  double s1 = zc * a03 + c * s02 * s0;
+  const double c1 = rxy * a03 - c * c02 * c0, cs0c0 = c * c0 * s0;
+  const double b0 = 1.5 * cs0c0 * ((rxy * s0 - zc * c0) * a0 - cs0c0);
+  s1 = s1 * a03 - b0 * s0;
+  const double cc = ec * (c1 * a03 - b0 * c0);
+  const double s12 = s1 * s1, cc2 = cc * cc;
+  return (rxy * cc + s0 * s1 - a * sqrt(ec2 * s12 + cc2)) / sqrt(s12 + cc2);
 }
 
 // ----------------------------------------------------------------------------- AO / TA / R (E/utils/utils.py:58-103)
@@ -208,7 +207,7 @@ ENV_DEV MissileParams missile_params(int kind) {
   return p;
 }
 struct Missile {
-  double pn, pe, pu, vn, ve, vu, theta, phi, alt, t, m, dtheta, dphi, d_prev;
+  double pn, pe, pu, vn, ve, vu, theta, phi, alt, t, m, dtheta, dphi, d_prev, st, ct;   // st, ct = sin/cos(theta), cached
   int status, kind, target, consec;
 };
 ENV_DEV void missile_load(const EnvView& v, int mid, Missile& m) {
@@ -216,6 +215,7 @@ ENV_DEV void missile_load(const EnvView& v, int mid, Missile& m) {
   m.vn = MD(v, MD_VEL_N, mid); m.ve = MD(v, MD_VEL_E, mid); m.vu = MD(v, MD_VEL_U, mid);
   m.theta = MD(v, MD_THETA, mid); m.phi = MD(v, MD_PHI, mid); m.alt = MD(v, MD_ALT, mid); m.t = MD(v, MD_T, mid);
   m.m = MD(v, MD_M, mid); m.dtheta = MD(v, MD_DTHETA, mid); m.dphi = MD(v, MD_DPHI, mid); m.d_prev = MD(v, MD_D_PREV, mid);
+  m.st = MD(v, MD_SIN_THETA, mid); m.ct = MD(v, MD_COS_THETA, mid);
   m.status = MI(v, MI_STATUS, mid); m.kind = MI(v, MI_KIND, mid); m.target = MI(v, MI_TARGET, mid); m.consec = MI(v, MI_CONSEC, mid);
 }
 ENV_DEV void missile_store(const EnvView& v, int mid, const Missile& m) {
@@ -223,6 +223,7 @@ ENV_DEV void missile_store(const EnvView& v, int mid, const Missile& m) {
   MD(v, MD_VEL_N, mid) = m.vn; MD(v, MD_VEL_E, mid) = m.ve; MD(v, MD_VEL_U, mid) = m.vu;
   MD(v, MD_THETA, mid) = m.theta; MD(v, MD_PHI, mid) = m.phi; MD(v, MD_ALT, mid) = m.alt; MD(v, MD_T, mid) = m.t;
   MD(v, MD_M, mid) = m.m; MD(v, MD_DTHETA, mid) = m.dtheta; MD(v, MD_DPHI, mid) = m.dphi; MD(v, MD_D_PREV, mid) = m.d_prev;
+  MD(v, MD_SIN_THETA, mid) = m.st; MD(v, MD_COS_THETA, mid) = m.ct;
   MI(v, MI_STATUS, mid) = m.status; MI(v, MI_CONSEC, mid) = m.consec;
 }
 // distance to the target: the R returned by _guidance (:563)
@@ -233,7 +234,7 @@ ENV_DEV double missile_distance(const Missile& m, const Feat& tg) {
 // _guidance (:556-576): proportional navigation; returns clipped (ny, nz) and the distance
 ENV_DEV void missile_guidance(const Missile& m, const MissileParams& pr, const Feat& tg, double& ny, double& nz, double& dist) {
   const double v_m = sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
-  const double theta_m = asin(m.vu / v_m);
+  // theta_m = arcsin(dz/v) enters only through its cosine (:569-570): cos(arcsin(x)) = |v_xy| / |v|
   const double ex = m.pn - tg.n, ey = m.pe - tg.e;
   const double Rxy = sqrt(ex * ex + ey * ey);
   const double ez = tg.u - m.pu;
@@ -243,7 +244,7 @@ ENV_DEV void missile_guidance(const Missile& m, const MissileParams& pr, const F
   const double dbeta = (dvy * dxt - dvx * dyt) / (Rxy * Rxy);
   const double deps = (dvz * (Rxy * Rxy) - dzt * (dxt * dvx + dyt * dvy)) / ((Rxyz * Rxyz) * Rxy);
   const double K = fmax(pr.K * (pr.t_max - m.t) / pr.t_max, 0.0);
-  const double ct = cos(theta_m);
+  const double ct = sqrt(m.vn * m.vn + m.ve * m.ve) / v_m;
   ny = env_clip(K * v_m / pr.g * ct * dbeta, -pr.nyz_max, pr.nyz_max);
   nz = env_clip(K * v_m / pr.g * deps + ct, -pr.nyz_max, pr.nyz_max);
   dist = Rxyz;
@@ -262,8 +263,7 @@ ENV_DEV void missile_state_trans(Missile& m, const MissileParams& pr, const GeoO
   const double rho = 1.225 * exp(-m.alt / 9300.0);
   const double D = 0.5 * pr.cD * S0 * rho * (v * v);
   const double nx = (T - D) / (m.m * pr.g);
-  double st, ct;
-  sincos(theta, &st, &ct);
+  double st = m.st, ct = m.ct;                 // sin/cos of the current pitch angle, kept from the previous update
   const double dv = pr.g * (nx - st);
   m.dphi = pr.g / v * (ny / ct);
   m.dtheta = pr.g / v * (nz - ct);
@@ -274,7 +274,7 @@ ENV_DEV void missile_state_trans(Missile& m, const MissileParams& pr, const GeoO
   sincos(theta, &st, &ct);
   sincos(phi, &sp, &cp);
   m.vn = v * ct * cp; m.ve = v * ct * sp; m.vu = v * st;
-  m.theta = theta; m.phi = phi;
+  m.theta = theta; m.phi = phi; m.st = st; m.ct = ct;
   if (m.t < pr.t_thrust) m.m = m.m - dt * pr.dm;
 }
 

@@ -58,6 +58,23 @@ ENV_DEV void derive_aircraft(const AcOut& o, const GeoOrigin& org, PubAc& p, dou
   w_mps = env_clip(o.w * 0.3048, -700.0, 700.0);
   vc_mps = env_clip(o.vc_fps * 0.3048, 0.0, 1400.0);
 }
+// The same publication straight from the frame scratch, for the substeps in which only the other lanes' missiles read
+// it: the geodetic sines and cosines are already there (Fukushima), so no inverse trigonometry and no sincos.
+ENV_DEV void publish_from_frame(const Frame& f, const GeoOrigin& org, PubAc& p) {
+  p.h = env_clip(f.h_asl * 0.3048, -500.0, 26000.0);
+  const double n = (WGS84_A * WGS84_A) / hypot(WGS84_A * f.cosLatGd, WGS84_B * f.sinLatGd);
+  const double x = (n + p.h) * f.cosLatGd * f.cosLon, y = (n + p.h) * f.cosLatGd * f.sinLon;
+  const double z = (n * ((WGS84_B / WGS84_A) * (WGS84_B / WGS84_A)) + p.h) * f.sinLatGd;
+  const double u = x - org.x0, v = y - org.y0, w = z - org.z0;
+  const double t = org.clo * u + org.slo * v;
+  p.f.e = -org.slo * u + org.clo * v;
+  p.f.u = org.cla * t + org.sla * w;
+  p.f.n = -org.sla * t + org.cla * w;
+  p.f.vn = env_clip(f.vel.x * 0.3048, -700.0, 700.0);
+  p.f.ve = env_clip(f.vel.y * 0.3048, -700.0, 700.0);
+  p.f.vd = env_clip(f.vel.z * 0.3048, -700.0, 700.0);
+  p.u_mps = env_clip(f.uvw.x * 0.3048, -700.0, 700.0);
+}
 ENV_DEV void store_derived(const EnvView& v, int row, const PubAc& p, double v_mps, double w_mps, double vc_mps) {
   AD(v, AD_POS_N, row) = p.f.n; AD(v, AD_POS_E, row) = p.f.e; AD(v, AD_POS_U, row) = p.f.u;
   AD(v, AD_VEL_N, row) = p.f.vn; AD(v, AD_VEL_E, row) = p.f.ve; AD(v, AD_VEL_D, row) = p.f.vd;
@@ -219,13 +236,11 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
       fdm_frame(a, p, s, f, sT, g_atmo, dt, fcs_dt, false);
       ran = true;
     }
-    // _update_properties (simulatior.py:238-257): only materialised when somebody reads it -- missiles in the air,
-    // the end of the step, or the aircraft's last frame (bloods <= 0 flipped it to SHOTDOWN above)
-    if (ran && (has_ms || k == K - 1 || status != ST_ALIVE)) {
-      fdm_outputs(a, f, o);
-      derive_aircraft(o, org, me, v_mps, w_mps, vc_mps);
-    }
+    // _update_properties (simulatior.py:238-257) is only materialised when somebody reads it: the other lanes' missiles
+    // need position / velocity every substep (published straight from the frame, no inverse trig); the full property
+    // set is extracted once, after the aircraft's last frame of the step (or of its life).
     if (has_ms) {
+      if (ran) publish_from_frame(f, org, me);
       me.status = status;
       sP[L.tid] = me;
       sWin[L.tid] = 0x7fffffff;
@@ -233,8 +248,12 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
       __syncwarp(L.gmask);
       missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, sc0 + k);
       __syncwarp(L.gmask);
-      if (sShot[L.tid]) status = ST_SHOTDOWN;                 // target_aircraft.shotdown() (simulatior.py:527)
+      if (sShot[L.tid] && status == ST_ALIVE) status = ST_SHOTDOWN;   // target_aircraft.shotdown() (simulatior.py:527)
       __syncwarp(L.gmask);
+    }
+    if (ran && (k == K - 1 || status != ST_ALIVE)) {
+      fdm_outputs(a, f, o);
+      derive_aircraft(o, org, me, v_mps, w_mps, vc_mps);
     }
   }
   if (L.valid) {
@@ -294,6 +313,7 @@ ENV_DEV int launch_missile(const StepCtx& c, int a, int target, int kind, int ke
   MD(v, MD_POS_N, mid) = pa.f.n; MD(v, MD_POS_E, mid) = pa.f.e; MD(v, MD_POS_U, mid) = pa.f.u;
   MD(v, MD_VEL_N, mid) = pa.f.vn; MD(v, MD_VEL_E, mid) = pa.f.ve; MD(v, MD_VEL_U, mid) = pa.f.vd;
   MD(v, MD_THETA, mid) = OUTF(v, O_PITCH, row); MD(v, MD_PHI, mid) = OUTF(v, O_HEADING, row);
+  { double st, ct; sincos(OUTF(v, O_PITCH, row), &st, &ct); MD(v, MD_SIN_THETA, mid) = st; MD(v, MD_COS_THETA, mid) = ct; }
   MD(v, MD_ALT, mid) = pa.h; MD(v, MD_T, mid) = 0.0; MD(v, MD_M, mid) = pr.m0; MD(v, MD_DTHETA, mid) = 0.0; MD(v, MD_DPHI, mid) = 0.0;
   MD(v, MD_D_PREV, mid) = INFINITY;
   MI(v, MI_STATUS, mid) = MS_LAUNCHED; MI(v, MI_KIND, mid) = kind; MI(v, MI_TARGET, mid) = target; MI(v, MI_CONSEC, mid) = 0;
@@ -541,7 +561,9 @@ ENV_DEV double reward_process(const StepCtx& c, int ri, int row, double new_rewa
   }
   return reward;
 }
-ENV_DEV double reward_one(const StepCtx& c, int ri, int a) {
+// geo[0..n) = get_AO_TA_R of agent a against each enemy in enemy order, computed once per agent per step (the reference
+// recomputes it inside every reward class)
+ENV_DEV double reward_one(const StepCtx& c, int ri, int a, const AoTaR* geo, int n) {
   const EnvView& v = c.v;
   const AcsTaskConfig& cfg = c.cfg;
   const AcsRewardSpec& r = cfg.rewards[ri];
@@ -559,11 +581,7 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a) {
     }
     case ACS_R_POSTURE: {             // posture_reward.py:26-75
       double nr = 0;
-      for (int j = 0; j < v.A; j++) {
-        if (same_team(cfg, a, j)) continue;
-        const AoTaR g = get_ao_ta_r(s.f, sP[j].f, false);
-        nr += posture_orientation((int)r.p0, g.AO, g.TA) * posture_range((int)r.p1, g.R / 1000, r.p2);
-      }
+      for (int i = 0; i < n; i++) nr += posture_orientation((int)r.p0, geo[i].AO, geo[i].TA) * posture_range((int)r.p1, geo[i].R / 1000, r.p2);
       return reward_process(c, ri, row, nr);
     }
     case ACS_R_EVENT: {               // event_driven_reward.py:15-34
@@ -622,9 +640,6 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a) {
     default: break;
   }
   // per-enemy geometry rewards share the (AO, TA, R) list
-  AoTaR geo[ACS_MAX_AGENTS];
-  int n = 0;
-  for (int j = 0; j < v.A; j++) if (!same_team(cfg, a, j)) geo[n++] = get_ao_ta_r(s.f, sP[j].f, false);
   double nr = 0;
   if (r.kind == ACS_R_COMBAT_GEOMETRY) {          // combat_geometry_reward.py:28-68 (index never advances; prev list only grows)
     if (!EI(v, EI_CG_VALID, env)) { ED(v, ED_CG_PREV0, env) = geo[0].AO; ED(v, ED_CG_PREV1, env) = geo[0].TA; EI(v, EI_CG_VALID, env) = 1; }
@@ -659,18 +674,64 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a) {
   }
   return reward_process(c, ri, row, nr);
 }
-// task.get_reward for agent a (gating per E/tasks/singlecombat_task.py:190-195, multiplecombat_task.py:147-151)
-ENV_DEV double agent_reward(const StepCtx& c, int a) {
+// Rewards whose evaluation order across the agents of an env matters (they share env-level state): the
+// first evaluation after a reset of the three "prev list" rewards, and MissilePostureReward's shared reference always.
+ENV_DEV bool reward_is_order_dependent(const StepCtx& c, int kind) {
+  const int env = c.L.env;
+  if (kind == ACS_R_MISSILE_POSTURE) return true;
+  if (kind == ACS_R_COMBAT_GEOMETRY) return !EI(c.v, EI_CG_VALID, env);
+  if (kind == ACS_R_GUN_TARGETTAIL) return !EI(c.v, EI_TT_VALID, env);
+  if (kind == ACS_R_GUN_WEZDOT) return !EI(c.v, EI_WD_VALID, env);
+  return false;
+}
+ENV_DEV int enemy_geometry(const StepCtx& c, int a, AoTaR* geo) {
+  int n = 0;
+  const PubAc* sP = c.sP + c.L.gbase;
+  for (int j = 0; j < c.v.A; j++) if (!same_team(c.cfg, a, j)) geo[n++] = get_ao_ta_r(sP[a].f, sP[j].f, false);
+  return n;
+}
+// task.get_reward gating for agent a (E/tasks/singlecombat_task.py:190-195, multiplecombat_task.py:147-151): true = the
+// agent gets no reward this step (and no reward function is evaluated for it)
+ENV_DEV bool reward_gated(const StepCtx& c, int a) {
   const int row = c.L.env * c.v.A + a;
   const PubAc& s = c.sP[c.L.gbase + a];
   if (c.cfg.reward_gate == ACS_G_DIE_FLAG) {
-    if (AI(c.v, AI_DIE_FLAG, row)) return 0.0;
+    if (AI(c.v, AI_DIE_FLAG, row)) return true;
     AI(c.v, AI_DIE_FLAG, row) = (s.status != ST_ALIVE);
   } else if (c.cfg.reward_gate == ACS_G_ALIVE) {
-    if (s.status != ST_ALIVE) return 0.0;
+    if (s.status != ST_ALIVE) return true;
+  }
+  return false;
+}
+// All agents' rewards of one env.  The reference evaluates agent by agent, reward class by reward class; the classes
+// without cross-agent state are evaluated by all lanes at once, the order-dependent ones lane after lane, and the
+// per-agent total is summed in the reference's class order.
+ENV_DEV double env_rewards(const StepCtx& c, bool valid) {
+  const Lane& L = c.L;
+  const int nr = c.cfg.n_rewards;
+  double vals[ACS_MAX_REWARDS];
+  AoTaR geo[ACS_MAX_AGENTS];
+  int n = 0;
+  bool gated = true;
+  unsigned serial = 0;
+  if (valid) {
+    gated = reward_gated(c, L.lane);
+    for (int ri = 0; ri < nr; ri++) if (reward_is_order_dependent(c, c.cfg.rewards[ri].kind)) serial |= 1u << ri;
+    if (!gated) {
+      n = enemy_geometry(c, L.lane, geo);
+      for (int ri = 0; ri < nr; ri++) if (!(serial >> ri & 1)) vals[ri] = reward_one(c, ri, L.lane, geo, n);
+    }
+  }
+  serial = __reduce_or_sync(L.gmask, serial);
+  if (serial) {
+    for (int a = 0; a < c.v.A; a++) {
+      if (valid && L.lane == a && !gated)
+        for (int ri = 0; ri < nr; ri++) if (serial >> ri & 1) vals[ri] = reward_one(c, ri, a, geo, n);
+      __syncwarp(L.gmask);
+    }
   }
   double tot = 0.0;
-  for (int ri = 0; ri < c.cfg.n_rewards; ri++) tot += reward_one(c, ri, a);
+  if (valid && !gated) for (int ri = 0; ri < nr; ri++) tot += vals[ri];
   return tot;
 }
 
@@ -793,15 +854,11 @@ __global__ void __launch_bounds__(128) k_env_post(const EnvView v, const __grid_
       if (L.valid && L.lane == a) cause = agent_termination(c, a);
       __syncwarp(L.gmask);
     }
-    for (int a = 0; a < A; a++) {
-      if (L.valid && L.lane == a) sRew[L.tid] = agent_reward(c, a);
-      __syncwarp(L.gmask);
-    }
+    sRew[L.tid] = env_rewards(c, L.valid);
+    __syncwarp(L.gmask);
   } else {
-    for (int a = 0; a < A; a++) {
-      if (L.valid && L.lane == a) sRew[L.tid] = agent_reward(c, a);
-      __syncwarp(L.gmask);
-    }
+    sRew[L.tid] = env_rewards(c, L.valid);
+    __syncwarp(L.gmask);
     if (cfg.team_mean) {                            // E/envs/multiplecombat_env.py:170-175
       double ego = 0.0, enm = 0.0;
       for (int j = 0; j < cfg.n_ego; j++) ego += sRew[L.gbase + j];
@@ -847,10 +904,13 @@ __global__ void __launch_bounds__(128) k_env_post(const EnvView v, const __grid_
 __global__ void __launch_bounds__(FDM_BLOCK) k_env_reset_fdm(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
                                                             const uint8_t* __restrict__ env_mask) {
   __shared__ double sT[F16_NTAB];
-  stage_tables(sT);
   const Lane L = lane_setup(v, lg);
-  if (!L.valid) return;
-  if (env_mask != nullptr && !env_mask[L.env]) return;
+  const bool on = L.valid && (env_mask == nullptr || env_mask[L.env]);
+  // the auto-reset launch follows every step; a block none of whose environments finished leaves before it touches the
+  // tables or the bulk of the code (cold after an L2 flush)
+  if (!__syncthreads_or(on)) return;
+  stage_tables(sT);
+  if (!on) return;
   const int N = v.rows;
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
   IcParams c;
@@ -890,6 +950,7 @@ __global__ void __launch_bounds__(128) k_env_reset_task(const EnvView v, const _
   const Lane L = lane_setup(v, lg);
   const int A = v.A;
   const bool on = L.valid && (env_mask == nullptr || env_mask[L.env]);
+  if (!__syncthreads_or(on)) return;
   PubAc me;
   me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
   if (on) {
@@ -923,11 +984,13 @@ __global__ void __launch_bounds__(128) k_env_reset_task(const EnvView v, const _
   __syncwarp(L.gmask);
   const StepCtx c{v, cfg, L, sP, 0};
   // reward_function.reset (E/reward_functions/reward_function_base.py:20-32): potential rewards seed pre_rewards
+  AoTaR geo[ACS_MAX_AGENTS];
+  const int n_geo = on ? enemy_geometry(c, L.lane, geo) : 0;
   for (int ri = 0; ri < cfg.n_rewards; ri++) {
     if (!cfg.rewards[ri].potential) continue;
     for (int a = 0; a < A; a++) {
       if (on && L.lane == a) {
-        const double r0 = reward_one(c, ri, a);
+        const double r0 = reward_one(c, ri, a, geo, n_geo);
         AD(v, AD_PRE_REWARD0 + ri, L.row) = r0;
       }
       __syncwarp(L.gmask);

@@ -71,6 +71,8 @@ FDM_DEV M33 mulABt(const M33& a, const M33& b) {  // a * b^T
   return r;
 }
 
+// Clip (J/models/flight_control/FGFCSComponent.cpp:266-290).  Two compare+select pairs: sm_100a has no fp64 min/max
+// instruction, fmin/fmax expand to more (NaN handling).
 FDM_DEV double f16_constrain(double lo, double v, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ------------------------------------------------------------------ table lookups (J/math/FGTable.cpp:443-517)
@@ -85,8 +87,19 @@ FDM_HELPER Bracket f16_bracket(const double* __restrict__ k, const int n, const 
 #pragma unroll
   for (int i = 1; i < n - 1; i++) r += (k[i] < key) ? 1 : 0;
   double f = (key - k[r - 1]) * k[n + r];
-  f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f);
-  b.r = r; b.f = f; b.above = key >= k[n - 1];
+  b.r = r; b.f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f); b.above = key >= k[n - 1];
+  return b;
+}
+// Uniformly spaced breakpoints (the alpha, beta and elevator grids): the row comes from one multiply, then one exact
+// fix-up step against the stored breakpoints reproduces the search rule bit for bit (the candidate is off by <= 1).
+FDM_DEV Bracket f16_bracket_u(const double* __restrict__ k, const int n, const double key, const double k0, const double inv_step) {
+  Bracket b;
+  const double t0 = (key - k0) * inv_step, t = t0 < 0.0 ? 0.0 : (t0 > (double)(n - 2) ? (double)(n - 2) : t0);
+  int r = 1 + (int)t;
+  if (r > 1 && k[r - 1] >= key) r--;
+  else if (r < n - 1 && k[r] < key) r++;
+  const double f = (key - k[r - 1]) * k[n + r];
+  b.r = r; b.f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f); b.above = key >= k[n - 1];
   return b;
 }
 // 1-D: clamp, no extrapolation.  Below the first key r = 1 and f = 0, which already yields v[0] exactly.
@@ -198,7 +211,13 @@ FDM_DEV void atmosphere_calculate(const AtmoConst& c, double altitude, Atmo& o) 
   else Pm = c.PB[b] * exp(-c.g0 * deltaH / (c.Reng * Tmb));
   o.T = Tm; o.P = Pm; o.rho = Pm / (c.Reng * Tm);
   o.a = sqrt(1.4 * c.Reng * Tm);
-  // CalculateDensityAltitude :464-492
+  // CalculateDensityAltitude :464-492.  On a standard day (the reference never biases temperature or pressure) the
+  // density altitude IS the geometric altitude: the reference's power-law inversion returns it to 6e-13 relative
+  // (tests/test_oracle_fdm.py::test_density_altitude_is_identity_on_a_standard_day), so the inversion is skipped.
+#ifndef ACS_EXACT_DENSITY_ALTITUDE
+  o.density_altitude = altitude;
+  return;
+#endif
   int d = 0;
   for (; d < 7; d++) if (o.rho >= c.DB[d + 1]) break;
   const double Ld = c.Lapse[d];
@@ -217,7 +236,11 @@ FDM_DEV double pitot_total_pressure(double mach, double p) {
 }
 FDM_DEV double mach_from_impact_pressure(double qc, double p) {
   const double A = qc / p + 1;
-  double M = sqrt(5.0 * (f16_powpos(A, 1. / 3.5) - 1));
+  // A^(1/3.5) = A^(2/7): fp32 seed, two Newton steps on y^7 = A^2 (relative error 1e-6 -> 3e-12 -> < 1 ulp)
+  double y = (double)exp2f(0.2857142857142857f * log2f((float)A));
+#pragma unroll
+  for (int i = 0; i < 2; i++) { const double y2 = y * y, y3 = y2 * y, y6 = y3 * y3; y -= (y6 * y - A * A) / (7.0 * y6); }
+  double M = sqrt(5.0 * (y - 1));
   if (M > 1.0)
     for (int i = 0; i < 10; i++) { const double y = 1 - 1.0 / (7.0 * M * M); M = 0.8812848543473311 * sqrt(A * ((y * y) * sqrt(y))); }
   return M;

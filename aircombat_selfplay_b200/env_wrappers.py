@@ -91,7 +91,7 @@ class BatchedVecEnv(VecEnv):
             self._views = b.host_views(self._host)
             self._act_host = torch.empty((num_envs, self.num_agents, self.core.act_dim), dtype=torch.int32).pin_memory()
             self._act_np = self._act_host.numpy()
-            self._act_dev = torch.empty_like(self._act_host, device=self.core.device)
+            self._act_dev = self.core._act_in          # the step graph's static input buffer: H2D lands directly in it
         src = {"info": self._views["info"], "heading": self.core.spec.obs_kind == ts.OBS_HEADING}
         self._infos = np.empty(num_envs, dtype=object)
         for i in range(num_envs):
@@ -108,6 +108,13 @@ class BatchedVecEnv(VecEnv):
     def _arr(self, name):
         a = self._views[name]
         return a.copy() if self.copy else a
+
+    def _share(self, obs):
+        """share_obs [N, A, A*D]: every agent's row is the concatenation of all agents' observations (reference
+        envs/JSBSim/envs/env_base.py:183-189), returned as a read-only stride-0 view of ``obs`` -- it is never copied
+        over PCIe or materialised; the runner's buffer insert makes the one copy it needs."""
+        N, A, D = obs.shape
+        return np.broadcast_to(obs.reshape(N, 1, A * D), (N, A, A * D))
 
     def _put_actions(self, actions):
         a = self._act_np
@@ -126,9 +133,8 @@ class BatchedVecEnv(VecEnv):
         with torch.cuda.device(self.core.device):
             self.core.reset()
             self._fetch()
-        if self.share:
-            return self._arr("obs"), self._arr("share_obs")
-        return self._arr("obs")
+        obs = self._arr("obs")
+        return (obs, self._share(obs)) if self.share else obs
 
     def step_async(self, actions):
         with torch.cuda.device(self.core.device):
@@ -146,7 +152,7 @@ class BatchedVecEnv(VecEnv):
         rewards = self._arr("rewards").reshape(N, A, 1)
         dones = self._views["dones"].astype(bool).reshape(N, A, 1)
         if self.share:
-            return obs, self._arr("share_obs"), rewards, dones, self._infos
+            return obs, self._share(obs), rewards, dones, self._infos
         return obs, rewards, dones, self._infos
 
     def render(self, mode, filepath):

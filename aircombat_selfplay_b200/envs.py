@@ -20,7 +20,7 @@ import torch
 from . import spaces
 from . import taskspec as ts
 from .capi import INFO_DIM, AcsError, EnvBatch
-from .controller import hierarchical_input, make_controller
+from .controller import hierarchical_input, hierarchical_luts, make_controller
 from .tasks import TASKS, load_spec, parse_config
 
 # done_condition strings of the reference's termination classes (without colorama codes), by ACS_T_* id
@@ -54,7 +54,7 @@ class BatchedEnv:
 
     def __init__(self, config_name: str, n_envs: int, device: int = 0, seed: int = 0, env_offset: int = 0,
                  config_dir: Optional[str] = None, substeps: Optional[int] = None, controller_path: Optional[str] = None,
-                 auto_reset: bool = True):
+                 auto_reset: bool = True, use_cuda_graph: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise AcsError("CUDA is not available; the simulator has no CPU fallback")
         self.config_name = config_name
@@ -83,10 +83,18 @@ class BatchedEnv:
         self._low = torch.zeros((n_envs, self.n_agents, 4 + self.spec.shoot_dim), dtype=torch.int32, device=self.device)
         if self.hier:
             self.controller = make_controller(self.device, controller_path)
+            self._luts = hierarchical_luts(self.device)
             self.rnn = torch.zeros((n_envs * self.n_agents, 128), dtype=torch.float32, device=self.device)
             # 1v1 hierarchical tasks force a climb below 3500 m (E/tasks/singlecombat_task.py:235-237)
             self._climb_below = 3500.0 if self.task["env"] == "1v1" else None
         self._was_reset = False
+        # hierarchical tasks: the whole step -- controller (~40 small PyTorch kernels) + the env kernels -- is captured once
+        # into a CUDA graph and replayed, one launch per step instead of a launch-bound train of tiny kernels.  Plain
+        # tasks launch their four kernels directly (a graph launch costs more than it saves there: measured +20%).
+        self.use_cuda_graph = self.hier if use_cuda_graph is None else bool(use_cuda_graph)
+        self._graph = None
+        self._act_in = torch.zeros((n_envs, self.n_agents, self.act_dim), dtype=torch.int32, device=self.device)
+        self._timing = False
 
     # ------------------------------------------------------------------ reference-shaped properties
     @property
@@ -104,7 +112,14 @@ class BatchedEnv:
     def seed(self, seed: int = 0):
         self.seed_value = int(seed or 0)
         self.batch.set_seed(self.seed_value)
+        self._graph = None          # the seed is a kernel parameter baked into the captured step
         return [seed]
+
+    def set_init_states(self, init_states):
+        """Per-aircraft initial conditions used by the following resets (reference reset_simulators /
+        reset_simulators_curriculum, E/envs/singlecombat_env.py:45-122)."""
+        self.batch.set_init_states(init_states)
+        self._graph = None
 
     def close(self):
         self.batch.close()
@@ -127,12 +142,39 @@ class BatchedEnv:
             return actions if actions.dtype == torch.int32 else actions.to(torch.int32)
         high = actions[..., :3].reshape(B * A, 3)
         obs = self.batch.obs.view(B * A, -1)
-        x = hierarchical_input(high, obs, self._climb_below)
-        low, self.rnn = self.controller(x, self.rnn)
+        x = hierarchical_input(high, obs, self._climb_below, self._luts)
+        low, h = self.controller(x, self.rnn)
+        self.rnn.copy_(h)                                  # in place: the buffer is captured by the CUDA graph
         self._low[..., :4] = low.view(B, A, 4)
         if self.spec.shoot_dim:
             self._low[..., 4:] = actions[..., 3:].to(torch.int32)
         return self._low
+
+    def _step_body(self, actions: torch.Tensor):
+        low = self.low_level_actions(actions)
+        out = self.batch.step(low.contiguous(), auto_reset=self.auto_reset)
+        if self.hier and self.auto_reset:
+            # task.reset re-zeroes the controller's recurrent state of the envs that were just reset
+            self.rnn.view(self.n_envs, self.n_agents, 128).mul_((1 - self.batch.env_done.view(-1, 1, 1)).to(torch.float32))
+        return out
+
+    def _capture(self):
+        if self.hier:      # warm the controller's cuBLAS / LayerNorm paths outside the capture, leaving no trace in the state
+            h0, low0 = self.rnn.clone(), self._low.clone()
+            for _ in range(3):
+                self.low_level_actions(self._act_in)
+            self.rnn.copy_(h0); self._low.copy_(low0)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._graph_out = self._step_body(self._act_in)
+        self._graph = g
+
+    def set_timing(self, on: bool):
+        """Per-kernel CUDA-event timing (bench).  Events recorded inside a captured graph cannot be queried, so timed
+        steps launch eagerly; the caller keeps the GPU busy ahead of them (bench.py) so the intervals hold no launch gaps."""
+        self._timing = bool(on)
+        self.batch.set_timing(on)
 
     def step(self, actions: torch.Tensor):
         """actions: integer tensor [n_envs, n_agents, act_dim] on this env's device."""
@@ -140,12 +182,14 @@ class BatchedEnv:
             raise AcsError("step() called before reset()")
         assert actions.shape == (self.n_envs, self.n_agents, self.act_dim), (tuple(actions.shape), self.act_dim)
         with torch.cuda.device(self.device):
-            low = self.low_level_actions(actions)
-            out = self.batch.step(low.contiguous(), auto_reset=self.auto_reset)
-            if self.hier and self.auto_reset:
-                # task.reset re-zeroes the controller's recurrent state of the envs that were just reset
-                self.rnn.view(self.n_envs, self.n_agents, 128).mul_((1 - self.batch.env_done.view(-1, 1, 1)).to(torch.float32))
-        return out
+            if not self.use_cuda_graph or self._timing:
+                return self._step_body(actions if actions.dtype == torch.int32 else actions.to(torch.int32))
+            if actions.data_ptr() != self._act_in.data_ptr():
+                self._act_in.copy_(actions)
+            if self._graph is None:
+                self._capture()
+            self._graph.replay()
+            return self._graph_out
 
 
 class LazyInfo(dict):

@@ -194,8 +194,17 @@ class CudaGen:
             name = f"bk{len(scope['brackets'])}"
             scope["brackets"][key] = name
             scope.setdefault("vars", set()).add(var)
-            scope.setdefault("decls", []).append(
-                f"  const Bracket {name} = f16_bracket(T + {off}, {len(keys)}, {self.pexpr(var)});")
+            k = [float(x) for x in keys]
+            # "uniform enough": every breakpoint within a quarter step of the straight line through the end points (the
+            # XML rounds radians to 4 digits), so the multiply lands within one row of the exact search result, which
+            # the fix-up step in f16_bracket_u then restores
+            step = (k[-1] - k[0]) / (len(k) - 1)
+            uniform = len(k) >= 12 and all(abs(k[i] - (k[0] + i * step)) <= 0.25 * step for i in range(len(k)))
+            if uniform:
+                call = f"f16_bracket_u(T + {off}, {len(k)}, {self.pexpr(var)}, {lit(k[0])}, {lit((len(k) - 1) / (k[-1] - k[0]))})"
+            else:
+                call = f"f16_bracket(T + {off}, {len(k)}, {self.pexpr(var)})"
+            scope.setdefault("decls", []).append(f"  const Bracket {name} = {call};")
         return scope["brackets"][key]
 
     def table_expr(self, t, scope):

@@ -202,12 +202,11 @@ def run_b200(args):
     acts_dev = torch.from_numpy(acts_host).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    # ---- device-resident arm
+    # ---- device-resident arm: the step (controller + env kernels) replays as one CUDA graph
     core.reset()
     for t in range(args.warmup):
         core.step(acts_dev[t])
     torch.cuda.synchronize(); _barrier(world)
-    batch.set_timing(True)
     sampler = ClockSampler(local); sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     done_envs = 0
@@ -216,11 +215,17 @@ def run_b200(args):
         ev[k][0].record(); core.step(acts_dev[args.warmup + k]); ev[k][1].record()
     torch.cuda.synchronize(); _barrier(world)
     clocks = sampler.stop()
-    kms, ksteps = batch.get_timing()
-    batch.set_timing(False)
     ms = sum(a.elapsed_time(b) for a, b in ev)
     ms = _max_over_ranks(ms, world, dev)
     value = world * n_envs * A * args.steps / (ms * 1e-3)
+    # ---- per-kernel breakdown of the same step (eager launches bracketed by CUDA events on the launching stream)
+    core.set_timing(True)
+    nk = min(args.steps, 50)
+    for k in range(nk):
+        flush.fill_(k & 0xFF)
+        core.step(acts_dev[args.warmup + k])
+    kms, ksteps = batch.get_timing()
+    core.set_timing(False)
 
     # ---- end to end through the VecEnv contract (host numpy in / out)
     ve.reset()

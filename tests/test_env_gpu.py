@@ -129,3 +129,20 @@ def test_env_offset_keeps_rng_streams_per_env():
         of = full.step(torch.tensor(a, device="cuda"), auto_reset=True)[0]
         oh = half.step(torch.tensor(a[8:], device="cuda"), auto_reset=True)[0]
         assert torch.equal(of[8:], oh)
+
+
+def test_device_share_obs_equals_the_broadcast_view():
+    """share_obs written by the kernel (device_share_obs=True) == the stride-0 view of obs used by default."""
+    from aircombat_selfplay_b200.capi import EnvBatch
+    spec = load_spec("scenario2/scenario2")
+    rng = np.random.default_rng(8)
+    a = EnvBatch(spec, 16, seed=2, device_share_obs=True)
+    b = EnvBatch(spec, 16, seed=2)
+    oa, sa = a.reset()
+    ob, sb = b.reset()
+    assert sa.shape == sb.shape == (16, 4, 84) and torch.equal(sa, sb) and torch.equal(oa, ob)
+    for _ in range(5):
+        act = torch.tensor(random_actions(rng, spec, 16), device="cuda")
+        _, sa, *_ = a.step(act, auto_reset=True)
+        _, sb, *_ = b.step(act, auto_reset=True)
+        assert torch.equal(sa, sb)
