@@ -82,6 +82,7 @@ def lib():
         L.acs_env_arena_field_name.argtypes = [i, i]
         L.acs_env_get_arena.argtypes = [vp, i, vp, vp]
         L.acs_env_set_arena.argtypes = [vp, i, vp, vp]
+        L.acs_env_arena_ptr.argtypes = [vp, i, ctypes.POINTER(vp)]
         L.acs_env_fdm.restype = vp
         L.acs_env_fdm.argtypes = [vp]
         L.acs_env_set_timing.argtypes = [vp, i]
@@ -314,6 +315,21 @@ class EnvBatch:
         dt = torch.int32 if ii.value else torch.float64
         t = torch.empty((nf.value, per.value), dtype=dt, device=self.device)
         _check(lib().acs_env_get_arena(self._h, which, ctypes.c_void_p(t.data_ptr()), _stream()))
+        names = [lib().acs_env_arena_field_name(which, k).decode() for k in range(nf.value)]
+        return names, t
+
+    def arena_view(self, name: str):
+        """(field names, tensor [n_fields, n_per_field]) aliasing the library's arena -- no copy; read-only by convention."""
+        which = ARENAS[name]
+        nf, per, ii = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _check(lib().acs_env_arena_info(self._h, which, ctypes.byref(nf), ctypes.byref(per), ctypes.byref(ii)))
+        ptr = ctypes.c_void_p()
+        _check(lib().acs_env_arena_ptr(self._h, which, ctypes.byref(ptr)))
+
+        class _Holder:       # CUDA array interface v3: lets torch wrap a raw device pointer it does not own
+            __cuda_array_interface__ = {"shape": (nf.value, per.value), "typestr": "<i4" if ii.value else "<f8",
+                                        "data": (ptr.value, False), "version": 3, "strides": None}
+        t = torch.as_tensor(_Holder(), device=self.device)
         names = [lib().acs_env_arena_field_name(which, k).decode() for k in range(nf.value)]
         return names, t
 

@@ -88,9 +88,13 @@ def make_controller(device, path=None, seed: int = 0) -> LowLevelController:
         ctl.load_reference_state_dict(torch.load(str(ck), map_location="cpu"))
         ctl.checkpoint = str(ck)
     else:
-        for p in ctl.parameters():
+        for name, p in ctl.named_parameters():      # every parameter from the seeded generator: instances are identical
             if p.dim() > 1:
                 p.data = torch.randn(p.shape, generator=g) / math.sqrt(p.shape[-1])
+            elif name.startswith(("ln", "norm")) and name.endswith("weight"):
+                p.data = torch.ones_like(p)
+            else:
+                p.data = 0.1 * torch.randn(p.shape, generator=g)
         ctl.checkpoint = None
     return ctl.to(device).eval()
 

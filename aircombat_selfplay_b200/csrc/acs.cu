@@ -435,6 +435,11 @@ int acs_env_get_arena(const AcsEnv* e, int which, void* dst_dev, void* stream) {
   CUDA_TRY(cudaMemcpyAsync(dst_dev, p, (size_t)nf * per * (ii ? sizeof(int) : sizeof(double)), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
+int acs_env_arena_ptr(const AcsEnv* e, int which, void** dev_ptr) {
+  if (!e || !dev_ptr) return fail("acs_env_arena_ptr: null argument");
+  int nf, per, ii;
+  return env_arena(e, which, dev_ptr, &nf, &per, &ii);
+}
 int acs_env_set_arena(AcsEnv* e, int which, const void* src_dev, void* stream) {
   if (!e || !src_dev) return fail("acs_env_set_arena: null argument");
   void* p; int nf, per, ii;

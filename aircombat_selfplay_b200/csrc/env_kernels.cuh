@@ -421,6 +421,11 @@ ENV_DEV void task_step_agent(const StepCtx& c, int a) {
       AI(v, AI_REM_MISSILES, row) = rem - 1;
       AI(v, AI_LAST_SHOOT_TIME, row) = c.cs;
     }
+  } else if (cfg.launch_kind == ACS_L_AUTO_GUN) {    // E/tasks/WVR_task.py:67-81, singlecombat_task.py:290-297
+    const int enemy = scenario_target(c, a);          // farthest enemy; no ammunition, no alive checks on either side
+    double distance, ang;
+    attack_geometry(sP[a], sP[enemy], distance, ang);
+    if (distance / 1000 < 3 && ang < 5) sP[enemy].bloods -= 5;
   } else if (cfg.launch_kind == ACS_L_SCENARIO) {    // E/tasks/scenario2_task.py:73-114
     const bool f_gun = alive && (shoot & 1) && AI(v, AI_REM_GUN, row) > 0;
     const bool f_9m = alive && (shoot & 2) && AI(v, AI_REM_9M, row) > 0;
@@ -526,6 +531,21 @@ ENV_DEV void write_obs(const StepCtx& c, int a, double* __restrict__ o) {
     for (int i = 0; i < 6; i++) o[9 + i] = r6[i];
     for (int i = 0; i < 15; i++) o[i] = env_clip(o[i], -10.0, 10.0);
     return;
+  }
+  if (k == ACS_OBS_1V1_RWR) {                      // E/tasks/scenario1_task.py:222-314: nearest LIVE enemy, else enemies[0]
+    int e = -1, first = -1;
+    double bd = INFINITY;
+    for (int j = 0; j < v.A; j++) {
+      if (same_team(cfg, a, j)) continue;
+      if (first < 0) first = j;
+      const double tx = sP[j].f.n - s.f.n, ty = sP[j].f.e - s.f.e, tz = sP[j].f.u - s.f.u;
+      const double d = sqrt(tx * tx + ty * ty + tz * tz);
+      if (sP[j].status == ST_ALIVE && d < bd) { bd = d; e = j; }   // stable sort by distance: the first minimum wins
+    }
+    if (e < 0) e = first;
+    obs_rel6(s, sP[e], false, r6);
+    for (int i = 0; i < 6; i++) o[9 + i] = r6[i];
+    return;                                          // missile_sim is hard-wired to None; [15..22] stay 0
   }
   if (k == ACS_OBS_1V1_MISSILE || k == ACS_OBS_NV_MISSILE) {   // E/tasks/singlecombat_with_missile_task.py:31-99; multiplecombat_with_missile_task.py:32-117
     const int ti = (k == ACS_OBS_1V1_MISSILE) ? 0 : (a < cfg.n_ego ? a : a - cfg.n_ego);

@@ -62,9 +62,10 @@ class BatchedEnv:
         self.spec = load_spec(config_name, config_dir, substeps)
         self.task_name = self.spec.name
         self.task = TASKS[self.task_name]
-        if self.spec.use_baseline:
-            raise NotImplementedError("use_baseline scenarios (rule-based opponents) are not part of this build yet; "
-                                      "use the Selfplay configs")
+        if self.spec.use_baseline and not self.task["hier"]:
+            raise NotImplementedError("use_baseline is wired for the hierarchical task families this fork ships (scenario1/2/3, "
+                                      "wvr, maneuver_curriculum); the LAG-style SingleCombatTask path calls "
+                                      "baseline_agent.get_action with a signature the fork's agents no longer have")
         self.n_envs, self.n_agents = n_envs, self.spec.n_agents
         self.device = torch.device("cuda", device)
         self.auto_reset = auto_reset
@@ -87,6 +88,11 @@ class BatchedEnv:
             self.rnn = torch.zeros((n_envs * self.n_agents, 128), dtype=torch.float32, device=self.device)
             # 1v1 hierarchical tasks force a climb below 3500 m (E/tasks/singlecombat_task.py:235-237)
             self._climb_below = 3500.0 if self.task["env"] == "1v1" else None
+        self.opponents = None
+        if self.spec.use_baseline:
+            from .opponents import DeviceState, RuleOpponents
+            self.opponents = RuleOpponents(self.spec.baseline_type, self.task["env"], self.spec.n_ego, self.spec.n_enm,
+                                           self.spec.substeps / self.spec.sim_freq, DeviceState(self.batch), n_envs, self.device)
         self._was_reset = False
         # hierarchical tasks: the whole step -- controller (~40 small PyTorch kernels) + the env kernels -- is captured once
         # into a CUDA graph and replayed, one launch per step instead of a launch-bound train of tiny kernels.  Plain
@@ -121,6 +127,17 @@ class BatchedEnv:
         self.batch.set_init_states(init_states)
         self._graph = None
 
+    def set_curriculum_angle(self, angle: int):
+        """Curriculum stage of the *_curriculum / wvr / maneuver_curriculum tasks: the following resets start from
+        ``reset_simulators_curriculum(angle)`` (E/envs/singlecombat_env.py:87-122, multiplecombat_env.py:185-248).  The
+        reference keeps one stage counter per env process, advanced by its own win-rate record; here the stage is
+        batch-wide and advanced by the caller (the per-step ``info`` carries what a win-rate record needs)."""
+        from .tasks import curriculum_init_states
+        if not self.spec.curriculum:
+            raise AcsError(f"task {self.task_name!r} has no curriculum reset")
+        self.curriculum_angle = int(angle)
+        self.set_init_states(curriculum_init_states(self.spec.env_kind, self.spec.yaml_init_states, self.curriculum_angle))
+
     def close(self):
         self.batch.close()
 
@@ -132,6 +149,8 @@ class BatchedEnv:
                     self.rnn.zero_()
                 else:
                     self.rnn.view(self.n_envs, self.n_agents, 128)[env_mask.bool()] = 0
+            if self.opponents is not None:
+                self.opponents.reset(env_mask)
             self._was_reset = True
             return self.batch.reset(env_mask)
 
@@ -143,11 +162,15 @@ class BatchedEnv:
         high = actions[..., :3].reshape(B * A, 3)
         obs = self.batch.obs.view(B * A, -1)
         x = hierarchical_input(high, obs, self._climb_below, self._luts)
+        if self.opponents is not None:      # the red team's controller input comes from its scripted agent, not from the action
+            x.view(B, A, 12)[:, self.spec.n_ego:] = self.opponents.inputs()
         low, h = self.controller(x, self.rnn)
         self.rnn.copy_(h)                                  # in place: the buffer is captured by the CUDA graph
         self._low[..., :4] = low.view(B, A, 4)
         if self.spec.shoot_dim:
             self._low[..., 4:] = actions[..., 3:].to(torch.int32)
+            if self.opponents is not None:  # scripted aircraft shoot everything when use_artillery, else nothing (scenario2_task.py:52-57)
+                self._low[:, self.spec.n_ego:, 4:] = 1 if self.spec.use_artillery else 0
         return self._low
 
     def _step_body(self, actions: torch.Tensor):
@@ -156,14 +179,20 @@ class BatchedEnv:
         if self.hier and self.auto_reset:
             # task.reset re-zeroes the controller's recurrent state of the envs that were just reset
             self.rnn.view(self.n_envs, self.n_agents, 128).mul_((1 - self.batch.env_done.view(-1, 1, 1)).to(torch.float32))
+            if self.opponents is not None:
+                self.opponents.reset(self.batch.env_done)
         return out
 
     def _capture(self):
         if self.hier:      # warm the controller's cuBLAS / LayerNorm paths outside the capture, leaving no trace in the state
-            h0, low0 = self.rnn.clone(), self._low.clone()
+            keep = [self.rnn, self._low]
+            if self.opponents is not None:
+                keep += [self.opponents.step, self.opponents.init_heading, self.opponents.has_init]
+            saved = [t.clone() for t in keep]
             for _ in range(3):
                 self.low_level_actions(self._act_in)
-            self.rnn.copy_(h0); self._low.copy_(low0)
+            for t, s0 in zip(keep, saved):
+                t.copy_(s0)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

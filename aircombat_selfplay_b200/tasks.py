@@ -68,6 +68,7 @@ _SCENARIO_REWARDS = ["AltitudeReward", "CombatGeometryReward", "EventDrivenRewar
 _TERMS_1V1 = [ts.T_LOW_ALTITUDE, ts.T_EXTREME_STATE, ts.T_OVERLOAD, ts.T_SAFE_RETURN, ts.T_TIMEOUT]      # E/tasks/singlecombat_task.py:34-40
 _TERMS_NVN = [ts.T_SAFE_RETURN, ts.T_EXTREME_STATE, ts.T_OVERLOAD, ts.T_LOW_ALTITUDE, ts.T_TIMEOUT]      # E/tasks/multiplecombat_task.py:33-39
 _TERMS_HEADING = [ts.T_UNREACH_HEADING, ts.T_EXTREME_STATE, ts.T_OVERLOAD, ts.T_LOW_ALTITUDE, ts.T_TIMEOUT]  # E/tasks/heading_task.py:20-26
+_TERMS_NO_SAFE_RETURN = [ts.T_LOW_ALTITUDE, ts.T_EXTREME_STATE, ts.T_OVERLOAD, ts.T_TIMEOUT]              # E/tasks/approach_task.py:24-29, WVR_task.py:32-37
 
 # task name -> (env kind, obs packer, reward classes, launch rule, shoot_dim, hierarchical, high-level action dims)
 # env kind: "control" (SingleControlEnv), "1v1" (SingleCombatEnv), "nvn" (MultipleCombatEnv)
@@ -76,10 +77,14 @@ _R_DODGE = ["PostureReward", "MissilePostureReward", "AltitudeReward", "EventDri
 _R_SHOOT = ["PostureReward", "AltitudeReward", "EventDrivenReward", "ShootPenaltyReward"]
 _R_SHOOT_NVN = ["PostureReward", "AltitudeReward", "EventDrivenReward", "ShootPenaltyReward", "MissilePostureReward"]
 _R_MANEUVER = ["AltitudeReward", "CombatGeometryReward", "EventDrivenReward", "GunBEHITReward", "GunTargetTailReward",
-               "GunWEZDOTReward", "GunWEZReward", "PostureReward", "RelativeAltitudeReward"]
+               "GunWEZDOTReward", "GunWEZReward", "PostureReward", "RelativeAltitudeReward"]       # singlecombat_task.py:267-277
+_R_WVR = ["PostureReward", "AltitudeReward", "EventDrivenReward", "CombatGeometryReward", "GunBEHITReward", "GunTargetTailReward",
+          "GunWEZReward", "GunWEZDOTReward"]                                                        # WVR_task.py:21-30
 TASKS: Dict[str, dict] = {
     # SingleControlEnv (E/envs/singlecontrol_env.py:16-23)
     "heading": dict(env="control", obs=ts.OBS_HEADING, rewards=["HeadingReward", "AltitudeReward"], launch=ts.L_NONE, shoot=0, hier=False),
+    "approach": dict(env="control", obs=ts.OBS_HEADING, rewards=["AltitudeReward"], launch=ts.L_NONE, shoot=0, hier=False,
+                     terms=_TERMS_NO_SAFE_RETURN),                                                                                      # ApproachTask
     # SingleCombatEnv: LAG task names (the fork's load_task dropped these branches; the classes exist)
     "singlecombat": dict(env="1v1", obs=ts.OBS_1V1, rewards=_R_BASE, launch=ts.L_NONE, shoot=0, hier=False),                                  # SingleCombatTask
     "hierarchical_singlecombat": dict(env="1v1", obs=ts.OBS_1V1, rewards=_R_BASE, launch=ts.L_NONE, shoot=0, hier=True),                      # HierarchicalSingleCombatTask
@@ -90,9 +95,11 @@ TASKS: Dict[str, dict] = {
     # SingleCombatEnv: this fork's names (E/envs/singlecombat_env.py:19-36)
     "scenario1": dict(env="1v1", obs=ts.OBS_1V1_MISSILE, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True),
     "scenario1_curriculum": dict(env="1v1", obs=ts.OBS_1V1_MISSILE, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True, curriculum=True),
-    "scenario1_for_KAI": dict(env="1v1", obs=ts.OBS_1V1_MISSILE, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True),
-    "maneuver_curriculum": dict(env="1v1", obs=ts.OBS_1V1, rewards=_R_MANEUVER, launch=ts.L_NONE, shoot=0, hier=True, curriculum=True, gun_step=True),
-    "wvr": dict(env="1v1", obs=ts.OBS_1V1, rewards=_R_MANEUVER, launch=ts.L_NONE, shoot=0, hier=True, gun_step=True),
+    "scenario1_rwr": dict(env="1v1", obs=ts.OBS_1V1_RWR, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True),
+    "scenario1_rwr_curriculum": dict(env="1v1", obs=ts.OBS_1V1_RWR, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True, curriculum=True),
+    "maneuver_curriculum": dict(env="1v1", obs=ts.OBS_1V1, rewards=_R_MANEUVER, launch=ts.L_AUTO_GUN, shoot=0, hier=True, curriculum=True),
+    "wvr": dict(env="1v1", obs=ts.OBS_1V1, rewards=_R_WVR, launch=ts.L_AUTO_GUN, shoot=0, hier=True, curriculum=True,
+                terms=_TERMS_NO_SAFE_RETURN),
     # MultipleCombatEnv (E/envs/multiplecombat_env.py:25-66)
     "multiplecombat": dict(env="nvn", obs=ts.OBS_MULTI, rewards=_R_BASE, launch=ts.L_NONE, shoot=0, hier=False),
     "hierarchical_multiplecombat": dict(env="nvn", obs=ts.OBS_MULTI, rewards=_R_BASE, launch=ts.L_NONE, shoot=0, hier=True),
@@ -101,20 +108,59 @@ TASKS: Dict[str, dict] = {
     "hierarchical_multiplecombat_shoot_nearest": dict(env="nvn", obs=ts.OBS_MULTI_MISSILE, rewards=_R_DODGE, launch=ts.L_RL_NEAREST, shoot=1, hier=True),  # multiplecombat_task.py:201
     "scenario2": dict(env="nvn", obs=ts.OBS_NV_MISSILE, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True),
     "scenario2_curriculum": dict(env="nvn", obs=ts.OBS_NV_MISSILE, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True, curriculum=True),
-    "scenario2_for_KAI": dict(env="nvn", obs=ts.OBS_NV_MISSILE, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True),
     "scenario2_nvn": dict(env="nvn", obs=ts.OBS_NVN, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True),
     "scenario2_nvn_curriculum": dict(env="nvn", obs=ts.OBS_NVN, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True, curriculum=True),
+    "scenario2_rwr": dict(env="nvn", obs=ts.OBS_NVN, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True, rwr=True),
+    "scenario2_rwr_curriculum": dict(env="nvn", obs=ts.OBS_NVN, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True, rwr=True, curriculum=True),
+    "scenario3_rwr": dict(env="nvn", obs=ts.OBS_NVN, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True, rwr=True),
+    "scenario3_rwr_curriculum": dict(env="nvn", obs=ts.OBS_NVN, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True, rwr=True, curriculum=True),
     "scenario3": dict(env="nvn", obs=ts.OBS_NV_MISSILE, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True),
     "scenario3_curriculum": dict(env="nvn", obs=ts.OBS_NV_MISSILE, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True, curriculum=True),
-    "scenario3_for_KAI": dict(env="nvn", obs=ts.OBS_NV_MISSILE, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True),
     "scenario3_nvn": dict(env="nvn", obs=ts.OBS_NVN, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True),
     "scenario3_nvn_curriculum": dict(env="nvn", obs=ts.OBS_NVN, rewards=_SCENARIO_REWARDS, launch=ts.L_SCENARIO, shoot=4, hier=True, curriculum=True),
 }
 
 
-def obs_dim_for(obs_kind: int, n_agents: int, n_aircraft_cfg: int) -> int:
+def curriculum_circle(center_lat, center_lon, radius_km, angle_deg):
+    """(lat, lon, heading) on the curriculum circle: E/utils/utils.py:126-155 (calculate_coordinates_heading_by_curriculum)."""
+    R = 6371
+    d = radius_km / R
+    clat, clon = math.radians(center_lat), math.radians(center_lon)
+    theta = math.radians(180 - angle_deg)
+    nlat = math.asin(math.sin(clat) * math.cos(d) + math.cos(clat) * math.sin(d) * math.cos(theta))
+    nlon = clon + math.atan2(math.sin(theta) * math.sin(d) * math.cos(clat), math.cos(d) - math.sin(clat) * math.sin(nlat))
+    heading = 2 * angle_deg if 0 <= angle_deg < 90 else 360 - 2 * angle_deg
+    return math.degrees(nlat), math.degrees(nlon), heading
+
+
+def curriculum_init_states(env_kind: str, rows, angle: int):
+    """Initial conditions of the curriculum tasks' reset: ``reset_simulators_curriculum(angle)`` of SingleCombatEnv
+    (E/envs/singlecombat_env.py:87-122) / MultipleCombatEnv (E/envs/multiplecombat_env.py:185-248).  ``rows`` are the yaml
+    init-state rows in aircraft order; only the entries the reference ``update``s are replaced -- for the N-v-N env that
+    is aircraft 0..3 whatever the team size (a 4v4 reset moves two ego aircraft onto the enemy start line; kept)."""
+    rows = [list(r) for r in rows]
+
+    def put(i, lat, lon, psi):
+        rows[i][0], rows[i][1], rows[i][2], rows[i][3], rows[i][4] = lon, lat, 20000.0, float(psi), 800.0
+    if env_kind == "1v1":
+        lat, lon, psi = curriculum_circle(60.1, 120.0, 11.119, angle)
+        put(0, lat, lon, psi)
+        put(1, 60.1, 120.0, 0.0)
+    elif env_kind == "nvn":
+        lat, lon, psi = curriculum_circle(60.1, 120.0, 11.119, angle)
+        put(0, lat, lon, psi)
+        lat, lon, psi = curriculum_circle(60.1, 120.01, 11.119, angle)
+        put(1, lat, lon, psi)
+        put(2, 60.1, 120.0, 0.0)
+        put(3, 60.1, 120.01, 0.0)
+    return rows
+
+
+def obs_dim_for(obs_kind: int, n_agents: int, n_aircraft_cfg: int, rwr: bool = False) -> int:
     if obs_kind == ts.OBS_HEADING:
         return 12
+    if obs_kind == ts.OBS_1V1_RWR:
+        return 23
     if obs_kind == ts.OBS_1V1:
         return 15
     if obs_kind in (ts.OBS_1V1_MISSILE, ts.OBS_NV_MISSILE):
@@ -124,12 +170,15 @@ def obs_dim_for(obs_kind: int, n_agents: int, n_aircraft_cfg: int) -> int:
     if obs_kind == ts.OBS_MULTI_MISSILE:
         return 9 + n_agents * 6                 # E/tasks/multiplecombat_task.py:213-217
     if obs_kind == ts.OBS_NVN:                  # E/tasks/scenario2_task.py:246-252: len(aircraft_configs)/2 for partners AND enemies
-        return int(9 + 6 * (n_aircraft_cfg / 2) + 6 * (n_aircraft_cfg / 2) + 6)
+        return int((11 if rwr else 9) + 6 * (n_aircraft_cfg / 2) + 6 * (n_aircraft_cfg / 2) + 6)   # *_rwr: num_ego_obs = 11 (:402)
     raise ValueError(obs_kind)
 
 
 def build_spec(cfg: dict, substeps_override=None) -> TaskSpec:
     name = cfg.get("task")
+    if name in ("scenario1_for_KAI", "scenario2_for_KAI", "scenario3_for_KAI"):
+        raise NotImplementedError(f"{name}: the KAI project tasks (hard-wired Korean-peninsula way-points and a socket link, "
+                                  "E/tasks/KAI_project_task.py) are outside the env-step scope (DESIGN.md section 8)")
     if name not in TASKS:
         raise NotImplementedError(f"Unknown taskname: {name}")
     t = TASKS[name]
@@ -151,29 +200,35 @@ def build_spec(cfg: dict, substeps_override=None) -> TaskSpec:
                     float(cfg.get("acceleration_limit_z", 10.0)))
     sp.center = tuple(float(x) for x in cfg.get("battle_field_center", (120.0, 60.0, 0.0)))
     sp.obs_kind = t["obs"]
-    sp.obs_dim = obs_dim_for(sp.obs_kind, sp.n_agents, len(uids))
+    sp.obs_dim = obs_dim_for(sp.obs_kind, sp.n_agents, len(uids), bool(t.get("rwr")))
     sp.act_kind = ts.ACT_HEADING if t["env"] == "control" else ts.ACT_COMBAT
     sp.shoot_dim = t["shoot"]
     sp.rewards = [_reward(cfg, c) for c in t["rewards"]]
     sp.use_artillery = bool(cfg.get("use_artillery", False))
     sp.use_baseline = bool(cfg.get("use_baseline", False))
+    sp.baseline_type = str(cfg.get("baseline_type", "")) if sp.use_baseline else ""
     sp.launch_kind = t["launch"]
     sp.max_attack_angle = float(cfg.get("max_attack_angle", 180))
     sp.max_attack_distance = float(cfg.get("max_attack_distance", math.inf))
     sp.min_attack_interval = int(cfg.get("min_attack_interval", 125))
     sp.num_missiles = [int(acs[u].get("missile", 0)) for u in order]
     sp.init_states = [init_state_row(acs[u].get("init_state")) for u in order]
+    sp.yaml_init_states = [list(r) for r in sp.init_states]
+    sp.env_kind, sp.curriculum = t["env"], bool(t.get("curriculum"))
+    if sp.curriculum:       # every reset of these tasks goes through reset_simulators_curriculum(curriculum_angle), stage 0 first
+        sp.init_states = curriculum_init_states(t["env"], sp.yaml_init_states, 0)
     if t["env"] == "control":
-        sp.terminations = list(_TERMS_HEADING)
+        sp.terminations = list(t.get("terms", _TERMS_HEADING))
         sp.dones_before_rewards, sp.team_mean, sp.share_obs, sp.reward_gate = True, False, False, ts.G_NONE
         a0 = acs[uids[0]]
-        sp.heading_increments = (float(a0["max_heading_increment"]), float(a0["max_altitude_increment"]),
-                                 float(a0["max_velocities_u_increment"]))
-        sp.check_interval = float(a0["check_interval"])
+        if ts.T_UNREACH_HEADING in sp.terminations:
+            sp.heading_increments = (float(a0["max_heading_increment"]), float(a0["max_altitude_increment"]),
+                                     float(a0["max_velocities_u_increment"]))
+            sp.check_interval = float(a0["check_interval"])
     elif t["env"] == "1v1":
         if sp.n_agents != 2:
             raise AssertionError("SingleCombatEnv only supports 1v1 scenarios!")   # E/envs/singlecombat_env.py:17
-        sp.terminations = list(_TERMS_1V1)
+        sp.terminations = list(t.get("terms", _TERMS_1V1))
         sp.dones_before_rewards, sp.team_mean, sp.share_obs, sp.reward_gate = True, False, False, ts.G_DIE_FLAG
     else:
         sp.terminations = list(_TERMS_NVN)

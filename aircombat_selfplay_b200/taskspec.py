@@ -18,7 +18,8 @@ OBS_1V1_MISSILE = 2    # singlecombat_with_missile_task.py:31-99 (21, 3-D, uncli
 OBS_NV_MISSILE = 3     # multiplecombat_with_missile_task.py:32-117 (21, enemy index = own index in team)
 OBS_MULTI = 4          # multiplecombat_task.py:105-135 (9+6(A-1), clipped)
 OBS_MULTI_MISSILE = 5  # multiplecombat_task.py:232-267 (9+6A, clipped then missile block)
-OBS_NVN = 6            # scenario2_task.py:256-316 (9 + 6*partners + 6*enemies + 6, unclipped)
+OBS_NVN = 6            # scenario2_task.py:256-316 (9 + 6*partners + 6*enemies + 6, unclipped); *_rwr: two trailing zeros more
+OBS_1V1_RWR = 7        # scenario1_task.py:222-314 (23: ego 9 + nearest live enemy 6; the missile block and RWR pair stay 0)
 
 # action normalisation
 ACT_HEADING = 0        # heading_task.py:102-110
@@ -42,6 +43,8 @@ L_RULE_LOCK = 1  # *DodgeMissileTask.step: lock-duration deque, AIM-9L (singleco
 L_RL_SINGLE = 2  # SingleCombatShootMissileTask.step (:194-204), target enemies[0], AIM-9L
 L_RL_NEAREST = 3 # multiplecombat_task.py:278-299, nearest enemy, angle/distance/interval gates, AIM-9L
 L_SCENARIO = 4   # scenario{1,2,3}_task.py step: gun / AIM-120B / AIM-9M / chaff
+L_AUTO_GUN = 5   # WVRTask.step (WVR_task.py:67-81) / Maneuver_curriculum.step (singlecombat_task.py:290-297): the gun fires by
+                 # itself whenever the farthest enemy is within 3 km and 5 degrees: -5 blood, no ammunition, no alive checks
 
 # reward gating (who gets a reward this step)
 G_NONE = 0       # BaseTask.get_reward (heading task)
@@ -86,7 +89,8 @@ class TaskSpec:
     reward_gate: int = G_NONE
     launch_kind: int = L_NONE
     use_artillery: bool = False
-    use_baseline: bool = False              # narrows the enemy's AIM-120B cone (scenario1_task.py:137-140)
+    use_baseline: bool = False              # scripted red team (opponents.py); also narrows its AIM-120B cone (scenario1_task.py:137-140)
+    baseline_type: str = ""                 # yaml baseline_type: pursue | maneuver (| loiter: NotImplementedError as in the reference)
     max_attack_angle: float = 180.0
     max_attack_distance: float = float("inf")
     min_attack_interval: int = 125
@@ -96,6 +100,10 @@ class TaskSpec:
     heading_increments: Tuple[float, float, float] = (180.0, 7000.0, 100.0)
     check_interval: float = 30.0
     fcs_dt: float = 1.0 / 120.0
+    # curriculum tasks (Scenario*_curriculum, WVRTask, Maneuver_curriculum): resets use the curriculum circle geometry
+    env_kind: str = "control"
+    curriculum: bool = False
+    yaml_init_states: List[List[float]] = field(default_factory=list)
 
     @property
     def n_agents(self):

@@ -78,12 +78,12 @@ int acs_get_outputs(const AcsHandle* h, double* dst_dev, void* stream);  /* [n_o
 #define ACS_INFO_DIM 4   /* per agent: done cause (-1 none, else ACS_T_*), status (0 alive,1 crash,2 shotdown), spare, spare */
 
 enum { ACS_OBS_HEADING = 0, ACS_OBS_1V1 = 1, ACS_OBS_1V1_MISSILE = 2, ACS_OBS_NV_MISSILE = 3, ACS_OBS_MULTI = 4,
-       ACS_OBS_MULTI_MISSILE = 5, ACS_OBS_NVN = 6 };
+       ACS_OBS_MULTI_MISSILE = 5, ACS_OBS_NVN = 6, ACS_OBS_1V1_RWR = 7 };
 enum { ACS_ACT_HEADING = 0, ACS_ACT_COMBAT = 1 };
 enum { ACS_R_ALTITUDE = 0, ACS_R_POSTURE, ACS_R_EVENT, ACS_R_MISSILE_POSTURE, ACS_R_SHOOT_PENALTY, ACS_R_HEADING,
        ACS_R_RELATIVE_ALTITUDE, ACS_R_COMBAT_GEOMETRY, ACS_R_GUN_BEHIT, ACS_R_GUN_TARGETTAIL, ACS_R_GUN_WEZ, ACS_R_GUN_WEZDOT };
 enum { ACS_T_UNREACH_HEADING = 0, ACS_T_EXTREME_STATE, ACS_T_OVERLOAD, ACS_T_LOW_ALTITUDE, ACS_T_TIMEOUT, ACS_T_SAFE_RETURN };
-enum { ACS_L_NONE = 0, ACS_L_RULE_LOCK, ACS_L_RL_SINGLE, ACS_L_RL_NEAREST, ACS_L_SCENARIO };
+enum { ACS_L_NONE = 0, ACS_L_RULE_LOCK, ACS_L_RL_SINGLE, ACS_L_RL_NEAREST, ACS_L_SCENARIO, ACS_L_AUTO_GUN };
 enum { ACS_G_NONE = 0, ACS_G_DIE_FLAG, ACS_G_ALIVE };
 
 typedef struct AcsRewardSpec {
@@ -151,6 +151,9 @@ int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double*
 int acs_env_arena_info(const AcsEnv* e, int which, int* n_fields, int* n_per_field, int* is_int);
 const char* acs_env_arena_field_name(int which, int field);
 int acs_env_get_arena(const AcsEnv* e, int which, void* dst_dev, void* stream);
+/* zero-copy: the device address of an arena (layout as acs_env_arena_info); valid for the life of the handle.  The host
+ * layer reads aircraft state through it for the rule-based opponents (E/model/baseline.py) without a copy per step. */
+int acs_env_arena_ptr(const AcsEnv* e, int which, void** dev_ptr);
 int acs_env_set_arena(AcsEnv* e, int which, const void* src_dev, void* stream);
 /* the FDM batch inside an env handle (for acs_fdm_* / acs_get_state on the same aircraft rows) */
 AcsHandle* acs_env_fdm(AcsEnv* e);

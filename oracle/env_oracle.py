@@ -542,6 +542,11 @@ class OracleEnv:
                     self._launch(a, agent.enemies[ti], 0, self.remaining_missiles[a])
                     self.remaining_missiles[a] -= 1
                     self.last_shoot_time[a] = self.current_step
+            elif sp.launch_kind == ts.L_AUTO_GUN:  # E/tasks/WVR_task.py:67-81, singlecombat_task.py:290-297
+                enemy = self._get_target(agent)
+                distance, ang = self._attack_geometry(agent, enemy)
+                if distance / 1000 < 3 and ang < 5:
+                    enemy.bloods -= 5
             elif sp.launch_kind == ts.L_SCENARIO:  # E/tasks/scenario2_task.py:73-114
                 sa = self.shoot_action[a]
                 f_gun = agent.is_alive and sa[0] and self.remaining_gun[a] > 0
@@ -614,6 +619,15 @@ class OracleEnv:
         if k == ts.OBS_1V1:
             o[9:15] = self._rel6(s, s.enemies[0], two_d=True)
             return np.clip(o, -10, 10)
+        if k == ts.OBS_1V1_RWR:  # E/tasks/scenario1_task.py:222-314
+            dist = sorted(((float(np.linalg.norm(e.position - s.position)), i) for i, e in enumerate(s.enemies)), key=lambda x: x[0])
+            target = 0
+            for _, i in dist:
+                if s.enemies[i].is_alive:
+                    target = i
+                    break
+            o[9:15] = self._rel6(s, s.enemies[target])
+            return o
         if k in (ts.OBS_1V1_MISSILE, ts.OBS_NV_MISSILE):
             ti = 0 if k == ts.OBS_1V1_MISSILE else (a if a < sp.n_ego else a - sp.n_ego)
             o[9:15] = self._rel6(s, s.enemies[ti])

@@ -4,7 +4,9 @@ import numpy as np
 
 CONFIGS = ["singlecontrol/heading", "1v1/NoWeapon/Selfplay", "1v1/ShootMissile/Selfplay", "1v1/DodgeMissile/Selfplay",
            "2v2/NoWeapon/Selfplay", "2v2/ShootMissile/HierarchySelfplay", "scenario1/scenario1", "scenario2/scenario2",
-           "scenario2/scenario2_nvn", "scenario3/scenario3", "scenario3/scenario3_nvn"]
+           "scenario2/scenario2_nvn", "scenario3/scenario3", "scenario3/scenario3_nvn", "singlecontrol/approach",
+           "scenario1/scenario1_rwr", "scenario2/scenario2_rwr", "scenario3/scenario3_rwr_curriculum", "scenario1/WVR_selfplay",
+           "scenario1/Maneuver_curriculum_selfplay", "scenario2/scenario2_curriculum"]
 
 
 def random_actions(rng, spec, n_envs, shoot_p=0.3, mode="random"):

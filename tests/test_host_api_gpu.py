@@ -198,3 +198,34 @@ def test_hierarchical_controller_runs_batched_on_device():
         assert np.isfinite(obs).all() and np.isfinite(rew).all()
     assert ve.core.rnn.abs().sum() > 0
     ve.close()
+
+
+@pytest.mark.parametrize("config,kind", [("scenario2/scenario2", "pursue"), ("scenario1/scenario1", "maneuver"),
+                                         ("scenario1/WVR_selfplay", "pursue")])
+def test_scripted_opponents_on_device(config, kind, tmp_path):
+    """use_baseline yamls: the red team is flown by the batched PursueAgent / ManeuverAgent (opponents.py); the enemy rows
+    of the action array are ignored, as in the reference."""
+    import yaml
+    from aircombat_selfplay_b200.tasks import parse_config
+    cfg = parse_config(config)
+    cfg.update({"use_baseline": True, "baseline_type": kind, "use_artillery": True})
+    (tmp_path / "vs").mkdir()
+    (tmp_path / "vs" / "cfg.yaml").write_text(yaml.safe_dump(cfg, sort_keys=False))
+    n = 64
+    envs = [BatchedEnv("vs/cfg", n, seed=1, config_dir=str(tmp_path)) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    assert envs[0].opponents is not None and envs[0].opponents.kind == kind
+    rng = np.random.default_rng(0)
+    A, D = envs[0].n_agents, envs[0].act_dim
+    for t in range(15):
+        a = rng.integers(0, 2, (n, A, D))
+        b = a.copy()
+        b[:, A // 2:] = rng.integers(0, 2, (n, A - A // 2, D))      # different garbage in the enemy rows
+        o0 = envs[0].step(torch.tensor(a, dtype=torch.int32, device="cuda"))[0].clone()
+        o1 = envs[1].step(torch.tensor(b, dtype=torch.int32, device="cuda"))[0].clone()
+        assert torch.equal(o0, o1)                                   # enemy action rows do not matter
+        assert torch.isfinite(o0).all()
+    assert envs[0].rnn.view(n, A, 128)[:, A // 2:].abs().sum() > 0   # the scripted agents' recurrent state is live
+    if kind == "maneuver":
+        assert int(envs[0].opponents.step.min()) == 15

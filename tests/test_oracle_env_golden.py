@@ -15,7 +15,8 @@ import pytest
 from aircombat_selfplay_b200.tasks import build_spec
 from oracle import env_oracle as eo
 
-GOLDEN = sorted((Path(__file__).resolve().parent / "golden").glob("env_*.npz"))
+# the *_vs_* files drive the red team with scripted agents: tests/test_opponents_golden.py
+GOLDEN = sorted(p for p in (Path(__file__).resolve().parent / "golden").glob("env_*.npz") if "_vs_" not in p.name)
 
 
 @pytest.fixture()

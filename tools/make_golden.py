@@ -223,7 +223,12 @@ def import_reference():
     real_load = torch.load
     torch.load = lambda *a, **k: {}
     from envs.JSBSim.model import baseline_actor
-    baseline_actor.BaselineActor.load_state_dict = lambda self, sd, *a, **k: None
+    # every BaselineActor the reference builds (the tasks' low-level policy, the scripted agents' actor) gets the seeded
+    # weights of tests/golden/controller.npz instead of baseline_model.pt (which the reference loads onto 'cuda')
+    _g = np.load(GOLDEN / "controller.npz")
+    _sd = {k[3:]: torch.from_numpy(_g[k]) for k in _g.files if k.startswith("sd:")}
+    _orig_lsd = torch.nn.Module.load_state_dict
+    baseline_actor.BaselineActor.load_state_dict = lambda self, sd, *a, **k: _orig_lsd(self, _sd)
     from envs.JSBSim.envs import env_base, multiplecombat_env, singlecombat_env, singlecontrol_env
     from envs.JSBSim.tasks import multiplecombat_task, singlecombat_task
     del real_load      # torch.load stays stubbed: the hierarchical Task constructors load baseline_model.pt onto 'cuda'
@@ -288,6 +293,9 @@ def actions_for(rng, A, shoot_dim, T, mode, shoot_p=0.3):
         act[..., 0:4] = np.array([20, 40, 20, 29])
     elif mode == "straight":
         act[..., 0:4] = np.array([20, 19, 20, 0])
+    elif mode == "chase":        # ego at full throttle behind an idling enemy on the same track: closes into gun range
+        act[..., 0:4] = np.array([20, 19, 20, 0])
+        act[:, : A // 2, 3] = 29
     if shoot_dim:
         act[..., 4:] = rng.random((T, A, shoot_dim)) < shoot_p
     return act
@@ -313,6 +321,23 @@ CASES = [
     ("scenario2_nvn_close", "nvn", None, base_config("scenario2_nvn", 2, 6, missile=2, lat_gap=0.06, max_steps=9000), 150, "smooth", 4),
     ("scenario3_close", "nvn", None, base_config("scenario3", 4, 6, missile=2, lat_gap=0.06, dh_enemy=-300.0, max_steps=9000), 120, "smooth", 4),
     ("scenario3_nvn_random", "nvn", None, base_config("scenario3_nvn", 4, 6, missile=2, max_steps=9000), 30, "random", 4),
+    ("approach_random", "control", None, base_config("approach", 0, 6, max_steps=10000), 40, "random", 0),
+    ("scenario2_rwr_close", "nvn", None, base_config("scenario2_rwr", 2, 6, missile=2, lat_gap=0.07, dh_enemy=200.0, max_steps=9000), 100, "smooth", 4),
+    ("scenario3_rwr_random", "nvn", None, base_config("scenario3_rwr", 4, 6, missile=2, max_steps=9000), 30, "random", 4),
+    # curriculum resets (stage 0: tail chase 11 km behind a north-bound enemy) + the automatic gun of WVRTask /
+    # Maneuver_curriculum: -5 blood per step inside 3 km and 5 degrees until the enemy is SHOTDOWN by blood
+    ("wvr_chase", "1v1", None, base_config("wvr", 1, 6, extra={"use_artillery": True}, max_steps=9000), 1500, "chase_cl", 0),
+    ("maneuver_curriculum_chase", "1v1", None, base_config("maneuver_curriculum", 1, 6, max_steps=9000), 1500, "chase_cl", 0),
+    ("scenario2_curriculum_random", "nvn", None, base_config("scenario2_curriculum", 2, 6, missile=2, max_steps=9000), 40, "random", 4),
+    # scripted red team (use_baseline): PursueAgent / ManeuverAgent drive the enemy through the BaselineActor GRU
+    ("scenario2_vs_pursue", "nvn", None, base_config("scenario2", 2, 6, missile=2, lat_gap=0.08, max_steps=9000,
+                                                     extra={"use_baseline": True, "baseline_type": "pursue", "use_artillery": True}), 120, "smooth", 4),
+    ("scenario1_vs_pursue", "1v1", None, base_config("scenario1", 1, 6, missile=2, lat_gap=0.08, max_steps=9000,
+                                                     extra={"use_baseline": True, "baseline_type": "pursue", "use_artillery": False}), 120, "smooth", 4),
+    ("scenario1_vs_maneuver", "1v1", None, base_config("scenario1", 1, 6, missile=2, max_steps=9000,
+                                                       extra={"use_baseline": True, "baseline_type": "maneuver", "use_artillery": False}), 400, "smooth", 4),
+    ("wvr_vs_pursue", "1v1", None, base_config("wvr", 1, 6, max_steps=9000,
+                                               extra={"use_baseline": True, "baseline_type": "pursue", "use_artillery": True}), 150, "smooth", 0),
     # guns (R < 3 km, AO < 5 deg: -5 blood per burst until SHOTDOWN by blood) and many chaff bursts
     ("scenario2_gun_chaff", "nvn", None, base_config("scenario2", 2, 6, missile=30, lat_gap=0.04, max_steps=9000), 120, "straight", 4, 0.8),
     ("scenario3_gun_chaff", "nvn", None, base_config("scenario3", 4, 6, missile=6, lat_gap=0.05, max_steps=9000), 100, "smooth", 4, 0.6),
@@ -345,7 +370,17 @@ def run_case(mods, name, kind, task_cls, cfg, T, mode, shoot_dim, shoot_p=0.3, s
     np.random.rand = lambda *a: 0.5          # chaff draw (env_base.py:153): always below 0.85; the oracle test pins u01 likewise
     A = len(cfg["aircraft_configs"])
     rng = np.random.default_rng(seed)
-    acts = actions_for(rng, A, shoot_dim, T, mode, shoot_p)
+    pilot = None
+    if mode == "chase_cl":
+        # closed-loop action generator: an altitude / wings-level hold flown on the ORACLE env stepped alongside, ego on
+        # high throttle behind an idling enemy -- only a way to produce an action sequence that reaches gun range; the
+        # recorded actions are then the inputs of both sides of the comparison
+        from aircombat_selfplay_b200.tasks import build_spec
+        pilot = eo.OracleEnv(build_spec(cfg), seed=seed, env_index=0)
+        pilot.reset()
+        acts = np.zeros((T, A, 4), dtype=np.int64)
+    else:
+        acts = actions_for(rng, A, shoot_dim, T, mode, shoot_p)
     keyed.begin_reset()
     r = env.reset()
     keyed.end_reset()
@@ -354,6 +389,12 @@ def run_case(mods, name, kind, task_cls, cfg, T, mode, shoot_dim, shoot_p=0.3, s
     cond, missiles, bloods, chaffs = [], [], [], []
     steps_done = 0
     for t in range(T):
+        if pilot is not None:
+            for k, sim in enumerate(pilot.sims):
+                e = 19 + int(round(np.clip(0.01 * (sim.h_sl_m - 6096) - 0.1 * sim.velocity[2], -8, 8)))
+                al = 20 - int(round(np.clip(sim.posture[0] * 15, -8, 8)))
+                acts[t, k] = [al, e, 20, 29 if k < A // 2 else 0]
+            pilot.step(acts[t])
         a = acts[t].astype(np.float64) if shoot_dim else acts[t]
         out = env.step(a)
         if kind == "nvn":
