@@ -100,3 +100,25 @@ def test_lazy_info_is_a_dict_view():
     assert infos[1]["current_step"] == 7 and "done_condition" in infos[1] and infos[1]["done_condition"][0] == "low_altitude"
     assert "done_condition" not in infos[0] and "heading_turn_counts" not in infos[0]
     assert dict(infos[1].items())["current_step"] == 7
+
+
+def test_shipped_configs_match_the_reference_yamls():
+    """Every yaml of the reference resolves to the same TaskSpec as the shipped file of the same name (only where the
+    reference tree is mounted: the build container)."""
+    import subprocess
+    import sys
+    ref = Path("/root/reference/envs/JSBSim/configs")
+    if not ref.exists():
+        pytest.skip("reference tree not mounted")
+    r = subprocess.run([sys.executable, str(Path(__file__).resolve().parents[1] / "tools" / "check_configs.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert r.stdout.count("[ok]") >= 39
+
+
+def test_every_shipped_config_resolves():
+    from aircombat_selfplay_b200.tasks import CONFIG_DIR
+    names = [f"{f.parent.relative_to(CONFIG_DIR)}/{f.stem}" for f in sorted(CONFIG_DIR.glob("**/*.yaml"))]
+    assert len(names) >= 45
+    for n in names:
+        sp = load_spec(n)
+        assert sp.obs_dim > 0 and len(sp.rewards) > 0 and len(sp.terminations) >= 4
