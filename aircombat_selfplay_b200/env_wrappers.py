@@ -156,7 +156,13 @@ class BatchedVecEnv(VecEnv):
         return obs, rewards, dones, self._infos
 
     def render(self, mode, filepath):
-        raise NotImplementedError("TacView rendering is outside the env-step hot path (DESIGN.md, out of scope)")
+        """reference DummyVecEnv.render (envs/env_wrappers.py:170-172): the TacView text log of env 0."""
+        if mode == "txt":
+            if getattr(self, "_acmi", None) is None:
+                from .tacview import AcmiWriter
+                self._acmi = AcmiWriter(self.core, 0)
+            step = int(self._views["info"][0, 0, 2])
+            self._acmi.write(filepath, step * self.core.time_interval)
 
     def close_extras(self):
         self.core.close()

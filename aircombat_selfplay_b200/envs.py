@@ -141,6 +141,35 @@ class BatchedEnv:
     def close(self):
         self.batch.close()
 
+    # ------------------------------------------------------------------ checkpoint / resume (the reference never saves env state)
+    def state_dict(self):
+        """Everything a bit-exact resume needs: the simulator's arenas, the last step's outputs (the hierarchical
+        controller reads the observation), the controller's recurrent state, the scripted opponents' counters."""
+        from .capi import ARENAS
+        sd = {f"arena:{k}": self.batch.arena(k)[1] for k in ARENAS}
+        sd["out_buf"] = self.batch.out_buf.clone()
+        if self.hier:
+            sd["rnn"] = self.rnn.clone()
+        if self.opponents is not None:
+            sd.update({"opp:step": self.opponents.step.clone(), "opp:init_heading": self.opponents.init_heading.clone(),
+                       "opp:has_init": self.opponents.has_init.clone()})
+        sd["seed"] = self.seed_value
+        return sd
+
+    def load_state_dict(self, sd):
+        from .capi import ARENAS
+        if int(sd["seed"]) != self.seed_value:
+            self.seed(int(sd["seed"]))            # NB: seed() restarts the episode counters; the arenas restore them below
+        for k in ARENAS:
+            self.batch.set_arena(k, sd[f"arena:{k}"].to(self.device).contiguous())
+        self.batch.out_buf.copy_(sd["out_buf"])
+        if self.hier:
+            self.rnn.copy_(sd["rnn"])
+        if self.opponents is not None:
+            self.opponents.step.copy_(sd["opp:step"]); self.opponents.init_heading.copy_(sd["opp:init_heading"])
+            self.opponents.has_init.copy_(sd["opp:has_init"])
+        self._was_reset = True
+
     # ------------------------------------------------------------------ device API
     def reset(self, env_mask: Optional[torch.Tensor] = None):
         with torch.cuda.device(self.device):
@@ -383,6 +412,15 @@ class _SingleEnvBase:
 
     def close(self):
         self.core.close()
+
+    def render(self, mode="txt", filepath="./JSBSimRecording.txt.acmi"):
+        """TacView text log (reference envs/JSBSim/envs/env_base.py:207-250); other modes raise as in the reference."""
+        if mode != "txt":
+            raise NotImplementedError
+        if getattr(self, "_acmi", None) is None:
+            from .tacview import AcmiWriter
+            self._acmi = AcmiWriter(self.core, 0)
+        self._acmi.write(filepath, self.current_step * self.time_interval)
 
     def _actions(self, action):
         """Legal inputs as in the reference: list / tuple / ndarray of per-agent actions, Tuple-space samples included."""

@@ -229,3 +229,42 @@ def test_scripted_opponents_on_device(config, kind, tmp_path):
     assert envs[0].rnn.view(n, A, 128)[:, A // 2:].abs().sum() > 0   # the scripted agents' recurrent state is live
     if kind == "maneuver":
         assert int(envs[0].opponents.step.min()) == 15
+
+
+def test_tacview_render(tmp_path):
+    env = SingleCombatEnv("1v1/ShootMissile/Selfplay")
+    env.reset()
+    path = tmp_path / "rec.txt.acmi"
+    for t in range(8):
+        env.step(np.array([[20, 19, 20, 10, 1], [20, 19, 20, 10, 1]]))
+        env.render(mode="txt", filepath=str(path))
+    text = path.read_text(encoding="utf-8-sig").splitlines()
+    assert text[0] == "FileType=text/acmi/tacview" and text[2].startswith("0,ReferenceTime=")
+    assert sum(l.startswith("#") for l in text) == 8
+    a = [l for l in text if l.startswith("A0100,T=")]
+    assert len(a) == 8 and "Name=F16" in a[0] and "Color=Blue" in a[0]
+    lon, lat, alt = (float(x) for x in a[0].split("T=")[1].split(",")[0].split("|")[:3])
+    assert abs(lon - 120.0) < 0.01 and abs(lat - 60.0) < 0.02 and 5000 < alt < 7000
+    assert any(l.startswith("A01004,T=") for l in text)          # the missile launched with uid = agent id + remaining count
+    with pytest.raises(NotImplementedError):
+        env.render(mode="human")
+
+
+@pytest.mark.parametrize("config", ["1v1/ShootMissile/Selfplay", "scenario2/scenario2"])
+def test_env_state_checkpoint_resumes_bit_exactly(config):
+    n = 32
+    env = BatchedEnv(config, n, seed=5)
+    env.reset()
+    rng = np.random.default_rng(1)
+    A, D = env.n_agents, env.act_dim
+    hi = 2 if env.hier else 30
+    acts = [torch.tensor(rng.integers(0, hi, (n, A, D)), dtype=torch.int32, device="cuda") for _ in range(24)]
+    for a in acts[:12]:
+        env.step(a)
+    sd = env.state_dict()
+    first = [env.step(a)[0].clone() for a in acts[12:]]
+    other = BatchedEnv(config, n, seed=5)       # a fresh process would do the same
+    other.load_state_dict(sd)
+    second = [other.step(a)[0].clone() for a in acts[12:]]
+    for x, y in zip(first, second):
+        assert torch.equal(x, y)
