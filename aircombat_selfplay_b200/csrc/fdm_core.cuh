@@ -389,9 +389,12 @@ FDM_DEV void location_derived(Frame& f, M33& Tec2l) {
 }
 
 // ============================================================== one FDM frame
-// integrate=false reproduces the suspended-integration passes of FGFDMExec::RunIC (dt = 0).
-FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double* __restrict__ T, const AtmoConst& ac,
-                       const double dt, const double fcs_dt, const bool trim_fuel_freeze) {
+// ============================================================== one FDM frame, stage by stage
+// The stages are separate functions so that the single-thread frame (fdm_frame) and the two-warp role split
+// (fdm_split.cuh) run the same arithmetic.  dt = 0 reproduces the suspended-integration passes of FGFDMExec::RunIC.
+struct WindAxes { double sa, ca, sb, cb; };
+
+FDM_DEV void fdm_stage_propagate(AcCore& a, Props& p, Frame& f, const double dt) {
   // ---------------- Propagate (J/models/FGPropagate.cpp:218-297)
   if (dt != 0.0) {
     a.sim_time += dt;  // FGFDMExec::IncrTime
@@ -440,6 +443,9 @@ FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
   // The FCS reads the Euler angles only as cos(pitch) * cos(roll) (fcs/n-pilot-z-correction), which is Tl2b(3,3); the
   // angles themselves are extracted once per interaction step in fdm_outputs.
   p.attitude_cos_pitch_cos_roll = f.Tl2b.m[2][2]; p.velocities_u_fps = f.uvw.x; p.velocities_v_fps = f.uvw.y;
+}
+
+FDM_DEV void fdm_stage_gravity(Frame& f) {
   // ---------------- Inertial: J2 gravity in ECEF (J/models/FGInertial.cpp:193-211)
   {
     const double ir = 1.0 / f.radius, sinLat = f.ecef.z * ir, adivr = EARTH_A * ir, preCommon = 1.5 * EARTH_J2 * adivr * adivr;
@@ -448,14 +454,18 @@ FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
     f.grav.y = -GMOverr2 * ((1.0 + (preCommon * xy)) * f.ecef.y * ir);
     f.grav.z = -GMOverr2 * ((1.0 + (preCommon * z)) * f.ecef.z * ir);
   }
+}
+
+FDM_DEV void fdm_stage_atmosphere(Props& p, Frame& f, const AtmoConst& ac) {
   // ---------------- Atmosphere at h = |r| - sea-level radius (J/models/FGPropagate.cpp:573-576, FGLocation.cpp:273-279)
   const double ecr = EARTH_B / EARTH_A;
   const double slr = EARTH_A * ecr / sqrt(1.0 - (1.0 - ecr * ecr) * f.cosLatGc * f.cosLatGc);
   f.h_asl = f.radius - slr;
   atmosphere_calculate(ac, f.h_asl, f.atm);
   p.atmosphere_density_altitude = f.atm.density_altitude;
-  // ---------------- FCS (generated)
-  f16_fcs(p, s, T, fcs_dt);
+}
+
+FDM_DEV void fdm_stage_massbalance(AcCore& a, Frame& f) {
   // ---------------- MassBalance (J/models/FGMassBalance.cpp:181-260)
   {
     const double tw = ((a.tank0 + a.tank1) + a.tank2) + a.tank3;
@@ -514,8 +524,11 @@ FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
     f.Jinv.m[1][0] = k2; f.Jinv.m[1][1] = k4; f.Jinv.m[1][2] = k5;
     f.Jinv.m[2][0] = k3; f.Jinv.m[2][1] = k5; f.Jinv.m[2][2] = k6;
   }
+}
+
+FDM_DEV void fdm_stage_auxiliary(const AcCore& a, Props& p, Frame& f, const AtmoConst& ac, WindAxes& w) {
+  double& sa = w.sa; double& ca = w.ca; double& sb = w.sb; double& cb = w.cb;
   // ---------------- Auxiliary (J/models/FGAuxiliary.cpp:134-231); accelerations are the previous frame's
-  double sa, ca, sb, cb;
   {
     const double U = f.uvw.x, V = f.uvw.y, W = f.uvw.z;
     const double AeroU2 = U * U, AeroV2 = V * V, AeroW2 = W * W, mUW = AeroU2 + AeroW2, Vt2 = mUW + AeroV2;
@@ -548,94 +561,120 @@ FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
     p.accelerations_n_pilot_y_norm = f.pilotN.y; p.accelerations_n_pilot_z_norm = f.pilotN.z;
     p.aero_h_b_mac_ft = (f.geodAlt - vMacz) / K_bw;
   }
-  // ---------------- Propulsion: turbine + fuel (J/models/propulsion/FGTurbine.cpp:107-272, FGPropulsion.cpp:113-260)
+}
+
+// turbine (J/models/propulsion/FGTurbine.cpp:107-272): engine state = a.N1, a.N2, a.N2norm, a.FF; `starved` is the flag
+// ConsumeFuel left last frame, `augmentation` the afterburner latch; returns the thrust
+FDM_DEV double fdm_stage_engine(AcCore& a, const Props& p, const Atmo& atm, const double qbar, const double* __restrict__ T,
+                                const AtmoConst& ac, const double dt, const bool starved, bool& augmentation) {
+  double idleT, milT, augT;
+  f16_engine_tables(p, T, idleT, milT, augT);
+  double ThrottlePos = p.fcs_throttle_pos_norm, AugmentCmd;
+  if (ThrottlePos > 1.0) { AugmentCmd = ThrottlePos - 1.0; ThrottlePos -= AugmentCmd; } else AugmentCmd = 0.0;
+  double thrust;
+  const double N1_factor = K_ENG_maxn1 - K_ENG_idlen1, N2_factor = K_ENG_maxn2 - K_ENG_idlen2;
+  auto seek = [dt](double v, double target, double accel, double decel) {
+    if (v > target) { v -= dt * decel; if (v < target) v = target; }
+    else if (v < target) { v += dt * accel; if (v > target) v = target; }
+    return v;
+  };
+  if (dt == 0.0) {  // tpTrim (:341-372)
+    const double idlethrust = K_ENG_milthrust * idleT, milthrust = (K_ENG_milthrust - idlethrust) * milT;
+    const double N2t = K_ENG_idlen2 + ThrottlePos * N2_factor, N2n = (N2t - K_ENG_idlen2) / N2_factor;
+    thrust = (idlethrust + (milthrust * N2n * N2n)) * (1.0 - 0.0);
+    if (AugmentCmd > 0.0) { const double tdiff = (K_ENG_maxthrust * augT) - thrust; thrust += (tdiff * AugmentCmd); }
+  } else if (starved) {  // tpOff (:172-194)
+    a.FF = seek(a.FF, 0, 1000.0, 10000.0);
+    a.N1 = seek(a.N1, qbar / 10.0, a.N1 / 2.0 + 0.1, a.N1 / 2.0);
+    a.N2 = seek(a.N2, qbar / 15.0, a.N2 / 2.0 + 0.1, a.N2 / 2.0);
+    augmentation = false;
+    thrust = 0.0;
+  } else {  // tpRun (:196-272)
+    const double idlethrust = K_ENG_milthrust * idleT, milthrust = (K_ENG_milthrust - idlethrust) * milT;
+    const double sigma = atm.rho / ac.SLdensity;
+    const double n = fmin(1.0, a.N2norm + 0.1);
+    const double sden = (1 + 3 * (1 - n) * (1 - n) * (1 - n) + (1 - sigma));
+    const double dbase = 90.0 / (K_ENG_bypassratio + 3.0);
+    const double up = (1.0 * dbase) / sden, dn2 = (3.0 * dbase) / sden, dn1 = (2.4 * dbase) / sden;
+    a.N2 = seek(a.N2, K_ENG_idlen2 + ThrottlePos * N2_factor, up, dn2);
+    a.N1 = seek(a.N1, K_ENG_idlen1 + ThrottlePos * N1_factor, up, dn1);
+    a.N2norm = (a.N2 - K_ENG_idlen2) / N2_factor;
+    thrust = idlethrust + (milthrust * a.N2norm * a.N2norm);
+    if (!augmentation) {
+      const double tsfc = K_ENG_tsfc * sqrt(atm.T / 389.7) * (0.84 + (1 - a.N2norm) * (1 - a.N2norm));
+      a.FF = seek(a.FF, thrust * tsfc, 1000.0, 10000.0);
+      if (a.FF < K_ENG_idleff) a.FF = K_ENG_idleff;
+    }
+    if (AugmentCmd > 0.0) {
+      augmentation = true;
+      const double tdiff = (K_ENG_maxthrust * augT) - thrust;
+      thrust += (tdiff * AugmentCmd);
+      a.FF = seek(a.FF, thrust * K_ENG_atsfc, 5000.0, 10000.0);
+    } else augmentation = false;
+  }
+  return thrust;
+}
+
+// FGPropulsion::ConsumeFuel (J/models/FGPropulsion.cpp:164-260): equal split over the tanks that still hold fuel;
+// returns the Starved flag the engine sees NEXT frame
+FDM_DEV bool fdm_stage_consume_fuel(AcCore& a, const double dt, const bool starved, const bool trim_fuel_freeze) {
+  // ConsumeFuel: equal split over tanks that still hold fuel; Starved takes effect next frame
+  bool starved_next = starved;
+  if (!trim_fuel_freeze) {
+    const int n_with = (a.tank0 > 0.0) + (a.tank1 > 0.0) + (a.tank2 > 0.0) + (a.tank3 > 0.0);
+    starved_next = (n_with == 0);
+    if (n_with > 0) {
+      const double per = ((a.FF / 3600.0) * dt) / n_with;
+      auto drain = [per](double& c) { if (c > 0.0) { if (c - per >= 0.0) c -= per; else c = 0.0; } };
+      drain(a.tank0); drain(a.tank1); drain(a.tank2); drain(a.tank3);
+    }
+  }
+  return starved_next;
+}
+
+// FGAerodynamics wind->body + FGAircraft sums + FGAccelerations; c[6] = DRAG, SIDE, LIFT, ROLL, PITCH, YAW build-ups
+FDM_DEV void fdm_stage_accelerations(AcCore& a, Frame& f, const WindAxes& w, const double c[6]) {
+  const double sa = w.sa, ca = w.ca, sb = w.sb, cb = w.cb;
+  // wind -> body (J/models/FGAerodynamics.cpp:205-214): drag and lift flip sign, F_b = Tw2b * F_w
+  const double fw0 = -c[0], fw1 = c[1], fw2 = -c[2];
+  V3 Fa;
+  Fa.x = (ca * cb) * fw0 + (-ca * sb) * fw1 + (-sa) * fw2;
+  Fa.y = sb * fw0 + cb * fw1 + 0.0 * fw2;
+  Fa.z = (sa * cb) * fw0 + (-sa * sb) * fw1 + ca * fw2;
+  const V3 rp = structural_to_body(f.cg, K_AERORP_X, K_AERORP_Y, K_AERORP_Z);
+  const V3 Ma = v3(c[3], c[4], c[5]) + cross(rp, Fa);
+  // thruster (J/models/propulsion/FGForce.cpp:78-91)
+  const V3 Fp = v3(f.thrust, 0.0, 0.0);
+  const V3 Mp = cross(structural_to_body(f.cg, K_THRUSTER_X, K_THRUSTER_Y, K_THRUSTER_Z), Fp);
+  const V3 F = Fa + Fp, M = Ma + Mp;
+  // Accelerations (J/models/FGAccelerations.cpp:138-207)
+  a.pqridot = mul(f.Jinv, M - cross(a.wi, mul(f.J, a.wi)));
+  const double rm = 1.0 / f.Mass;
+  a.bodyaccel = v3(F.x * rm, F.y * rm, F.z * rm);
+  // vUVWidot = Tb2i * vBodyAccel + Tec2i * vGravAccel
+  const V3 gi = v3(f.cos_epa * f.grav.x - f.sin_epa * f.grav.y, f.sin_epa * f.grav.x + f.cos_epa * f.grav.y, f.grav.z);
+  a.uvwidot = mulT(f.Ti2b, a.bodyaccel) + gi;
+}
+
+FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double* __restrict__ T, const AtmoConst& ac,
+                       const double dt, const double fcs_dt, const bool trim_fuel_freeze) {
+  fdm_stage_propagate(a, p, f, dt);
+  fdm_stage_gravity(f);
+  fdm_stage_atmosphere(p, f, ac);
+  f16_fcs(p, s, T, fcs_dt);
+  fdm_stage_massbalance(a, f);
+  WindAxes w;
+  fdm_stage_auxiliary(a, p, f, ac, w);
   {
-    double idleT, milT, augT;
-    f16_engine_tables(p, T, idleT, milT, augT);
-    int flags = (int)a.engflags;
-    const bool starved = flags & 1;
+    const int flags = (int)a.engflags;
     bool augmentation = flags & 2;
-    double ThrottlePos = p.fcs_throttle_pos_norm, AugmentCmd;
-    if (ThrottlePos > 1.0) { AugmentCmd = ThrottlePos - 1.0; ThrottlePos -= AugmentCmd; } else AugmentCmd = 0.0;
-    double thrust;
-    const double N1_factor = K_ENG_maxn1 - K_ENG_idlen1, N2_factor = K_ENG_maxn2 - K_ENG_idlen2;
-    auto seek = [dt](double v, double target, double accel, double decel) {
-      if (v > target) { v -= dt * decel; if (v < target) v = target; }
-      else if (v < target) { v += dt * accel; if (v > target) v = target; }
-      return v;
-    };
-    if (dt == 0.0) {  // tpTrim (:341-372)
-      const double idlethrust = K_ENG_milthrust * idleT, milthrust = (K_ENG_milthrust - idlethrust) * milT;
-      const double N2t = K_ENG_idlen2 + ThrottlePos * N2_factor, N2n = (N2t - K_ENG_idlen2) / N2_factor;
-      thrust = (idlethrust + (milthrust * N2n * N2n)) * (1.0 - 0.0);
-      if (AugmentCmd > 0.0) { const double tdiff = (K_ENG_maxthrust * augT) - thrust; thrust += (tdiff * AugmentCmd); }
-    } else if (starved) {  // tpOff (:172-194)
-      a.FF = seek(a.FF, 0, 1000.0, 10000.0);
-      a.N1 = seek(a.N1, f.qbar / 10.0, a.N1 / 2.0 + 0.1, a.N1 / 2.0);
-      a.N2 = seek(a.N2, f.qbar / 15.0, a.N2 / 2.0 + 0.1, a.N2 / 2.0);
-      augmentation = false;
-      thrust = 0.0;
-    } else {  // tpRun (:196-272)
-      const double idlethrust = K_ENG_milthrust * idleT, milthrust = (K_ENG_milthrust - idlethrust) * milT;
-      const double sigma = f.atm.rho / ac.SLdensity;
-      const double n = fmin(1.0, a.N2norm + 0.1);
-      const double sden = (1 + 3 * (1 - n) * (1 - n) * (1 - n) + (1 - sigma));
-      const double dbase = 90.0 / (K_ENG_bypassratio + 3.0);
-      const double up = (1.0 * dbase) / sden, dn2 = (3.0 * dbase) / sden, dn1 = (2.4 * dbase) / sden;
-      a.N2 = seek(a.N2, K_ENG_idlen2 + ThrottlePos * N2_factor, up, dn2);
-      a.N1 = seek(a.N1, K_ENG_idlen1 + ThrottlePos * N1_factor, up, dn1);
-      a.N2norm = (a.N2 - K_ENG_idlen2) / N2_factor;
-      thrust = idlethrust + (milthrust * a.N2norm * a.N2norm);
-      if (!augmentation) {
-        const double tsfc = K_ENG_tsfc * sqrt(f.atm.T / 389.7) * (0.84 + (1 - a.N2norm) * (1 - a.N2norm));
-        a.FF = seek(a.FF, thrust * tsfc, 1000.0, 10000.0);
-        if (a.FF < K_ENG_idleff) a.FF = K_ENG_idleff;
-      }
-      if (AugmentCmd > 0.0) {
-        augmentation = true;
-        const double tdiff = (K_ENG_maxthrust * augT) - thrust;
-        thrust += (tdiff * AugmentCmd);
-        a.FF = seek(a.FF, thrust * K_ENG_atsfc, 5000.0, 10000.0);
-      } else augmentation = false;
-    }
-    f.thrust = thrust;
-    // ConsumeFuel: equal split over tanks that still hold fuel; Starved takes effect next frame
-    bool starved_next = starved;
-    if (!trim_fuel_freeze) {
-      const int n_with = (a.tank0 > 0.0) + (a.tank1 > 0.0) + (a.tank2 > 0.0) + (a.tank3 > 0.0);
-      starved_next = (n_with == 0);
-      if (n_with > 0) {
-        const double per = ((a.FF / 3600.0) * dt) / n_with;
-        auto drain = [per](double& c) { if (c > 0.0) { if (c - per >= 0.0) c -= per; else c = 0.0; } };
-        drain(a.tank0); drain(a.tank1); drain(a.tank2); drain(a.tank3);
-      }
-    }
+    f.thrust = fdm_stage_engine(a, p, f.atm, f.qbar, T, ac, dt, flags & 1, augmentation);
+    const bool starved_next = fdm_stage_consume_fuel(a, dt, flags & 1, trim_fuel_freeze);
     a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
   }
-  // ---------------- Aerodynamics (generated coefficient build-up) + Aircraft + Accelerations
-  {
-    double c[6];
-    f16_aero(p, T, 2 * f.Vt, c);
-    // wind -> body (J/models/FGAerodynamics.cpp:205-214): drag and lift flip sign, F_b = Tw2b * F_w
-    const double fw0 = -c[0], fw1 = c[1], fw2 = -c[2];
-    V3 Fa;
-    Fa.x = (ca * cb) * fw0 + (-ca * sb) * fw1 + (-sa) * fw2;
-    Fa.y = sb * fw0 + cb * fw1 + 0.0 * fw2;
-    Fa.z = (sa * cb) * fw0 + (-sa * sb) * fw1 + ca * fw2;
-    const V3 rp = structural_to_body(f.cg, K_AERORP_X, K_AERORP_Y, K_AERORP_Z);
-    const V3 Ma = v3(c[3], c[4], c[5]) + cross(rp, Fa);
-    // thruster (J/models/propulsion/FGForce.cpp:78-91)
-    const V3 Fp = v3(f.thrust, 0.0, 0.0);
-    const V3 Mp = cross(structural_to_body(f.cg, K_THRUSTER_X, K_THRUSTER_Y, K_THRUSTER_Z), Fp);
-    const V3 F = Fa + Fp, M = Ma + Mp;
-    // Accelerations (J/models/FGAccelerations.cpp:138-207)
-    a.pqridot = mul(f.Jinv, M - cross(a.wi, mul(f.J, a.wi)));
-    const double rm = 1.0 / f.Mass;
-    a.bodyaccel = v3(F.x * rm, F.y * rm, F.z * rm);
-    // vUVWidot = Tb2i * vBodyAccel + Tec2i * vGravAccel
-    const V3 gi = v3(f.cos_epa * f.grav.x - f.sin_epa * f.grav.y, f.sin_epa * f.grav.x + f.cos_epa * f.grav.y, f.grav.z);
-    a.uvwidot = mulT(f.Ti2b, a.bodyaccel) + gi;
-  }
+  double c[6];
+  f16_aero(p, T, 2 * f.Vt, c);
+  fdm_stage_accelerations(a, f, w, c);
 }
 
 // outputs of the frame that has just run (what the reference reads back through get_property_value)

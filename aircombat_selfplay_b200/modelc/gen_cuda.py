@@ -61,15 +61,19 @@ class CudaGen:
         self.ir = ir
         self.props = prop_list(ir)
         self.tab = []          # packed doubles
+        self.packed = {}       # tuple(values) -> offset
         self.keyarrays = {}    # tuple(keys) -> offset
         self.out = []
         self.analyse()
 
     # ------------------------------------------------------------------ table blob
     def pack(self, arr):
-        off = len(self.tab)
-        self.tab.extend(float(x) for x in arr)
-        return off
+        """Append to the table blob; identical arrays are stored once (the split aero functions re-reference them)."""
+        key = tuple(float(x) for x in arr)
+        if key not in self.packed:
+            self.packed[key] = len(self.tab)
+            self.tab.extend(key)
+        return self.packed[key]
 
     def keys_off(self, keys):
         """Breakpoint vector followed by its reciprocal spacings: k[n + r] = 1 / (k[r] - k[r-1]), k[n] unused."""
@@ -310,14 +314,31 @@ class CudaGen:
         assert not (scope.get("vars", set()) & written), "bracket variable written inside the FCS"
         return "\n".join(scope.get("decls", []) + code)
 
-    def gen_aero(self):
+    def aero_reads(self, axes):
+        """Properties the coefficient functions of the given axes read (pre-functions they use included)."""
+        reads = set()
+        for ax in self.ir["aero_axes"]:
+            if ax["axis"] in axes:
+                for f in ax["functions"]:
+                    reads |= set(self.fac_reads(f["factors"]))
+        for f in self.ir["aero_pre"]:
+            if f["name"] in reads:
+                reads |= set(self.fac_reads(f["factors"]))
+        return reads
+
+    def gen_aero(self, axes=None):
+        axes = axes or AXES
+        reads = self.aero_reads(axes)
         scope = {"brackets": {}, "code": []}
         code = scope["code"]
         for f in self.ir["aero_pre"]:
-            code.append(f"  p.{cid(f['name'])} = {self.product(f['factors'], scope)};")
+            if f["name"] in reads:
+                code.append(f"  p.{cid(f['name'])} = {self.product(f['factors'], scope)};")
         code.append("  // FGAerodynamics::Run: bi2vel/ci2vel after the pre-functions (J/models/FGAerodynamics.cpp:152-158)")
         code.append("  if (twovel != 0) { p.aero_bi2vel = K_bw / twovel; p.aero_ci2vel = K_cbarw / twovel; }")
         for ax in self.ir["aero_axes"]:
+            if ax["axis"] not in axes:
+                continue
             i = AXES.index(ax["axis"])
             code.append(f"  // axis {ax['axis']}")
             code.append(f"  {{ double acc = 0.0;")
@@ -419,6 +440,27 @@ class CudaGen:
         o.append("__device__ __forceinline__ void f16_aero(Props& p, const double* __restrict__ T, const double twovel, double f[6]) {")
         o.append(aero)
         o.append("}")
+        # ---- two-warp role split (csrc/fdm_split.cuh): role A = equations of motion + force axes + roll moment, role B =
+        # flight controls + engine + pitch / yaw moments.  The exchange lists are derived from the same dataflow.
+        axes_a, axes_b = ["DRAG", "SIDE", "LIFT", "ROLL"], ["PITCH", "YAW"]
+        o.append("__device__ __forceinline__ void f16_aero_A(Props& p, const double* __restrict__ T, const double twovel, double f[6]) {")
+        o.append(self.gen_aero(axes_a))
+        o.append("}")
+        o.append("__device__ __forceinline__ void f16_aero_B(Props& p, const double* __restrict__ T, const double twovel, double f[6]) {")
+        o.append(self.gen_aero(axes_b))
+        o.append("}")
+        fcs_written = {x for c in ir["fcs"] for x in c["outputs"]} | {"fcs/speedbrake-pos-rad", "fcs/throttle-pos-norm"}
+        core_pub = [x for st, pubs in CORE_PUBLISH if st in ("atmosphere", "auxiliary") for x in (pubs or [])]
+        fcs_reads = set()
+        for c in ir["fcs"]:
+            fcs_reads |= set(self.comp_reads(c))
+        need_b = self.aero_reads(axes_b) | {"velocities/mach", "atmosphere/density-altitude"} | fcs_reads
+        x_aux = [x for x in core_pub if x in need_b and x not in self.consts]
+        x_surf = sorted(x for x in self.aero_reads(axes_a) if x in fcs_written and x not in self.consts)
+        x_early = ["attitude/cos-pitch-cos-roll", "velocities/u-fps", "velocities/v-fps"]
+        for nm, lst in (("EARLY", x_early), ("AUX", x_aux), ("SURF", x_surf)):
+            o.append(f"#define F16_X_{nm}(X) " + " ".join(f"X(p.{cid(x)})" for x in lst))
+            o.append(f"#define F16_N_X_{nm} {len(lst)}")
         o.append("__device__ __forceinline__ void f16_engine_tables(const Props& p, const double* __restrict__ T, double& idle, double& mil, double& aug) {")
         o.append(eng)
         o.append("}")
