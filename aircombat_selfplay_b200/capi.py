@@ -85,6 +85,7 @@ def lib():
         L.acs_env_arena_ptr.argtypes = [vp, i, ctypes.POINTER(vp)]
         L.acs_env_fdm.restype = vp
         L.acs_env_fdm.argtypes = [vp]
+        L.acs_env_set_option.argtypes = [vp, cp, i]
         L.acs_env_set_timing.argtypes = [vp, i]
         L.acs_env_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i), i]
         L.acs_bench_fp64_peak.argtypes = [i, ctypes.POINTER(ctypes.c_double)]
@@ -295,6 +296,10 @@ class EnvBatch:
                                   _ptr(self.dones, torch.uint8), _ptr(self.info, torch.int32), _ptr(self.env_done, torch.uint8),
                                   int(auto_reset), _stream()))
         return self.obs, self.share_obs, self.rewards, self.dones, self.info
+
+    def set_option(self, name: str, value: int):
+        """Tuning knobs of include/acs.h (``frame_split``: 0 one thread per aircraft, 1 two-warp frame, -1 auto)."""
+        _check(lib().acs_env_set_option(self._h, name.encode(), int(value)))
 
     # ---- measurement
     def set_timing(self, on: bool):

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <cmath>
@@ -48,6 +49,18 @@ __device__ __forceinline__ void store_state(double* __restrict__ st, int N, int 
   F16_CARRIED_FIELDS(ST)
 #undef ST
 }
+// two-warp frame: role A (ROLE_B = false) owns the core fields and the carried properties the core models publish, role B
+// the flight-control side (commands, FCS outputs, PID states); the ownership predicate folds at compile time
+template <bool ROLE_B>
+__device__ __forceinline__ void store_state_role(double* __restrict__ st, int N, int i, const AcCore& a, const Props& p, const FcsState& s) {
+  int k = 0;
+#define ST(name, expr) { if (!ROLE_B) st[(size_t)k * N + i] = expr; k++; }
+  FDM_CORE_FIELDS(ST)
+#undef ST
+#define ST(name, expr) { constexpr bool b_ = F16_CARRIED_ROLE_B(name); if (b_ == ROLE_B) st[(size_t)k * N + i] = expr; k++; }
+  F16_CARRIED_FIELDS(ST)
+#undef ST
+}
 __device__ __forceinline__ void store_out(double* __restrict__ out, int N, int i, const AcOut& o) {
   int k = 0;
 #define ST(name, expr) out[(size_t)(k++) * N + i] = expr;
@@ -68,6 +81,19 @@ __device__ __forceinline__ void stage_tables(double* sT) {
 #define ACS_FDM_MIN_BLOCKS 1
 #endif
 constexpr int FDM_BLOCK = ACS_FDM_BLOCK;
+// two-warp frame: aircraft per block (each gets one thread of role A and one of role B), and the axes role A builds
+#ifndef ACS_SPLIT_SLOTS
+#define ACS_SPLIT_SLOTS 64
+#endif
+#ifndef ACS_SPLIT_AXES_A
+#define ACS_SPLIT_AXES_A 0   // measured best on B200: role A keeps the engine, role B builds all six axes (one set of brackets)
+#endif
+#ifndef ACS_SPLIT_AUTO_LANES_PER_SM
+#define ACS_SPLIT_AUTO_LANES_PER_SM 128
+#endif
+constexpr int SPLIT_SLOTS = ACS_SPLIT_SLOTS;
+constexpr int SPLIT_AXES_A = ACS_SPLIT_AXES_A, SPLIT_AXES_B = 63 & ~SPLIT_AXES_A;
+static_assert(SPLIT_SLOTS % 32 == 0 && SPLIT_SLOTS >= 32 && SPLIT_SLOTS <= 128, "pairs of whole warps, at most 4 pairs per block");
 
 __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_fdm_run(double* __restrict__ state, double* __restrict__ out,
                                                       const uint8_t* __restrict__ alive, int N, int n_frames, double dt,
@@ -254,6 +280,8 @@ struct AcsEnv {
   AcsHandle* fdm;
   EnvView v;
   int G, lg;   // lanes per env (1, 2, 4 or 8) and its log2
+  int frame_split = -1;          // substep kernel: 0 one thread per aircraft, 1 two-warp frame, -1 by batch size
+  int split_max_threads = 0;     // auto: use the two-warp frame up to this many aircraft lanes
   bool timing = false;
   std::vector<cudaEvent_t> ev;   // 4 events per timed step: before substeps, after substeps, after post, after reset
   size_t ev_used = 0;
@@ -325,8 +353,25 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
   CUDA_TRY(cudaMalloc(&v.mi, sizeof(int) * N_MI * ms));      CUDA_TRY(cudaMemset(v.mi, 0, sizeof(int) * N_MI * ms));
   // episode counters start at -1 so the first reset is episode 0
   CUDA_TRY(cudaMemset(v.ei + (size_t)EI_EPISODE * B, 0xff, sizeof(int) * B));
+  // substep-kernel choice: the two-warp frame wins while the batch leaves SM sub-partitions idle
+  {
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    e->split_max_threads = prop.multiProcessorCount * ACS_SPLIT_AUTO_LANES_PER_SM;
+    if (const char* s = std::getenv("ACS_FRAME_SPLIT")) e->frame_split = std::atoi(s);
+  }
   *out = e;
   return 0;
+}
+
+int acs_env_set_option(AcsEnv* e, const char* name, int value) {
+  if (!e || !name) return fail("acs_env_set_option: null argument");
+  if (!std::strcmp(name, "frame_split")) {
+    if (value < -1 || value > 1) return fail("acs_env_set_option: frame_split must be -1 (auto), 0 or 1");
+    e->frame_split = value;
+    return 0;
+  }
+  return fail(std::string("acs_env_set_option: unknown option ") + name);
 }
 
 int acs_env_destroy(AcsEnv* e) {
@@ -372,7 +417,9 @@ int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double*
   cudaStream_t st = (cudaStream_t)stream;
   const int threads = e->v.B * e->G;
   if (e->timing) timing_event(e, st);
-  k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
+  const bool split = e->frame_split == 1 || (e->frame_split < 0 && threads <= e->split_max_threads);
+  if (split) k_env_substeps_split<<<(threads + SPLIT_SLOTS - 1) / SPLIT_SLOTS, 2 * SPLIT_SLOTS, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
+  else k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   CUDA_TRY(cudaGetLastError());
   if (e->timing) timing_event(e, st);
   k_env_post<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg, obs_dev, share_obs_dev, rewards_dev, dones_dev, info_dev, env_done_dev);
@@ -447,6 +494,20 @@ int acs_env_set_arena(AcsEnv* e, int which, const void* src_dev, void* stream) {
   CUDA_TRY(cudaMemcpyAsync(p, src_dev, (size_t)nf * per * (ii ? sizeof(int) : sizeof(double)), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
+
+#ifdef ACS_SPLIT_PROFILE
+int acs_debug_split_profile(long long* out16) {
+  CUDA_TRY(cudaMemcpyFromSymbol(out16, g_split_prof, sizeof(long long) * 16));
+  return 0;
+}
+#endif
+
+#ifdef ACS_FRAME_PROFILE
+int acs_debug_frame_profile(long long* out16) {
+  CUDA_TRY(cudaMemcpyFromSymbol(out16, g_frame_prof, sizeof(long long) * 16));
+  return 0;
+}
+#endif
 
 int acs_bench_fp64_peak(int device, double* flops_out) {
   if (!flops_out) return fail("acs_bench_fp64_peak: null argument");

@@ -267,6 +267,237 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
   }
 }
 
+// ---------------------------------------------------------------------------------------------- two-warp frame
+// Latency variant of k_env_substeps for batches too small to fill the machine (the headline 4096-env config puts one
+// warp on fewer than half of the 592 SM sub-partitions, so a step costs one warp's dependent-issue latency).  Each
+// aircraft is integrated by TWO threads in two different warps of the block, running the stage functions of fdm_frame
+// concurrently:
+//
+//   role A (warps 0 .. S/32-1)                           role B (warps S/32 .. 2S/32-1)
+//   Propagate                    -- EARLY, run flag -->
+//   ------------------------------------------------ pair barrier 1
+//   Inertial, Atmosphere, MassBalance, Auxiliary         FCS (inputs: last frame's auxiliary values, as in JSBSim)
+//                                -- AUX, 2 Vt      -->   <-- SURF --
+//   ------------------------------------------------ pair barrier 2
+//   Propulsion, aero axes SPLIT_AXES_A                   aero axes SPLIT_AXES_B
+//                                                        <-- axis sums --
+//   ------------------------------------------------ pair barrier 3
+//   Aircraft + Accelerations, missiles / chaff
+//
+// Every value is computed by the same expression as in fdm_frame, only on another thread; the exchange lists are
+// generated from the model's dataflow (F16_X_* in gen/f16_gen.cuh).  A pair synchronises on its own named barrier
+// (64 threads), so pairs never wait for each other.  Buffer reuse: EARLY aliases SURF and the axis sums alias AUX --
+// in both cases the reader of the first finishes (same thread) before it writes the second, and the next writer of
+// the first is behind a later barrier.
+constexpr int SPLIT_N_BUF1 = F16_N_X_SURF > F16_N_X_EARLY ? F16_N_X_SURF : F16_N_X_EARLY;
+constexpr int SPLIT_N_BUF2 = (F16_N_X_AUX + 1) > 6 ? (F16_N_X_AUX + 1) : 6;
+
+#ifdef ACS_SPLIT_PROFILE
+// cycle stamps of the first pair of block 0 (tuning builds only): [role][segment] accumulated over the K frames
+__device__ long long g_split_prof[2][8];
+#define PROF_DECL long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pc_ = clock64(); const bool prof_ = blockIdx.x == 0 && slot == 0;
+#define PROF(i) { const long long n_ = clock64(); pt_[i] += n_ - pc_; pc_ = n_; }
+#define PROF_OUT(r) if (prof_) { for (int i_ = 0; i_ < 8; i_++) g_split_prof[r][i_] = pt_[i_]; }
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_OUT(r)
+#endif
+ENV_DEV void pair_barrier(const int id) { __syncwarp(); asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const EnvView v, const __grid_constant__ AcsTaskConfig cfg,
+                                                                          const int lg, const int32_t* __restrict__ actions) {
+  __shared__ double sT[F16_NTAB];
+  __shared__ PubAc sP[SPLIT_SLOTS];
+  __shared__ int sWin[SPLIT_SLOTS];
+  __shared__ int sShot[SPLIT_SLOTS];
+  __shared__ PubChaff sCh[SPLIT_SLOTS];
+  __shared__ double sX1[SPLIT_N_BUF1][SPLIT_SLOTS];
+  __shared__ double sX2[SPLIT_N_BUF2][SPLIT_SLOTS];
+  __shared__ int sRun[SPLIT_SLOTS];
+  stage_tables(sT);
+  const bool role_b = threadIdx.x >= SPLIT_SLOTS;            // warp-uniform
+  const int slot = threadIdx.x - (role_b ? SPLIT_SLOTS : 0);
+  const int bar = 1 + (slot >> 5);                           // barrier 0 is __syncthreads
+  Lane L;
+  {
+    const int G = 1 << lg, gid = blockIdx.x * SPLIT_SLOTS + slot;
+    L.tid = slot; L.env = gid >> lg; L.lane = gid & (G - 1); L.gbase = slot - L.lane;
+    L.valid = (L.env < v.B) && (L.lane < v.A);
+    L.row = L.env * v.A + L.lane;
+    L.gmask = ((1u << G) - 1u) << ((unsigned)(slot & 31) & ~(unsigned)(G - 1));
+  }
+  const int N = v.rows, K = cfg.substeps;
+  const double dt = cfg.sim_dt, fcs_dt = cfg.fcs_dt;
+#define XW1(e) sX1[xi++][slot] = e;
+#define XR1(e) e = sX1[xi++][slot];
+#define XW2(e) sX2[xi++][slot] = e;
+#define XR2(e) e = sX2[xi++][slot];
+
+  if (role_b) {
+    // ================================================================ role B: flight controls + its aero axes
+    Props p; FcsState s;
+    bool loaded = false;
+    if (L.valid) {
+      // normalize_action + set_property_values(action_var) with the catalog clip (E/tasks/heading_task.py:102-110,
+      // E/tasks/singlecombat_task.py:141-153, E/core/catalog.py:192-197); applied to dead aircraft too
+      const int adim = 4 + cfg.shoot_dim;
+      const int32_t* act = actions + (size_t)L.row * adim;
+      double u0, u1, u2, u3;
+      if (cfg.act_kind == ACS_ACT_HEADING) {
+        u0 = act[0] * 2. / (41 - 1.) - 1.; u1 = act[1] * 2. / (41 - 1.) - 1.; u2 = act[2] * 2. / (41 - 1.) - 1.; u3 = act[3] * 0.5 / (30 - 1.) + 0.4;
+      } else {
+        u0 = act[0] / 20. - 1.; u1 = act[1] / 20. - 1.; u2 = act[2] / 20. - 1.; u3 = act[3] / 58. + 0.4;
+      }
+      u0 = env_clip(u0, -1.0, 1.0); u1 = env_clip(u1, -1.0, 1.0); u2 = env_clip(u2, -1.0, 1.0); u3 = env_clip(u3, 0.0, 0.9);
+      int shoot = 0;
+      for (int k = 0; k < cfg.shoot_dim; k++) shoot |= (act[4 + k] != 0) << k;
+      if (cfg.shoot_dim > 0) AI(v, AI_SHOOT, L.row) = shoot;
+      if (AI(v, AI_STATUS, L.row) == ST_ALIVE) {
+        AcCore a;   // only the carried properties are live on this side; the core loads are dead code
+        f16_props_init(p, s);
+        load_state(v.fdm, N, L.row, a, p, s);
+        p.fcs_aileron_cmd_norm = u0; p.fcs_elevator_cmd_norm = u1; p.fcs_rudder_cmd_norm = u2; p.fcs_throttle_cmd_norm = u3;
+        loaded = true;
+      } else {
+        v.fdm[(size_t)(F_CMD0 + 0) * N + L.row] = u0; v.fdm[(size_t)(F_CMD0 + 1) * N + L.row] = u1;
+        v.fdm[(size_t)(F_CMD0 + 2) * N + L.row] = u2; v.fdm[(size_t)(F_CMD0 + 3) * N + L.row] = u3;
+      }
+    }
+    PROF_DECL
+    for (int k = 0; k < K; k++) {
+      PROF(0)
+      pair_barrier(bar);                                       // 1: EARLY + run flag are there
+      PROF(1)
+      const bool ran = sRun[slot] != 0;
+      if (ran) {
+        { int xi = 0; F16_X_EARLY(XR1) }
+        f16_fcs(p, s, sT, fcs_dt);
+        { int xi = 0; F16_X_SURF(XW1) }
+      }
+      PROF(2)
+      pair_barrier(bar);                                       // 2: AUX is there, SURF is out
+      PROF(3)
+      if (ran) {
+        double twovel, c[6];
+        { int xi = 0; F16_X_AUX(XR2) twovel = sX2[xi][slot]; }
+        f16_aero<SPLIT_AXES_B>(p, sT, twovel, c);
+#pragma unroll
+        for (int i = 0; i < 6; i++) if (SPLIT_AXES_B & (1 << i)) sX2[i][slot] = c[i];
+      }
+      PROF(4)
+      pair_barrier(bar);                                       // 3: axis sums are out
+      PROF(5)
+    }
+    PROF_OUT(1)
+    if (loaded) {
+      AcCore a;
+      store_state_role<true>(v.fdm, N, L.row, a, p, s);
+    }
+    return;
+  }
+
+  // ================================================================== role A: everything else (as k_env_substeps)
+  const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
+  AcCore a; Props p; FcsState s; Frame f;
+  PubAc me;
+  double v_mps = 0, w_mps = 0, vc_mps = 0;
+  int status = ST_CRASH;
+  bool has_ms = false;
+  me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
+  if (L.valid) {
+    load_pub(v, L.row, me);
+    status = me.status;
+    has_ms = (AI(v, AI_N_LAUNCHED, L.row) > 0) || (AI(v, AI_CH_STATE, L.row) == CH_ACTIVE);
+    if (status == ST_ALIVE) {
+      f16_props_init(p, s);
+      load_state(v.fdm, N, L.row, a, p, s);
+    }
+  }
+  {
+    const unsigned b = __ballot_sync(L.gmask, has_ms);
+    has_ms = (b & L.gmask) != 0;
+  }
+  const bool was_alive = L.valid && status == ST_ALIVE;
+  const int sc0 = (L.env < v.B) ? EI(v, EI_SUBSTEP_COUNT, L.env) : 0;
+  AcOut o;
+  PROF_DECL
+  for (int k = 0; k < K; k++) {
+    PROF(7)
+    bool ran = false;
+    if (L.valid && status == ST_ALIVE) {                     // AircraftSimulator.run (simulatior.py:210-229)
+      if (me.bloods <= 0) status = ST_SHOTDOWN;
+      ran = true;
+      fdm_stage_propagate(a, p, f, dt);
+      { int xi = 0; F16_X_EARLY(XW1) }
+    }
+    sRun[slot] = ran;
+    PROF(0)
+    pair_barrier(bar);                                         // 1
+    PROF(1)
+    WindAxes w;
+    if (ran) {
+      fdm_stage_gravity(f);
+      fdm_stage_atmosphere(p, f, g_atmo);
+      fdm_stage_massbalance(a, f);
+      fdm_stage_auxiliary(a, p, f, g_atmo, w);
+      { int xi = 0; F16_X_AUX(XW2) sX2[xi][slot] = 2 * f.Vt; }
+    }
+    PROF(2)
+    pair_barrier(bar);                                         // 2
+    PROF(3)
+    double c[6];
+    if (ran) {
+      { int xi = 0; F16_X_SURF(XR1) }
+      const int flags = (int)a.engflags;
+      bool augmentation = flags & 2;
+      f.thrust = fdm_stage_engine(a, p, f.atm, f.qbar, sT, g_atmo, dt, flags & 1, augmentation);
+      const bool starved_next = fdm_stage_consume_fuel(a, dt, flags & 1, false);
+      a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
+      f16_aero<SPLIT_AXES_A>(p, sT, 2 * f.Vt, c);
+    }
+    PROF(4)
+    pair_barrier(bar);                                         // 3
+    PROF(5)
+    if (ran) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) if (SPLIT_AXES_B & (1 << i)) c[i] = sX2[i][slot];
+      fdm_stage_accelerations(a, f, w, c);
+    }
+    PROF(6)
+    if (has_ms) {
+      if (ran) publish_from_frame(f, org, me);
+      me.status = status;
+      sP[L.tid] = me;
+      sWin[L.tid] = 0x7fffffff;
+      sShot[L.tid] = 0;
+      __syncwarp(L.gmask);
+      missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, sc0 + k);
+      __syncwarp(L.gmask);
+      if (sShot[L.tid] && status == ST_ALIVE) status = ST_SHOTDOWN;   // target_aircraft.shotdown() (simulatior.py:527)
+      __syncwarp(L.gmask);
+    }
+    if (ran && (k == K - 1 || status != ST_ALIVE)) {
+      fdm_outputs(a, f, o);
+      derive_aircraft(o, org, me, v_mps, w_mps, vc_mps);
+    }
+  }
+  PROF_OUT(0)
+  if (L.valid) {
+    if (was_alive) {
+      store_state_role<false>(v.fdm, N, L.row, a, p, s);
+      store_out(v.out, N, L.row, o);
+      store_derived(v, L.row, me, v_mps, w_mps, vc_mps);
+    }
+    AI(v, AI_STATUS, L.row) = status;
+    if (L.lane == 0) EI(v, EI_SUBSTEP_COUNT, L.env) = sc0 + K;
+  }
+#undef XW1
+#undef XR1
+#undef XW2
+#undef XR2
+}
+
 // ============================================================================================== per-step logic
 struct StepCtx {
   const EnvView& v;

@@ -19,6 +19,11 @@
 #else
 #define FDM_HELPER __device__ __forceinline__
 #endif
+// compile-time string equality (field-ownership predicates of the generated header fold to constants)
+__host__ __device__ constexpr bool f16_streq(const char* a, const char* b) {
+  while (*a && *a == *b) { ++a; ++b; }
+  return *a == *b;
+}
 
 static constexpr double RADTODEG = 180.0 / 3.14159265358979323846;
 static constexpr double DEGTORAD = 3.14159265358979323846 / 180.0;
@@ -656,15 +661,32 @@ FDM_DEV void fdm_stage_accelerations(AcCore& a, Frame& f, const WindAxes& w, con
   a.uvwidot = mulT(f.Ti2b, a.bodyaccel) + gi;
 }
 
+#ifdef ACS_FRAME_PROFILE
+// tuning builds only: cycles per stage of thread 0 of block 0, accumulated (acs_debug_frame_profile)
+__device__ long long g_frame_prof[16];
+#define FPROF(i) if (fprof_) { const long long n_ = clock64(); g_frame_prof[i] += n_ - fpc_; fpc_ = n_; }
+#else
+#define FPROF(i)
+#endif
 FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double* __restrict__ T, const AtmoConst& ac,
                        const double dt, const double fcs_dt, const bool trim_fuel_freeze) {
+#ifdef ACS_FRAME_PROFILE
+  const bool fprof_ = blockIdx.x == 0 && threadIdx.x == 0 && dt != 0.0;
+  long long fpc_ = clock64();
+#endif
   fdm_stage_propagate(a, p, f, dt);
+  FPROF(0)
   fdm_stage_gravity(f);
+  FPROF(1)
   fdm_stage_atmosphere(p, f, ac);
+  FPROF(2)
   f16_fcs(p, s, T, fcs_dt);
+  FPROF(3)
   fdm_stage_massbalance(a, f);
+  FPROF(4)
   WindAxes w;
   fdm_stage_auxiliary(a, p, f, ac, w);
+  FPROF(5)
   {
     const int flags = (int)a.engflags;
     bool augmentation = flags & 2;
@@ -672,9 +694,20 @@ FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
     const bool starved_next = fdm_stage_consume_fuel(a, dt, flags & 1, trim_fuel_freeze);
     a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
   }
+  FPROF(6)
   double c[6];
-  f16_aero(p, T, 2 * f.Vt, c);
+#ifdef ACS_FRAME_PROFILE
+  f16_aero<1>(p, T, 2 * f.Vt, c); FPROF(7)
+  f16_aero<2>(p, T, 2 * f.Vt, c); FPROF(8)
+  f16_aero<4>(p, T, 2 * f.Vt, c); FPROF(9)
+  f16_aero<8>(p, T, 2 * f.Vt, c); FPROF(10)
+  f16_aero<16>(p, T, 2 * f.Vt, c); FPROF(11)
+  f16_aero<32>(p, T, 2 * f.Vt, c); FPROF(12)
+#else
+  f16_aero<63>(p, T, 2 * f.Vt, c);
+#endif
   fdm_stage_accelerations(a, f, w, c);
+  FPROF(13)
 }
 
 // outputs of the frame that has just run (what the reference reads back through get_property_value)

@@ -326,22 +326,19 @@ class CudaGen:
                 reads |= set(self.fac_reads(f["factors"]))
         return reads
 
-    def gen_aero(self, axes=None):
-        axes = axes or AXES
-        reads = self.aero_reads(axes)
+    def gen_aero(self):
+        """Body of f16_aero<AXMASK>: the brackets and pre-functions come first (pure, so the ones an axis subset does not
+        use are removed by the compiler), each axis build-up sits under its mask bit."""
         scope = {"brackets": {}, "code": []}
         code = scope["code"]
         for f in self.ir["aero_pre"]:
-            if f["name"] in reads:
-                code.append(f"  p.{cid(f['name'])} = {self.product(f['factors'], scope)};")
+            code.append(f"  p.{cid(f['name'])} = {self.product(f['factors'], scope)};")
         code.append("  // FGAerodynamics::Run: bi2vel/ci2vel after the pre-functions (J/models/FGAerodynamics.cpp:152-158)")
         code.append("  if (twovel != 0) { p.aero_bi2vel = K_bw / twovel; p.aero_ci2vel = K_cbarw / twovel; }")
         for ax in self.ir["aero_axes"]:
-            if ax["axis"] not in axes:
-                continue
             i = AXES.index(ax["axis"])
             code.append(f"  // axis {ax['axis']}")
-            code.append(f"  {{ double acc = 0.0;")
+            code.append(f"  if (AXMASK & {1 << i}) {{ double acc = 0.0;")
             for f in ax["functions"]:
                 code.append(f"    acc += {self.product(f['factors'], scope)};  // {f['name']}")
             code.append(f"    f[{i}] = acc; }}")
@@ -437,30 +434,34 @@ class CudaGen:
         o.append("__device__ __forceinline__ void f16_fcs(Props& p, FcsState& s, const double* __restrict__ T, const double fcs_dt) {")
         o.append(fcs)
         o.append("}")
+        o.append("// AXMASK selects the axes to build (bit i = DRAG, SIDE, LIFT, ROLL, PITCH, YAW); f[i] is written only for those")
+        o.append("template <int AXMASK = 63>")
         o.append("__device__ __forceinline__ void f16_aero(Props& p, const double* __restrict__ T, const double twovel, double f[6]) {")
         o.append(aero)
         o.append("}")
-        # ---- two-warp role split (csrc/fdm_split.cuh): role A = equations of motion + force axes + roll moment, role B =
-        # flight controls + engine + pitch / yaw moments.  The exchange lists are derived from the same dataflow.
-        axes_a, axes_b = ["DRAG", "SIDE", "LIFT", "ROLL"], ["PITCH", "YAW"]
-        o.append("__device__ __forceinline__ void f16_aero_A(Props& p, const double* __restrict__ T, const double twovel, double f[6]) {")
-        o.append(self.gen_aero(axes_a))
-        o.append("}")
-        o.append("__device__ __forceinline__ void f16_aero_B(Props& p, const double* __restrict__ T, const double twovel, double f[6]) {")
-        o.append(self.gen_aero(axes_b))
-        o.append("}")
+        # ---- two-warp frame (csrc/env_kernels.cuh, k_env_substeps_split): role A = equations of motion, atmosphere,
+        # auxiliary, engine and a subset of the aero axes; role B = flight controls and the other axes.  The exchange
+        # and ownership lists come from the same dataflow as the carried-state list: reads the other role does not use
+        # are dead code on its side.
         fcs_written = {x for c in ir["fcs"] for x in c["outputs"]} | {"fcs/speedbrake-pos-rad", "fcs/throttle-pos-norm"}
         core_pub = [x for st, pubs in CORE_PUBLISH if st in ("atmosphere", "auxiliary") for x in (pubs or [])]
         fcs_reads = set()
         for c in ir["fcs"]:
             fcs_reads |= set(self.comp_reads(c))
-        need_b = self.aero_reads(axes_b) | {"velocities/mach", "atmosphere/density-altitude"} | fcs_reads
+        need_b = self.aero_reads(AXES) | fcs_reads
         x_aux = [x for x in core_pub if x in need_b and x not in self.consts]
-        x_surf = sorted(x for x in self.aero_reads(axes_a) if x in fcs_written and x not in self.consts)
-        x_early = ["attitude/cos-pitch-cos-roll", "velocities/u-fps", "velocities/v-fps"]
+        x_surf = sorted(x for x in (self.aero_reads(AXES) | {"fcs/throttle-pos-norm"}) if x in fcs_written and x not in self.consts)
+        # the FCS reads pitch / roll only as cos(pitch) * cos(roll) (see product()), which Propagate publishes directly
+        x_early = ["attitude/cos-pitch-cos-roll"] + [x for x in CORE_PUBLISH[0][1] if x in fcs_reads and not x.startswith("attitude/")]
         for nm, lst in (("EARLY", x_early), ("AUX", x_aux), ("SURF", x_surf)):
             o.append(f"#define F16_X_{nm}(X) " + " ".join(f"X(p.{cid(x)})" for x in lst))
             o.append(f"#define F16_N_X_{nm} {len(lst)}")
+        own_b, own_a = [], []
+        for r in rows:
+            name = r.split('"')[1]
+            (own_b if (name in INPUT_PROPS or name in fcs_written or name.startswith("pid:")) else own_a).append(name)
+        o.append("// carried fields stored by the flight-control role (B) of the two-warp frame; the rest belong to role A")
+        o.append("#define F16_CARRIED_ROLE_B(name) (" + " || ".join(f'f16_streq(name, "{n}")' for n in own_b) + ")")
         o.append("__device__ __forceinline__ void f16_engine_tables(const Props& p, const double* __restrict__ T, double& idle, double& mil, double& aug) {")
         o.append(eng)
         o.append("}")

@@ -158,6 +158,13 @@ int acs_env_set_arena(AcsEnv* e, int which, const void* src_dev, void* stream);
 /* the FDM batch inside an env handle (for acs_fdm_* / acs_get_state on the same aircraft rows) */
 AcsHandle* acs_env_fdm(AcsEnv* e);
 
+/* Tuning knob (no reference counterpart).  "frame_split": which substep kernel acs_env_step launches -- 0 = one thread per
+ * aircraft (throughput kernel), 1 = the two-warp frame (two threads in two warps per aircraft running the stages of one
+ * FDM frame concurrently; lower latency while the batch leaves SM sub-partitions idle), -1 = choose by batch size
+ * (default; the environment variable ACS_FRAME_SPLIT overrides the default at acs_env_create).  Both kernels evaluate
+ * the same expressions.  Returns non-zero for an unknown option or value. */
+int acs_env_set_option(AcsEnv* e, const char* name, int value);
+
 /* Measurement (no reference counterpart): with timing on, acs_env_step brackets each of its kernels with CUDA events on the
  * caller's stream (event-record nodes when the stream is being captured into a CUDA graph, so the intervals contain no
  * launch gaps); acs_env_get_timing synchronises those events and returns the accumulated milliseconds per kernel --

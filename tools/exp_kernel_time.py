@@ -6,9 +6,11 @@ import numpy as np, torch
 from aircombat_selfplay_b200.capi import EnvBatch
 from aircombat_selfplay_b200.tasks import load_spec
 
-def run(config, n_envs, steps=20, warm=5):
+def run(config, n_envs, steps=20, warm=5, split=None):
     spec = load_spec(config, substeps_override=12)
     b = EnvBatch(spec, n_envs, seed=0)
+    if split is not None:
+        b.set_option("frame_split", split)
     b.reset()
     rng = np.random.default_rng(0)
     A = spec.n_agents
@@ -25,9 +27,11 @@ def run(config, n_envs, steps=20, warm=5):
     return ms["substeps"] / n, ms["post"] / n, ms["reset"] / n
 
 tag = os.environ.get("ACS_LIB", "default").split("/")[-1]
-out = [tag]
-for config, n in (("1v1/NoWeapon/Selfplay", 4096), ("1v1/NoWeapon/Selfplay", 65536), ("1v1/NoWeapon/Selfplay", 262144), ("2v2/ShootMissile/HierarchySelfplay", 8192)):
-    s, p, r = run(config, n)
-    A = load_spec(config).n_agents
-    out.append(f"{config.split('/')[0]}x{n}: sub {s:.3f} ms post {p:.3f} reset {r:.3f} -> {n * A / (s + p + r) / 1e3:.1f} M/s")
-print(" | ".join(out), flush=True)
+sizes = [int(x) for x in os.environ.get("EXP_SIZES", "4096,16384,65536").split(",")]
+for split in (0, 1):
+    out = [tag, f"split={split}"]
+    for config, n in [("1v1/NoWeapon/Selfplay", n) for n in sizes] + [("2v2/ShootMissile/HierarchySelfplay", 8192)]:
+        s, p, r = run(config, n, split=split)
+        A = load_spec(config).n_agents
+        out.append(f"{config.split('/')[0]}x{n}: sub {s:.3f} ms post {p:.3f} reset {r:.3f} -> {n * A / (s + p + r) / 1e3:.1f} M/s")
+    print(" | ".join(out), flush=True)

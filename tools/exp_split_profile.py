@@ -1,0 +1,28 @@
+"""Tuning experiment (needs a -DACS_SPLIT_PROFILE build, ACS_LIB=...): cycle stamps of one pair of the two-warp frame."""
+import ctypes, os, sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np, torch
+from aircombat_selfplay_b200 import capi
+from aircombat_selfplay_b200.capi import EnvBatch
+from aircombat_selfplay_b200.tasks import load_spec
+
+spec = load_spec("1v1/NoWeapon/Selfplay", substeps_override=12)
+n = 4096
+b = EnvBatch(spec, n, seed=0)
+b.set_option("frame_split", 1)
+b.reset()
+rng = np.random.default_rng(0)
+for t in range(6):
+    act = torch.tensor(np.concatenate([rng.integers(0, 41, (n, 2, 3)), rng.integers(0, 30, (n, 2, 1))], axis=-1).astype(np.int32), device="cuda")
+    b.step(act, auto_reset=True)
+torch.cuda.synchronize()
+out = (ctypes.c_longlong * 16)()
+capi.lib().acs_debug_split_profile.argtypes = [ctypes.c_void_p]
+assert capi.lib().acs_debug_split_profile(out) == 0
+a, bb = list(out[:8]), list(out[8:])
+K = 12
+print(os.environ.get("ACS_LIB"), "cycles per frame (avg over 12)")
+print("A: pre+propagate %d | wait1 %d | grav..aux %d | wait2 %d | engine+aeroA %d | wait3 %d | accel %d | tail(missile/out) %d" % tuple(x // K for x in (a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7])))
+print("B: idle-top %d | wait1 %d | fcs %d | wait2 %d | aeroB %d | wait3 %d" % tuple(x // K for x in bb[:6]))
+print("A total/frame", sum(a) // K, "B total/frame", sum(bb) // K)
