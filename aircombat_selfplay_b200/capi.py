@@ -86,6 +86,7 @@ def lib():
         L.acs_env_fdm.restype = vp
         L.acs_env_fdm.argtypes = [vp]
         L.acs_env_set_option.argtypes = [vp, cp, i]
+        L.acs_env_get_option.argtypes = [vp, cp, ctypes.POINTER(i)]
         L.acs_env_set_timing.argtypes = [vp, i]
         L.acs_env_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i), i]
         L.acs_bench_fp64_peak.argtypes = [i, ctypes.POINTER(ctypes.c_double)]
@@ -300,6 +301,11 @@ class EnvBatch:
     def set_option(self, name: str, value: int):
         """Tuning knobs of include/acs.h (``frame_split``: 0 one thread per aircraft, 1 two-warp frame, -1 auto)."""
         _check(lib().acs_env_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        out = ctypes.c_int()
+        _check(lib().acs_env_get_option(self._h, name.encode(), ctypes.byref(out)))
+        return out.value
 
     # ---- measurement
     def set_timing(self, on: bool):

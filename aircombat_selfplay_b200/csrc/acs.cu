@@ -182,6 +182,14 @@ static void host_atmo(AtmoConst& c) {
     } else Tm = t[0] + G * c.Lapse[0];
     c.Tmb[b] = Tm;
   }
+  // reciprocals / exponents the device code multiplies by (fdm_core.cuh, AtmoConst)
+  c.invdH[0] = 0.0;
+  for (int r = 1; r < 9; r++) c.invdH[r] = 1.0 / (h[r] - h[r - 1]);
+  for (int b = 0; b < 8; b++) {
+    c.Pexp[b] = c.Lapse[b] != 0.0 ? c.g0 / (c.Reng * c.Lapse[b]) : 0.0;
+    c.Piso[b] = -c.g0 / (c.Reng * c.Tmb[b]);
+  }
+  c.invSLdensity = 1.0 / c.SLdensity;
 }
 
 static int find_state_field(const char* name) {
@@ -372,6 +380,17 @@ int acs_env_set_option(AcsEnv* e, const char* name, int value) {
     return 0;
   }
   return fail(std::string("acs_env_set_option: unknown option ") + name);
+}
+
+int acs_env_get_option(const AcsEnv* e, const char* name, int* value) {
+  if (!e || !name || !value) return fail("acs_env_get_option: null argument");
+  if (!std::strcmp(name, "frame_split")) { *value = e->frame_split; return 0; }
+  if (!std::strcmp(name, "frame_split_effective")) {   // what the next acs_env_step launches
+    const int threads = e->v.B * e->G;
+    *value = (e->frame_split == 1 || (e->frame_split < 0 && threads <= e->split_max_threads)) ? 1 : 0;
+    return 0;
+  }
+  return fail(std::string("acs_env_get_option: unknown option ") + name);
 }
 
 int acs_env_destroy(AcsEnv* e) {

@@ -293,17 +293,23 @@ constexpr int SPLIT_N_BUF1 = F16_N_X_SURF > F16_N_X_EARLY ? F16_N_X_SURF : F16_N
 constexpr int SPLIT_N_BUF2 = (F16_N_X_AUX + 1) > 6 ? (F16_N_X_AUX + 1) : 6;
 
 #ifdef ACS_SPLIT_PROFILE
-// cycle stamps of the first pair of block 0 (tuning builds only): [role][segment] accumulated over the K frames
+// tuning builds only: absolute clock64 stamps of one frame of the first pair of block 0, taken inside the same asm
+// statement as the barrier (arrival / release), so the compiler cannot move them relative to it
 __device__ long long g_split_prof[2][8];
-#define PROF_DECL long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pc_ = clock64(); const bool prof_ = blockIdx.x == 0 && slot == 0;
-#define PROF(i) { const long long n_ = clock64(); pt_[i] += n_ - pc_; pc_ = n_; }
+#define PROF_DECL long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int pi_ = 0; const bool prof_ = blockIdx.x == 0 && slot == 0;
+#define PROF_FRAME(k) pi_ = ((k) == 6) ? 0 : 8;
+#define PROF_TOP(k) { if ((k) == 6) pt_[6] = clock64(); if ((k) == 7) pt_[7] = clock64(); }
 #define PROF_OUT(r) if (prof_) { for (int i_ = 0; i_ < 8; i_++) g_split_prof[r][i_] = pt_[i_]; }
+#define pair_barrier(id) { long long t0_, t1_; __syncwarp(); \
+  asm volatile("mov.u64 %0, %%clock64;\n\tbar.sync %2, 64;\n\tmov.u64 %1, %%clock64;" : "=l"(t0_), "=l"(t1_) : "r"(id) : "memory"); \
+  if (pi_ < 8) { pt_[pi_] = t0_; pt_[pi_ + 1] = t1_; pi_ += 2; } }
 #else
 #define PROF_DECL
-#define PROF(i)
+#define PROF_FRAME(k)
+#define PROF_TOP(k)
 #define PROF_OUT(r)
-#endif
 ENV_DEV void pair_barrier(const int id) { __syncwarp(); asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+#endif
 
 __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const EnvView v, const __grid_constant__ AcsTaskConfig cfg,
                                                                           const int lg, const int32_t* __restrict__ actions) {
@@ -366,18 +372,15 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
     }
     PROF_DECL
     for (int k = 0; k < K; k++) {
-      PROF(0)
+      PROF_FRAME(k)
       pair_barrier(bar);                                       // 1: EARLY + run flag are there
-      PROF(1)
       const bool ran = sRun[slot] != 0;
       if (ran) {
         { int xi = 0; F16_X_EARLY(XR1) }
         f16_fcs(p, s, sT, fcs_dt);
         { int xi = 0; F16_X_SURF(XW1) }
       }
-      PROF(2)
       pair_barrier(bar);                                       // 2: AUX is there, SURF is out
-      PROF(3)
       if (ran) {
         double twovel, c[6];
         { int xi = 0; F16_X_AUX(XR2) twovel = sX2[xi][slot]; }
@@ -385,9 +388,7 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
 #pragma unroll
         for (int i = 0; i < 6; i++) if (SPLIT_AXES_B & (1 << i)) sX2[i][slot] = c[i];
       }
-      PROF(4)
       pair_barrier(bar);                                       // 3: axis sums are out
-      PROF(5)
     }
     PROF_OUT(1)
     if (loaded) {
@@ -423,7 +424,8 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
   AcOut o;
   PROF_DECL
   for (int k = 0; k < K; k++) {
-    PROF(7)
+    PROF_FRAME(k)
+    PROF_TOP(k)
     bool ran = false;
     if (L.valid && status == ST_ALIVE) {                     // AircraftSimulator.run (simulatior.py:210-229)
       if (me.bloods <= 0) status = ST_SHOTDOWN;
@@ -432,9 +434,7 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
       { int xi = 0; F16_X_EARLY(XW1) }
     }
     sRun[slot] = ran;
-    PROF(0)
     pair_barrier(bar);                                         // 1
-    PROF(1)
     WindAxes w;
     if (ran) {
       fdm_stage_gravity(f);
@@ -443,9 +443,7 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
       fdm_stage_auxiliary(a, p, f, g_atmo, w);
       { int xi = 0; F16_X_AUX(XW2) sX2[xi][slot] = 2 * f.Vt; }
     }
-    PROF(2)
     pair_barrier(bar);                                         // 2
-    PROF(3)
     double c[6];
     if (ran) {
       { int xi = 0; F16_X_SURF(XR1) }
@@ -456,15 +454,12 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
       a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
       f16_aero<SPLIT_AXES_A>(p, sT, 2 * f.Vt, c);
     }
-    PROF(4)
     pair_barrier(bar);                                         // 3
-    PROF(5)
     if (ran) {
 #pragma unroll
       for (int i = 0; i < 6; i++) if (SPLIT_AXES_B & (1 << i)) c[i] = sX2[i][slot];
       fdm_stage_accelerations(a, f, w, c);
     }
-    PROF(6)
     if (has_ms) {
       if (ran) publish_from_frame(f, org, me);
       me.status = status;

@@ -170,8 +170,9 @@ FDM_HELPER double f16_kinemat2(const double d0, const double d1, const double t1
   Input = f16_constrain(d0, Input, d1);
   if (dt > 0.0 && !f16_equal_to_roundoff(Input, Output)) {
     if (t1 <= 0.0) return Input;
-    const double Rate = (d1 - d0) / t1;
-    const double ThisDt = fabs((Input - Output) / Rate);
+    // d0, d1, t1 are literals: Rate and its reciprocal fold at compile time (no fp64 division on the actuator chain)
+    const double Rate = (d1 - d0) / t1, invRate = t1 / (d1 - d0);
+    const double ThisDt = fabs((Input - Output) * invRate);
     if (dt < ThisDt) { if (Output < Input) Output += dt * Rate; else Output -= dt * Rate; }
     else Output = Input;
   }
@@ -187,6 +188,9 @@ FDM_HELPER double f16_powpos(const double x, const double y) { return exp(y * lo
 struct AtmoConst {
   double H[9], Tt[9], Lapse[8], PB[9], DB[9], Tmb[8];  // Tmb[b] = GetTemperature(GeometricAltitude(H[b]))
   double Reng, g0, EarthRadius, SLdensity, StdDaySLsoundspeed, StdDaySLpressure;
+  // per-layer constants of the expressions below, so that no division by a constant is left on the device:
+  // invdH[r] = 1 / (H[r] - H[r-1]), Pexp[b] = g0 / (Reng * Lapse[b]), Piso[b] = -g0 / (Reng * Tmb[b]), invSLdensity
+  double invdH[9], Pexp[8], Piso[8], invSLdensity;
 };
 struct Atmo { double T, P, rho, a, density_altitude; };
 FDM_DEV double atmo_geopot(const AtmoConst& c, double h) { return (h * c.EarthRadius) / (c.EarthRadius + h); }
@@ -201,7 +205,7 @@ FDM_DEV void atmosphere_calculate(const AtmoConst& c, double altitude, Atmo& o) 
     else {
       int r = 1;
       while (r < 8 && c.H[r] < G) r++;
-      double f = (G - c.H[r - 1]) / (c.H[r] - c.H[r - 1]);
+      double f = (G - c.H[r - 1]) * c.invdH[r];
       if (f > 1.0) f = 1.0;
       Tm = f * (c.Tt[r] - c.Tt[r - 1]) + c.Tt[r - 1];
     }
@@ -212,8 +216,8 @@ FDM_DEV void atmosphere_calculate(const AtmoConst& c, double altitude, Atmo& o) 
   for (; b < 7; ++b) { const double testAlt = c.H[b + 1]; if (G < testAlt) break; BaseAlt = testAlt; }
   const double Tmb = c.Tmb[b], deltaH = G - BaseAlt, Lmb = c.Lapse[b];
   double Pm;
-  if (Lmb != 0.0) Pm = c.PB[b] * f16_powpos(Tmb / (Tmb + Lmb * deltaH), c.g0 / (c.Reng * Lmb));
-  else Pm = c.PB[b] * exp(-c.g0 * deltaH / (c.Reng * Tmb));
+  if (Lmb != 0.0) Pm = c.PB[b] * f16_powpos(Tmb / (Tmb + Lmb * deltaH), c.Pexp[b]);
+  else Pm = c.PB[b] * exp(c.Piso[b] * deltaH);
   o.T = Tm; o.P = Pm; o.rho = Pm / (c.Reng * Tm);
   o.a = sqrt(1.4 * c.Reng * Tm);
   // CalculateDensityAltitude :464-492.  On a standard day (the reference never biases temperature or pressure) the
@@ -564,7 +568,7 @@ FDM_DEV void fdm_stage_auxiliary(const AcCore& a, Props& p, Frame& f, const Atmo
     p.velocities_mach = f.mach; p.velocities_vc_kts = f.vcas * FPSTOKTS; p.velocities_vg_fps = Vground;
     p.velocities_p_aero_rad_sec = f.pqr.x; p.velocities_q_aero_rad_sec = f.pqr.y; p.velocities_r_aero_rad_sec = f.pqr.z;
     p.accelerations_n_pilot_y_norm = f.pilotN.y; p.accelerations_n_pilot_z_norm = f.pilotN.z;
-    p.aero_h_b_mac_ft = (f.geodAlt - vMacz) / K_bw;
+    p.aero_h_b_mac_ft = (f.geodAlt - vMacz) * (1.0 / K_bw);
   }
 }
 
@@ -596,17 +600,18 @@ FDM_DEV double fdm_stage_engine(AcCore& a, const Props& p, const Atmo& atm, cons
     thrust = 0.0;
   } else {  // tpRun (:196-272)
     const double idlethrust = K_ENG_milthrust * idleT, milthrust = (K_ENG_milthrust - idlethrust) * milT;
-    const double sigma = atm.rho / ac.SLdensity;
+    const double sigma = atm.rho * ac.invSLdensity;
     const double n = fmin(1.0, a.N2norm + 0.1);
     const double sden = (1 + 3 * (1 - n) * (1 - n) * (1 - n) + (1 - sigma));
     const double dbase = 90.0 / (K_ENG_bypassratio + 3.0);
-    const double up = (1.0 * dbase) / sden, dn2 = (3.0 * dbase) / sden, dn1 = (2.4 * dbase) / sden;
+    const double rden = 1.0 / sden;   // one reciprocal for the three spool rates
+    const double up = (1.0 * dbase) * rden, dn2 = (3.0 * dbase) * rden, dn1 = (2.4 * dbase) * rden;
     a.N2 = seek(a.N2, K_ENG_idlen2 + ThrottlePos * N2_factor, up, dn2);
     a.N1 = seek(a.N1, K_ENG_idlen1 + ThrottlePos * N1_factor, up, dn1);
-    a.N2norm = (a.N2 - K_ENG_idlen2) / N2_factor;
+    a.N2norm = (a.N2 - K_ENG_idlen2) * (1.0 / N2_factor);
     thrust = idlethrust + (milthrust * a.N2norm * a.N2norm);
     if (!augmentation) {
-      const double tsfc = K_ENG_tsfc * sqrt(atm.T / 389.7) * (0.84 + (1 - a.N2norm) * (1 - a.N2norm));
+      const double tsfc = K_ENG_tsfc * sqrt(atm.T * (1.0 / 389.7)) * (0.84 + (1 - a.N2norm) * (1 - a.N2norm));
       a.FF = seek(a.FF, thrust * tsfc, 1000.0, 10000.0);
       if (a.FF < K_ENG_idleff) a.FF = K_ENG_idleff;
     }
@@ -629,7 +634,9 @@ FDM_DEV bool fdm_stage_consume_fuel(AcCore& a, const double dt, const bool starv
     const int n_with = (a.tank0 > 0.0) + (a.tank1 > 0.0) + (a.tank2 > 0.0) + (a.tank3 > 0.0);
     starved_next = (n_with == 0);
     if (n_with > 0) {
-      const double per = ((a.FF / 3600.0) * dt) / n_with;
+      // n_with is 1..4: its reciprocal is a select, not a division
+      const double inv_n = n_with == 2 ? 0.5 : (n_with == 4 ? 0.25 : (n_with == 1 ? 1.0 : 1.0 / 3.0));
+      const double per = ((a.FF * (1.0 / 3600.0)) * dt) * inv_n;
       auto drain = [per](double& c) { if (c > 0.0) { if (c - per >= 0.0) c -= per; else c = 0.0; } };
       drain(a.tank0); drain(a.tank1); drain(a.tank2); drain(a.tank3);
     }
@@ -808,8 +815,9 @@ FDM_DEV void fdm_reset(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
   a.wi = v3(ic.p, ic.q, ic.r) + mul(Ti2b, Omega);
   a.vi = mulT(Ti2b, icUVW) + cross(Omega, a.ri);
   // RunIC: two suspended-integration passes (Initialize()'s Run + RunIC's Run), then InitializeDerivatives
-  fdm_frame(a, p, s, f, T, ac, 0.0, fcs_dt, false);
-  fdm_frame(a, p, s, f, T, ac, 0.0, fcs_dt, false);
+  // (one copy of the frame code, run twice: the reset kernel executes cold, its cost is instruction fetch)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) fdm_frame(a, p, s, f, T, ac, 0.0, fcs_dt, false);
   a.dqv0 = a.vi; a.dqv1 = a.vi; a.dqa0 = a.uvwidot;
   // engine.init_running(): N2 = IdleN2 + ThrottlePos*N2_factor with the throttle still at its IC value
   {
@@ -838,7 +846,8 @@ FDM_DEV void fdm_reset(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
     bool augmentation = false;
     double currentThrust = 0, lastThrust = -1;
     int steady_count = 0, j = 0;
-    bool steady = false;
+    bool steady = false, pAug = false;
+    double pN1 = -1.0, pN2 = -1.0, pFF = -1.0;
     while (!steady && j < 6000) {
       const double n = fmin(1.0, a.N2norm + 0.1);
       const double sden = (1 + 3 * (1 - n) * (1 - n) * (1 - n) + (1 - sigma));
@@ -862,6 +871,10 @@ FDM_DEV void fdm_reset(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
       if (fabs(lastThrust - currentThrust) < 0.0001) { steady_count++; if (steady_count > 120) steady = true; }
       else steady_count = 0;
       j++;
+      // Exact shortcut: once an iteration leaves the whole engine state bit-identical, every further iteration is the
+      // same map on the same state, so the reference's count to 120 equal thrusts ends with exactly this state.
+      if (a.N1 == pN1 && a.N2 == pN2 && a.FF == pFF && augmentation == pAug && lastThrust == currentThrust) break;
+      pN1 = a.N1; pN2 = a.N2; pFF = a.FF; pAug = augmentation;
     }
     f.thrust = currentThrust;
     a.engflags = (double)(augmentation ? 2 : 0);

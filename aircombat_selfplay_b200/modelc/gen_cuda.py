@@ -272,8 +272,10 @@ class CudaGen:
             elif t == "aerosurface_scale":
                 code.append(f"    {{ const double in = {ins[0]};")
                 if c["zero_centered"]:
-                    code.append(f"      if (in == 0.0) out = 0.0; else if (in > 0) out = (in / {lit(c['in_max'])}) * {lit(c['out_max'])}; "
-                                f"else out = (in / {lit(c['in_min'])}) * {lit(c['out_min'])};")
+                    def over(d):   # in / d; a domain limit other than 0, +-1 becomes a multiplication by its reciprocal
+                        return f"(in / {lit(d)})" if d in (0.0, 1.0, -1.0) else f"(in * (1.0 / {lit(d)}))"
+                    code.append(f"      if (in == 0.0) out = 0.0; else if (in > 0) out = {over(c['in_max'])} * {lit(c['out_max'])}; "
+                                f"else out = {over(c['in_min'])} * {lit(c['out_min'])};")
                 else:
                     code.append(f"      out = {lit(c['out_min'])} + ((in - {lit(c['in_min'])}) / ({lit(c['in_max'])} - {lit(c['in_min'])})) * "
                                 f"({lit(c['out_max'])} - {lit(c['out_min'])});")
@@ -334,7 +336,7 @@ class CudaGen:
         for f in self.ir["aero_pre"]:
             code.append(f"  p.{cid(f['name'])} = {self.product(f['factors'], scope)};")
         code.append("  // FGAerodynamics::Run: bi2vel/ci2vel after the pre-functions (J/models/FGAerodynamics.cpp:152-158)")
-        code.append("  if (twovel != 0) { p.aero_bi2vel = K_bw / twovel; p.aero_ci2vel = K_cbarw / twovel; }")
+        code.append("  if (twovel != 0) { const double r2v = 1.0 / twovel; p.aero_bi2vel = K_bw * r2v; p.aero_ci2vel = K_cbarw * r2v; }")
         for ax in self.ir["aero_axes"]:
             i = AXES.index(ax["axis"])
             code.append(f"  // axis {ax['axis']}")

@@ -47,15 +47,51 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic(kernel: str, config: str, n_envs: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this exact workload (profiles/traffic.json, written next to the ncu summaries); null when there is none."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        return json.loads(p.read_text()).get(f"{kernel}|{config}|{n_envs}")
+    return None
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a
+    thread every 2 ms (the timed region of the small configs lasts tens of milliseconds, shorter than one `nvidia-smi
+    -lms` period); `nvidia-smi` is the fallback when NVML cannot be loaded."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.h = index, [], None, None, None
+        self.sm, self.mask, self.mx, self._stop = [], 0, None, threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except TypeError:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [x for x in vis.split(",") if x.strip().isdigit()]
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(int(ids[self.index]) if self.index < len(ids) else self.index)
 
     def start(self):
+        try:
+            self.nvml, self.h = self._nvml_handle()
+            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -64,11 +100,33 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1)
+            n, names = self.nvml, []
+            for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+                bit = getattr(n, attr, None) or getattr(n, attr.replace("ClocksEventReason", "ClocksThrottleReason"), 0)
+                if bit and (self.mask & bit):
+                    names.append(name)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": names, "samples": len(sm),
+                    "source": "nvml, 2 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -87,7 +145,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 def _dist_init(backend):
@@ -247,8 +306,9 @@ def run_b200(args):
     bytes_per_agent_step = (2 * n_state + n_out + 11 + 11) * 8 + 2 * 4 + (4 + spec.shoot_dim) * 4
     k_ms = kms["substeps"] / max(ksteps, 1)
     ach = n_envs * A * bytes_per_agent_step / (k_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_env_substeps", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_agent_step": bytes_per_agent_step,
+    kname = "k_env_substeps_split" if batch.get_option("frame_split_effective") else "k_env_substeps"
+    roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": _ncu_traffic(kname, config, n_envs), "peak_source": peak_src, "algorithmic_bytes_per_agent_step": bytes_per_agent_step,
             "kernel_ms": k_ms, "kernel_share_of_step": kms["substeps"] / max(sum(kms.values()), 1e-12),
             "post_ms": kms["post"] / max(ksteps, 1), "reset_ms": kms["reset"] / max(ksteps, 1),
             "note": "the fused K-substep kernel is fp64-pipe/latency bound, not HBM bound (DESIGN.md section 5); fp64 view below"}

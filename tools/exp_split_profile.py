@@ -21,8 +21,7 @@ out = (ctypes.c_longlong * 16)()
 capi.lib().acs_debug_split_profile.argtypes = [ctypes.c_void_p]
 assert capi.lib().acs_debug_split_profile(out) == 0
 a, bb = list(out[:8]), list(out[8:])
-K = 12
-print(os.environ.get("ACS_LIB"), "cycles per frame (avg over 12)")
-print("A: pre+propagate %d | wait1 %d | grav..aux %d | wait2 %d | engine+aeroA %d | wait3 %d | accel %d | tail(missile/out) %d" % tuple(x // K for x in (a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7])))
-print("B: idle-top %d | wait1 %d | fcs %d | wait2 %d | aeroB %d | wait3 %d" % tuple(x // K for x in bb[:6]))
-print("A total/frame", sum(a) // K, "B total/frame", sum(bb) // K)
+t0 = a[6]
+print(os.environ.get("ACS_LIB"), "timeline of frame 6 of pair 0 (cycles after role A's loop top)")
+print("A: loop top 0 | arrive b1 %d release %d | arrive b2 %d release %d | arrive b3 %d release %d | next loop top %d" % tuple(x - t0 for x in a[:6] + [a[7]]))
+print("B:            | arrive b1 %d release %d | arrive b2 %d release %d | arrive b3 %d release %d" % tuple(x - t0 for x in bb[:6]))
