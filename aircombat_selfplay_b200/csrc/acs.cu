@@ -288,12 +288,16 @@ struct AcsEnv {
   AcsHandle* fdm;
   EnvView v;
   int G, lg;   // lanes per env (1, 2, 4 or 8) and its log2
+  EnvView tpl;                   // one-env arena holding the reset template (tpl.fdm == nullptr: none, e.g. the heading task)
+  bool tpl_enabled = true;
   int frame_split = -1;          // substep kernel: 0 one thread per aircraft, 1 two-warp frame, -1 by batch size
   int split_max_threads = 0;     // auto: use the two-warp frame up to this many aircraft lanes
   bool timing = false;
   std::vector<cudaEvent_t> ev;   // 4 events per timed step: before substeps, after substeps, after post, after reset
   size_t ev_used = 0;
 };
+
+static int build_reset_template(AcsEnv* e);
 
 static cudaEvent_t timing_event(AcsEnv* e, cudaStream_t st) {
   if (e->ev_used == e->ev.size()) { cudaEvent_t x; cudaEventCreate(&x); e->ev.push_back(x); }
@@ -361,6 +365,19 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
   CUDA_TRY(cudaMalloc(&v.mi, sizeof(int) * N_MI * ms));      CUDA_TRY(cudaMemset(v.mi, 0, sizeof(int) * N_MI * ms));
   // episode counters start at -1 so the first reset is episode 0
   CUDA_TRY(cudaMemset(v.ei + (size_t)EI_EPISODE * B, 0xff, sizeof(int) * B));
+  // reset template (k_env_reset_task): every task with fixed per-lane initial conditions
+  std::memset(&e->tpl, 0, sizeof(EnvView));
+  if (const char* s = std::getenv("ACS_RESET_TEMPLATE")) e->tpl_enabled = std::atoi(s) != 0;
+  if (cfg->obs_kind != ACS_OBS_HEADING && e->tpl_enabled) {
+    EnvView& t = e->tpl;
+    t.B = 1; t.A = A; t.S = v.S; t.rows = A;
+    CUDA_TRY(cudaMalloc(&t.fdm, sizeof(double) * N_STATE * A)); CUDA_TRY(cudaMalloc(&t.out, sizeof(double) * FDM_N_OUT * A));
+    CUDA_TRY(cudaMalloc(&t.ad, sizeof(double) * N_AD * A));     CUDA_TRY(cudaMalloc(&t.ai, sizeof(int) * N_AI * A));
+    CUDA_TRY(cudaMalloc(&t.ed, sizeof(double) * N_ED));         CUDA_TRY(cudaMalloc(&t.ei, sizeof(int) * N_EI));
+    CUDA_TRY(cudaMemset(t.ad, 0, sizeof(double) * N_AD * A));   CUDA_TRY(cudaMemset(t.ai, 0, sizeof(int) * N_AI * A));
+    CUDA_TRY(cudaMemset(t.ed, 0, sizeof(double) * N_ED));       CUDA_TRY(cudaMemset(t.ei, 0, sizeof(int) * N_EI));
+    if (build_reset_template(e)) return 1;
+  }
   // substep-kernel choice: the two-warp frame wins while the batch leaves SM sub-partitions idle
   {
     cudaDeviceProp prop;
@@ -382,6 +399,21 @@ int acs_env_set_option(AcsEnv* e, const char* name, int value) {
   return fail(std::string("acs_env_set_option: unknown option ") + name);
 }
 
+} // extern "C"
+
+// sim.reload() of every lane on the one-env template arena (legacy stream, synchronous: called at create / when the
+// initial conditions change, never on the step path)
+static int build_reset_template(AcsEnv* e) {
+  if (e->tpl.fdm == nullptr) return 0;
+  CUDA_TRY(cudaDeviceSynchronize());
+  k_env_reset_fdm<<<1, FDM_BLOCK>>>(e->tpl, e->cfg, e->lg, nullptr);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  return 0;
+}
+
+extern "C" {
+
 int acs_env_get_option(const AcsEnv* e, const char* name, int* value) {
   if (!e || !name || !value) return fail("acs_env_get_option: null argument");
   if (!std::strcmp(name, "frame_split")) { *value = e->frame_split; return 0; }
@@ -397,6 +429,7 @@ int acs_env_destroy(AcsEnv* e) {
   if (!e) return 0;
   cudaSetDevice(e->fdm->device);
   cudaFree(e->v.ad); cudaFree(e->v.ai); cudaFree(e->v.ed); cudaFree(e->v.ei); cudaFree(e->v.md); cudaFree(e->v.mi);
+  if (e->tpl.fdm) { cudaFree(e->tpl.fdm); cudaFree(e->tpl.out); cudaFree(e->tpl.ad); cudaFree(e->tpl.ai); cudaFree(e->tpl.ed); cudaFree(e->tpl.ei); }
   for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
   acs_destroy(e->fdm);
   delete e;
@@ -406,7 +439,7 @@ int acs_env_destroy(AcsEnv* e) {
 int acs_env_set_init_states(AcsEnv* e, const double* init_host) {
   if (!e || !init_host) return fail("acs_env_set_init_states: null argument");
   std::memcpy(e->cfg.init_state, init_host, sizeof(double) * 12 * e->v.A);
-  return 0;
+  return build_reset_template(e);
 }
 
 AcsHandle* acs_env_fdm(AcsEnv* e) { return e ? e->fdm : nullptr; }
@@ -422,9 +455,11 @@ int acs_env_reset(AcsEnv* e, const uint8_t* env_mask_dev, double* obs_dev, doubl
   if (!e || !obs_dev) return fail("acs_env_reset: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int threads = e->v.B * e->G;
-  k_env_reset_fdm<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, env_mask_dev);
-  CUDA_TRY(cudaGetLastError());
-  k_env_reset_task<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg, env_mask_dev, obs_dev, share_obs_dev);
+  if (e->tpl.fdm == nullptr) {
+    k_env_reset_fdm<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, env_mask_dev);
+    CUDA_TRY(cudaGetLastError());
+  }
+  k_env_reset_task<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg, env_mask_dev, obs_dev, share_obs_dev, e->tpl);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -1189,9 +1189,13 @@ __global__ void __launch_bounds__(FDM_BLOCK) k_env_reset_fdm(const EnvView v, co
   AI(v, AI_STATUS, L.row) = ST_ALIVE;
 }
 // Stage 2: task.reset + reward-function resets + get_obs for masked envs.
+// With a reset template (tpl.fdm != nullptr) stage 1 is folded in: every task but the heading task reloads each aircraft
+// from fixed per-lane initial conditions, so sim.reload() always produces the same state.  It is computed once per
+// handle by k_env_reset_fdm on a one-env arena (acs_env_create / acs_env_set_init_states) and copied here -- bit-identical
+// to recomputing it, and the auto-reset that follows every step no longer launches the 2-frame FDM reload.
 __global__ void __launch_bounds__(128) k_env_reset_task(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
                                                         const uint8_t* __restrict__ env_mask, double* __restrict__ obs,
-                                                        double* __restrict__ share_obs) {
+                                                        double* __restrict__ share_obs, const EnvView tpl) {
   __shared__ PubAc sP[128];
   const Lane L = lane_setup(v, lg);
   const int A = v.A;
@@ -1199,6 +1203,16 @@ __global__ void __launch_bounds__(128) k_env_reset_task(const EnvView v, const _
   if (!__syncthreads_or(on)) return;
   PubAc me;
   me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
+  if (on && tpl.fdm != nullptr) {
+    const int row = L.row, N = v.rows, l = L.lane;
+    for (int k = 0; k < FDM_N_CORE + F16_N_CARRIED; k++) v.fdm[(size_t)k * N + row] = tpl.fdm[k * A + l];
+    for (int k = 0; k < FDM_N_OUT; k++) v.out[(size_t)k * N + row] = tpl.out[k * A + l];
+    // what store_derived and the tail of k_env_reset_fdm write
+    const int adf[12] = {AD_POS_N, AD_POS_E, AD_POS_U, AD_VEL_N, AD_VEL_E, AD_VEL_D, AD_H_SL_M, AD_U_MPS, AD_V_MPS, AD_W_MPS, AD_VC_MPS, AD_BLOODS};
+#pragma unroll
+    for (int k = 0; k < 12; k++) AD(v, adf[k], row) = tpl.ad[adf[k] * A + l];
+    AI(v, AI_STATUS, row) = ST_ALIVE;
+  }
   if (on) {
     const int row = L.row;
     const int nm = cfg.num_missiles[L.lane];

@@ -179,3 +179,31 @@ def test_two_warp_frame_matches_one_thread_frame():
     (_, sa), (_, sb) = bs[0].arena("fdm"), bs[1].arena("fdm")
     scale = sa.abs().amax(dim=1, keepdim=True).clamp_min(1.0)
     assert float(((sa - sb).abs() / scale).max()) < 1e-8
+
+
+def test_reset_template_is_bit_identical_to_a_recomputed_reload(monkeypatch):
+    """Fixed per-lane initial conditions: the auto-reset copies the FDM reload computed once per handle (reset template)
+    instead of recomputing it; both give the same bits, also after set_init_states."""
+    from aircombat_selfplay_b200.capi import EnvBatch
+    spec = load_spec("scenario2/scenario2")
+    spec.max_steps = 4
+    n = 70
+    bs = []
+    for tpl in ("0", "1"):
+        monkeypatch.setenv("ACS_RESET_TEMPLATE", tpl)
+        b = EnvBatch(spec, n, seed=3)
+        b.reset()
+        bs.append(b)
+    rng = np.random.default_rng(1)
+    for t in range(10):
+        if t == 5:
+            init = close_init_states(spec, np.random.default_rng(7))
+            for b in bs:
+                b.set_init_states(init)
+        act = torch.tensor(random_actions(rng, spec, n), device="cuda")
+        for b in bs:
+            b.step(act, auto_reset=True)
+        assert torch.equal(bs[0].out_buf, bs[1].out_buf), t
+    for name in ("fdm", "out", "ac_d", "ac_i", "env_i"):
+        assert torch.equal(bs[0].arena(name)[1], bs[1].arena(name)[1]), name
+    assert int(bs[0].arena("env_i")[1][bs[0].arena("env_i")[0].index("episode")].min()) >= 2
