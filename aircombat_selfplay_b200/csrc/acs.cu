@@ -290,6 +290,7 @@ struct AcsEnv {
   int G, lg;   // lanes per env (1, 2, 4 or 8) and its log2
   EnvView tpl;                   // one-env arena holding the reset template (tpl.fdm == nullptr: none, e.g. the heading task)
   bool tpl_enabled = true;
+  bool fused_reset = true;       // auto-reset inside k_env_post (needs the template)
   int frame_split = -1;          // substep kernel: 0 one thread per aircraft, 1 two-warp frame, -1 by batch size
   int split_max_threads = 0;     // auto: use the two-warp frame up to this many aircraft lanes
   bool timing = false;
@@ -368,6 +369,7 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
   // reset template (k_env_reset_task): every task with fixed per-lane initial conditions
   std::memset(&e->tpl, 0, sizeof(EnvView));
   if (const char* s = std::getenv("ACS_RESET_TEMPLATE")) e->tpl_enabled = std::atoi(s) != 0;
+  if (const char* s = std::getenv("ACS_FUSED_RESET")) e->fused_reset = std::atoi(s) != 0;
   if (cfg->obs_kind != ACS_OBS_HEADING && e->tpl_enabled) {
     EnvView& t = e->tpl;
     t.B = 1; t.A = A; t.S = v.S; t.rows = A;
@@ -476,11 +478,13 @@ int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double*
   else k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   CUDA_TRY(cudaGetLastError());
   if (e->timing) timing_event(e, st);
-  k_env_post<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg, obs_dev, share_obs_dev, rewards_dev, dones_dev, info_dev, env_done_dev);
+  const int fuse = (auto_reset && e->tpl.fdm != nullptr && e->fused_reset) ? 1 : 0;
+  k_env_post<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg, obs_dev, share_obs_dev, rewards_dev, dones_dev, info_dev, env_done_dev,
+                                                   fuse, e->tpl);
   CUDA_TRY(cudaGetLastError());
   if (e->timing) timing_event(e, st);
   int rc = 0;
-  if (auto_reset) rc = acs_env_reset(e, env_done_dev, obs_dev, share_obs_dev, stream);
+  if (auto_reset && !fuse) rc = acs_env_reset(e, env_done_dev, obs_dev, share_obs_dev, stream);
   if (e->timing) timing_event(e, st);
   return rc;
 }

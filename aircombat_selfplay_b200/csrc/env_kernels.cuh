@@ -1050,9 +1050,17 @@ ENV_DEV int agent_termination(const StepCtx& c, int a) {
   return -1;
 }
 
+__device__ __noinline__ void reset_task_lanes(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const bool on, PubAc* sP,
+                                              double* __restrict__ obs, double* __restrict__ share_obs, const EnvView& tpl);
+
+// fuse_reset != 0 (auto-reset with a reset template, i.e. every task but the heading task): an env whose agents are all
+// done is reset right here -- rewards / dones / info of the terminal step are already written, the reset observation
+// replaces the terminal one (R/envs/env_wrappers.py:191-204) -- instead of by two more kernel launches whose code
+// would be fetched cold.
 __global__ void __launch_bounds__(128) k_env_post(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg, double* __restrict__ obs,
                                                   double* __restrict__ share_obs, double* __restrict__ rewards,
-                                                  uint8_t* __restrict__ dones, int32_t* __restrict__ info, uint8_t* __restrict__ env_done) {
+                                                  uint8_t* __restrict__ dones, int32_t* __restrict__ info, uint8_t* __restrict__ env_done,
+                                                  const int fuse_reset, const EnvView tpl) {
   __shared__ PubAc sP[128];
   __shared__ double sRew[128];
   __shared__ int sDone[128];
@@ -1143,6 +1151,12 @@ __global__ void __launch_bounds__(128) k_env_post(const EnvView v, const __grid_
       EI(v, EI_CURRENT_STEP, L.env) = cs;
     }
   }
+  if (fuse_reset) {
+    bool all = L.valid;
+    for (int j = 0; j < A; j++) all = all && sDone[L.gbase + j];
+    // the reset synchronises the lanes of each env on their mask: the whole warp takes the call together
+    if (__any_sync(0xffffffffu, all)) reset_task_lanes(v, cfg, L, all, sP, obs, share_obs, tpl);
+  }
 }
 
 // ============================================================================================== reset
@@ -1193,24 +1207,42 @@ __global__ void __launch_bounds__(FDM_BLOCK) k_env_reset_fdm(const EnvView v, co
 // from fixed per-lane initial conditions, so sim.reload() always produces the same state.  It is computed once per
 // handle by k_env_reset_fdm on a one-env arena (acs_env_create / acs_env_set_init_states) and copied here -- bit-identical
 // to recomputing it, and the auto-reset that follows every step no longer launches the 2-frame FDM reload.
-__global__ void __launch_bounds__(128) k_env_reset_task(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
-                                                        const uint8_t* __restrict__ env_mask, double* __restrict__ obs,
-                                                        double* __restrict__ share_obs, const EnvView tpl) {
-  __shared__ PubAc sP[128];
-  const Lane L = lane_setup(v, lg);
+// The lanes of the environments being reset (`on`): used by k_env_reset_task and, fused, by k_env_post's auto-reset.
+// sP is the block's PubAc exchange array; every lane of the warp calls this (warp-level syncs on the env's lane mask).
+__device__ __noinline__ void reset_task_lanes(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const bool on, PubAc* sP,
+                                              double* __restrict__ obs, double* __restrict__ share_obs, const EnvView& tpl) {
   const int A = v.A;
-  const bool on = L.valid && (env_mask == nullptr || env_mask[L.env]);
-  if (!__syncthreads_or(on)) return;
   PubAc me;
   me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
   if (on && tpl.fdm != nullptr) {
     const int row = L.row, N = v.rows, l = L.lane;
-    for (int k = 0; k < FDM_N_CORE + F16_N_CARRIED; k++) v.fdm[(size_t)k * N + row] = tpl.fdm[k * A + l];
-    for (int k = 0; k < FDM_N_OUT; k++) v.out[(size_t)k * N + row] = tpl.out[k * A + l];
+    // batches of independent loads first, then the stores: the two arenas may alias as far as the compiler knows, and a
+    // load -> store -> load chain would pay one (cold) memory round trip per field
+    const double* __restrict__ tf = tpl.fdm; const double* __restrict__ to = tpl.out; const double* __restrict__ ta = tpl.ad;
+    constexpr int NS = FDM_N_CORE + F16_N_CARRIED, CH = 25;
+    static_assert(NS % CH == 0 && FDM_N_OUT == CH, "template copy is written for 25-field batches");
+#pragma unroll 1
+    for (int k0 = 0; k0 < NS; k0 += CH) {
+      double t[CH];
+#pragma unroll
+      for (int j = 0; j < CH; j++) t[j] = __ldg(tf + (k0 + j) * A + l);
+#pragma unroll
+      for (int j = 0; j < CH; j++) v.fdm[(size_t)(k0 + j) * N + row] = t[j];
+    }
+    {
+      double t[CH];
+#pragma unroll
+      for (int j = 0; j < CH; j++) t[j] = __ldg(to + j * A + l);
+#pragma unroll
+      for (int j = 0; j < CH; j++) v.out[(size_t)j * N + row] = t[j];
+    }
     // what store_derived and the tail of k_env_reset_fdm write
     const int adf[12] = {AD_POS_N, AD_POS_E, AD_POS_U, AD_VEL_N, AD_VEL_E, AD_VEL_D, AD_H_SL_M, AD_U_MPS, AD_V_MPS, AD_W_MPS, AD_VC_MPS, AD_BLOODS};
+    double t[12];
 #pragma unroll
-    for (int k = 0; k < 12; k++) AD(v, adf[k], row) = tpl.ad[adf[k] * A + l];
+    for (int k = 0; k < 12; k++) t[k] = __ldg(ta + adf[k] * A + l);
+#pragma unroll
+    for (int k = 0; k < 12; k++) AD(v, adf[k], row) = t[k];
     AI(v, AI_STATUS, row) = ST_ALIVE;
   }
   if (on) {
@@ -1264,4 +1296,14 @@ __global__ void __launch_bounds__(128) k_env_reset_task(const EnvView v, const _
     const double* src = obs + (size_t)L.env * A * D;
     for (int i = 0; i < A * D; i++) so[i] = src[i];
   }
+}
+
+__global__ void __launch_bounds__(128) k_env_reset_task(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
+                                                        const uint8_t* __restrict__ env_mask, double* __restrict__ obs,
+                                                        double* __restrict__ share_obs, const EnvView tpl) {
+  __shared__ PubAc sP[128];
+  const Lane L = lane_setup(v, lg);
+  const bool on = L.valid && (env_mask == nullptr || env_mask[L.env]);
+  if (!__syncthreads_or(on)) return;
+  reset_task_lanes(v, cfg, L, on, sP, obs, share_obs, tpl);
 }

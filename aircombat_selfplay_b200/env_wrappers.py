@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import taskspec as ts
+from .capi import AcsError
 from .envs import BatchedEnv, LazyInfo, _SingleEnvBase
 
 
@@ -97,6 +98,10 @@ class BatchedVecEnv(VecEnv):
         for i in range(num_envs):
             self._infos[i] = LazyInfo(src, i)
         self._pending = False
+        # the whole host-facing step -- pinned H2D of the actions, (controller +) env kernels, D2H of the packed outputs --
+        # replays as ONE CUDA graph: one launch per step instead of a copy, four kernels and a copy
+        self.use_cuda_graph = True
+        self._g, self._g_epoch = None, -1
         self.h2d_bytes_per_step = self._act_host.numel() * 4
         self.d2h_bytes_per_step = self._host.numel()
 
@@ -116,7 +121,7 @@ class BatchedVecEnv(VecEnv):
         N, A, D = obs.shape
         return np.broadcast_to(obs.reshape(N, 1, A * D), (N, A, A * D))
 
-    def _put_actions(self, actions):
+    def _put_actions(self, actions, h2d=True):
         a = self._act_np
         if isinstance(actions, np.ndarray) and actions.shape == a.shape:
             np.copyto(a, actions, casting="unsafe")
@@ -126,7 +131,8 @@ class BatchedVecEnv(VecEnv):
                     if isinstance(x, (tuple, list)):
                         x = np.concatenate([np.atleast_1d(np.asarray(y)).ravel() for y in x])
                     a[i, j, :] = np.asarray(x).ravel()
-        self._act_dev.copy_(self._act_host, non_blocking=True)
+        if h2d:
+            self._act_dev.copy_(self._act_host, non_blocking=True)
 
     # ------------------------------------------------------------------ VecEnv
     def reset(self):
@@ -136,16 +142,40 @@ class BatchedVecEnv(VecEnv):
         obs = self._arr("obs")
         return (obs, self._share(obs)) if self.share else obs
 
+    def _capture(self):
+        core = self.core
+        core._warm_for_capture()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._act_dev.copy_(self._act_host, non_blocking=True)
+            core._step_body(self._act_dev)
+            self._host.copy_(core.batch.out_buf, non_blocking=True)
+        self._g, self._g_epoch = g, core._epoch
+
     def step_async(self, actions):
-        with torch.cuda.device(self.core.device):
-            self._put_actions(actions)
-            self.core.step(self._act_dev)
+        core = self.core
+        with torch.cuda.device(core.device):
+            if self.use_cuda_graph and not core._timing:
+                if not core._was_reset:
+                    raise AcsError("step() called before reset()")
+                self._put_actions(actions, h2d=False)
+                if self._g is None or self._g_epoch != core._epoch:
+                    self._capture()
+                self._g.replay()
+                self._graphed = True
+            else:
+                self._put_actions(actions)
+                core.step(self._act_dev)
+                self._graphed = False
         self._pending = True
 
     def step_wait(self):
         assert self._pending, "step_wait() without step_async()"
         with torch.cuda.device(self.core.device):
-            self._fetch()
+            if self._graphed:      # the D2H copy is the graph's last node
+                torch.cuda.current_stream(self.core.device).synchronize()
+            else:
+                self._fetch()
         self._pending = False
         N, A = self.num_envs, self.num_agents
         obs = self._arr("obs")

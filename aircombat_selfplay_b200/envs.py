@@ -99,6 +99,7 @@ class BatchedEnv:
         # tasks launch their four kernels directly (a graph launch costs more than it saves there: measured +20%).
         self.use_cuda_graph = self.hier if use_cuda_graph is None else bool(use_cuda_graph)
         self._graph = None
+        self._epoch = 0             # bumped whenever a captured step goes stale (host wrappers hold graphs of their own)
         self._act_in = torch.zeros((n_envs, self.n_agents, self.act_dim), dtype=torch.int32, device=self.device)
         self._timing = False
 
@@ -119,6 +120,7 @@ class BatchedEnv:
         self.seed_value = int(seed or 0)
         self.batch.set_seed(self.seed_value)
         self._graph = None          # the seed is a kernel parameter baked into the captured step
+        self._epoch += 1
         return [seed]
 
     def set_init_states(self, init_states):
@@ -126,6 +128,7 @@ class BatchedEnv:
         reset_simulators_curriculum, E/envs/singlecombat_env.py:45-122)."""
         self.batch.set_init_states(init_states)
         self._graph = None
+        self._epoch += 1
 
     def set_curriculum_angle(self, angle: int):
         """Curriculum stage of the *_curriculum / wvr / maneuver_curriculum tasks: the following resets start from
@@ -212,7 +215,7 @@ class BatchedEnv:
                 self.opponents.reset(self.batch.env_done)
         return out
 
-    def _capture(self):
+    def _warm_for_capture(self):
         if self.hier:      # warm the controller's cuBLAS / LayerNorm paths outside the capture, leaving no trace in the state
             keep = [self.rnn, self._low]
             if self.opponents is not None:
@@ -223,6 +226,9 @@ class BatchedEnv:
             for t, s0 in zip(keep, saved):
                 t.copy_(s0)
         torch.cuda.synchronize(self.device)
+
+    def _capture(self):
+        self._warm_for_capture()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._graph_out = self._step_body(self._act_in)

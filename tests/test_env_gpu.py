@@ -189,8 +189,9 @@ def test_reset_template_is_bit_identical_to_a_recomputed_reload(monkeypatch):
     spec.max_steps = 4
     n = 70
     bs = []
-    for tpl in ("0", "1"):
+    for tpl, fused in (("0", "0"), ("1", "0"), ("1", "1")):
         monkeypatch.setenv("ACS_RESET_TEMPLATE", tpl)
+        monkeypatch.setenv("ACS_FUSED_RESET", fused)       # auto-reset inside k_env_post instead of two more launches
         b = EnvBatch(spec, n, seed=3)
         b.reset()
         bs.append(b)
@@ -203,7 +204,8 @@ def test_reset_template_is_bit_identical_to_a_recomputed_reload(monkeypatch):
         act = torch.tensor(random_actions(rng, spec, n), device="cuda")
         for b in bs:
             b.step(act, auto_reset=True)
-        assert torch.equal(bs[0].out_buf, bs[1].out_buf), t
-    for name in ("fdm", "out", "ac_d", "ac_i", "env_i"):
+        assert torch.equal(bs[0].out_buf, bs[1].out_buf) and torch.equal(bs[0].out_buf, bs[2].out_buf), t
+    for name in ("fdm", "out", "ac_d", "ac_i", "env_d", "env_i", "ms_d", "ms_i"):
         assert torch.equal(bs[0].arena(name)[1], bs[1].arena(name)[1]), name
+        assert torch.equal(bs[0].arena(name)[1], bs[2].arena(name)[1]), name
     assert int(bs[0].arena("env_i")[1][bs[0].arena("env_i")[0].index("episode")].min()) >= 2

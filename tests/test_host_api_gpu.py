@@ -186,6 +186,39 @@ def test_vecenv_matches_device_api_and_auto_resets():
     ve.close(); ref.close()
 
 
+@pytest.mark.parametrize("config", ["1v1/NoWeapon/Selfplay", "scenario2/scenario2"])
+def test_whole_step_graph_equals_eager_launches(config, monkeypatch):
+    """VecEnv.step replays one CUDA graph (pinned H2D of the actions, controller + env kernels, D2H of the packed outputs);
+    it returns the same bits as the eager launch sequence, auto-resets included (episodes capped at 6 steps)."""
+    import aircombat_selfplay_b200.envs as envs_mod
+    orig = envs_mod.load_spec
+
+    def short(*args, **kw):
+        spec = orig(*args, **kw)
+        spec.max_steps = 6
+        return spec
+    monkeypatch.setattr(envs_mod, "load_spec", short)
+    n = 48
+    cls = ShareBatchedVecEnv if config.startswith("scenario") else BatchedVecEnv
+    a, b = cls(config, n, seed=5), cls(config, n, seed=5)
+    b.use_cuda_graph = False
+    a.reset(); b.reset()
+    rng = np.random.default_rng(0)
+    A, D = a.num_agents, a.core.act_dim
+    for t in range(14):
+        if a.core.hier:
+            act = np.concatenate([rng.integers(0, 3, (n, A, 1)), rng.integers(0, 5, (n, A, 1)), rng.integers(0, 3, (n, A, 1)),
+                                  rng.integers(0, 2, (n, A, D - 3))], axis=-1)
+        else:
+            act = np.concatenate([rng.integers(0, 41, (n, A, 3)), rng.integers(0, 30, (n, A, 1))], axis=-1)
+        oa, ob = a.step(act), b.step(act)
+        for x, y in zip(oa[:-1], ob[:-1]):
+            assert np.array_equal(np.asarray(x), np.asarray(y)), t
+        assert oa[-1][0]["current_step"] == ob[-1][0]["current_step"] == t % 6 + 1
+    assert a._g is not None and b._g is None
+    a.close(); b.close()
+
+
 def test_hierarchical_controller_runs_batched_on_device():
     ve = ShareBatchedVecEnv("scenario2/scenario2", 32, seed=1)
     assert ve.action_space.__class__.__name__ == "Tuple" and ve.core.act_dim == 7
