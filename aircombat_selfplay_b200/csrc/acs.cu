@@ -424,6 +424,10 @@ int acs_env_get_option(const AcsEnv* e, const char* name, int* value) {
     *value = (e->frame_split == 1 || (e->frame_split < 0 && threads <= e->split_max_threads)) ? 1 : 0;
     return 0;
   }
+  if (!std::strcmp(name, "launches_per_step")) {       // kernels one auto-resetting acs_env_step launches
+    *value = (e->tpl.fdm != nullptr && e->fused_reset) ? 2 : (e->tpl.fdm != nullptr ? 3 : 4);
+    return 0;
+  }
   return fail(std::string("acs_env_get_option: unknown option ") + name);
 }
 

@@ -5,7 +5,7 @@ Contract: `python bench.py --gpus N --steps K --warmup W` (under torchrun for N 
   value         whole-job agent-steps/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
   e2e           the same metric through the reference-facing VecEnv API: HOST numpy actions in, host obs / rewards /
                 dones out, both copies inside the timed region
-  roofline      the dominant kernel (k_env_substeps) against the measured HBM peak, plus the fp64-pipe view
+  roofline      the dominant kernel (k_env_substeps_split or k_env_substeps, by batch size) against the measured HBM peak, plus the fp64-pipe view
   cpu_baseline  the CPU oracle port of the same workload on the host cores (rank 0, N=1 only; bounded sample)
 `--impl reference` times the reference-shaped CPU path instead: the restated Python env layer over the restated C++
 FDM, one worker process per host core -- DESIGN.md section 3 explains why the real JSBSim cannot run here.
@@ -328,7 +328,7 @@ def run_b200(args):
             "config": {"workload": desc, "scenario": config, "envs_per_gpu": n_envs, "agents_per_env": A, "substeps": SUBSTEPS,
                        "sim_freq": 60, "auto_reset": True, "l2": "flushed between timed steps (256 MB fill)",
                        "controller": ("batched GRU low-level controller in PyTorch" if core.hier else "none (direct stick/throttle classes)")},
-            "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks, "roofline": roof,
+            "e2e": e2e, "gpu_launches": batch.get_option("launches_per_step") * args.steps, "clocks": clocks, "roofline": roof,
             "episodes_finished_in_e2e": done_envs}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -366,8 +366,9 @@ def main():
     ap.add_argument("--no-fp64-peak", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="wall budget of the CPU baseline sample")
     ap.add_argument("--ref-rounds", type=int, default=10, help="--impl reference: env-steps per bench step")
-    ap.add_argument("--flops-per-substep", type=float, default=3713.0,
-                    help="fp64 FLOPs per aircraft per substep (counted from the ncu instruction mix, DESIGN.md section 5)")
+    ap.add_argument("--flops-per-substep", type=float, default=2090.0,
+                    help="fp64 FLOPs per aircraft per substep: 2*DFMA + DMUL + DADD thread instructions of the committed ncu "
+                         "capture (profiles/r1_k_env_substeps_split_4096envs_final.txt: 25 075 per aircraft per 12-substep step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -164,7 +164,8 @@ AcsHandle* acs_env_fdm(AcsEnv* e);
  * (default; the environment variable ACS_FRAME_SPLIT overrides the default at acs_env_create).  Both kernels evaluate
  * the same expressions.  Returns non-zero for an unknown option or value. */
 int acs_env_set_option(AcsEnv* e, const char* name, int value);
-/* reads an option back; "frame_split_effective" = 1 if the next acs_env_step launches the two-warp frame */
+/* reads an option back; "frame_split_effective" = 1 if the next acs_env_step launches the two-warp frame;
+ * "launches_per_step" = kernels one auto-resetting acs_env_step launches (2 when the reset is fused into k_env_post) */
 int acs_env_get_option(const AcsEnv* e, const char* name, int* value);
 
 /* Measurement (no reference counterpart): with timing on, acs_env_step brackets each of its kernels with CUDA events on the
