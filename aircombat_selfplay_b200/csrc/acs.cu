@@ -288,8 +288,10 @@ struct AcsEnv {
   AcsHandle* fdm;
   EnvView v;
   int G, lg;   // lanes per env (1, 2, 4 or 8) and its log2
-  EnvView tpl;                   // one-env arena holding the reset template (tpl.fdm == nullptr: none, e.g. the heading task)
-  bool tpl_enabled = true;
+  ResetTpl tpl;                  // reset template (tpl.t.fdm == nullptr: none, e.g. the heading task)
+  char* tpl_block = nullptr;     // the one allocation behind the template
+  double* tpl_obs = nullptr;     // [A][obs_dim]
+  int tpl_mode = 2;              // 0 none, 1 FDM reload only, 2 whole reset (ACS_RESET_TEMPLATE)
   bool fused_reset = true;       // auto-reset inside k_env_post (needs the template)
   int frame_split = -1;          // substep kernel: 0 one thread per aircraft, 1 two-warp frame, -1 by batch size
   int split_max_threads = 0;     // auto: use the two-warp frame up to this many aircraft lanes
@@ -366,18 +368,33 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
   CUDA_TRY(cudaMalloc(&v.mi, sizeof(int) * N_MI * ms));      CUDA_TRY(cudaMemset(v.mi, 0, sizeof(int) * N_MI * ms));
   // episode counters start at -1 so the first reset is episode 0
   CUDA_TRY(cudaMemset(v.ei + (size_t)EI_EPISODE * B, 0xff, sizeof(int) * B));
-  // reset template (k_env_reset_task): every task with fixed per-lane initial conditions
-  std::memset(&e->tpl, 0, sizeof(EnvView));
-  if (const char* s = std::getenv("ACS_RESET_TEMPLATE")) e->tpl_enabled = std::atoi(s) != 0;
+  // reset template: every task with fixed per-lane initial conditions
+  std::memset(&e->tpl, 0, sizeof(ResetTpl));
+  if (const char* s = std::getenv("ACS_RESET_TEMPLATE")) e->tpl_mode = std::atoi(s);
   if (const char* s = std::getenv("ACS_FUSED_RESET")) e->fused_reset = std::atoi(s) != 0;
-  if (cfg->obs_kind != ACS_OBS_HEADING && e->tpl_enabled) {
-    EnvView& t = e->tpl;
+  if (cfg->obs_kind != ACS_OBS_HEADING && e->tpl_mode > 0) {
+    EnvView& t = e->tpl.t;
     t.B = 1; t.A = A; t.S = v.S; t.rows = A;
-    CUDA_TRY(cudaMalloc(&t.fdm, sizeof(double) * N_STATE * A)); CUDA_TRY(cudaMalloc(&t.out, sizeof(double) * FDM_N_OUT * A));
-    CUDA_TRY(cudaMalloc(&t.ad, sizeof(double) * N_AD * A));     CUDA_TRY(cudaMalloc(&t.ai, sizeof(int) * N_AI * A));
-    CUDA_TRY(cudaMalloc(&t.ed, sizeof(double) * N_ED));         CUDA_TRY(cudaMalloc(&t.ei, sizeof(int) * N_EI));
-    CUDA_TRY(cudaMemset(t.ad, 0, sizeof(double) * N_AD * A));   CUDA_TRY(cudaMemset(t.ai, 0, sizeof(int) * N_AI * A));
-    CUDA_TRY(cudaMemset(t.ed, 0, sizeof(double) * N_ED));       CUDA_TRY(cudaMemset(t.ei, 0, sizeof(int) * N_EI));
+    // one contiguous block (256-byte aligned pieces): arenas of one env, reset observation, field lists
+    const size_t n64max = (size_t)(N_STATE + FDM_N_OUT + N_AD) * A + (size_t)N_MD * A * v.S + N_ED;
+    const size_t n32max = (size_t)N_AI * A + (size_t)N_MI * A * v.S + N_EI;
+    const size_t sz[13] = {sizeof(double) * N_STATE * A, sizeof(double) * FDM_N_OUT * A, sizeof(double) * N_AD * A, sizeof(int) * N_AI * A,
+                           sizeof(double) * N_ED, sizeof(int) * N_EI, sizeof(double) * N_MD * A * v.S, sizeof(int) * N_MI * A * v.S,
+                           sizeof(double) * A * cfg->obs_dim, sizeof(double) * n64max, sizeof(int) * n64max, sizeof(int) * n32max,
+                           sizeof(int) * n32max};
+    size_t off[14] = {0};
+    for (int k = 0; k < 13; k++) off[k + 1] = off[k] + ((sz[k] + 255) / 256) * 256;
+    char* blk = nullptr;
+    CUDA_TRY(cudaMalloc(&blk, off[13]));
+    e->tpl_block = blk;
+    t.fdm = (double*)(blk + off[0]); t.out = (double*)(blk + off[1]); t.ad = (double*)(blk + off[2]); t.ai = (int*)(blk + off[3]);
+    t.ed = (double*)(blk + off[4]);  t.ei = (int*)(blk + off[5]);     t.md = (double*)(blk + off[6]); t.mi = (int*)(blk + off[7]);
+    e->tpl_obs = (double*)(blk + off[8]);
+    e->tpl.obs = e->tpl_obs;
+    e->tpl.v64 = (double*)(blk + off[9]); e->tpl.d64 = (int*)(blk + off[10]);
+    e->tpl.v32 = (int*)(blk + off[11]);   e->tpl.d32 = (int*)(blk + off[12]);
+    // what a resetting warp reads: observation + packed words (the arenas in front are only read in FDM-only mode)
+    e->tpl.base = blk + off[8]; e->tpl.bytes = (int)(off[13] - off[8]);
     if (build_reset_template(e)) return 1;
   }
   // substep-kernel choice: the two-warp frame wins while the batch leaves SM sub-partitions idle
@@ -403,14 +420,63 @@ int acs_env_set_option(AcsEnv* e, const char* name, int value) {
 
 } // extern "C"
 
-// sim.reload() of every lane on the one-env template arena (legacy stream, synchronous: called at create / when the
-// initial conditions change, never on the step path)
+// reset() of one env on the template arenas (legacy stream, synchronous: called at create / when the initial conditions
+// change, never on the step path).  Run twice over two different fill patterns: a word that comes out the same both
+// times is one reset() writes (and its value does not depend on what was there); the others it leaves alone.
 static int build_reset_template(AcsEnv* e) {
-  if (e->tpl.fdm == nullptr) return 0;
+  ResetTpl& tp = e->tpl;
+  EnvView& t = tp.t;
+  if (t.fdm == nullptr) return 0;
+  tp.full = 0; tp.n64 = tp.n32 = 0;
+  const int A = t.A, S = t.S, D = e->cfg.obs_dim;
+  struct Arena { void* p; int nf, per; size_t elt; };
+  const Arena ar[8] = {{t.fdm, N_STATE, A, 8}, {t.out, FDM_N_OUT, A, 8}, {t.ad, N_AD, A, 8}, {t.ai, N_AI, A, 4},
+                       {t.ed, N_ED, 1, 8},     {t.ei, N_EI, 1, 4},       {t.md, N_MD, A * S, 8}, {t.mi, N_MI, A * S, 4}};
+  std::vector<unsigned char> snap[2][8];
+  ResetTpl none;
+  std::memset(&none, 0, sizeof(none));
   CUDA_TRY(cudaDeviceSynchronize());
-  k_env_reset_fdm<<<1, FDM_BLOCK>>>(e->tpl, e->cfg, e->lg, nullptr);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaDeviceSynchronize());
+  for (int pass = 0; pass < 2; pass++) {
+    for (int k = 0; k < 8; k++) CUDA_TRY(cudaMemset(ar[k].p, pass ? 0x55 : 0x00, ar[k].elt * ar[k].nf * ar[k].per));
+    CUDA_TRY(cudaMemset(e->tpl_obs, 0, sizeof(double) * A * D));
+    k_env_reset_fdm<<<1, FDM_BLOCK>>>(t, e->cfg, e->lg, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    k_env_reset_task<<<1, 128>>>(t, e->cfg, e->lg, nullptr, e->tpl_obs, nullptr, none);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int k = 0; k < 8; k++) {
+      snap[pass][k].resize(ar[k].elt * ar[k].nf * ar[k].per);
+      CUDA_TRY(cudaMemcpy(snap[pass][k].data(), ar[k].p, snap[pass][k].size(), cudaMemcpyDeviceToHost));
+    }
+  }
+  if (e->tpl_mode < 2) return 0;
+  std::vector<double> v64; std::vector<int> d64, v32, d32;
+  for (int k = 0; k < 8; k++) {
+    for (int f = 0; f < ar[k].nf; f++) {
+      int same = 0;
+      for (int j = 0; j < ar[k].per; j++) {
+        const size_t o = ((size_t)f * ar[k].per + j) * ar[k].elt;
+        same += std::memcmp(&snap[0][k][o], &snap[1][k][o], ar[k].elt) == 0;
+      }
+      if (same != ar[k].per) {
+        if (same != 0) return 0;     // written for some lanes / slots only: keep the computed reset
+        continue;
+      }
+      for (int j = 0; j < ar[k].per; j++) {
+        const size_t o = ((size_t)f * ar[k].per + j) * ar[k].elt;
+        const int d = (k << 24) | (f << 12) | j;
+        if (ar[k].elt == 8) { double x; std::memcpy(&x, &snap[1][k][o], 8); v64.push_back(x); d64.push_back(d); }
+        else { int x; std::memcpy(&x, &snap[1][k][o], 4); v32.push_back(x); d32.push_back(d); }
+      }
+    }
+  }
+  if (ar[6].per >= 4096 || N_STATE >= 4096) return 0;
+  CUDA_TRY(cudaMemcpy((void*)tp.v64, v64.data(), sizeof(double) * v64.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy((void*)tp.d64, d64.data(), sizeof(int) * d64.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy((void*)tp.v32, v32.data(), sizeof(int) * v32.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy((void*)tp.d32, d32.data(), sizeof(int) * d32.size(), cudaMemcpyHostToDevice));
+  tp.n64 = (int)v64.size(); tp.n32 = (int)v32.size();
+  tp.full = 1;
   return 0;
 }
 
@@ -424,8 +490,9 @@ int acs_env_get_option(const AcsEnv* e, const char* name, int* value) {
     *value = (e->frame_split == 1 || (e->frame_split < 0 && threads <= e->split_max_threads)) ? 1 : 0;
     return 0;
   }
+  if (!std::strcmp(name, "reset_template")) { *value = e->tpl.t.fdm == nullptr ? 0 : (e->tpl.full ? 2 : 1); return 0; }
   if (!std::strcmp(name, "launches_per_step")) {       // kernels one auto-resetting acs_env_step launches
-    *value = (e->tpl.fdm != nullptr && e->fused_reset) ? 2 : (e->tpl.fdm != nullptr ? 3 : 4);
+    *value = (e->tpl.t.fdm != nullptr && e->fused_reset) ? 2 : ((e->tpl.t.fdm != nullptr) ? 3 : 4);
     return 0;
   }
   return fail(std::string("acs_env_get_option: unknown option ") + name);
@@ -435,7 +502,7 @@ int acs_env_destroy(AcsEnv* e) {
   if (!e) return 0;
   cudaSetDevice(e->fdm->device);
   cudaFree(e->v.ad); cudaFree(e->v.ai); cudaFree(e->v.ed); cudaFree(e->v.ei); cudaFree(e->v.md); cudaFree(e->v.mi);
-  if (e->tpl.fdm) { cudaFree(e->tpl.fdm); cudaFree(e->tpl.out); cudaFree(e->tpl.ad); cudaFree(e->tpl.ai); cudaFree(e->tpl.ed); cudaFree(e->tpl.ei); }
+  if (e->tpl_block) cudaFree(e->tpl_block);
   for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
   acs_destroy(e->fdm);
   delete e;
@@ -461,7 +528,7 @@ int acs_env_reset(AcsEnv* e, const uint8_t* env_mask_dev, double* obs_dev, doubl
   if (!e || !obs_dev) return fail("acs_env_reset: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int threads = e->v.B * e->G;
-  if (e->tpl.fdm == nullptr) {
+  if (e->tpl.t.fdm == nullptr) {
     k_env_reset_fdm<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, env_mask_dev);
     CUDA_TRY(cudaGetLastError());
   }
@@ -482,7 +549,7 @@ int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double*
   else k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   CUDA_TRY(cudaGetLastError());
   if (e->timing) timing_event(e, st);
-  const int fuse = (auto_reset && e->tpl.fdm != nullptr && e->fused_reset) ? 1 : 0;
+  const int fuse = (auto_reset && e->tpl.t.fdm != nullptr && e->fused_reset) ? 1 : 0;
   k_env_post<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg, obs_dev, share_obs_dev, rewards_dev, dones_dev, info_dev, env_done_dev,
                                                    fuse, e->tpl);
   CUDA_TRY(cudaGetLastError());

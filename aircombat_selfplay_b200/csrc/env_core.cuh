@@ -77,6 +77,24 @@ struct EnvView {
   double* md; int* mi;     // [N_MD][rows*S], [N_MI][rows*S]
   int B, A, S, rows;
 };
+// Reset template of a handle (acs.cu, build_reset_template).  Every task but the heading task resets an env to the same
+// state each time (fixed per-lane initial conditions, no random draw), so reset() is run once on a one-env arena `t`.
+// full != 0: the words reset() writes (found by running it over two different fill patterns) are kept packed --
+// v64[i] / v32[i] is the value of word d64[i] / d32[i] = arena << 24 | field << 12 | index within the env -- and a reset
+// is a warp-cooperative scatter of those words plus the reset observation (reset_copy_warp).
+struct ResetTpl {
+  EnvView t;            // t.fdm == nullptr: no template.  full == 0: only the FDM reload (fdm / out / derived ad fields) is used
+  const double* obs;    // [A][obs_dim] reset observation
+  const double* v64; const int* d64; int n64;   // arenas 0 fdm, 1 out, 2 ad, 4 ed, 6 md
+  const int* v32; const int* d32; int n32;      // arenas 3 ai, 5 ei, 7 mi
+  int full;
+  const char* base;     // the template is one contiguous block [base, base + bytes)
+  int bytes;
+};
+// The template is a few KB read by the few warps that reset an env, i.e. cold; a warp asks for all of its lines at once.
+__device__ __forceinline__ void tpl_prefetch(const ResetTpl& tp) {
+  for (int o = (threadIdx.x & 31) * 128; o < tp.bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp.base + o));
+}
 #define AD(v, f, row) (v).ad[(size_t)(f) * (v).rows + (row)]
 #define AI(v, f, row) (v).ai[(size_t)(f) * (v).rows + (row)]
 #define ED(v, f, env) (v).ed[(size_t)(f) * (v).B + (env)]

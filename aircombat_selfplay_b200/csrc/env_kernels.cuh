@@ -1051,21 +1051,22 @@ ENV_DEV int agent_termination(const StepCtx& c, int a) {
 }
 
 __device__ __noinline__ void reset_task_lanes(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const bool on, PubAc* sP,
-                                              double* __restrict__ obs, double* __restrict__ share_obs, const EnvView& tpl);
+                                              double* __restrict__ obs, double* __restrict__ share_obs, const ResetTpl& tp);
 
 // fuse_reset != 0 (auto-reset with a reset template, i.e. every task but the heading task): an env whose agents are all
 // done is reset right here -- rewards / dones / info of the terminal step are already written, the reset observation
 // replaces the terminal one (R/envs/env_wrappers.py:191-204) -- instead of by two more kernel launches whose code
 // would be fetched cold.
-__global__ void __launch_bounds__(128) k_env_post(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg, double* __restrict__ obs,
+__global__ void __launch_bounds__(128) k_env_post(const __grid_constant__ EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg, double* __restrict__ obs,
                                                   double* __restrict__ share_obs, double* __restrict__ rewards,
                                                   uint8_t* __restrict__ dones, int32_t* __restrict__ info, uint8_t* __restrict__ env_done,
-                                                  const int fuse_reset, const EnvView tpl) {
+                                                  const int fuse_reset, const __grid_constant__ ResetTpl tpl) {
   __shared__ PubAc sP[128];
   __shared__ double sRew[128];
   __shared__ int sDone[128];
   const Lane L = lane_setup(v, lg);
   const int A = v.A;
+  if (fuse_reset && tpl.full) tpl_prefetch(tpl);     // long before the first env of this warp can need it
   PubAc me;
   me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
   if (L.valid) load_pub(v, L.row, me);
@@ -1209,8 +1210,54 @@ __global__ void __launch_bounds__(FDM_BLOCK) k_env_reset_fdm(const EnvView v, co
 // to recomputing it, and the auto-reset that follows every step no longer launches the 2-frame FDM reload.
 // The lanes of the environments being reset (`on`): used by k_env_reset_task and, fused, by k_env_post's auto-reset.
 // sP is the block's PubAc exchange array; every lane of the warp calls this (warp-level syncs on the env's lane mask).
+// The whole reset as a copy of the template (ResetTpl::full), by the whole warp: for every env of the warp that is being
+// reset, the 32 lanes scatter the packed template words (coalesced reads, 32 independent words in flight per iteration,
+// a dozen instructions of code -- the per-lane, per-arena unrolled copy this replaces spent its time fetching its own
+// cold instructions).  Every lane of the warp must call this; `on` lanes belong to envs being reset.
+ENV_DEV void reset_copy_warp(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const bool on, double* __restrict__ obs,
+                             double* __restrict__ share_obs, const ResetTpl& tp) {
+  const unsigned wl = threadIdx.x & 31;
+  __syncwarp();   // the step logic's own stores to these words (terminal obs, status, bloods) are ordered before the scatter
+  unsigned leaders = __ballot_sync(0xffffffffu, on && L.lane == 0);
+  const int A = v.A, S = v.S, AD_ = A * cfg.obs_dim;
+  while (leaders) {
+    const int src = __ffs(leaders) - 1;
+    leaders &= leaders - 1;
+    const int env = __shfl_sync(0xffffffffu, L.env, src);
+    const size_t row0 = (size_t)env * A;
+#pragma unroll 2
+    for (int w = wl; w < tp.n64; w += 32) {
+      const int d = __ldg(tp.d64 + w);
+      const double x = __ldg(tp.v64 + w);
+      const int k = d >> 24, f = (d >> 12) & 0xfff, j = d & 0xfff;
+      double* b = k == 0 ? v.fdm : (k == 1 ? v.out : (k == 2 ? v.ad : (k == 6 ? v.md : v.ed)));
+      const size_t stride = k == 6 ? (size_t)v.rows * S : (k == 4 ? (size_t)v.B : (size_t)v.rows);
+      const size_t i0 = k == 6 ? row0 * S + j : (k == 4 ? (size_t)env : row0 + j);
+      b[f * stride + i0] = x;
+    }
+#pragma unroll 2
+    for (int w = wl; w < tp.n32; w += 32) {
+      const int d = __ldg(tp.d32 + w);
+      const int x = __ldg(tp.v32 + w);
+      const int k = d >> 24, f = (d >> 12) & 0xfff, j = d & 0xfff;
+      int* b = k == 3 ? v.ai : (k == 7 ? v.mi : v.ei);
+      const size_t stride = k == 7 ? (size_t)v.rows * S : (k == 5 ? (size_t)v.B : (size_t)v.rows);
+      const size_t i0 = k == 7 ? row0 * S + j : (k == 5 ? (size_t)env : row0 + j);
+      b[f * stride + i0] = x;
+    }
+    if (wl == 0) EI(v, EI_EPISODE, env) = EI(v, EI_EPISODE, env) + 1;     // the one read-modify-write of reset()
+    for (int w = wl; w < AD_; w += 32) {
+      const double x = __ldg(tp.obs + w);
+      obs[row0 * cfg.obs_dim + w] = x;
+      if (share_obs) for (int a = 0; a < A; a++) share_obs[(row0 + a) * (size_t)AD_ + w] = x;
+    }
+  }
+}
+
 __device__ __noinline__ void reset_task_lanes(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const bool on, PubAc* sP,
-                                              double* __restrict__ obs, double* __restrict__ share_obs, const EnvView& tpl) {
+                                              double* __restrict__ obs, double* __restrict__ share_obs, const ResetTpl& tp) {
+  if (tp.full) { reset_copy_warp(v, cfg, L, on, obs, share_obs, tp); return; }
+  const EnvView& tpl = tp.t;
   const int A = v.A;
   PubAc me;
   me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
@@ -1298,12 +1345,13 @@ __device__ __noinline__ void reset_task_lanes(const EnvView& v, const AcsTaskCon
   }
 }
 
-__global__ void __launch_bounds__(128) k_env_reset_task(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
+__global__ void __launch_bounds__(128) k_env_reset_task(const __grid_constant__ EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
                                                         const uint8_t* __restrict__ env_mask, double* __restrict__ obs,
-                                                        double* __restrict__ share_obs, const EnvView tpl) {
+                                                        double* __restrict__ share_obs, const __grid_constant__ ResetTpl tpl) {
   __shared__ PubAc sP[128];
   const Lane L = lane_setup(v, lg);
   const bool on = L.valid && (env_mask == nullptr || env_mask[L.env]);
   if (!__syncthreads_or(on)) return;
+  if (tpl.full) tpl_prefetch(tpl);
   reset_task_lanes(v, cfg, L, on, sP, obs, share_obs, tpl);
 }

@@ -181,31 +181,41 @@ def test_two_warp_frame_matches_one_thread_frame():
     assert float(((sa - sb).abs() / scale).max()) < 1e-8
 
 
-def test_reset_template_is_bit_identical_to_a_recomputed_reload(monkeypatch):
-    """Fixed per-lane initial conditions: the auto-reset copies the FDM reload computed once per handle (reset template)
-    instead of recomputing it; both give the same bits, also after set_init_states."""
+@pytest.mark.parametrize("name", ["scenario2/scenario2", "1v1/ShootMissile/Selfplay", "2v2/NoWeapon/Selfplay", "scenario3/scenario3"])
+def test_reset_template_is_bit_identical_to_a_recomputed_reset(name, monkeypatch):
+    """Fixed per-lane initial conditions: reset() always produces the same env state, so it is computed once per handle and
+    the (auto-)reset copies it -- mode 1 the FDM reload only, mode 2 every word reset() writes plus the reset observation,
+    fused into k_env_post or in its own launch.  All give the bits of the recomputed reset (mode 0), in every arena, also
+    after set_init_states."""
     from aircombat_selfplay_b200.capi import EnvBatch
-    spec = load_spec("scenario2/scenario2")
+    spec = load_spec(name)
     spec.max_steps = 4
     n = 70
     bs = []
-    for tpl, fused in (("0", "0"), ("1", "0"), ("1", "1")):
+    for tpl, fused in (("0", "0"), ("1", "0"), ("2", "0"), ("2", "1")):
         monkeypatch.setenv("ACS_RESET_TEMPLATE", tpl)
-        monkeypatch.setenv("ACS_FUSED_RESET", fused)       # auto-reset inside k_env_post instead of two more launches
+        monkeypatch.setenv("ACS_FUSED_RESET", fused)
         b = EnvBatch(spec, n, seed=3)
+        assert b.get_option("reset_template") == int(tpl)
         b.reset()
         bs.append(b)
     rng = np.random.default_rng(1)
-    for t in range(10):
+    for t in range(11):
         if t == 5:
             init = close_init_states(spec, np.random.default_rng(7))
             for b in bs:
                 b.set_init_states(init)
+        if t == 8:          # an explicit masked reset goes through the same template
+            mask = torch.tensor(np.arange(n) % 3 == 0, device="cuda").to(torch.uint8)
+            for b in bs:
+                b.reset(mask)
         act = torch.tensor(random_actions(rng, spec, n), device="cuda")
         for b in bs:
             b.step(act, auto_reset=True)
-        assert torch.equal(bs[0].out_buf, bs[1].out_buf) and torch.equal(bs[0].out_buf, bs[2].out_buf), t
-    for name in ("fdm", "out", "ac_d", "ac_i", "env_d", "env_i", "ms_d", "ms_i"):
-        assert torch.equal(bs[0].arena(name)[1], bs[1].arena(name)[1]), name
-        assert torch.equal(bs[0].arena(name)[1], bs[2].arena(name)[1]), name
-    assert int(bs[0].arena("env_i")[1][bs[0].arena("env_i")[0].index("episode")].min()) >= 2
+        for b in bs[1:]:
+            assert torch.equal(bs[0].out_buf, b.out_buf), t
+    for name_ in ("fdm", "out", "ac_d", "ac_i", "env_d", "env_i", "ms_d", "ms_i"):
+        for b in bs[1:]:
+            assert torch.equal(bs[0].arena(name_)[1], b.arena(name_)[1]), name_
+    names, ei = bs[0].arena("env_i")
+    assert int(ei[names.index("episode")].min()) >= 2
