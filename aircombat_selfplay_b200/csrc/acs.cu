@@ -295,12 +295,23 @@ struct AcsEnv {
   bool fused_reset = true;       // auto-reset inside k_env_post (needs the template)
   int frame_split = -1;          // substep kernel: 0 one thread per aircraft, 1 two-warp frame, -1 by batch size
   int split_max_threads = 0;     // auto: use the two-warp frame up to this many aircraft lanes
+  int n_sms = 0;
   bool timing = false;
   std::vector<cudaEvent_t> ev;   // 4 events per timed step: before substeps, after substeps, after post, after reset
   size_t ev_used = 0;
 };
 
 static int build_reset_template(AcsEnv* e);
+// which substep kernel acs_env_step launches: 0 one thread, 1 two warps, 2 three warps per aircraft
+static int frame_split_effective(const AcsEnv* e) {
+  if (e->frame_split >= 0) return e->frame_split;
+  const int lanes = e->v.B * e->G;
+  // three warps per aircraft while every block still gets an SM of its own (one wave), two warps up to 128 aircraft per
+  // SM, one thread per aircraft beyond (measured crossovers on B200)
+  if (lanes <= e->n_sms * S3) return 2;
+  if (lanes <= e->split_max_threads) return 1;
+  return 0;
+}
 
 static cudaEvent_t timing_event(AcsEnv* e, cudaStream_t st) {
   if (e->ev_used == e->ev.size()) { cudaEvent_t x; cudaEventCreate(&x); e->ev.push_back(x); }
@@ -402,6 +413,7 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     e->split_max_threads = prop.multiProcessorCount * ACS_SPLIT_AUTO_LANES_PER_SM;
+    e->n_sms = prop.multiProcessorCount;
     if (const char* s = std::getenv("ACS_FRAME_SPLIT")) e->frame_split = std::atoi(s);
   }
   *out = e;
@@ -411,7 +423,7 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
 int acs_env_set_option(AcsEnv* e, const char* name, int value) {
   if (!e || !name) return fail("acs_env_set_option: null argument");
   if (!std::strcmp(name, "frame_split")) {
-    if (value < -1 || value > 1) return fail("acs_env_set_option: frame_split must be -1 (auto), 0 or 1");
+    if (value < -1 || value > 2) return fail("acs_env_set_option: frame_split must be -1 (auto), 0, 1 or 2");
     e->frame_split = value;
     return 0;
   }
@@ -486,8 +498,7 @@ int acs_env_get_option(const AcsEnv* e, const char* name, int* value) {
   if (!e || !name || !value) return fail("acs_env_get_option: null argument");
   if (!std::strcmp(name, "frame_split")) { *value = e->frame_split; return 0; }
   if (!std::strcmp(name, "frame_split_effective")) {   // what the next acs_env_step launches
-    const int threads = e->v.B * e->G;
-    *value = (e->frame_split == 1 || (e->frame_split < 0 && threads <= e->split_max_threads)) ? 1 : 0;
+    *value = frame_split_effective(e);
     return 0;
   }
   if (!std::strcmp(name, "reset_template")) { *value = e->tpl.t.fdm == nullptr ? 0 : (e->tpl.full ? 2 : 1); return 0; }
@@ -544,8 +555,9 @@ int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double*
   cudaStream_t st = (cudaStream_t)stream;
   const int threads = e->v.B * e->G;
   if (e->timing) timing_event(e, st);
-  const bool split = e->frame_split == 1 || (e->frame_split < 0 && threads <= e->split_max_threads);
-  if (split) k_env_substeps_split<<<(threads + SPLIT_SLOTS - 1) / SPLIT_SLOTS, 2 * SPLIT_SLOTS, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
+  const int split = frame_split_effective(e);
+  if (split == 2) k_env_substeps_split3<<<(threads + S3 - 1) / S3, 3 * S3, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
+  else if (split == 1) k_env_substeps_split<<<(threads + SPLIT_SLOTS - 1) / SPLIT_SLOTS, 2 * SPLIT_SLOTS, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   else k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   CUDA_TRY(cudaGetLastError());
   if (e->timing) timing_event(e, st);

@@ -493,6 +493,258 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
 #undef XR2
 }
 
+// ---------------------------------------------------------------------------------------------- three-warp frame
+// One more warp per 32 aircraft.  ncu of the two-warp frame shows role A never waiting and role B waiting for half of its
+// time: A's chain Propagate -> Atmosphere -> Auxiliary -> Propulsion -> Accelerations is the critical path.  Here the
+// atmosphere and the air-data half of Auxiliary (dynamic pressure, Mach, calibrated airspeed) move to a third role, which
+// then shares the aerodynamic axes with the flight-control role:
+//
+//   role A (equations of motion)        role B (flight controls)          role C (air data)
+//   Propagate        -- E: cos(pitch)cos(roll), u, v, w, |r|, cos(lat_gc), run flag -->
+//   ------------------------------------------------------------------------------------ triple barrier 1
+//   Inertial, MassBalance,              FCS                                Atmosphere, air-data half
+//   kinematic half of Auxiliary                                            of Auxiliary
+//        -- K: alpha, beta, rates, pilot g, ... -->    -- S: surfaces -->    -- R: qbar, Mach, Vc, T, rho, h -->
+//   ------------------------------------------------------------------------------------ triple barrier 2
+//   Propulsion                          axes SIDE, ROLL, YAW               axes DRAG, LIFT, PITCH
+//                                            -- axis sums -->                   -- axis sums -->
+//   ------------------------------------------------------------------------------------ triple barrier 3
+//   Aircraft + Accelerations, missiles / chaff
+//
+// Same stage functions, same expressions, same ownership of the carried state as the two-warp frame (role C owns none:
+// what it computes is re-published every frame).  Every exchange buffer has one writer and is rewritten only behind a
+// barrier all of its readers have passed.
+#ifndef ACS_SPLIT3_SLOTS
+#define ACS_SPLIT3_SLOTS 64     // measured: 64 slots (two warps per role share an instruction stream) 0.087 ms, 32 slots 0.093 ms
+#endif
+constexpr int S3 = ACS_SPLIT3_SLOTS;
+constexpr int S3_AXES_B = (1 << 1) | (1 << 3) | (1 << 5), S3_AXES_C = 63 & ~S3_AXES_B;
+static_assert(S3 % 32 == 0 && S3 >= 32 && 3 * S3 <= 384, "whole warps, at most 4 triples per block");
+
+#define TRIPLE_BARRIER(id) { __syncwarp(); asm volatile("bar.sync %0, 96;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView v, const __grid_constant__ AcsTaskConfig cfg,
+                                                                  const int lg, const int32_t* __restrict__ actions) {
+  __shared__ double sT[F16_NTAB];
+  __shared__ PubAc sP[S3];
+  __shared__ int sWin[S3];
+  __shared__ int sShot[S3];
+  __shared__ PubChaff sCh[S3];
+  __shared__ double sE[6][S3];                  // A -> B, C
+  __shared__ double sK[F16_N_X_KIN + 1][S3];    // A -> B, C  (+ 2 Vt)
+  __shared__ double sS[F16_N_X_SURF][S3];       // B -> A, C
+  __shared__ double sR[F16_N_X_AIR + 5][S3];    // C -> A, B  (+ T, rho, h, Vc in ft/s, density altitude)
+  __shared__ double sSum[6][S3];                // B, C -> A
+  __shared__ int sRun[S3];
+  stage_tables(sT);
+  // warp-uniform role: 0 = A, 1 = B, 2 = C (which thread group takes which role makes no measurable difference)
+#ifndef ACS_S3_ORDER
+#define ACS_S3_ORDER 12       // decimal digits: role of thread group 0, 1, 2
+#endif
+  const int group = threadIdx.x / S3;
+  const int role = group == 0 ? (ACS_S3_ORDER / 100) : (group == 1 ? (ACS_S3_ORDER / 10) % 10 : ACS_S3_ORDER % 10);
+  const int slot = threadIdx.x - group * S3;
+  const int bar = 1 + (slot >> 5);
+  Lane L;
+  {
+    const int G = 1 << lg, gid = blockIdx.x * S3 + slot;
+    L.tid = slot; L.env = gid >> lg; L.lane = gid & (G - 1); L.gbase = slot - L.lane;
+    L.valid = (L.env < v.B) && (L.lane < v.A);
+    L.row = L.env * v.A + L.lane;
+    L.gmask = ((1u << G) - 1u) << ((unsigned)(slot & 31) & ~(unsigned)(G - 1));
+  }
+  const int N = v.rows, K = cfg.substeps;
+  const double dt = cfg.sim_dt, fcs_dt = cfg.fcs_dt;
+#define XW(buf, e) buf[xi++][slot] = e;
+#define XR(buf, e) e = buf[xi++][slot];
+#define XW_K(e) XW(sK, e)
+#define XR_K(e) XR(sK, e)
+#define XW_S(e) XW(sS, e)
+#define XR_S(e) XR(sS, e)
+#define XW_R(e) XW(sR, e)
+#define XR_R(e) XR(sR, e)
+
+  if (role == 1) {
+    // ================================================================ role B: flight controls + axes SIDE, ROLL, YAW
+    Props p; FcsState s;
+    bool loaded = false;
+    if (L.valid) {
+      const int adim = 4 + cfg.shoot_dim;
+      const int32_t* act = actions + (size_t)L.row * adim;
+      double u0, u1, u2, u3;
+      if (cfg.act_kind == ACS_ACT_HEADING) {
+        u0 = act[0] * 2. / (41 - 1.) - 1.; u1 = act[1] * 2. / (41 - 1.) - 1.; u2 = act[2] * 2. / (41 - 1.) - 1.; u3 = act[3] * 0.5 / (30 - 1.) + 0.4;
+      } else {
+        u0 = act[0] / 20. - 1.; u1 = act[1] / 20. - 1.; u2 = act[2] / 20. - 1.; u3 = act[3] / 58. + 0.4;
+      }
+      u0 = env_clip(u0, -1.0, 1.0); u1 = env_clip(u1, -1.0, 1.0); u2 = env_clip(u2, -1.0, 1.0); u3 = env_clip(u3, 0.0, 0.9);
+      int shoot = 0;
+      for (int k = 0; k < cfg.shoot_dim; k++) shoot |= (act[4 + k] != 0) << k;
+      if (cfg.shoot_dim > 0) AI(v, AI_SHOOT, L.row) = shoot;
+      if (AI(v, AI_STATUS, L.row) == ST_ALIVE) {
+        AcCore a;   // only the carried properties are live on this side; the core loads are dead code
+        f16_props_init(p, s);
+        load_state(v.fdm, N, L.row, a, p, s);
+        p.fcs_aileron_cmd_norm = u0; p.fcs_elevator_cmd_norm = u1; p.fcs_rudder_cmd_norm = u2; p.fcs_throttle_cmd_norm = u3;
+        loaded = true;
+      } else {
+        v.fdm[(size_t)(F_CMD0 + 0) * N + L.row] = u0; v.fdm[(size_t)(F_CMD0 + 1) * N + L.row] = u1;
+        v.fdm[(size_t)(F_CMD0 + 2) * N + L.row] = u2; v.fdm[(size_t)(F_CMD0 + 3) * N + L.row] = u3;
+      }
+    }
+    for (int k = 0; k < K; k++) {
+      TRIPLE_BARRIER(bar)                                      // 1
+      const bool ran = sRun[slot] != 0;
+      if (ran) {
+        p.attitude_cos_pitch_cos_roll = sE[0][slot]; p.velocities_u_fps = sE[1][slot]; p.velocities_v_fps = sE[2][slot];
+        f16_fcs(p, s, sT, fcs_dt);
+        { int xi = 0; F16_X_SURF(XW_S) }
+      }
+      TRIPLE_BARRIER(bar)                                      // 2
+      if (ran) {
+        double twovel, c[6];
+        { int xi = 0; F16_X_KIN(XR_K) twovel = sK[xi][slot]; }
+        { int xi = 0; F16_X_AIR(XR_R) }
+        f16_aero<S3_AXES_B>(p, sT, twovel, c);
+#pragma unroll
+        for (int i = 0; i < 6; i++) if (S3_AXES_B & (1 << i)) sSum[i][slot] = c[i];
+      }
+      TRIPLE_BARRIER(bar)                                      // 3
+    }
+    if (loaded) {
+      AcCore a;
+      store_state_role<true>(v.fdm, N, L.row, a, p, s);
+    }
+    return;
+  }
+  if (role == 2) {
+    // ================================================================ role C: air data + axes DRAG, LIFT, PITCH (no state)
+    Props p; FcsState s;
+    f16_props_init(p, s);
+    Frame f;
+    for (int k = 0; k < K; k++) {
+      TRIPLE_BARRIER(bar)                                      // 1
+      const bool ran = sRun[slot] != 0;
+      if (ran) {
+        f.uvw.x = sE[1][slot]; f.uvw.y = sE[2][slot]; f.uvw.z = sE[3][slot]; f.radius = sE[4][slot]; f.cosLatGc = sE[5][slot];
+        fdm_stage_atmosphere(p, f, g_atmo);
+        fdm_airspeed(f);
+        fdm_stage_aux_air(p, f, g_atmo);
+        { int xi = 0; F16_X_AIR(XW_R) sR[xi][slot] = f.atm.T; sR[xi + 1][slot] = f.atm.rho; sR[xi + 2][slot] = f.h_asl;
+          sR[xi + 3][slot] = f.vcas; sR[xi + 4][slot] = p.atmosphere_density_altitude; }
+      }
+      TRIPLE_BARRIER(bar)                                      // 2
+      if (ran) {
+        double c[6];
+        { int xi = 0; F16_X_KIN(XR_K) }
+        { int xi = 0; F16_X_SURF(XR_S) }
+        f16_aero<S3_AXES_C>(p, sT, 2 * f.Vt, c);
+#pragma unroll
+        for (int i = 0; i < 6; i++) if (S3_AXES_C & (1 << i)) sSum[i][slot] = c[i];
+      }
+      TRIPLE_BARRIER(bar)                                      // 3
+    }
+    return;
+  }
+
+  // ================================================================== role A: equations of motion, propulsion, missiles
+  const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
+  AcCore a; Props p; FcsState s; Frame f;
+  PubAc me;
+  double v_mps = 0, w_mps = 0, vc_mps = 0;
+  int status = ST_CRASH;
+  bool has_ms = false;
+  me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
+  if (L.valid) {
+    load_pub(v, L.row, me);
+    status = me.status;
+    has_ms = (AI(v, AI_N_LAUNCHED, L.row) > 0) || (AI(v, AI_CH_STATE, L.row) == CH_ACTIVE);
+    if (status == ST_ALIVE) {
+      f16_props_init(p, s);
+      load_state(v.fdm, N, L.row, a, p, s);
+    }
+  }
+  {
+    const unsigned b = __ballot_sync(L.gmask, has_ms);
+    has_ms = (b & L.gmask) != 0;
+  }
+  const bool was_alive = L.valid && status == ST_ALIVE;
+  const int sc0 = (L.env < v.B) ? EI(v, EI_SUBSTEP_COUNT, L.env) : 0;
+  AcOut o;
+  for (int k = 0; k < K; k++) {
+    bool ran = false;
+    if (L.valid && status == ST_ALIVE) {                     // AircraftSimulator.run (simulatior.py:210-229)
+      if (me.bloods <= 0) status = ST_SHOTDOWN;
+      ran = true;
+      fdm_stage_propagate(a, p, f, dt);
+      sE[0][slot] = p.attitude_cos_pitch_cos_roll; sE[1][slot] = f.uvw.x; sE[2][slot] = f.uvw.y; sE[3][slot] = f.uvw.z;
+      sE[4][slot] = f.radius; sE[5][slot] = f.cosLatGc;
+    }
+    sRun[slot] = ran;
+    TRIPLE_BARRIER(bar)                                        // 1
+    WindAxes w;
+    if (ran) {
+      fdm_stage_gravity(f);
+      fdm_stage_massbalance(a, f);
+      fdm_stage_aux_kin(a, p, f, w);
+      { int xi = 0; F16_X_KIN(XW_K) sK[xi][slot] = 2 * f.Vt; }
+    }
+    TRIPLE_BARRIER(bar)                                        // 2
+    if (ran) {
+      // what the frame keeps of role C's work: the engine reads Mach / density altitude / qbar / T / rho, the outputs h, Mach, Vc
+      { int xi = 0; F16_X_AIR(XR_R) f.atm.T = sR[xi][slot]; f.atm.rho = sR[xi + 1][slot]; f.h_asl = sR[xi + 2][slot];
+        f.vcas = sR[xi + 3][slot]; p.atmosphere_density_altitude = sR[xi + 4][slot]; }
+      f.qbar = p.aero_qbar_psf; f.mach = p.velocities_mach;
+      { int xi = 0; F16_X_SURF(XR_S) }
+      const int flags = (int)a.engflags;
+      bool augmentation = flags & 2;
+      f.thrust = fdm_stage_engine(a, p, f.atm, f.qbar, sT, g_atmo, dt, flags & 1, augmentation);
+      const bool starved_next = fdm_stage_consume_fuel(a, dt, flags & 1, false);
+      a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
+    }
+    TRIPLE_BARRIER(bar)                                        // 3
+    if (ran) {
+      double c[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) c[i] = sSum[i][slot];
+      fdm_stage_accelerations(a, f, w, c);
+    }
+    if (has_ms) {
+      if (ran) publish_from_frame(f, org, me);
+      me.status = status;
+      sP[L.tid] = me;
+      sWin[L.tid] = 0x7fffffff;
+      sShot[L.tid] = 0;
+      __syncwarp(L.gmask);
+      missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, sc0 + k);
+      __syncwarp(L.gmask);
+      if (sShot[L.tid] && status == ST_ALIVE) status = ST_SHOTDOWN;   // target_aircraft.shotdown() (simulatior.py:527)
+      __syncwarp(L.gmask);
+    }
+    if (ran && (k == K - 1 || status != ST_ALIVE)) {
+      fdm_outputs(a, f, o);
+      derive_aircraft(o, org, me, v_mps, w_mps, vc_mps);
+    }
+  }
+  if (L.valid) {
+    if (was_alive) {
+      store_state_role<false>(v.fdm, N, L.row, a, p, s);
+      store_out(v.out, N, L.row, o);
+      store_derived(v, L.row, me, v_mps, w_mps, vc_mps);
+    }
+    AI(v, AI_STATUS, L.row) = status;
+    if (L.lane == 0) EI(v, EI_SUBSTEP_COUNT, L.env) = sc0 + K;
+  }
+#undef XW
+#undef XR
+#undef XW_K
+#undef XR_K
+#undef XW_S
+#undef XR_S
+#undef XW_R
+#undef XR_R
+}
+
 // ============================================================================================== per-step logic
 struct StepCtx {
   const EnvView& v;

@@ -311,7 +311,7 @@ struct Frame {
   V3 uvw, pqr, vel;        // body velocity, body rates (wrt ECEF), NED velocity
   V3 grav;                 // ECEF gravity
   Atmo atm;
-  double alpha, beta, Vt, qbar, mach, vcas;
+  double alpha, beta, Vt, Vt2, qbar, mach, vcas;
   V3 pilotN;
   double Mass; V3 cg; M33 J, Jinv;
   double thrust;
@@ -535,41 +535,55 @@ FDM_DEV void fdm_stage_massbalance(AcCore& a, Frame& f) {
   }
 }
 
-FDM_DEV void fdm_stage_auxiliary(const AcCore& a, Props& p, Frame& f, const AtmoConst& ac, WindAxes& w) {
+// ---------------- Auxiliary (J/models/FGAuxiliary.cpp:134-231), in two halves so that the multi-warp frames can run the
+// air-data half next to the atmosphere it depends on: `kin` needs the body velocities, rates and last frame's
+// accelerations, `air` the true airspeed and the atmosphere.  Called back to back they are FGAuxiliary::Run.
+FDM_DEV double fdm_airspeed(Frame& f) {   // Vt^2 and Vt from the body velocities (no wind: the reference never sets one)
+  const double U = f.uvw.x, V = f.uvw.y, W = f.uvw.z;
+  const double AeroU2 = U * U, AeroV2 = V * V, AeroW2 = W * W, mUW = AeroU2 + AeroW2;
+  f.Vt2 = mUW + AeroV2;
+  f.Vt = sqrt(f.Vt2);
+  return mUW;
+}
+FDM_DEV void fdm_stage_aux_kin(const AcCore& a, Props& p, Frame& f, WindAxes& w) {
   double& sa = w.sa; double& ca = w.ca; double& sb = w.sb; double& cb = w.cb;
-  // ---------------- Auxiliary (J/models/FGAuxiliary.cpp:134-231); accelerations are the previous frame's
-  {
-    const double U = f.uvw.x, V = f.uvw.y, W = f.uvw.z;
-    const double AeroU2 = U * U, AeroV2 = V * V, AeroW2 = W * W, mUW = AeroU2 + AeroW2, Vt2 = mUW + AeroV2;
-    f.Vt = sqrt(Vt2);
-    f.alpha = 0.0; f.beta = 0.0;
-    sa = 0.0; ca = 1.0; sb = 0.0; cb = 1.0;
-    if (f.Vt > 0.001) {
-      // the wind->body matrix needs only sines and cosines of alpha and beta: ratios of the velocity components
-      const double sUW = sqrt(mUW), iVt = 1.0 / f.Vt;
-      f.beta = atan2(V, sUW); sb = V * iVt; cb = sUW * iVt;
-      if (mUW >= 1E-6) { const double iUW = 1.0 / sUW; f.alpha = atan2(W, U); sa = W * iUW; ca = U * iUW; }
-    }
-    f.qbar = (0.5 * f.atm.rho) * Vt2;
-    f.mach = f.Vt / f.atm.a;
-    const double Vground = sqrt(f.vel.x * f.vel.x + f.vel.y * f.vel.y);
-    if (fabs(f.mach) > 0.0) {
-      const double qc = pitot_total_pressure(f.mach, f.atm.P) - f.atm.P;
-      f.vcas = ac.StdDaySLsoundspeed * mach_from_impact_pressure(qc, ac.StdDaySLpressure);
-    } else f.vcas = 0.0;
-    const V3 eye = structural_to_body(f.cg, K_EYEPOINT_X, K_EYEPOINT_Y, K_EYEPOINT_Z);
-    V3 pa = a.bodyaccel + cross(a.pqridot, eye);
-    pa = pa + cross(a.wi, cross(a.wi, eye));
-    const double rg = 1.0 / G_ACCEL_REF;
-    f.pilotN = v3(pa.x * rg, pa.y * rg, pa.z * rg);
-    const V3 rp = structural_to_body(f.cg, K_AERORP_X, K_AERORP_Y, K_AERORP_Z);
-    const double vMacz = f.Tl2b.m[0][2] * rp.x + f.Tl2b.m[1][2] * rp.y + f.Tl2b.m[2][2] * rp.z;  // (Tb2l * RPBody)(3)
-    p.aero_alpha_rad = f.alpha; p.aero_alpha_deg = f.alpha * RADTODEG; p.aero_beta_rad = f.beta; p.aero_qbar_psf = f.qbar;
-    p.velocities_mach = f.mach; p.velocities_vc_kts = f.vcas * FPSTOKTS; p.velocities_vg_fps = Vground;
-    p.velocities_p_aero_rad_sec = f.pqr.x; p.velocities_q_aero_rad_sec = f.pqr.y; p.velocities_r_aero_rad_sec = f.pqr.z;
-    p.accelerations_n_pilot_y_norm = f.pilotN.y; p.accelerations_n_pilot_z_norm = f.pilotN.z;
-    p.aero_h_b_mac_ft = (f.geodAlt - vMacz) * (1.0 / K_bw);
+  // accelerations are the previous frame's
+  const double U = f.uvw.x, V = f.uvw.y, W = f.uvw.z;
+  const double mUW = fdm_airspeed(f);
+  f.alpha = 0.0; f.beta = 0.0;
+  sa = 0.0; ca = 1.0; sb = 0.0; cb = 1.0;
+  if (f.Vt > 0.001) {
+    // the wind->body matrix needs only sines and cosines of alpha and beta: ratios of the velocity components
+    const double sUW = sqrt(mUW), iVt = 1.0 / f.Vt;
+    f.beta = atan2(V, sUW); sb = V * iVt; cb = sUW * iVt;
+    if (mUW >= 1E-6) { const double iUW = 1.0 / sUW; f.alpha = atan2(W, U); sa = W * iUW; ca = U * iUW; }
   }
+  const double Vground = sqrt(f.vel.x * f.vel.x + f.vel.y * f.vel.y);
+  const V3 eye = structural_to_body(f.cg, K_EYEPOINT_X, K_EYEPOINT_Y, K_EYEPOINT_Z);
+  V3 pa = a.bodyaccel + cross(a.pqridot, eye);
+  pa = pa + cross(a.wi, cross(a.wi, eye));
+  const double rg = 1.0 / G_ACCEL_REF;
+  f.pilotN = v3(pa.x * rg, pa.y * rg, pa.z * rg);
+  const V3 rp = structural_to_body(f.cg, K_AERORP_X, K_AERORP_Y, K_AERORP_Z);
+  const double vMacz = f.Tl2b.m[0][2] * rp.x + f.Tl2b.m[1][2] * rp.y + f.Tl2b.m[2][2] * rp.z;  // (Tb2l * RPBody)(3)
+  p.aero_alpha_rad = f.alpha; p.aero_alpha_deg = f.alpha * RADTODEG; p.aero_beta_rad = f.beta;
+  p.velocities_vg_fps = Vground;
+  p.velocities_p_aero_rad_sec = f.pqr.x; p.velocities_q_aero_rad_sec = f.pqr.y; p.velocities_r_aero_rad_sec = f.pqr.z;
+  p.accelerations_n_pilot_y_norm = f.pilotN.y; p.accelerations_n_pilot_z_norm = f.pilotN.z;
+  p.aero_h_b_mac_ft = (f.geodAlt - vMacz) * (1.0 / K_bw);
+}
+FDM_DEV void fdm_stage_aux_air(Props& p, Frame& f, const AtmoConst& ac) {   // needs f.Vt2, f.Vt, f.atm
+  f.qbar = (0.5 * f.atm.rho) * f.Vt2;
+  f.mach = f.Vt / f.atm.a;
+  if (fabs(f.mach) > 0.0) {
+    const double qc = pitot_total_pressure(f.mach, f.atm.P) - f.atm.P;
+    f.vcas = ac.StdDaySLsoundspeed * mach_from_impact_pressure(qc, ac.StdDaySLpressure);
+  } else f.vcas = 0.0;
+  p.aero_qbar_psf = f.qbar; p.velocities_mach = f.mach; p.velocities_vc_kts = f.vcas * FPSTOKTS;
+}
+FDM_DEV void fdm_stage_auxiliary(const AcCore& a, Props& p, Frame& f, const AtmoConst& ac, WindAxes& w) {
+  fdm_stage_aux_kin(a, p, f, w);
+  fdm_stage_aux_air(p, f, ac);
 }
 
 // turbine (J/models/propulsion/FGTurbine.cpp:107-272): engine state = a.N1, a.N2, a.N2norm, a.FF; `starved` is the flag

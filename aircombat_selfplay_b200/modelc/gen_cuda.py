@@ -455,7 +455,10 @@ class CudaGen:
         x_surf = sorted(x for x in (self.aero_reads(AXES) | {"fcs/throttle-pos-norm"}) if x in fcs_written and x not in self.consts)
         # the FCS reads pitch / roll only as cos(pitch) * cos(roll) (see product()), which Propagate publishes directly
         x_early = ["attitude/cos-pitch-cos-roll"] + [x for x in CORE_PUBLISH[0][1] if x in fcs_reads and not x.startswith("attitude/")]
-        for nm, lst in (("EARLY", x_early), ("AUX", x_aux), ("SURF", x_surf)):
+        air = ("aero/qbar-psf", "velocities/mach", "velocities/vc-kts")     # published by the air-data half of Auxiliary
+        x_kin = [x for x in x_aux if x not in air]
+        x_air = [x for x in x_aux if x in air]
+        for nm, lst in (("EARLY", x_early), ("AUX", x_aux), ("KIN", x_kin), ("AIR", x_air), ("SURF", x_surf)):
             o.append(f"#define F16_X_{nm}(X) " + " ".join(f"X(p.{cid(x)})" for x in lst))
             o.append(f"#define F16_N_X_{nm} {len(lst)}")
         own_b, own_a = [], []

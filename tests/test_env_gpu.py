@@ -13,7 +13,7 @@ from tests.env_parity import CONFIGS, Pair, close_init_states, compare_reset, co
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[0, 1], ids=["one-thread-frame", "two-warp-frame"], autouse=True)
+@pytest.fixture(params=[0, 1, 2], ids=["one-thread-frame", "two-warp-frame", "three-warp-frame"], autouse=True)
 def frame_split(request, monkeypatch):
     """Every parity case runs against both substep kernels (include/acs.h, acs_env_set_option "frame_split"); the
     variable is read at acs_env_create."""
@@ -156,14 +156,14 @@ def test_device_share_obs_equals_the_broadcast_view():
         assert torch.equal(sa, sb)
 
 
-def test_two_warp_frame_matches_one_thread_frame():
-    """The two substep kernels evaluate the same expressions on different threads: states agree to rounding of the
+def test_multi_warp_frames_match_one_thread_frame():
+    """The three substep kernels evaluate the same expressions on different threads: states agree to rounding of the
     compiler's FMA contraction choices, flags exactly (ragged batch: 1000 envs x 4 lanes is not a multiple of a block)."""
     from aircombat_selfplay_b200.capi import EnvBatch
     spec = load_spec("scenario2/scenario2")
     n = 1000
     bs = []
-    for split in (0, 1):
+    for split in (0, 1, 2):
         b = EnvBatch(spec, n, seed=9)
         b.set_option("frame_split", split)
         b.set_init_states(close_init_states(spec, np.random.default_rng(1)))
@@ -172,13 +172,15 @@ def test_two_warp_frame_matches_one_thread_frame():
     rng = np.random.default_rng(5)
     for t in range(20):
         act = torch.tensor(random_actions(rng, spec, n, mode="smooth"), device="cuda")
-        ra = bs[0].step(act, auto_reset=True)
-        rb = bs[1].step(act, auto_reset=True)
-        assert torch.equal(ra[3], rb[3]) and torch.equal(ra[4], rb[4]), t           # dones, info
-        assert torch.allclose(ra[2], rb[2], rtol=0, atol=1e-6), t                   # rewards
-    (_, sa), (_, sb) = bs[0].arena("fdm"), bs[1].arena("fdm")
+        ra = [x.clone() for x in bs[0].step(act, auto_reset=True)]
+        for b in bs[1:]:
+            rb = b.step(act, auto_reset=True)
+            assert torch.equal(ra[3], rb[3]) and torch.equal(ra[4], rb[4]), t           # dones, info
+            assert torch.allclose(ra[2], rb[2], rtol=0, atol=1e-6), t                   # rewards
+    sa = bs[0].arena("fdm")[1]
     scale = sa.abs().amax(dim=1, keepdim=True).clamp_min(1.0)
-    assert float(((sa - sb).abs() / scale).max()) < 1e-8
+    for b in bs[1:]:
+        assert float(((sa - b.arena("fdm")[1]).abs() / scale).max()) < 1e-8
 
 
 @pytest.mark.parametrize("name", ["scenario2/scenario2", "1v1/ShootMissile/Selfplay", "2v2/NoWeapon/Selfplay", "scenario3/scenario3"])
