@@ -293,6 +293,7 @@ struct AcsEnv {
   double* tpl_obs = nullptr;     // [A][obs_dim]
   int tpl_mode = 2;              // 0 none, 1 FDM reload only, 2 whole reset (ACS_RESET_TEMPLATE)
   bool fused_reset = true;       // auto-reset inside k_env_post (needs the template)
+  bool post_split = true;        // get_obs on its own warps in k_env_post where that is legal (ACS_POST_SPLIT)
   int frame_split = -1;          // substep kernel: 0 one thread per aircraft, 1 two-warp frame, -1 by batch size
   int split_max_threads = 0;     // auto: use the two-warp frame up to this many aircraft lanes
   int n_sms = 0;
@@ -383,6 +384,7 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
   std::memset(&e->tpl, 0, sizeof(ResetTpl));
   if (const char* s = std::getenv("ACS_RESET_TEMPLATE")) e->tpl_mode = std::atoi(s);
   if (const char* s = std::getenv("ACS_FUSED_RESET")) e->fused_reset = std::atoi(s) != 0;
+  if (const char* s = std::getenv("ACS_POST_SPLIT")) e->post_split = std::atoi(s) != 0;
   if (cfg->obs_kind != ACS_OBS_HEADING && e->tpl_mode > 0) {
     EnvView& t = e->tpl.t;
     t.B = 1; t.A = A; t.S = v.S; t.rows = A;
@@ -562,8 +564,10 @@ int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double*
   CUDA_TRY(cudaGetLastError());
   if (e->timing) timing_event(e, st);
   const int fuse = (auto_reset && e->tpl.t.fdm != nullptr && e->fused_reset) ? 1 : 0;
-  k_env_post<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg, obs_dev, share_obs_dev, rewards_dev, dones_dev, info_dev, env_done_dev,
-                                                   fuse, e->tpl);
+  const int obs_split = (e->post_split && e->cfg.launch_kind == ACS_L_NONE && !e->cfg.use_artillery &&
+                         e->cfg.obs_kind != ACS_OBS_HEADING) ? 1 : 0;
+  k_env_post<<<(threads + 127) / 128, obs_split ? 256 : 128, 0, st>>>(e->v, e->cfg, e->lg, obs_dev, share_obs_dev, rewards_dev, dones_dev,
+                                                                      info_dev, env_done_dev, fuse, e->tpl, obs_split);
   CUDA_TRY(cudaGetLastError());
   if (e->timing) timing_event(e, st);
   int rc = 0;

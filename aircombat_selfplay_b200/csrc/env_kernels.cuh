@@ -1309,25 +1309,45 @@ __device__ __noinline__ void reset_task_lanes(const EnvView& v, const AcsTaskCon
 // done is reset right here -- rewards / dones / info of the terminal step are already written, the reset observation
 // replaces the terminal one (R/envs/env_wrappers.py:191-204) -- instead of by two more kernel launches whose code
 // would be fetched cold.
-__global__ void __launch_bounds__(128) k_env_post(const __grid_constant__ EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg, double* __restrict__ obs,
+//
+// obs_split != 0 (blockDim = 256): get_obs runs on a second set of four warps next to the terminations and rewards.  The
+// kernel executes every instruction once, so its time is the fetch of its own instruction stream; two streams fetch in
+// parallel.  Legal when nothing the step logic writes is read by get_obs: no weapons (task.step is empty) and not the
+// heading task (UnreachHeading re-targets what the observation shows); get_obs precedes terminations and rewards in the
+// reference (E/envs/env_base.py:155-171), and here it reads its own copy of the pre-termination aircraft state.
+__global__ void __launch_bounds__(256) k_env_post(const __grid_constant__ EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg, double* __restrict__ obs,
                                                   double* __restrict__ share_obs, double* __restrict__ rewards,
                                                   uint8_t* __restrict__ dones, int32_t* __restrict__ info, uint8_t* __restrict__ env_done,
-                                                  const int fuse_reset, const __grid_constant__ ResetTpl tpl) {
-  __shared__ PubAc sP[128];
+                                                  const int fuse_reset, const __grid_constant__ ResetTpl tpl, const int obs_split) {
+  __shared__ PubAc sP2[2][128];
   __shared__ double sRew[128];
   __shared__ int sDone[128];
-  const Lane L = lane_setup(v, lg);
+  const int obs_role = obs_split ? (threadIdx.x >> 7) : 0;      // warp-uniform
+  PubAc* sP = sP2[obs_role];
+  Lane L;
+  {
+    const int G = 1 << lg, slot = threadIdx.x & 127, gid = blockIdx.x * 128 + slot;
+    L.tid = slot; L.env = gid >> lg; L.lane = gid & (G - 1); L.gbase = slot - L.lane;
+    L.valid = (L.env < v.B) && (L.lane < v.A);
+    L.row = L.env * v.A + L.lane;
+    L.gmask = ((1u << G) - 1u) << ((unsigned)(slot & 31) & ~(unsigned)(G - 1));
+  }
   const int A = v.A;
-  if (fuse_reset && tpl.full) tpl_prefetch(tpl);     // long before the first env of this warp can need it
+  if (fuse_reset && tpl.full && !obs_role) tpl_prefetch(tpl);     // long before the first env of this warp can need it
   PubAc me;
   me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
   if (L.valid) load_pub(v, L.row, me);
   sP[L.tid] = me;
-  sRew[L.tid] = 0.0;
-  sDone[L.tid] = 1;
   const int cs = (L.env < v.B) ? EI(v, EI_CURRENT_STEP, L.env) + 1 : 0;
   __syncwarp(L.gmask);
   const StepCtx c{v, cfg, L, sP, cs};
+  if (obs_role) {
+    if (L.valid) write_obs(c, L.lane, obs + ((size_t)L.env * A + L.lane) * cfg.obs_dim);
+    __syncthreads();        // pairs with the one below: the observations are complete
+    return;
+  }
+  sRew[L.tid] = 0.0;
+  sDone[L.tid] = 1;
   // ---- task.step: artillery (E/tasks/singlecombat_task.py:163-188), then the launch rules, agents in dict order
   if (cfg.use_artillery) {
     for (int a = 0; a < A; a++) {
@@ -1352,7 +1372,7 @@ __global__ void __launch_bounds__(128) k_env_post(const __grid_constant__ EnvVie
     }
   }
   // ---- get_obs (every agent, before terminations / rewards)
-  if (L.valid) write_obs(c, L.lane, obs + ((size_t)L.env * A + L.lane) * cfg.obs_dim);
+  if (!obs_split && L.valid) write_obs(c, L.lane, obs + ((size_t)L.env * A + L.lane) * cfg.obs_dim);
   __syncwarp(L.gmask);
   // ---- dones and rewards in the reference's order
   int cause = -1;
@@ -1381,6 +1401,7 @@ __global__ void __launch_bounds__(128) k_env_post(const __grid_constant__ EnvVie
   }
   if (L.valid) sDone[L.tid] = cause >= 0;
   __syncwarp(L.gmask);
+  if (obs_split) __syncthreads();     // the observation warps are done (share_obs and the reset below read / replace obs)
   if (L.valid) {
     const size_t oa = (size_t)L.env * A + L.lane;
     rewards[oa] = sRew[L.tid];

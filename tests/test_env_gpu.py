@@ -221,3 +221,27 @@ def test_reset_template_is_bit_identical_to_a_recomputed_reset(name, monkeypatch
             assert torch.equal(bs[0].arena(name_)[1], b.arena(name_)[1]), name_
     names, ei = bs[0].arena("env_i")
     assert int(ei[names.index("episode")].min()) >= 2
+
+
+@pytest.mark.parametrize("name", ["1v1/NoWeapon/Selfplay", "2v2/NoWeapon/Selfplay"])
+def test_observation_warps_give_the_same_bits(name, monkeypatch):
+    """k_env_post with get_obs on its own warps (no-weapon tasks) == the single-pass kernel, bit for bit, resets included."""
+    from aircombat_selfplay_b200.capi import EnvBatch
+    spec = load_spec(name)
+    spec.max_steps = 5
+    n = 333
+    bs = []
+    for on in ("0", "1"):
+        monkeypatch.setenv("ACS_POST_SPLIT", on)
+        b = EnvBatch(spec, n, seed=2)
+        b.set_init_states(low_init_states(spec))
+        b.reset()
+        bs.append(b)
+    rng = np.random.default_rng(4)
+    for t in range(12):
+        act = torch.tensor(random_actions(rng, spec, n, mode="dive" if t % 2 else "random"), device="cuda")
+        for b in bs:
+            b.step(act, auto_reset=True)
+        assert torch.equal(bs[0].out_buf, bs[1].out_buf), t
+    for arena in ("fdm", "out", "ac_d", "ac_i", "env_d", "env_i"):
+        assert torch.equal(bs[0].arena(arena)[1], bs[1].arena(arena)[1]), arena
