@@ -12,30 +12,30 @@ acts = np.concatenate([rng.integers(0, 41, (300, n, 2, 3)), rng.integers(0, 30, 
 ve.reset()
 for t in range(20):
     ve.step(acts[t])
-T = {"put": 0.0, "step": 0.0, "fetch": 0.0, "post": 0.0, "sync_only": 0.0}
-N = 200
-torch.cuda.synchronize()
-t_all = time.perf_counter()
-for t in range(N):
-    t0 = time.perf_counter()
-    with torch.cuda.device(ve.core.device):
-        ve._put_actions(acts[20 + t])
-        t1 = time.perf_counter()
-        ve.core.step(ve._act_dev)
-        t2 = time.perf_counter()
-        ve._host.copy_(ve.core.batch.out_buf, non_blocking=True)
-        t2b = time.perf_counter()
-        torch.cuda.current_stream(ve.core.device).synchronize()
-        t3 = time.perf_counter()
-    ve._pending = True
-    out = ve.step_wait.__wrapped__(ve) if hasattr(ve.step_wait, "__wrapped__") else None
-    t4 = time.perf_counter()
-    T["put"] += t1 - t0; T["step"] += t2 - t1; T["fetch"] += t2b - t2; T["sync_only"] += t3 - t2b; T["post"] += t4 - t3
-total = time.perf_counter() - t_all
-print("per step (us):", {k: round(v / N * 1e6, 1) for k, v in T.items()}, "total", round(total / N * 1e6, 1))
-# plain loop for comparison
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-for t in range(N):
-    ve.step(acts[20 + t])
-print("ve.step per step (us):", round((time.perf_counter() - t0) / N * 1e6, 1))
+import time
+N = 300
+def timed(fn):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for t in range(N): fn(t)
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / N * 1e6
+print("ve.step                      %.1f us" % timed(lambda t: ve.step(acts[20 + t % 250])))
+print("  _put_actions(h2d=False)    %.1f us" % timed(lambda t: ve._put_actions(acts[20 + t % 250], h2d=False)))
+def replay_sync(t):
+    ve._g.replay(); torch.cuda.current_stream().synchronize()
+print("  graph replay + sync        %.1f us" % timed(replay_sync))
+g2 = torch.cuda.CUDAGraph()
+ve.core._warm_for_capture()
+with torch.cuda.graph(g2):
+    ve.core._step_body(ve._act_dev)
+def replay2(t):
+    g2.replay(); torch.cuda.current_stream().synchronize()
+print("  kernels-only graph + sync  %.1f us" % timed(replay2))
+def h2d(t):
+    ve._act_dev.copy_(ve._act_host, non_blocking=True); torch.cuda.current_stream().synchronize()
+print("  H2D only + sync            %.1f us" % timed(h2d))
+def d2h(t):
+    ve._host.copy_(ve.core.batch.out_buf, non_blocking=True); torch.cuda.current_stream().synchronize()
+print("  D2H only + sync            %.1f us" % timed(d2h))
+def wait_only(t):
+    ve._pending = True; ve._graphed = True; ve.step_wait()
+print("  step_wait python only      %.1f us" % timed(wait_only))
