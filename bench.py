@@ -366,9 +366,9 @@ def main():
     ap.add_argument("--no-fp64-peak", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="wall budget of the CPU baseline sample")
     ap.add_argument("--ref-rounds", type=int, default=10, help="--impl reference: env-steps per bench step")
-    ap.add_argument("--flops-per-substep", type=float, default=2090.0,
+    ap.add_argument("--flops-per-substep", type=float, default=2064.0,
                     help="fp64 FLOPs per aircraft per substep: 2*DFMA + DMUL + DADD thread instructions of the committed ncu "
-                         "capture (profiles/r1_k_env_substeps_split_4096envs_final.txt: 25 075 per aircraft per 12-substep step)")
+                         "capture (profiles/r1_k_env_substeps_split3_4096envs_final.txt: 24 770 per aircraft per 12-substep step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
