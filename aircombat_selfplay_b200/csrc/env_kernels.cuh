@@ -175,6 +175,129 @@ __device__ __noinline__ void missile_phase(const EnvView& v, const AcsTaskConfig
   }
 }
 
+// ---------------------------------------------------------------------------------------------- shared by the substep kernels
+// lane of an aircraft slot (the multi-warp frames give several threads the same slot)
+ENV_DEV Lane lane_of_slot(const EnvView& v, const int lg, const int slot, const int gid) {
+  Lane L;
+  const int G = 1 << lg;
+  L.tid = slot; L.env = gid >> lg; L.lane = gid & (G - 1); L.gbase = slot - L.lane;
+  L.valid = (L.env < v.B) && (L.lane < v.A);
+  L.row = L.env * v.A + L.lane;
+  L.gmask = ((1u << G) - 1u) << ((unsigned)(slot & 31) & ~(unsigned)(G - 1));
+  return L;
+}
+
+// normalize_action + set_property_values(action_var) with the catalog clip (E/tasks/heading_task.py:102-110,
+// E/tasks/singlecombat_task.py:141-153, E/core/catalog.py:192-197); the shoot bits go to the aircraft arena
+struct Controls { double u0, u1, u2, u3; };
+ENV_DEV Controls decode_action(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const int32_t* __restrict__ actions) {
+  const int adim = 4 + cfg.shoot_dim;
+  const int32_t* act = actions + (size_t)L.row * adim;
+  Controls c;
+  if (cfg.act_kind == ACS_ACT_HEADING) {
+    c.u0 = act[0] * 2. / (41 - 1.) - 1.; c.u1 = act[1] * 2. / (41 - 1.) - 1.; c.u2 = act[2] * 2. / (41 - 1.) - 1.; c.u3 = act[3] * 0.5 / (30 - 1.) + 0.4;
+  } else {
+    c.u0 = act[0] / 20. - 1.; c.u1 = act[1] / 20. - 1.; c.u2 = act[2] / 20. - 1.; c.u3 = act[3] / 58. + 0.4;
+  }
+  c.u0 = env_clip(c.u0, -1.0, 1.0); c.u1 = env_clip(c.u1, -1.0, 1.0); c.u2 = env_clip(c.u2, -1.0, 1.0); c.u3 = env_clip(c.u3, 0.0, 0.9);
+  int shoot = 0;
+  for (int k = 0; k < cfg.shoot_dim; k++) shoot |= (act[4 + k] != 0) << k;
+  if (cfg.shoot_dim > 0) AI(v, AI_SHOOT, L.row) = shoot;
+  return c;
+}
+// The command side of an aircraft at the start of a step: the actions are applied to dead aircraft too (they only stop
+// running); returns true when the carried state was loaded (aircraft alive), with the commands set.
+ENV_DEV bool load_commanded(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const int32_t* __restrict__ actions, const bool alive,
+                            AcCore& a, Props& p, FcsState& s) {
+  const int N = v.rows;
+  const Controls c = decode_action(v, cfg, L, actions);
+  if (alive) {
+    f16_props_init(p, s);
+    load_state(v.fdm, N, L.row, a, p, s);
+    p.fcs_aileron_cmd_norm = c.u0; p.fcs_elevator_cmd_norm = c.u1; p.fcs_rudder_cmd_norm = c.u2; p.fcs_throttle_cmd_norm = c.u3;
+    return true;
+  }
+  v.fdm[(size_t)(F_CMD0 + 0) * N + L.row] = c.u0; v.fdm[(size_t)(F_CMD0 + 1) * N + L.row] = c.u1;
+  v.fdm[(size_t)(F_CMD0 + 2) * N + L.row] = c.u2; v.fdm[(size_t)(F_CMD0 + 3) * N + L.row] = c.u3;
+  return false;
+}
+
+// What the thread that integrates an aircraft carries through a step besides the FDM state.
+struct EomLane {
+  PubAc me;
+  double v_mps, w_mps, vc_mps;
+  int status, sc0;
+  bool has_ms, was_alive;
+  AcOut o;
+};
+ENV_DEV void eom_begin(const EnvView& v, const Lane& L, EomLane& E) {
+  E.v_mps = E.w_mps = E.vc_mps = 0;
+  E.status = ST_CRASH; E.has_ms = false;
+  E.me.status = ST_CRASH; E.me.bloods = 0; E.me.h = 0; E.me.u_mps = 0;
+  E.me.f.n = E.me.f.e = E.me.f.u = E.me.f.vn = E.me.f.ve = E.me.f.vd = 0;
+  if (L.valid) {
+    load_pub(v, L.row, E.me);
+    E.status = E.me.status;
+    E.has_ms = (AI(v, AI_N_LAUNCHED, L.row) > 0) || (AI(v, AI_CH_STATE, L.row) == CH_ACTIVE);
+  }
+  // an env needs the per-substep exchange only while it has missiles or chaff in the air
+  const unsigned b = __ballot_sync(L.gmask, E.has_ms);
+  E.has_ms = (b & L.gmask) != 0;
+  E.was_alive = L.valid && E.status == ST_ALIVE;
+  E.sc0 = (L.env < v.B) ? EI(v, EI_SUBSTEP_COUNT, L.env) : 0;
+}
+// AircraftSimulator.run's gate (simulatior.py:210-229): an aircraft whose bloods ran out turns SHOTDOWN and still
+// integrates this frame
+ENV_DEV bool eom_runs(const Lane& L, EomLane& E) {
+  if (!(L.valid && E.status == ST_ALIVE)) return false;
+  if (E.me.bloods <= 0) E.status = ST_SHOTDOWN;
+  return true;
+}
+// After the aircraft's frame of substep k: missiles / chaff of the env, then the property read-back.
+// _update_properties (simulatior.py:238-257) is only materialised when somebody reads it: the other lanes' missiles need
+// position / velocity every substep (published straight from the frame, no inverse trig); the full property set is
+// extracted once, after the aircraft's last frame of the step (or of its life).
+ENV_DEV void eom_after_frame(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const GeoOrigin& org, EomLane& E, const AcCore& a,
+                             const Frame& f, const bool ran, const int k, const int K, PubAc* sP, int* sWin, int* sShot, PubChaff* sCh) {
+  if (E.has_ms) {
+    if (ran) publish_from_frame(f, org, E.me);
+    E.me.status = E.status;
+    sP[L.tid] = E.me;
+    sWin[L.tid] = 0x7fffffff;
+    sShot[L.tid] = 0;
+    __syncwarp(L.gmask);
+    missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, E.sc0 + k);
+    __syncwarp(L.gmask);
+    if (sShot[L.tid] && E.status == ST_ALIVE) E.status = ST_SHOTDOWN;   // target_aircraft.shotdown() (simulatior.py:527)
+    __syncwarp(L.gmask);
+  }
+  if (ran && (k == K - 1 || E.status != ST_ALIVE)) {
+    fdm_outputs(a, f, E.o);
+    derive_aircraft(E.o, org, E.me, E.v_mps, E.w_mps, E.vc_mps);
+  }
+}
+// end of the step; OWN_ALL: this thread also owns the flight-control side of the carried state (one-thread frame)
+template <bool OWN_ALL>
+ENV_DEV void eom_end(const EnvView& v, const Lane& L, const EomLane& E, const AcCore& a, const Props& p, const FcsState& s, const int K) {
+  if (!L.valid) return;
+  if (E.was_alive) {
+    if (OWN_ALL) store_state(v.fdm, v.rows, L.row, a, p, s);
+    else store_state_role<false>(v.fdm, v.rows, L.row, a, p, s);
+    store_out(v.out, v.rows, L.row, E.o);
+    store_derived(v, L.row, E.me, E.v_mps, E.w_mps, E.vc_mps);
+  }
+  AI(v, AI_STATUS, L.row) = E.status;
+  if (L.lane == 0) EI(v, EI_SUBSTEP_COUNT, L.env) = E.sc0 + K;
+}
+// Propulsion of one frame (engine + fuel), as fdm_frame runs it
+ENV_DEV void eom_propulsion(AcCore& a, const Props& p, Frame& f, const double* __restrict__ T, const double dt) {
+  const int flags = (int)a.engflags;
+  bool augmentation = flags & 2;
+  f.thrust = fdm_stage_engine(a, p, f.atm, f.qbar, T, g_atmo, dt, flags & 1, augmentation);
+  const bool starved_next = fdm_stage_consume_fuel(a, dt, flags & 1, false);
+  a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
+}
+
 __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
                                                            const int32_t* __restrict__ actions) {
   __shared__ double sT[F16_NTAB];
@@ -184,87 +307,19 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
   __shared__ PubChaff sCh[FDM_BLOCK];
   stage_tables(sT);
   const Lane L = lane_setup(v, lg);
-  const int N = v.rows, K = cfg.substeps;
+  const int K = cfg.substeps;
   const double dt = cfg.sim_dt, fcs_dt = cfg.fcs_dt;
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
-
   AcCore a; Props p; FcsState s; Frame f;
-  PubAc me;
-  double v_mps = 0, w_mps = 0, vc_mps = 0;
-  int status = ST_CRASH;
-  bool has_ms = false;
-  me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
-  if (L.valid) {
-    load_pub(v, L.row, me);
-    status = me.status;
-    has_ms = (AI(v, AI_N_LAUNCHED, L.row) > 0) || (AI(v, AI_CH_STATE, L.row) == CH_ACTIVE);
-    // ---- normalize_action + set_property_values(action_var) with the catalog clip (E/tasks/heading_task.py:102-110,
-    //      E/tasks/singlecombat_task.py:141-153, E/core/catalog.py:192-197); applied to dead aircraft too
-    const int adim = 4 + cfg.shoot_dim;
-    const int32_t* act = actions + (size_t)L.row * adim;
-    double u0, u1, u2, u3;
-    if (cfg.act_kind == ACS_ACT_HEADING) {
-      u0 = act[0] * 2. / (41 - 1.) - 1.; u1 = act[1] * 2. / (41 - 1.) - 1.; u2 = act[2] * 2. / (41 - 1.) - 1.; u3 = act[3] * 0.5 / (30 - 1.) + 0.4;
-    } else {
-      u0 = act[0] / 20. - 1.; u1 = act[1] / 20. - 1.; u2 = act[2] / 20. - 1.; u3 = act[3] / 58. + 0.4;
-    }
-    u0 = env_clip(u0, -1.0, 1.0); u1 = env_clip(u1, -1.0, 1.0); u2 = env_clip(u2, -1.0, 1.0); u3 = env_clip(u3, 0.0, 0.9);
-    int shoot = 0;
-    for (int k = 0; k < cfg.shoot_dim; k++) shoot |= (act[4 + k] != 0) << k;
-    if (cfg.shoot_dim > 0) AI(v, AI_SHOOT, L.row) = shoot;
-    if (status == ST_ALIVE) {
-      f16_props_init(p, s);
-      load_state(v.fdm, N, L.row, a, p, s);
-      p.fcs_aileron_cmd_norm = u0; p.fcs_elevator_cmd_norm = u1; p.fcs_rudder_cmd_norm = u2; p.fcs_throttle_cmd_norm = u3;
-    } else {
-      v.fdm[(size_t)(F_CMD0 + 0) * N + L.row] = u0; v.fdm[(size_t)(F_CMD0 + 1) * N + L.row] = u1;
-      v.fdm[(size_t)(F_CMD0 + 2) * N + L.row] = u2; v.fdm[(size_t)(F_CMD0 + 3) * N + L.row] = u3;
-    }
-  }
-  // an env needs the per-substep exchange only while it has missiles or chaff in the air
-  {
-    const unsigned b = __ballot_sync(L.gmask, has_ms);
-    has_ms = (b & L.gmask) != 0;
-  }
-  const bool was_alive = L.valid && status == ST_ALIVE;
-  const int sc0 = (L.env < v.B) ? EI(v, EI_SUBSTEP_COUNT, L.env) : 0;
-  AcOut o;
+  EomLane E;
+  eom_begin(v, L, E);
+  if (L.valid) load_commanded(v, cfg, L, actions, E.status == ST_ALIVE, a, p, s);
   for (int k = 0; k < K; k++) {
-    bool ran = false;
-    if (L.valid && status == ST_ALIVE) {                     // AircraftSimulator.run (simulatior.py:210-229)
-      if (me.bloods <= 0) status = ST_SHOTDOWN;
-      fdm_frame(a, p, s, f, sT, g_atmo, dt, fcs_dt, false);
-      ran = true;
-    }
-    // _update_properties (simulatior.py:238-257) is only materialised when somebody reads it: the other lanes' missiles
-    // need position / velocity every substep (published straight from the frame, no inverse trig); the full property
-    // set is extracted once, after the aircraft's last frame of the step (or of its life).
-    if (has_ms) {
-      if (ran) publish_from_frame(f, org, me);
-      me.status = status;
-      sP[L.tid] = me;
-      sWin[L.tid] = 0x7fffffff;
-      sShot[L.tid] = 0;
-      __syncwarp(L.gmask);
-      missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, sc0 + k);
-      __syncwarp(L.gmask);
-      if (sShot[L.tid] && status == ST_ALIVE) status = ST_SHOTDOWN;   // target_aircraft.shotdown() (simulatior.py:527)
-      __syncwarp(L.gmask);
-    }
-    if (ran && (k == K - 1 || status != ST_ALIVE)) {
-      fdm_outputs(a, f, o);
-      derive_aircraft(o, org, me, v_mps, w_mps, vc_mps);
-    }
+    const bool ran = eom_runs(L, E);
+    if (ran) fdm_frame(a, p, s, f, sT, g_atmo, dt, fcs_dt, false);
+    eom_after_frame(v, cfg, L, org, E, a, f, ran, k, K, sP, sWin, sShot, sCh);
   }
-  if (L.valid) {
-    if (was_alive) {
-      store_state(v.fdm, N, L.row, a, p, s);
-      store_out(v.out, N, L.row, o);
-      store_derived(v, L.row, me, v_mps, w_mps, vc_mps);
-    }
-    AI(v, AI_STATUS, L.row) = status;
-    if (L.lane == 0) EI(v, EI_SUBSTEP_COUNT, L.env) = sc0 + K;
-  }
+  eom_end<true>(v, L, E, a, p, s, K);
 }
 
 // ---------------------------------------------------------------------------------------------- two-warp frame
@@ -325,15 +380,8 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
   const bool role_b = threadIdx.x >= SPLIT_SLOTS;            // warp-uniform
   const int slot = threadIdx.x - (role_b ? SPLIT_SLOTS : 0);
   const int bar = 1 + (slot >> 5);                           // barrier 0 is __syncthreads
-  Lane L;
-  {
-    const int G = 1 << lg, gid = blockIdx.x * SPLIT_SLOTS + slot;
-    L.tid = slot; L.env = gid >> lg; L.lane = gid & (G - 1); L.gbase = slot - L.lane;
-    L.valid = (L.env < v.B) && (L.lane < v.A);
-    L.row = L.env * v.A + L.lane;
-    L.gmask = ((1u << G) - 1u) << ((unsigned)(slot & 31) & ~(unsigned)(G - 1));
-  }
-  const int N = v.rows, K = cfg.substeps;
+  const Lane L = lane_of_slot(v, lg, slot, blockIdx.x * SPLIT_SLOTS + slot);
+  const int K = cfg.substeps;
   const double dt = cfg.sim_dt, fcs_dt = cfg.fcs_dt;
 #define XW1(e) sX1[xi++][slot] = e;
 #define XR1(e) e = sX1[xi++][slot];
@@ -343,33 +391,8 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
   if (role_b) {
     // ================================================================ role B: flight controls + its aero axes
     Props p; FcsState s;
-    bool loaded = false;
-    if (L.valid) {
-      // normalize_action + set_property_values(action_var) with the catalog clip (E/tasks/heading_task.py:102-110,
-      // E/tasks/singlecombat_task.py:141-153, E/core/catalog.py:192-197); applied to dead aircraft too
-      const int adim = 4 + cfg.shoot_dim;
-      const int32_t* act = actions + (size_t)L.row * adim;
-      double u0, u1, u2, u3;
-      if (cfg.act_kind == ACS_ACT_HEADING) {
-        u0 = act[0] * 2. / (41 - 1.) - 1.; u1 = act[1] * 2. / (41 - 1.) - 1.; u2 = act[2] * 2. / (41 - 1.) - 1.; u3 = act[3] * 0.5 / (30 - 1.) + 0.4;
-      } else {
-        u0 = act[0] / 20. - 1.; u1 = act[1] / 20. - 1.; u2 = act[2] / 20. - 1.; u3 = act[3] / 58. + 0.4;
-      }
-      u0 = env_clip(u0, -1.0, 1.0); u1 = env_clip(u1, -1.0, 1.0); u2 = env_clip(u2, -1.0, 1.0); u3 = env_clip(u3, 0.0, 0.9);
-      int shoot = 0;
-      for (int k = 0; k < cfg.shoot_dim; k++) shoot |= (act[4 + k] != 0) << k;
-      if (cfg.shoot_dim > 0) AI(v, AI_SHOOT, L.row) = shoot;
-      if (AI(v, AI_STATUS, L.row) == ST_ALIVE) {
-        AcCore a;   // only the carried properties are live on this side; the core loads are dead code
-        f16_props_init(p, s);
-        load_state(v.fdm, N, L.row, a, p, s);
-        p.fcs_aileron_cmd_norm = u0; p.fcs_elevator_cmd_norm = u1; p.fcs_rudder_cmd_norm = u2; p.fcs_throttle_cmd_norm = u3;
-        loaded = true;
-      } else {
-        v.fdm[(size_t)(F_CMD0 + 0) * N + L.row] = u0; v.fdm[(size_t)(F_CMD0 + 1) * N + L.row] = u1;
-        v.fdm[(size_t)(F_CMD0 + 2) * N + L.row] = u2; v.fdm[(size_t)(F_CMD0 + 3) * N + L.row] = u3;
-      }
-    }
+    AcCore unused;      // only the carried properties are live on this side; the core loads / stores are dead code
+    const bool loaded = L.valid && load_commanded(v, cfg, L, actions, AI(v, AI_STATUS, L.row) == ST_ALIVE, unused, p, s);
     PROF_DECL
     for (int k = 0; k < K; k++) {
       PROF_FRAME(k)
@@ -391,45 +414,22 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
       pair_barrier(bar);                                       // 3: axis sums are out
     }
     PROF_OUT(1)
-    if (loaded) {
-      AcCore a;
-      store_state_role<true>(v.fdm, N, L.row, a, p, s);
-    }
+    if (loaded) store_state_role<true>(v.fdm, v.rows, L.row, unused, p, s);
     return;
   }
 
   // ================================================================== role A: everything else (as k_env_substeps)
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
   AcCore a; Props p; FcsState s; Frame f;
-  PubAc me;
-  double v_mps = 0, w_mps = 0, vc_mps = 0;
-  int status = ST_CRASH;
-  bool has_ms = false;
-  me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
-  if (L.valid) {
-    load_pub(v, L.row, me);
-    status = me.status;
-    has_ms = (AI(v, AI_N_LAUNCHED, L.row) > 0) || (AI(v, AI_CH_STATE, L.row) == CH_ACTIVE);
-    if (status == ST_ALIVE) {
-      f16_props_init(p, s);
-      load_state(v.fdm, N, L.row, a, p, s);
-    }
-  }
-  {
-    const unsigned b = __ballot_sync(L.gmask, has_ms);
-    has_ms = (b & L.gmask) != 0;
-  }
-  const bool was_alive = L.valid && status == ST_ALIVE;
-  const int sc0 = (L.env < v.B) ? EI(v, EI_SUBSTEP_COUNT, L.env) : 0;
-  AcOut o;
+  EomLane E;
+  eom_begin(v, L, E);
+  if (E.was_alive) { f16_props_init(p, s); load_state(v.fdm, v.rows, L.row, a, p, s); }
   PROF_DECL
   for (int k = 0; k < K; k++) {
     PROF_FRAME(k)
     PROF_TOP(k)
-    bool ran = false;
-    if (L.valid && status == ST_ALIVE) {                     // AircraftSimulator.run (simulatior.py:210-229)
-      if (me.bloods <= 0) status = ST_SHOTDOWN;
-      ran = true;
+    const bool ran = eom_runs(L, E);
+    if (ran) {
       fdm_stage_propagate(a, p, f, dt);
       { int xi = 0; F16_X_EARLY(XW1) }
     }
@@ -447,11 +447,7 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
     double c[6];
     if (ran) {
       { int xi = 0; F16_X_SURF(XR1) }
-      const int flags = (int)a.engflags;
-      bool augmentation = flags & 2;
-      f.thrust = fdm_stage_engine(a, p, f.atm, f.qbar, sT, g_atmo, dt, flags & 1, augmentation);
-      const bool starved_next = fdm_stage_consume_fuel(a, dt, flags & 1, false);
-      a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
+      eom_propulsion(a, p, f, sT, dt);
       f16_aero<SPLIT_AXES_A>(p, sT, 2 * f.Vt, c);
     }
     pair_barrier(bar);                                         // 3
@@ -460,33 +456,10 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
       for (int i = 0; i < 6; i++) if (SPLIT_AXES_B & (1 << i)) c[i] = sX2[i][slot];
       fdm_stage_accelerations(a, f, w, c);
     }
-    if (has_ms) {
-      if (ran) publish_from_frame(f, org, me);
-      me.status = status;
-      sP[L.tid] = me;
-      sWin[L.tid] = 0x7fffffff;
-      sShot[L.tid] = 0;
-      __syncwarp(L.gmask);
-      missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, sc0 + k);
-      __syncwarp(L.gmask);
-      if (sShot[L.tid] && status == ST_ALIVE) status = ST_SHOTDOWN;   // target_aircraft.shotdown() (simulatior.py:527)
-      __syncwarp(L.gmask);
-    }
-    if (ran && (k == K - 1 || status != ST_ALIVE)) {
-      fdm_outputs(a, f, o);
-      derive_aircraft(o, org, me, v_mps, w_mps, vc_mps);
-    }
+    eom_after_frame(v, cfg, L, org, E, a, f, ran, k, K, sP, sWin, sShot, sCh);
   }
   PROF_OUT(0)
-  if (L.valid) {
-    if (was_alive) {
-      store_state_role<false>(v.fdm, N, L.row, a, p, s);
-      store_out(v.out, N, L.row, o);
-      store_derived(v, L.row, me, v_mps, w_mps, vc_mps);
-    }
-    AI(v, AI_STATUS, L.row) = status;
-    if (L.lane == 0) EI(v, EI_SUBSTEP_COUNT, L.env) = sc0 + K;
-  }
+  eom_end<false>(v, L, E, a, p, s, K);
 #undef XW1
 #undef XR1
 #undef XW2
@@ -545,15 +518,8 @@ __global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView
   const int role = group == 0 ? (ACS_S3_ORDER / 100) : (group == 1 ? (ACS_S3_ORDER / 10) % 10 : ACS_S3_ORDER % 10);
   const int slot = threadIdx.x - group * S3;
   const int bar = 1 + (slot >> 5);
-  Lane L;
-  {
-    const int G = 1 << lg, gid = blockIdx.x * S3 + slot;
-    L.tid = slot; L.env = gid >> lg; L.lane = gid & (G - 1); L.gbase = slot - L.lane;
-    L.valid = (L.env < v.B) && (L.lane < v.A);
-    L.row = L.env * v.A + L.lane;
-    L.gmask = ((1u << G) - 1u) << ((unsigned)(slot & 31) & ~(unsigned)(G - 1));
-  }
-  const int N = v.rows, K = cfg.substeps;
+  const Lane L = lane_of_slot(v, lg, slot, blockIdx.x * S3 + slot);
+  const int K = cfg.substeps;
   const double dt = cfg.sim_dt, fcs_dt = cfg.fcs_dt;
 #define XW(buf, e) buf[xi++][slot] = e;
 #define XR(buf, e) e = buf[xi++][slot];
@@ -567,31 +533,8 @@ __global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView
   if (role == 1) {
     // ================================================================ role B: flight controls + axes SIDE, ROLL, YAW
     Props p; FcsState s;
-    bool loaded = false;
-    if (L.valid) {
-      const int adim = 4 + cfg.shoot_dim;
-      const int32_t* act = actions + (size_t)L.row * adim;
-      double u0, u1, u2, u3;
-      if (cfg.act_kind == ACS_ACT_HEADING) {
-        u0 = act[0] * 2. / (41 - 1.) - 1.; u1 = act[1] * 2. / (41 - 1.) - 1.; u2 = act[2] * 2. / (41 - 1.) - 1.; u3 = act[3] * 0.5 / (30 - 1.) + 0.4;
-      } else {
-        u0 = act[0] / 20. - 1.; u1 = act[1] / 20. - 1.; u2 = act[2] / 20. - 1.; u3 = act[3] / 58. + 0.4;
-      }
-      u0 = env_clip(u0, -1.0, 1.0); u1 = env_clip(u1, -1.0, 1.0); u2 = env_clip(u2, -1.0, 1.0); u3 = env_clip(u3, 0.0, 0.9);
-      int shoot = 0;
-      for (int k = 0; k < cfg.shoot_dim; k++) shoot |= (act[4 + k] != 0) << k;
-      if (cfg.shoot_dim > 0) AI(v, AI_SHOOT, L.row) = shoot;
-      if (AI(v, AI_STATUS, L.row) == ST_ALIVE) {
-        AcCore a;   // only the carried properties are live on this side; the core loads are dead code
-        f16_props_init(p, s);
-        load_state(v.fdm, N, L.row, a, p, s);
-        p.fcs_aileron_cmd_norm = u0; p.fcs_elevator_cmd_norm = u1; p.fcs_rudder_cmd_norm = u2; p.fcs_throttle_cmd_norm = u3;
-        loaded = true;
-      } else {
-        v.fdm[(size_t)(F_CMD0 + 0) * N + L.row] = u0; v.fdm[(size_t)(F_CMD0 + 1) * N + L.row] = u1;
-        v.fdm[(size_t)(F_CMD0 + 2) * N + L.row] = u2; v.fdm[(size_t)(F_CMD0 + 3) * N + L.row] = u3;
-      }
-    }
+    AcCore unused;      // only the carried properties are live on this side; the core loads / stores are dead code
+    const bool loaded = L.valid && load_commanded(v, cfg, L, actions, AI(v, AI_STATUS, L.row) == ST_ALIVE, unused, p, s);
     for (int k = 0; k < K; k++) {
       TRIPLE_BARRIER(bar)                                      // 1
       const bool ran = sRun[slot] != 0;
@@ -611,10 +554,7 @@ __global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView
       }
       TRIPLE_BARRIER(bar)                                      // 3
     }
-    if (loaded) {
-      AcCore a;
-      store_state_role<true>(v.fdm, N, L.row, a, p, s);
-    }
+    if (loaded) store_state_role<true>(v.fdm, v.rows, L.row, unused, p, s);
     return;
   }
   if (role == 2) {
@@ -650,32 +590,12 @@ __global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView
   // ================================================================== role A: equations of motion, propulsion, missiles
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
   AcCore a; Props p; FcsState s; Frame f;
-  PubAc me;
-  double v_mps = 0, w_mps = 0, vc_mps = 0;
-  int status = ST_CRASH;
-  bool has_ms = false;
-  me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
-  if (L.valid) {
-    load_pub(v, L.row, me);
-    status = me.status;
-    has_ms = (AI(v, AI_N_LAUNCHED, L.row) > 0) || (AI(v, AI_CH_STATE, L.row) == CH_ACTIVE);
-    if (status == ST_ALIVE) {
-      f16_props_init(p, s);
-      load_state(v.fdm, N, L.row, a, p, s);
-    }
-  }
-  {
-    const unsigned b = __ballot_sync(L.gmask, has_ms);
-    has_ms = (b & L.gmask) != 0;
-  }
-  const bool was_alive = L.valid && status == ST_ALIVE;
-  const int sc0 = (L.env < v.B) ? EI(v, EI_SUBSTEP_COUNT, L.env) : 0;
-  AcOut o;
+  EomLane E;
+  eom_begin(v, L, E);
+  if (E.was_alive) { f16_props_init(p, s); load_state(v.fdm, v.rows, L.row, a, p, s); }
   for (int k = 0; k < K; k++) {
-    bool ran = false;
-    if (L.valid && status == ST_ALIVE) {                     // AircraftSimulator.run (simulatior.py:210-229)
-      if (me.bloods <= 0) status = ST_SHOTDOWN;
-      ran = true;
+    const bool ran = eom_runs(L, E);
+    if (ran) {
       fdm_stage_propagate(a, p, f, dt);
       sE[0][slot] = p.attitude_cos_pitch_cos_roll; sE[1][slot] = f.uvw.x; sE[2][slot] = f.uvw.y; sE[3][slot] = f.uvw.z;
       sE[4][slot] = f.radius; sE[5][slot] = f.cosLatGc;
@@ -696,11 +616,7 @@ __global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView
         f.vcas = sR[xi + 3][slot]; p.atmosphere_density_altitude = sR[xi + 4][slot]; }
       f.qbar = p.aero_qbar_psf; f.mach = p.velocities_mach;
       { int xi = 0; F16_X_SURF(XR_S) }
-      const int flags = (int)a.engflags;
-      bool augmentation = flags & 2;
-      f.thrust = fdm_stage_engine(a, p, f.atm, f.qbar, sT, g_atmo, dt, flags & 1, augmentation);
-      const bool starved_next = fdm_stage_consume_fuel(a, dt, flags & 1, false);
-      a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
+      eom_propulsion(a, p, f, sT, dt);
     }
     TRIPLE_BARRIER(bar)                                        // 3
     if (ran) {
@@ -709,32 +625,9 @@ __global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView
       for (int i = 0; i < 6; i++) c[i] = sSum[i][slot];
       fdm_stage_accelerations(a, f, w, c);
     }
-    if (has_ms) {
-      if (ran) publish_from_frame(f, org, me);
-      me.status = status;
-      sP[L.tid] = me;
-      sWin[L.tid] = 0x7fffffff;
-      sShot[L.tid] = 0;
-      __syncwarp(L.gmask);
-      missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, sc0 + k);
-      __syncwarp(L.gmask);
-      if (sShot[L.tid] && status == ST_ALIVE) status = ST_SHOTDOWN;   // target_aircraft.shotdown() (simulatior.py:527)
-      __syncwarp(L.gmask);
-    }
-    if (ran && (k == K - 1 || status != ST_ALIVE)) {
-      fdm_outputs(a, f, o);
-      derive_aircraft(o, org, me, v_mps, w_mps, vc_mps);
-    }
+    eom_after_frame(v, cfg, L, org, E, a, f, ran, k, K, sP, sWin, sShot, sCh);
   }
-  if (L.valid) {
-    if (was_alive) {
-      store_state_role<false>(v.fdm, N, L.row, a, p, s);
-      store_out(v.out, N, L.row, o);
-      store_derived(v, L.row, me, v_mps, w_mps, vc_mps);
-    }
-    AI(v, AI_STATUS, L.row) = status;
-    if (L.lane == 0) EI(v, EI_SUBSTEP_COUNT, L.env) = sc0 + K;
-  }
+  eom_end<false>(v, L, E, a, p, s, K);
 #undef XW
 #undef XR
 #undef XW_K
@@ -1324,14 +1217,7 @@ __global__ void __launch_bounds__(256) k_env_post(const __grid_constant__ EnvVie
   __shared__ int sDone[128];
   const int obs_role = obs_split ? (threadIdx.x >> 7) : 0;      // warp-uniform
   PubAc* sP = sP2[obs_role];
-  Lane L;
-  {
-    const int G = 1 << lg, slot = threadIdx.x & 127, gid = blockIdx.x * 128 + slot;
-    L.tid = slot; L.env = gid >> lg; L.lane = gid & (G - 1); L.gbase = slot - L.lane;
-    L.valid = (L.env < v.B) && (L.lane < v.A);
-    L.row = L.env * v.A + L.lane;
-    L.gmask = ((1u << G) - 1u) << ((unsigned)(slot & 31) & ~(unsigned)(G - 1));
-  }
+  const Lane L = lane_of_slot(v, lg, threadIdx.x & 127, blockIdx.x * 128 + (threadIdx.x & 127));
   const int A = v.A;
   if (fuse_reset && tpl.full && !obs_role) tpl_prefetch(tpl);     // long before the first env of this warp can need it
   PubAc me;
