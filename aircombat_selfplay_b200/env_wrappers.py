@@ -180,7 +180,9 @@ class BatchedVecEnv(VecEnv):
         N, A = self.num_envs, self.num_agents
         obs = self._arr("obs")
         rewards = self._arr("rewards").reshape(N, A, 1)
-        dones = self._views["dones"].astype(bool).reshape(N, A, 1)
+        dones = self._views["dones"].view(np.bool_).reshape(N, A, 1)     # the kernel writes 0 / 1: a view, not a conversion
+        if self.copy:
+            dones = dones.copy()
         if self.share:
             return obs, self._share(obs), rewards, dones, self._infos
         return obs, rewards, dones, self._infos
