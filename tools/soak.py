@@ -1,0 +1,36 @@
+"""Soak run: thousands of steps of random actions on every substep kernel; no NaN, no fault counter, same episode statistics."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np, torch
+from aircombat_selfplay_b200.capi import EnvBatch
+from aircombat_selfplay_b200.tasks import load_spec
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+for cfg, n in (("1v1/NoWeapon/Selfplay", 4096), ("2v2/ShootMissile/HierarchySelfplay", 1024), ("scenario3/scenario3", 512), ("singlecontrol/heading", 2048)):
+    spec = load_spec(cfg, substeps_override=12)
+    A = spec.n_agents
+    stats = []
+    for split in (0, 1, 2):
+        b = EnvBatch(spec, n, seed=0)
+        b.set_option("frame_split", split)
+        b.reset()
+        g = torch.Generator(device="cuda"); g.manual_seed(1)
+        ndone = torch.zeros((), device="cuda", dtype=torch.int64)
+        rsum = torch.zeros((), device="cuda", dtype=torch.float64)
+        bad = torch.zeros((), device="cuda", dtype=torch.int64)
+        for t in range(steps):
+            act = torch.cat([torch.randint(0, 41, (n, A, 3), device="cuda", generator=g), torch.randint(0, 30, (n, A, 1), device="cuda", generator=g),
+                             (torch.rand((n, A, spec.shoot_dim), device="cuda", generator=g) < 0.05).long()], dim=-1).to(torch.int32)
+            obs, _, rew, done, info = b.step(act, auto_reset=True)
+            ndone += b.env_done.sum(); rsum += rew.sum(); bad += (~torch.isfinite(obs)).sum() + (~torch.isfinite(rew)).sum()
+        names, ei = b.arena("env_i")
+        faults = int(ei[names.index("faults")].sum())
+        stats.append((int(ndone), float(rsum), int(bad), faults))
+        b.close()
+    print(cfg, "episodes / reward sum / non-finite / faults per kernel:", stats, flush=True)
+    assert all(s[2] == 0 and s[3] == 0 for s in stats), stats
+    # the kernels round differently in the last bit (FMA contraction); over thousands of steps of close combat that is
+    # enough to move an occasional episode boundary, so the statistics agree closely, not exactly
+    assert max(s[0] for s in stats) - min(s[0] for s in stats) <= max(2, stats[0][0] // 200), "episode counts differ between kernels"
+    assert abs(stats[1][1] - stats[0][1]) <= 2e-2 * abs(stats[0][1]) + 1.0
+print("soak ok")
