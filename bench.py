@@ -100,14 +100,21 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def _poll(self):
+    def poll_once(self):
+        """One sample now (called by the bench while the timed launches are still in flight, so that even a timed region
+        shorter than the polling period is sampled under load)."""
         n = self.nvml
+        if n is None:
+            return
+        try:
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+            self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            pass
+
+    def _poll(self):
         while not self._stop.is_set():
-            try:
-                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
-                self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-            except Exception:
-                pass
+            self.poll_once()
             time.sleep(0.002)
 
     def _pump(self):
@@ -272,6 +279,7 @@ def run_b200(args):
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
         ev[k][0].record(); core.step(acts_dev[args.warmup + k]); ev[k][1].record()
+    sampler.poll_once()                     # the launches above run ahead of the device: this sample is under load
     torch.cuda.synchronize(); _barrier(world)
     clocks = sampler.stop()
     ms = sum(a.elapsed_time(b) for a, b in ev)
