@@ -139,16 +139,19 @@ def test_env_offset_keeps_rng_streams_per_env():
         assert torch.equal(of[8:], oh)
 
 
-def test_device_share_obs_equals_the_broadcast_view():
-    """share_obs written by the kernel (device_share_obs=True) == the stride-0 view of obs used by default."""
+@pytest.mark.parametrize("name", ["scenario2/scenario2", "2v2/NoWeapon/Selfplay"])
+def test_device_share_obs_equals_the_broadcast_view(name):
+    """share_obs written by the kernel (device_share_obs=True) == the stride-0 view of obs used by default (the no-weapon
+    config takes the observation-warp path of k_env_post and, with short episodes, the fused template reset)."""
     from aircombat_selfplay_b200.capi import EnvBatch
-    spec = load_spec("scenario2/scenario2")
+    spec = load_spec(name)
+    spec.max_steps = 3
     rng = np.random.default_rng(8)
     a = EnvBatch(spec, 16, seed=2, device_share_obs=True)
     b = EnvBatch(spec, 16, seed=2)
     oa, sa = a.reset()
     ob, sb = b.reset()
-    assert sa.shape == sb.shape == (16, 4, 84) and torch.equal(sa, sb) and torch.equal(oa, ob)
+    assert sa.shape == sb.shape == (16, 4, 4 * spec.obs_dim) and torch.equal(sa, sb) and torch.equal(oa, ob)
     for _ in range(5):
         act = torch.tensor(random_actions(rng, spec, 16), device="cuda")
         _, sa, *_ = a.step(act, auto_reset=True)
