@@ -416,6 +416,7 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     e->split_max_threads = prop.multiProcessorCount * ACS_SPLIT_AUTO_LANES_PER_SM;
     e->n_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaFuncSetAttribute(k_env_substeps_split4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S4_DYN_SMEM));
     if (const char* s = std::getenv("ACS_FRAME_SPLIT")) e->frame_split = std::atoi(s);
   }
   *out = e;
@@ -425,7 +426,7 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
 int acs_env_set_option(AcsEnv* e, const char* name, int value) {
   if (!e || !name) return fail("acs_env_set_option: null argument");
   if (!std::strcmp(name, "frame_split")) {
-    if (value < -1 || value > 2) return fail("acs_env_set_option: frame_split must be -1 (auto), 0, 1 or 2");
+    if (value < -1 || value > 3) return fail("acs_env_set_option: frame_split must be -1 (auto), 0, 1, 2 or 3");
     e->frame_split = value;
     return 0;
   }
@@ -558,7 +559,8 @@ int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double*
   const int threads = e->v.B * e->G;
   if (e->timing) timing_event(e, st);
   const int split = frame_split_effective(e);
-  if (split == 2) k_env_substeps_split3<<<(threads + S3 - 1) / S3, 3 * S3, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
+  if (split == 3) k_env_substeps_split4<<<(threads + S4 - 1) / S4, 4 * S4, S4_DYN_SMEM, st>>>(e->v, e->cfg, e->lg, actions_dev);
+  else if (split == 2) k_env_substeps_split3<<<(threads + S3 - 1) / S3, 3 * S3, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   else if (split == 1) k_env_substeps_split<<<(threads + SPLIT_SLOTS - 1) / SPLIT_SLOTS, 2 * SPLIT_SLOTS, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   else k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   CUDA_TRY(cudaGetLastError());

@@ -638,6 +638,253 @@ __global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView
 #undef XR_R
 }
 
+// ---------------------------------------------------------------------------------------------- four-warp frame
+// The position chain of Propagate -- inertial position (Adams-Bashforth 3 on PAST velocities), earth rotation angle,
+// ECEF location, geodetic latitude / altitude, local frame -- and the gravity and atmosphere that hang off it depend only
+// on the inertial velocity the previous frame ended with.  A fourth role computes them ONE FRAME AHEAD, so they leave
+// the critical path altogether:
+//
+//   role A (equations of motion)      role B (flight controls)   role C (air data)           role D (position, look-ahead)
+//   Accelerations of frame k-1, missiles;                        reads atmosphere(k) from L
+//   attitude / rate / velocity update, reads L(k), body matrices
+//        -- E: cos(pitch)cos(roll), u, v, w, v_inertial(k), run flag -->
+//   --------------------------------------------------------------------------------------------- barrier 1 (all four)
+//   MassBalance, kinematic Auxiliary   FCS                        air-data Auxiliary          position(k+1), location,
+//        -- K -->                          -- S -->                   -- R: qbar, Mach, Vc -->    gravity, atmosphere
+//   ----------------------------------------------------------------------- barrier 2 (A, B, C)  ... -> L(k+1)
+//   Propulsion                         axes SIDE ROLL YAW         axes DRAG LIFT PITCH
+//   --------------------------------------------------------------------------------------------- barrier 3 (all four)
+//
+// L is read by A and C only between barrier 3 of frame k-1 and barrier 1 of frame k, and written by D only between
+// barrier 1 and barrier 3 of frame k: one buffer.  D runs ahead of the aircraft's status: when the aircraft does not run
+// frame k (shot down in frame k-1), D rolls its four state vectors back to the frame that did run.  The last frame of a
+// step computes no look-ahead (the next step's first frame is computed by D's prologue from the stored state).
+#ifndef ACS_SPLIT4_SLOTS
+#define ACS_SPLIT4_SLOTS 64
+#endif
+constexpr int S4 = ACS_SPLIT4_SLOTS;
+static_assert(S4 % 32 == 0 && S4 >= 32 && S4 <= 128, "whole warps, at most 4 quads per block (two named barriers each)");
+#define S4_L_FIELDS(X) X(ri_x) X(ri_y) X(f.sin_epa) X(f.cos_epa) X(f.ecef.x) X(f.ecef.y) X(f.ecef.z) X(f.radius) X(f.rxy) X(f.geodAlt) \
+  X(f.sinLatGd) X(f.cosLatGd) X(f.sinLon) X(f.cosLon) X(f.cosLatGc) X(f.gd_s1) X(f.gd_cc) \
+  X(f.Ti2l.m[0][0]) X(f.Ti2l.m[0][1]) X(f.Ti2l.m[0][2]) X(f.Ti2l.m[1][0]) X(f.Ti2l.m[1][1]) X(f.Ti2l.m[1][2]) \
+  X(f.Ti2l.m[2][0]) X(f.Ti2l.m[2][1]) X(f.Ti2l.m[2][2]) X(f.grav.x) X(f.grav.y) X(f.grav.z) X(f.h_asl) X(f.atm.T) X(f.atm.rho) \
+  X(p.atmosphere_density_altitude)
+constexpr int S4_NL = 33 + 2;                        // the list above + atm.P, atm.a (role C only)
+constexpr int S4_NE = 7, S4_NK = F16_N_X_KIN + 1, S4_NS = F16_N_X_SURF, S4_NR = F16_N_X_AIR + 1, S4_NSUM = 6;
+constexpr int S4_ROWS = S4_NL + S4_NE + S4_NK + S4_NS + S4_NR + S4_NSUM;
+constexpr size_t S4_DYN_SMEM = sizeof(double) * S4_ROWS * S4;
+
+#define QUAD_BARRIER_ALL(q) { __syncwarp(); asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * (q)) : "memory"); }
+#define QUAD_BARRIER_ABC(q) { __syncwarp(); asm volatile("bar.sync %0, 96;" ::"r"(2 + 2 * (q)) : "memory"); }
+
+// core state fields owned by role D of the four-warp frame (position chain); names of FDM_CORE_FIELDS
+#define S4_CORE_ROLE_D(name) (f16_streq(name, "ri_x") || f16_streq(name, "ri_y") || f16_streq(name, "ri_z") || f16_streq(name, "epa") || \
+  f16_streq(name, "dqv0_x") || f16_streq(name, "dqv0_y") || f16_streq(name, "dqv0_z") || f16_streq(name, "dqv1_x") || \
+  f16_streq(name, "dqv1_y") || f16_streq(name, "dqv1_z"))
+// ROLE: 0 = A (core minus D's fields + the carried properties the core publishes), 3 = D (position chain)
+template <int ROLE>
+ENV_DEV void store_state_role4(double* __restrict__ st, int N, int i, const AcCore& a, const Props& p, const FcsState& s) {
+  int k = 0;
+#define ST(name, expr) { constexpr bool d_ = S4_CORE_ROLE_D(name); if (d_ == (ROLE == 3)) st[(size_t)k * N + i] = expr; k++; }
+  FDM_CORE_FIELDS(ST)
+#undef ST
+#define ST(name, expr) { constexpr bool b_ = F16_CARRIED_ROLE_B(name); if (!b_ && ROLE == 0) st[(size_t)k * N + i] = expr; k++; }
+  F16_CARRIED_FIELDS(ST)
+#undef ST
+}
+
+__global__ void __launch_bounds__(4 * S4, 1) k_env_substeps_split4(const EnvView v, const __grid_constant__ AcsTaskConfig cfg,
+                                                                  const int lg, const int32_t* __restrict__ actions) {
+  __shared__ double sT[F16_NTAB];
+  __shared__ PubAc sP[S4];
+  __shared__ int sWin[S4];
+  __shared__ int sShot[S4];
+  __shared__ PubChaff sCh[S4];
+  __shared__ int sRun[S4];
+  extern __shared__ double sDyn[];
+  double (*sL)[S4] = reinterpret_cast<double (*)[S4]>(sDyn);
+  double (*sE)[S4] = sL + S4_NL;
+  double (*sK)[S4] = sE + S4_NE;
+  double (*sS)[S4] = sK + S4_NK;
+  double (*sR)[S4] = sS + S4_NS;
+  double (*sSum)[S4] = sR + S4_NR;
+  stage_tables(sT);
+  const int role = threadIdx.x / S4;            // warp-uniform: 0 = A, 1 = B, 2 = C, 3 = D
+  const int slot = threadIdx.x - role * S4;
+  const int quad = slot >> 5;
+  const Lane L = lane_of_slot(v, lg, slot, blockIdx.x * S4 + slot);
+  const int K = cfg.substeps;
+  const double dt = cfg.sim_dt, fcs_dt = cfg.fcs_dt;
+#define XW(buf, e) buf[xi++][slot] = e;
+#define XR(buf, e) e = buf[xi++][slot];
+#define XW_K(e) XW(sK, e)
+#define XR_K(e) XR(sK, e)
+#define XW_S(e) XW(sS, e)
+#define XR_S(e) XR(sS, e)
+#define XW_R(e) XW(sR, e)
+#define XR_R(e) XR(sR, e)
+#define XW_L(e) XW(sL, e)
+#define XR_L(e) XR(sL, e)
+
+  if (role == 3) {
+    // ================================================================ role D: position chain, one frame ahead
+    AcCore a; Props p; FcsState s; Frame f;
+    bool loaded = false;
+    if (L.valid && AI(v, AI_STATUS, L.row) == ST_ALIVE) {
+      f16_props_init(p, s);
+      load_state(v.fdm, v.rows, L.row, a, p, s);     // ri, dqv0, dqv1, epa (+ the velocity the last step ended with) are live
+      loaded = true;
+    }
+    V3 pri = a.ri, pq0 = a.dqv0, pq1 = a.dqv1;        // the state of the last frame that is known to have run
+    double pepa = a.epa;
+    bool ahead = false;
+    auto look_ahead = [&](const V3& v0) {
+      pri = a.ri; pq0 = a.dqv0; pq1 = a.dqv1; pepa = a.epa;
+      fdm_propagate_pos(a, f, v0, dt);
+      fdm_stage_gravity(f);
+      fdm_stage_atmosphere(p, f, g_atmo);
+      const double ri_x = a.ri.x, ri_y = a.ri.y;
+      { int xi = 0; S4_L_FIELDS(XW_L) sL[xi][slot] = f.atm.P; sL[xi + 1][slot] = f.atm.a; }
+      ahead = true;
+    };
+    if (loaded) look_ahead(a.vi);                        // frame 0 of this step
+    QUAD_BARRIER_ALL(quad)                               // 0: L(0) is there
+    for (int k = 0; k < K; k++) {
+      QUAD_BARRIER_ALL(quad)                             // 1
+      const bool ran = sRun[slot] != 0;
+      if (!ran) {
+        if (ahead) { a.ri = pri; a.dqv0 = pq0; a.dqv1 = pq1; a.epa = pepa; ahead = false; }   // that frame never ran
+      } else if (k < K - 1) {
+        look_ahead(v3(sE[4][slot], sE[5][slot], sE[6][slot]));
+      } else ahead = false;
+      QUAD_BARRIER_ALL(quad)                             // 3: L(k+1) is there
+    }
+    if (loaded) store_state_role4<3>(v.fdm, v.rows, L.row, a, p, s);
+    return;
+  }
+  if (role == 1) {
+    // ================================================================ role B: flight controls + axes SIDE, ROLL, YAW
+    Props p; FcsState s;
+    AcCore unused;      // only the carried properties are live on this side; the core loads / stores are dead code
+    const bool loaded = L.valid && load_commanded(v, cfg, L, actions, AI(v, AI_STATUS, L.row) == ST_ALIVE, unused, p, s);
+    QUAD_BARRIER_ALL(quad)                               // 0
+    for (int k = 0; k < K; k++) {
+      QUAD_BARRIER_ALL(quad)                             // 1
+      const bool ran = sRun[slot] != 0;
+      if (ran) {
+        p.attitude_cos_pitch_cos_roll = sE[0][slot]; p.velocities_u_fps = sE[1][slot]; p.velocities_v_fps = sE[2][slot];
+        f16_fcs(p, s, sT, fcs_dt);
+        { int xi = 0; F16_X_SURF(XW_S) }
+      }
+      QUAD_BARRIER_ABC(quad)                             // 2
+      if (ran) {
+        double twovel, c[6];
+        { int xi = 0; F16_X_KIN(XR_K) twovel = sK[xi][slot]; }
+        { int xi = 0; F16_X_AIR(XR_R) }
+        f16_aero<S3_AXES_B>(p, sT, twovel, c);
+#pragma unroll
+        for (int i = 0; i < 6; i++) if (S3_AXES_B & (1 << i)) sSum[i][slot] = c[i];
+      }
+      QUAD_BARRIER_ALL(quad)                             // 3
+    }
+    if (loaded) store_state_role<true>(v.fdm, v.rows, L.row, unused, p, s);
+    return;
+  }
+  if (role == 2) {
+    // ================================================================ role C: air data + axes DRAG, LIFT, PITCH (no state)
+    Props p; FcsState s;
+    f16_props_init(p, s);
+    Frame f;
+    QUAD_BARRIER_ALL(quad)                               // 0
+    for (int k = 0; k < K; k++) {
+      // the atmosphere of this frame, computed ahead by D (must be read before D overwrites L after barrier 1)
+      f.atm.T = sL[30][slot]; f.atm.rho = sL[31][slot]; f.atm.P = sL[33][slot]; f.atm.a = sL[34][slot];
+      QUAD_BARRIER_ALL(quad)                             // 1
+      const bool ran = sRun[slot] != 0;
+      if (ran) {
+        f.uvw.x = sE[1][slot]; f.uvw.y = sE[2][slot]; f.uvw.z = sE[3][slot];
+        fdm_airspeed(f);
+        fdm_stage_aux_air(p, f, g_atmo);
+        { int xi = 0; F16_X_AIR(XW_R) sR[xi][slot] = f.vcas; }
+      }
+      QUAD_BARRIER_ABC(quad)                             // 2
+      if (ran) {
+        double c[6];
+        { int xi = 0; F16_X_KIN(XR_K) }
+        { int xi = 0; F16_X_SURF(XR_S) }
+        f16_aero<S3_AXES_C>(p, sT, 2 * f.Vt, c);
+#pragma unroll
+        for (int i = 0; i < 6; i++) if (S3_AXES_C & (1 << i)) sSum[i][slot] = c[i];
+      }
+      QUAD_BARRIER_ALL(quad)                             // 3
+    }
+    return;
+  }
+
+  // ================================================================== role A: equations of motion, propulsion, missiles
+  const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
+  AcCore a; Props p; FcsState s; Frame f;
+  EomLane E;
+  eom_begin(v, L, E);
+  if (E.was_alive) { f16_props_init(p, s); load_state(v.fdm, v.rows, L.row, a, p, s); }
+  QUAD_BARRIER_ALL(quad)                                 // 0
+  for (int k = 0; k < K; k++) {
+    const bool ran = eom_runs(L, E);
+    if (ran) {
+      V3 v0;
+      fdm_propagate_rot(a, dt, v0);
+      double ri_x, ri_y;
+      { int xi = 0; S4_L_FIELDS(XR_L) }
+      fdm_propagate_combine(a, p, f, ri_x, ri_y);
+      sE[0][slot] = p.attitude_cos_pitch_cos_roll; sE[1][slot] = f.uvw.x; sE[2][slot] = f.uvw.y; sE[3][slot] = f.uvw.z;
+      sE[4][slot] = a.vi.x; sE[5][slot] = a.vi.y; sE[6][slot] = a.vi.z;
+    }
+    sRun[slot] = ran;
+    QUAD_BARRIER_ALL(quad)                               // 1
+    WindAxes w;
+    if (ran) {
+      fdm_stage_massbalance(a, f);
+      fdm_stage_aux_kin(a, p, f, w);
+      { int xi = 0; F16_X_KIN(XW_K) sK[xi][slot] = 2 * f.Vt; }
+    }
+    QUAD_BARRIER_ABC(quad)                               // 2
+    if (ran) {
+      { int xi = 0; F16_X_AIR(XR_R) f.vcas = sR[xi][slot]; }
+      f.qbar = p.aero_qbar_psf; f.mach = p.velocities_mach;
+      { int xi = 0; F16_X_SURF(XR_S) }
+      eom_propulsion(a, p, f, sT, dt);
+    }
+    QUAD_BARRIER_ALL(quad)                               // 3
+    if (ran) {
+      double c[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) c[i] = sSum[i][slot];
+      fdm_stage_accelerations(a, f, w, c);
+    }
+    eom_after_frame(v, cfg, L, org, E, a, f, ran, k, K, sP, sWin, sShot, sCh);
+  }
+  // as eom_end<false>, minus the position chain role D stores
+  if (L.valid) {
+    if (E.was_alive) {
+      store_state_role4<0>(v.fdm, v.rows, L.row, a, p, s);
+      store_out(v.out, v.rows, L.row, E.o);
+      store_derived(v, L.row, E.me, E.v_mps, E.w_mps, E.vc_mps);
+    }
+    AI(v, AI_STATUS, L.row) = E.status;
+    if (L.lane == 0) EI(v, EI_SUBSTEP_COUNT, L.env) = E.sc0 + K;
+  }
+#undef XW
+#undef XR
+#undef XW_K
+#undef XR_K
+#undef XW_S
+#undef XR_S
+#undef XW_R
+#undef XR_R
+#undef XW_L
+#undef XR_L
+}
+
 // ============================================================================================== per-step logic
 struct StepCtx {
   const EnvView& v;

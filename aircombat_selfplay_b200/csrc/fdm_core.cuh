@@ -305,6 +305,7 @@ struct AcOut {
 // ------------------------------------------------------------------ per-frame scratch shared between the model stages
 struct Frame {
   M33 Ti2b, Tl2b;          // body matrices of this frame
+  M33 Ti2l;                // inertial -> local (NED) of this frame's position
   double sin_epa, cos_epa;
   V3 ecef;                 // vLocation
   double radius, rxy, geodAlt, sinLatGd, cosLatGd, sinLon, cosLon, cosLatGc, h_asl, gd_s1, gd_cc;
@@ -403,8 +404,13 @@ FDM_DEV void location_derived(Frame& f, M33& Tec2l) {
 // (fdm_split.cuh) run the same arithmetic.  dt = 0 reproduces the suspended-integration passes of FGFDMExec::RunIC.
 struct WindAxes { double sa, ca, sb, cb; };
 
-FDM_DEV void fdm_stage_propagate(AcCore& a, Props& p, Frame& f, const double dt) {
-  // ---------------- Propagate (J/models/FGPropagate.cpp:218-297)
+// Propagate (J/models/FGPropagate.cpp:218-297) in three parts.  The position chain -- inertial position (Adams-Bashforth 3
+// on the PAST velocities), earth rotation angle, ECEF location, geodetic quantities, local frame -- does not depend on
+// this frame's velocity or attitude update, only on the velocity the previous frame ended with, so a multi-warp frame
+// computes it (and the gravity and atmosphere that hang off it) one frame ahead on another warp.  Called in the order
+// rot, pos, combine on one thread they are FGPropagate::Run.
+FDM_DEV void fdm_propagate_rot(AcCore& a, const double dt, V3& vi_before) {   // attitude, rates, inertial velocity
+  vi_before = a.vi;   // the position integrator uses the velocity from before this frame's velocity update (:228-231)
   if (dt != 0.0) {
     a.sim_time += dt;  // FGFDMExec::IncrTime
     // quaternion: rectangular Euler on qdot of the previous frame's state, then normalise (:371-470)
@@ -418,16 +424,18 @@ FDM_DEV void fdm_stage_propagate(AcCore& a, Props& p, Frame& f, const double dt)
       if (!(n == 0.0 || fabs(n - 1.000) < 1e-10)) { const double rn = 1.0 / n; a.q0 *= rn; a.q1 *= rn; a.q2 *= rn; a.q3 *= rn; }
     }
     a.wi = a.wi + dt * a.pqridot;                                                        // eRectEuler
-    {                                                                                     // eAdamsBashforth3 on position
-      const V3 v0 = a.vi;
-      a.ri = a.ri + ((1 / 12.0) * dt) * (23.0 * v0 - 16.0 * a.dqv0 + 5.0 * a.dqv1);
-      a.dqv1 = a.dqv0; a.dqv0 = v0;
-    }
     {                                                                                     // eAdamsBashforth2 on velocity
       const V3 a0 = a.uvwidot;
       a.vi = a.vi + dt * (1.5 * a0 - 0.5 * a.dqa0);
       a.dqa0 = a0;
     }
+  }
+}
+// position state = a.ri, a.dqv0, a.dqv1, a.epa; v0 = the inertial velocity before this frame's update
+FDM_DEV void fdm_propagate_pos(AcCore& a, Frame& f, const V3& v0, const double dt) {
+  if (dt != 0.0) {                                                                        // eAdamsBashforth3 on position
+    a.ri = a.ri + ((1 / 12.0) * dt) * (23.0 * v0 - 16.0 * a.dqv0 + 5.0 * a.dqv1);
+    a.dqv1 = a.dqv0; a.dqv0 = v0;
   }
   a.epa += EARTH_OMEGA * dt;
   sincos(a.epa, &f.sin_epa, &f.cos_epa);
@@ -436,22 +444,31 @@ FDM_DEV void fdm_stage_propagate(AcCore& a, Props& p, Frame& f, const double dt)
   M33 Tec2l;
   location_derived(f, Tec2l);
   // Ti2l = Tec2l * Ti2ec with Ti2ec = Rz(epa): only the first two columns mix (J/models/FGPropagate.cpp:475-496)
-  M33 Ti2l;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
-    Ti2l.m[i][0] = Tec2l.m[i][0] * f.cos_epa - Tec2l.m[i][1] * f.sin_epa;
-    Ti2l.m[i][1] = Tec2l.m[i][0] * f.sin_epa + Tec2l.m[i][1] * f.cos_epa;
-    Ti2l.m[i][2] = Tec2l.m[i][2];
+    f.Ti2l.m[i][0] = Tec2l.m[i][0] * f.cos_epa - Tec2l.m[i][1] * f.sin_epa;
+    f.Ti2l.m[i][1] = Tec2l.m[i][0] * f.sin_epa + Tec2l.m[i][1] * f.cos_epa;
+    f.Ti2l.m[i][2] = Tec2l.m[i][2];
   }
+}
+// body matrices and velocities from the attitude / velocity of `rot` and the position / local frame of `pos`
+// (ri_x, ri_y: inertial position components the earth-rate term needs)
+FDM_DEV void fdm_propagate_combine(const AcCore& a, Props& p, Frame& f, const double ri_x, const double ri_y) {
   f.Ti2b = quat_T(a.q0, a.q1, a.q2, a.q3);
-  f.Tl2b = mulABt(f.Ti2b, Ti2l);        // Ti2b * Tl2i
+  f.Tl2b = mulABt(f.Ti2b, f.Ti2l);        // Ti2b * Tl2i
   // Omega = (0, 0, w): Omega x r = (-w y, w x, 0); Ti2b * Omega = w * third column of Ti2b
-  f.uvw = mul(f.Ti2b, v3(a.vi.x + EARTH_OMEGA * a.ri.y, a.vi.y - EARTH_OMEGA * a.ri.x, a.vi.z));
+  f.uvw = mul(f.Ti2b, v3(a.vi.x + EARTH_OMEGA * ri_y, a.vi.y - EARTH_OMEGA * ri_x, a.vi.z));
   f.pqr = v3(a.wi.x - EARTH_OMEGA * f.Ti2b.m[0][2], a.wi.y - EARTH_OMEGA * f.Ti2b.m[1][2], a.wi.z - EARTH_OMEGA * f.Ti2b.m[2][2]);
   f.vel = mulT(f.Tl2b, f.uvw);
   // The FCS reads the Euler angles only as cos(pitch) * cos(roll) (fcs/n-pilot-z-correction), which is Tl2b(3,3); the
   // angles themselves are extracted once per interaction step in fdm_outputs.
   p.attitude_cos_pitch_cos_roll = f.Tl2b.m[2][2]; p.velocities_u_fps = f.uvw.x; p.velocities_v_fps = f.uvw.y;
+}
+FDM_DEV void fdm_stage_propagate(AcCore& a, Props& p, Frame& f, const double dt) {
+  V3 v0;
+  fdm_propagate_rot(a, dt, v0);
+  fdm_propagate_pos(a, f, v0, dt);
+  fdm_propagate_combine(a, p, f, a.ri.x, a.ri.y);
 }
 
 FDM_DEV void fdm_stage_gravity(Frame& f) {

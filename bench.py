@@ -314,7 +314,7 @@ def run_b200(args):
     bytes_per_agent_step = (2 * n_state + n_out + 11 + 11) * 8 + 2 * 4 + (4 + spec.shoot_dim) * 4
     k_ms = kms["substeps"] / max(ksteps, 1)
     ach = n_envs * A * bytes_per_agent_step / (k_ms * 1e-3) / 1e9
-    kname = ("k_env_substeps", "k_env_substeps_split", "k_env_substeps_split3")[batch.get_option("frame_split_effective")]
+    kname = ("k_env_substeps", "k_env_substeps_split", "k_env_substeps_split3", "k_env_substeps_split4")[batch.get_option("frame_split_effective")]
     roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": _ncu_traffic(kname, config, n_envs), "peak_source": peak_src, "algorithmic_bytes_per_agent_step": bytes_per_agent_step,
             "kernel_ms": k_ms, "kernel_share_of_step": kms["substeps"] / max(sum(kms.values()), 1e-12),

@@ -159,8 +159,9 @@ int acs_env_set_arena(AcsEnv* e, int which, const void* src_dev, void* stream);
 AcsHandle* acs_env_fdm(AcsEnv* e);
 
 /* Tuning knob (no reference counterpart).  "frame_split": which substep kernel acs_env_step launches -- 0 = one thread per
- * aircraft (throughput kernel), 1 = the two-warp frame (two threads in two warps per aircraft running the stages of one
- * FDM frame concurrently; lower latency while the batch leaves SM sub-partitions idle), -1 = choose by batch size
+ * aircraft (throughput kernel), 1 / 2 / 3 = the two- / three- / four-warp frame (that many threads in different warps
+ * per aircraft running the stages of one FDM frame concurrently; lower latency while the batch leaves SM
+ * sub-partitions idle; 3 is opt-in only), -1 = choose by batch size
  * (default; the environment variable ACS_FRAME_SPLIT overrides the default at acs_env_create).  Both kernels evaluate
  * the same expressions.  Returns non-zero for an unknown option or value. */
 int acs_env_set_option(AcsEnv* e, const char* name, int value);

@@ -13,7 +13,7 @@ from tests.env_parity import CONFIGS, Pair, close_init_states, compare_reset, co
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["one-thread-frame", "two-warp-frame", "three-warp-frame"], autouse=True)
+@pytest.fixture(params=[0, 1, 2, 3], ids=["one-thread-frame", "two-warp-frame", "three-warp-frame", "four-warp-frame"], autouse=True)
 def frame_split(request, monkeypatch):
     """Every parity case runs against both substep kernels (include/acs.h, acs_env_set_option "frame_split"); the
     variable is read at acs_env_create."""
@@ -166,7 +166,7 @@ def test_multi_warp_frames_match_one_thread_frame():
     spec = load_spec("scenario2/scenario2")
     n = 1000
     bs = []
-    for split in (0, 1, 2):
+    for split in (0, 1, 2, 3):
         b = EnvBatch(spec, n, seed=9)
         b.set_option("frame_split", split)
         b.set_init_states(close_init_states(spec, np.random.default_rng(1)))

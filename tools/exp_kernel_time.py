@@ -28,7 +28,7 @@ def run(config, n_envs, steps=20, warm=5, split=None):
 
 tag = os.environ.get("ACS_LIB", "default").split("/")[-1]
 sizes = [int(x) for x in os.environ.get("EXP_SIZES", "4096,16384,65536").split(",")]
-for split in (0, 1, 2):
+for split in (0, 1, 2, 3):
     out = [tag, f"split={split}"]
     for config, n in [("1v1/NoWeapon/Selfplay", n) for n in sizes] + [("2v2/ShootMissile/HierarchySelfplay", 8192)]:
         s, p, r = run(config, n, split=split)

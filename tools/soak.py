@@ -10,7 +10,7 @@ for cfg, n in (("1v1/NoWeapon/Selfplay", 4096), ("2v2/ShootMissile/HierarchySelf
     spec = load_spec(cfg, substeps_override=12)
     A = spec.n_agents
     stats = []
-    for split in (0, 1, 2):
+    for split in (0, 1, 2, 3):
         b = EnvBatch(spec, n, seed=0)
         b.set_option("frame_split", split)
         b.reset()
