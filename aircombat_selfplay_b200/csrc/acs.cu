@@ -475,6 +475,16 @@ static int build_reset_template(AcsEnv* e) {
       }
       if (same != ar[k].per) {
         if (same != 0) return 0;     // written for some lanes / slots only: keep the computed reset
+        // A word that differs between the passes must be one reset() leaves alone, i.e. still the fill pattern in both
+        // (the episode counter, the one read-modify-write reset_copy_warp knows about, excepted).  Anything else is a
+        // value that depends on what was there before: not a template, keep the computed reset.
+        if (!(k == 5 && f == EI_EPISODE)) {
+          for (int j = 0; j < ar[k].per; j++) {
+            const size_t o = ((size_t)f * ar[k].per + j) * ar[k].elt;
+            for (size_t b = 0; b < ar[k].elt; b++)
+              if (snap[0][k][o + b] != 0x00 || snap[1][k][o + b] != 0x55) return 0;
+          }
+        }
         continue;
       }
       for (int j = 0; j < ar[k].per; j++) {
