@@ -1,0 +1,31 @@
+"""Tuning experiment: time of the PyTorch side of a hierarchical step (controller + action plumbing) vs the env kernels."""
+import sys, time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import numpy as np, torch
+from aircombat_selfplay_b200.envs import BatchedEnv
+n = 8192
+env = BatchedEnv("2v2/ShootMissile/HierarchySelfplay", n, seed=0, substeps=12)
+env.reset()
+A = env.n_agents
+rng = np.random.default_rng(0)
+acts = torch.tensor(np.concatenate([rng.integers(0, 3, (n, A, 1)), rng.integers(0, 5, (n, A, 1)), rng.integers(0, 3, (n, A, 1)),
+                                    (rng.random((n, A, env.act_dim - 3)) < 0.05).astype(np.int64)], axis=-1).astype(np.int32), device="cuda")
+for _ in range(20): env.step(acts)
+def timed(fn, reps=50):
+    torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1) / reps
+print("whole step (graph)            %.3f ms" % timed(lambda: env.step(acts)))
+g = torch.cuda.CUDAGraph()
+env._warm_for_capture()
+with torch.cuda.graph(g):
+    env.low_level_actions(env._act_in)
+print("low_level_actions (graph)     %.3f ms" % timed(g.replay))
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(5): g.replay()
+    torch.cuda.synchronize()
+rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:14]
+for r in rows: print("  %-70s n=%3d  %.1f us each" % (r.key[:70], r.count, r.device_time_total / max(r.count, 1)))
