@@ -17,8 +17,11 @@ python bench.py --envs 262144 --steps 30 --warmup 5 --no-cpu-baseline > $out/${t
 if [ $? -eq 0 ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 250 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-fp64-peak > $out/${tag}_ncu_launches.log 2>&1
+  # (regex:k_env_substeps matches whichever substep kernel the batch size selects: k_env_substeps[_split|_split3|_split4])
   ncu --set full --clock-control none --import-source on -k regex:k_env_substeps --launch-skip 4 --launch-count 1 \
     -o $out/${tag}_substeps -f python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-fp64-peak > $out/${tag}_ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_env_post --launch-skip 260 --launch-count 1 \
+    -o $out/${tag}_post -f python bench.py --steps 300 --warmup 3 --no-cpu-baseline --no-fp64-peak > $out/${tag}_ncu_post.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:k_env_substeps --launch-skip 4 --launch-count 1 \
     -o $out/${tag}_substeps_65536 -f python bench.py --envs 65536 --steps 5 --warmup 3 --no-cpu-baseline --no-fp64-peak > $out/${tag}_ncu_full2.log 2>&1
 fi
