@@ -1,4 +1,7 @@
-"""Tuning experiment (needs a -DACS_FRAME_PROFILE build, ACS_LIB=...): cycles per FDM stage of one thread."""
+"""Tuning experiment (needs a -DACS_FRAME_PROFILE build, ACS_LIB=...): cycles per FDM stage of one thread.
+
+The stamps serialise the stages (no overlap across them), so the total is ~20 % above the uninstrumented frame and a
+stage run alone on its own warp (multi-warp frames) can differ from its share here; use for relative sizes."""
 import ctypes, os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))

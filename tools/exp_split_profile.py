@@ -1,4 +1,8 @@
-"""Tuning experiment (needs a -DACS_SPLIT_PROFILE build, ACS_LIB=...): cycle stamps of one pair of the two-warp frame."""
+"""Tuning experiment (needs a -DACS_SPLIT_PROFILE build, ACS_LIB=...): cycle stamps of one pair of the two-warp frame.
+
+NOTE: ptxas schedules the clock reads freely relative to BAR.SYNC, so the stamps do not delimit the barrier waits
+reliably; the per-instruction `stall_barrier` samples of an ncu capture (tools/ncu_summary.py) are
+what the role-balance numbers in DESIGN.md come from.  Kept for coarse per-frame totals only."""
 import ctypes, os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
