@@ -466,6 +466,71 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
 #undef XR2
 }
 
+// exchange-list accessors of the three- / four-warp frames (row = position in the generated list, column = aircraft slot)
+#define XW(buf, e) buf[xi++][slot] = e;
+#define XR(buf, e) e = buf[xi++][slot];
+#define XW_K(e) XW(sK, e)
+#define XR_K(e) XR(sK, e)
+#define XW_S(e) XW(sS, e)
+#define XR_S(e) XR(sS, e)
+#define XW_R(e) XW(sR, e)
+#define XR_R(e) XR(sR, e)
+#define XW_L(e) XW(sL, e)
+#define XR_L(e) XR(sL, e)
+
+// Barrier sets: the three-warp frame synchronises its three roles at every barrier; in the four-warp frame the look-ahead
+// role stays out of barrier 2 (it publishes nothing the others wait for there), and a barrier 0 ends its prologue.
+struct TripleSync {
+  int id;
+  ENV_DEV void b0() const {}
+  ENV_DEV void b1() const { __syncwarp(); asm volatile("bar.sync %0, 96;" ::"r"(id) : "memory"); }
+  ENV_DEV void b2() const { b1(); }
+  ENV_DEV void b3() const { b1(); }
+};
+struct QuadSync {
+  int quad;
+  ENV_DEV void b0() const { __syncwarp(); asm volatile("bar.sync %0, 128;" ::"r"(1 + 2 * quad) : "memory"); }
+  ENV_DEV void b1() const { b0(); }
+  ENV_DEV void b2() const { __syncwarp(); asm volatile("bar.sync %0, 96;" ::"r"(2 + 2 * quad) : "memory"); }
+  ENV_DEV void b3() const { b0(); }
+};
+
+constexpr int S3_AXES_B = (1 << 1) | (1 << 3) | (1 << 5), S3_AXES_C = 63 & ~S3_AXES_B;
+
+// Role B of the three- and four-warp frames: the flight controls between barriers 1 and 2, the axes SIDE, ROLL, YAW between
+// 2 and 3; owns the commands, FCS outputs and PID states of the carried state.
+template <int NS, class Sync>
+ENV_DEV void role_fcs_axes(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const int32_t* __restrict__ actions,
+                           const double* __restrict__ sT, const int slot, const Sync sync, const int* sRun, double (*sE)[NS],
+                           double (*sK)[NS], double (*sS)[NS], double (*sR)[NS], double (*sSum)[NS]) {
+  const int K = cfg.substeps;
+  const double fcs_dt = cfg.fcs_dt;
+  Props p; FcsState s;
+  AcCore unused;      // only the carried properties are live on this side; the core loads / stores are dead code
+  const bool loaded = L.valid && load_commanded(v, cfg, L, actions, AI(v, AI_STATUS, L.row) == ST_ALIVE, unused, p, s);
+  sync.b0();
+  for (int k = 0; k < K; k++) {
+    sync.b1();
+    const bool ran = sRun[slot] != 0;
+    if (ran) {
+      p.attitude_cos_pitch_cos_roll = sE[0][slot]; p.velocities_u_fps = sE[1][slot]; p.velocities_v_fps = sE[2][slot];
+      f16_fcs(p, s, sT, fcs_dt);
+      { int xi = 0; F16_X_SURF(XW_S) }
+    }
+    sync.b2();
+    if (ran) {
+      double twovel, c[6];
+      { int xi = 0; F16_X_KIN(XR_K) twovel = sK[xi][slot]; }
+      { int xi = 0; F16_X_AIR(XR_R) }
+      f16_aero<S3_AXES_B>(p, sT, twovel, c);
+#pragma unroll
+      for (int i = 0; i < 6; i++) if (S3_AXES_B & (1 << i)) sSum[i][slot] = c[i];
+    }
+    sync.b3();
+  }
+  if (loaded) store_state_role<true>(v.fdm, v.rows, L.row, unused, p, s);
+}
+
 // ---------------------------------------------------------------------------------------------- three-warp frame
 // One more warp per 32 aircraft.  ncu of the two-warp frame shows role A never waiting and role B waiting for half of its
 // time: A's chain Propagate -> Atmosphere -> Auxiliary -> Propulsion -> Accelerations is the critical path.  Here the
@@ -491,7 +556,6 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const
 #define ACS_SPLIT3_SLOTS 64     // measured: 64 slots (two warps per role share an instruction stream) 0.087 ms, 32 slots 0.093 ms
 #endif
 constexpr int S3 = ACS_SPLIT3_SLOTS;
-constexpr int S3_AXES_B = (1 << 1) | (1 << 3) | (1 << 5), S3_AXES_C = 63 & ~S3_AXES_B;
 static_assert(S3 % 32 == 0 && S3 >= 32 && 3 * S3 <= 384, "whole warps, at most 4 triples per block");
 
 #define TRIPLE_BARRIER(id) { __syncwarp(); asm volatile("bar.sync %0, 96;" ::"r"(id) : "memory"); }
@@ -521,40 +585,9 @@ __global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView
   const Lane L = lane_of_slot(v, lg, slot, blockIdx.x * S3 + slot);
   const int K = cfg.substeps;
   const double dt = cfg.sim_dt, fcs_dt = cfg.fcs_dt;
-#define XW(buf, e) buf[xi++][slot] = e;
-#define XR(buf, e) e = buf[xi++][slot];
-#define XW_K(e) XW(sK, e)
-#define XR_K(e) XR(sK, e)
-#define XW_S(e) XW(sS, e)
-#define XR_S(e) XR(sS, e)
-#define XW_R(e) XW(sR, e)
-#define XR_R(e) XR(sR, e)
 
   if (role == 1) {
-    // ================================================================ role B: flight controls + axes SIDE, ROLL, YAW
-    Props p; FcsState s;
-    AcCore unused;      // only the carried properties are live on this side; the core loads / stores are dead code
-    const bool loaded = L.valid && load_commanded(v, cfg, L, actions, AI(v, AI_STATUS, L.row) == ST_ALIVE, unused, p, s);
-    for (int k = 0; k < K; k++) {
-      TRIPLE_BARRIER(bar)                                      // 1
-      const bool ran = sRun[slot] != 0;
-      if (ran) {
-        p.attitude_cos_pitch_cos_roll = sE[0][slot]; p.velocities_u_fps = sE[1][slot]; p.velocities_v_fps = sE[2][slot];
-        f16_fcs(p, s, sT, fcs_dt);
-        { int xi = 0; F16_X_SURF(XW_S) }
-      }
-      TRIPLE_BARRIER(bar)                                      // 2
-      if (ran) {
-        double twovel, c[6];
-        { int xi = 0; F16_X_KIN(XR_K) twovel = sK[xi][slot]; }
-        { int xi = 0; F16_X_AIR(XR_R) }
-        f16_aero<S3_AXES_B>(p, sT, twovel, c);
-#pragma unroll
-        for (int i = 0; i < 6; i++) if (S3_AXES_B & (1 << i)) sSum[i][slot] = c[i];
-      }
-      TRIPLE_BARRIER(bar)                                      // 3
-    }
-    if (loaded) store_state_role<true>(v.fdm, v.rows, L.row, unused, p, s);
+    role_fcs_axes<S3>(v, cfg, L, actions, sT, slot, TripleSync{bar}, sRun, sE, sK, sS, sR, sSum);
     return;
   }
   if (role == 2) {
@@ -628,14 +661,6 @@ __global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView
     eom_after_frame(v, cfg, L, org, E, a, f, ran, k, K, sP, sWin, sShot, sCh);
   }
   eom_end<false>(v, L, E, a, p, s, K);
-#undef XW
-#undef XR
-#undef XW_K
-#undef XR_K
-#undef XW_S
-#undef XR_S
-#undef XW_R
-#undef XR_R
 }
 
 // ---------------------------------------------------------------------------------------------- four-warp frame
@@ -715,16 +740,6 @@ __global__ void __launch_bounds__(4 * S4, 1) k_env_substeps_split4(const EnvView
   const Lane L = lane_of_slot(v, lg, slot, blockIdx.x * S4 + slot);
   const int K = cfg.substeps;
   const double dt = cfg.sim_dt, fcs_dt = cfg.fcs_dt;
-#define XW(buf, e) buf[xi++][slot] = e;
-#define XR(buf, e) e = buf[xi++][slot];
-#define XW_K(e) XW(sK, e)
-#define XR_K(e) XR(sK, e)
-#define XW_S(e) XW(sS, e)
-#define XR_S(e) XR(sS, e)
-#define XW_R(e) XW(sR, e)
-#define XR_R(e) XR(sR, e)
-#define XW_L(e) XW(sL, e)
-#define XR_L(e) XR(sL, e)
 
   if (role == 3) {
     // ================================================================ role D: position chain, one frame ahead
@@ -763,31 +778,7 @@ __global__ void __launch_bounds__(4 * S4, 1) k_env_substeps_split4(const EnvView
     return;
   }
   if (role == 1) {
-    // ================================================================ role B: flight controls + axes SIDE, ROLL, YAW
-    Props p; FcsState s;
-    AcCore unused;      // only the carried properties are live on this side; the core loads / stores are dead code
-    const bool loaded = L.valid && load_commanded(v, cfg, L, actions, AI(v, AI_STATUS, L.row) == ST_ALIVE, unused, p, s);
-    QUAD_BARRIER_ALL(quad)                               // 0
-    for (int k = 0; k < K; k++) {
-      QUAD_BARRIER_ALL(quad)                             // 1
-      const bool ran = sRun[slot] != 0;
-      if (ran) {
-        p.attitude_cos_pitch_cos_roll = sE[0][slot]; p.velocities_u_fps = sE[1][slot]; p.velocities_v_fps = sE[2][slot];
-        f16_fcs(p, s, sT, fcs_dt);
-        { int xi = 0; F16_X_SURF(XW_S) }
-      }
-      QUAD_BARRIER_ABC(quad)                             // 2
-      if (ran) {
-        double twovel, c[6];
-        { int xi = 0; F16_X_KIN(XR_K) twovel = sK[xi][slot]; }
-        { int xi = 0; F16_X_AIR(XR_R) }
-        f16_aero<S3_AXES_B>(p, sT, twovel, c);
-#pragma unroll
-        for (int i = 0; i < 6; i++) if (S3_AXES_B & (1 << i)) sSum[i][slot] = c[i];
-      }
-      QUAD_BARRIER_ALL(quad)                             // 3
-    }
-    if (loaded) store_state_role<true>(v.fdm, v.rows, L.row, unused, p, s);
+    role_fcs_axes<S4>(v, cfg, L, actions, sT, slot, QuadSync{quad}, sRun, sE, sK, sS, sR, sSum);
     return;
   }
   if (role == 2) {
@@ -873,6 +864,8 @@ __global__ void __launch_bounds__(4 * S4, 1) k_env_substeps_split4(const EnvView
     AI(v, AI_STATUS, L.row) = E.status;
     if (L.lane == 0) EI(v, EI_SUBSTEP_COUNT, L.env) = E.sc0 + K;
   }
+}
+
 #undef XW
 #undef XR
 #undef XW_K
@@ -883,7 +876,6 @@ __global__ void __launch_bounds__(4 * S4, 1) k_env_substeps_split4(const EnvView
 #undef XR_R
 #undef XW_L
 #undef XR_L
-}
 
 // ============================================================================================== per-step logic
 struct StepCtx {
