@@ -1,14 +1,20 @@
-// env_kernels.cuh -- the three env-layer kernels (sm_100a), one thread per aircraft, the G = 1/2/4/8 lanes of one
-// environment adjacent inside a warp so cross-aircraft exchange is shared memory + __syncwarp on the group's lane mask:
+// env_kernels.cuh -- the env-layer kernels (sm_100a).  The G = 1/2/4/8 lanes of one environment are adjacent inside a warp, so
+// cross-aircraft exchange is shared memory + __syncwarp on the group's lane mask:
 //
-//   k_env_substeps   actions -> controls, then the agent_interaction_steps substep loop with the FDM state in registers:
+//   k_env_substeps[_split|_split3|_split4]
+//                    actions -> controls, then the agent_interaction_steps substep loop with the FDM state in registers:
 //                    aircraft run(), missile run() (PN guidance + fused proximity fuze), chaff run(), chaff x missile test
-//                    (E/envs/env_base.py:131-154, E/core/simulatior.py:210-229,520-533)
+//                    (E/envs/env_base.py:131-154, E/core/simulatior.py:210-229,520-533).  One thread per aircraft, or -- for
+//                    batches too small to fill the machine -- two / three / four threads in different warps per aircraft
+//                    running the stages of one frame concurrently (acs.cu picks by batch size; same expressions in all)
 //   k_env_post       task.step (weapon launches), get_obs, get_reward, get_termination, packing
-//                    (E/envs/env_base.py:155-173, E/envs/multiplecombat_env.py:161-182)
-//   k_env_reset      masked per-env reset: sim.reload() for every aircraft, task.reset, reward resets, get_obs
+//                    (E/envs/env_base.py:155-173, E/envs/multiplecombat_env.py:161-182), and -- fused -- the auto-reset of
+//                    every env whose agents are all done, as a scatter of the handle's reset template
+//   k_env_reset_fdm, k_env_reset_task
+//                    masked per-env reset: sim.reload() for every aircraft, task.reset, reward resets, get_obs
 //                    (E/envs/env_base.py:98-113); with the mask = "all agents done" this is the VecEnv auto-reset
-//                    (R/envs/env_wrappers.py:191-204)
+//                    (R/envs/env_wrappers.py:191-204).  Used by explicit reset(), to build the reset template, and by
+//                    the heading task (random initial conditions: no template)
 #pragma once
 
 static constexpr int F_SIM_TIME = FDM_N_CORE - 1;  // "sim_time" is the last core field
