@@ -248,3 +248,32 @@ def test_observation_warps_give_the_same_bits(name, monkeypatch):
         assert torch.equal(bs[0].out_buf, bs[1].out_buf), t
     for arena in ("fdm", "out", "ac_d", "ac_i", "env_d", "env_i"):
         assert torch.equal(bs[0].arena(arena)[1], bs[1].arena(arena)[1]), arena
+
+
+def test_single_env_single_substep():
+    """Smallest launch: one env, one substep per step (a block of mostly idle lanes; K = 1 means every frame is both the
+    first and the last of its step, the four-warp frame computes no look-ahead inside the loop)."""
+    _run("1v1/NoWeapon/Selfplay", n_envs=1, steps=12, mode="random", substeps=1)
+    _run("scenario2/scenario2", n_envs=1, steps=12, mode="smooth", init="close", substeps=1)
+
+
+@pytest.mark.parametrize("name,n", [("1v1/NoWeapon/Selfplay", 65536), ("2v2/ShootMissile/HierarchySelfplay", 16384)])
+def test_full_size_batches_are_replicas(name, n, frame_split):
+    """BASELINE.json sizes, through a size-independent property: the combat tasks start every env from the same state, so
+    with the same action rows every env of the batch must stay bit-identical to env 0 (grid / lane indexing, reset
+    template scatter and auto-reset at full size)."""
+    from aircombat_selfplay_b200.capi import EnvBatch
+    spec = load_spec(name, substeps_override=12)
+    spec.max_steps = 4
+    b = EnvBatch(spec, n, seed=1)
+    obs0 = b.reset()[0].clone()
+    assert torch.equal(obs0, obs0[:1].expand_as(obs0))
+    rng = np.random.default_rng(3)
+    for t in range(6):
+        row = torch.tensor(random_actions(rng, spec, 1), device="cuda")
+        obs, _, rew, done, info = b.step(row.expand(n, -1, -1).contiguous(), auto_reset=True)
+        assert torch.equal(obs, obs[:1].expand_as(obs)), t
+        assert torch.equal(rew, rew[:1].expand_as(rew)) and torch.equal(done, done[:1].expand_as(done)), t
+    names, ei = b.arena("env_i")
+    assert int(ei[names.index("episode")].min()) == int(ei[names.index("episode")].max()) == 1
+    b.close()
