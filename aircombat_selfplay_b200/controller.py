@@ -69,25 +69,46 @@ class LowLevelController(nn.Module):
         self.load_state_dict(m)
 
 
-def find_checkpoint(path=None):
-    """``baseline_model.pt`` lookup: explicit path, $ACS_BASELINE_MODEL, then ``<package>/model/baseline_model.pt``."""
-    cands = [path, os.environ.get("ACS_BASELINE_MODEL"), Path(__file__).resolve().parent / "model" / "baseline_model.pt"]
-    for c in cands:
-        if c and Path(c).exists():
+def find_checkpoint(path=None, config_dir=None):
+    """``baseline_model.pt`` lookup (the reference loads ``<envs/JSBSim>/model/baseline_model.pt`` and raises when it is
+    absent, envs/JSBSim/tasks/singlecombat_task.py:208-213): an explicit ``path`` or ``$ACS_BASELINE_MODEL`` MUST exist;
+    otherwise ``<package>/model/baseline_model.pt``, then -- when the yaml files come from a reference checkout
+    (``config_dir=<...>/envs/JSBSim/configs``) -- that checkout's ``model/baseline_model.pt``.  None when nothing is found."""
+    for what, c in (("controller_path", path), ("$ACS_BASELINE_MODEL", os.environ.get("ACS_BASELINE_MODEL"))):
+        if c:
+            if not Path(c).exists():
+                raise FileNotFoundError(f"{what} = {c!r} does not exist (low-level controller checkpoint baseline_model.pt)")
             return Path(c)
+    cands = [Path(__file__).resolve().parent / "model" / "baseline_model.pt"]
+    if config_dir:
+        cands.append(Path(config_dir).resolve().parent / "model" / "baseline_model.pt")
+    for c in cands:
+        if c.exists():
+            return c
     return None
 
 
-def make_controller(device, path=None, seed: int = 0) -> LowLevelController:
-    """The controller on ``device``.  Without a checkpoint the weights are a seeded random init of the same architecture
-    (benchmarks and shape tests; the flight behaviour then is of course not the trained one)."""
-    ck = find_checkpoint(path)
+def make_controller(device, path=None, seed: int = 0, config_dir=None, allow_random: bool = False) -> LowLevelController:
+    """The controller on ``device`` with the weights of the reference's ``baseline_model.pt``.
+
+    The checkpoint is not part of this repository.  Without one this RAISES, as the reference's ``torch.load`` does --
+    every hierarchical task (scenario1/2/3, wvr, maneuver_curriculum, Hierarchy* yamls, the scripted opponents) would
+    otherwise fly a random low-level policy without saying so.  ``allow_random=True`` (or ``ACS_ALLOW_RANDOM_CONTROLLER=1``)
+    is the explicit opt-in for benchmarks and shape tests: a seeded random init of the same architecture, i.e. the same
+    arithmetic and memory traffic, not the trained flight behaviour."""
+    ck = find_checkpoint(path, config_dir)
     g = torch.Generator().manual_seed(seed)
     ctl = LowLevelController()
     if ck is not None:
         ctl.load_reference_state_dict(torch.load(str(ck), map_location="cpu"))
         ctl.checkpoint = str(ck)
     else:
+        if not (allow_random or os.environ.get("ACS_ALLOW_RANDOM_CONTROLLER") == "1"):
+            from .capi import AcsError
+            raise AcsError("baseline_model.pt (the low-level controller of the hierarchical tasks) was not found: pass "
+                           "controller_path=, set $ACS_BASELINE_MODEL, copy it to aircombat_selfplay_b200/model/, or point "
+                           "config_dir at a reference checkout's envs/JSBSim/configs; allow_random_controller=True opts in to "
+                           "random-init weights (benchmarks / shape tests only)")
         for name, p in ctl.named_parameters():      # every parameter from the seeded generator: instances are identical
             if p.dim() > 1:
                 p.data = torch.randn(p.shape, generator=g) / math.sqrt(p.shape[-1])

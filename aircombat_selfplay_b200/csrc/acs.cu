@@ -357,6 +357,7 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
   if (cfg->substeps <= 0 || cfg->obs_dim <= 0) return fail("acs_env_create: substeps and obs_dim must be positive");
   if (cfg->shoot_dim != 0 && cfg->shoot_dim != 1 && cfg->shoot_dim != 4) return fail("acs_env_create: shoot_dim must be 0, 1 or 4");
   if (cfg->lock_len > 64) return fail("acs_env_create: lock_len > 64 is not supported");
+  if (cfg->n_missile_slots > 64) return fail("acs_env_create: more than 64 missile slots per aircraft are not supported");
   if (std::strcmp(STATE_NAMES[F_SIM_TIME], "sim_time") || std::strcmp(STATE_NAMES[F_CMD0], "fcs/aileron-cmd-norm") ||
       std::strcmp(STATE_NAMES[F_CMD0 + 3], "fcs/throttle-cmd-norm"))
     return fail("acs_env_create: FDM state layout changed (sim_time / control fields)");

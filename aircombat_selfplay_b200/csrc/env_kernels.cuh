@@ -95,51 +95,54 @@ ENV_DEV void load_pub(const EnvView& v, int row, PubAc& p) {
 }
 
 // ============================================================================================== substep kernel
+// Which launched missiles still need run(): every one that can still move or change status.  A missile is INERT -- run()
+// can no longer change anything observable -- once it is MISS and (its target is dead | t > t_max | |v| < v_min): all three
+// are permanent within an episode and send every later run() into the MISS branch without a state transition
+// (E/core/simulatior.py:528-531; only t, distance_pre and the increment window keep changing, and nothing reads them).
+// A HIT missile is NOT inert: its next run() turns it MISS (target no longer alive), which the step's rewards observe.
+ENV_DEV bool missile_inert(const EnvView& v, const int mid, const int env) {
+  if (MI(v, MI_STATUS, mid) != MS_MISS) return false;
+  const MissileParams pr = missile_params(MI(v, MI_KIND, mid));
+  if (AI(v, AI_STATUS, env * v.A + MI(v, MI_TARGET, mid)) != ST_ALIVE) return true;
+  if (MD(v, MD_T, mid) > pr.t_max) return true;
+  const double vn = MD(v, MD_VEL_N, mid), ve = MD(v, MD_VEL_E, mid), vu = MD(v, MD_VEL_U, mid);
+  return sqrt(vn * vn + ve * ve + vu * vu) < pr.v_min;
+}
+// bit s = slot s of this aircraft holds a missile that still runs (slots >= 64 cannot exist: acs_env_create caps S)
+ENV_DEV unsigned long long live_missiles(const EnvView& v, const Lane& L) {
+  unsigned long long live = 0;
+  const int nl = AI(v, AI_N_LAUNCHED, L.row);
+  for (int s = 0; s < nl; s++) {
+    const int mid = L.row * v.S + s;
+    if (MI(v, MI_DETACHED, mid) || missile_inert(v, mid, L.env)) continue;
+    live |= 1ull << s;
+  }
+  return live;
+}
+
 // The missile phase of one substep for the lanes of one env (E/envs/env_base.py:141-154).  Reference order inside a
 // substep: every aircraft run(), then every missile run() in dict order, then every chaff run(), then the
-// chaff x missile test.  Missiles are processed in parallel by their shooter's lane; the only order-dependent outcome
-// -- two missiles inside the fuze radius of one target in the same substep, where the first in dict order scores the
-// HIT and later ones see a dead target and go MISS -- is resolved with a shared-memory atomicMin on the dict order.
+// chaff x missile test.  Missiles are processed in parallel by their shooter's lane, each lane walking its own list of
+// live slots (so a warp iterates max-over-lanes of the LIVE count, not of the launched count); the only order-dependent
+// outcome -- two missiles inside the fuze radius of one target in the same substep, where the first in dict order scores
+// the HIT and later ones see a dead target and go MISS -- is resolved with a shared-memory atomicMin on the dict order.
+// The chaff x missile test of a missile depends on nothing but that missile's position after its own run() and the
+// chaff clouds (which no missile influences), so chaff run() is moved in front of the missiles' and the test is folded
+// into the same traversal as run(): one pass fewer, and none at all while the env has no effective chaff.
 __device__ __noinline__ void missile_phase(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const GeoOrigin& org,
-                                           PubAc* sP, int* sWin, int* sShot, PubChaff* sCh, int substep_count) {
+                                           PubAc* sP, int* sWin, int* sShot, PubChaff* sCh, int substep_count,
+                                           unsigned long long& live_io) {
   const double dt = cfg.sim_dt;
-  const int nl = L.valid ? AI(v, AI_N_LAUNCHED, L.row) : 0;
   const int maxlen = (int)(5.0 / dt);
+  unsigned long long live = live_io;
   // ---- phase 1: who is inside its fuze radius (uses the state before this substep's missile moves)
-  for (int s = 0; s < nl; s++) {
-    const int mid = L.row * v.S + s;
-    if (MI(v, MI_DETACHED, mid)) continue;
-    Missile m;
-    missile_load(v, mid, m);
-    const MissileParams pr = missile_params(m.kind);
-    const double d = missile_distance(m, sP[L.gbase + m.target].f);
-    if (d < pr.Rc && m.status != MS_MISS) atomicMin(&sWin[L.gbase + m.target], MI(v, MI_ORDER, mid));
-  }
-  __syncwarp(L.gmask);
-  // ---- phase 2: MissileSimulator.run() (:520-533)
-  for (int s = 0; s < nl; s++) {
-    const int mid = L.row * v.S + s;
-    if (MI(v, MI_DETACHED, mid)) continue;
-    Missile m;
-    missile_load(v, mid, m);
-    const MissileParams pr = missile_params(m.kind);
-    const PubAc& tg = sP[L.gbase + m.target];
-    m.t += dt;
-    double ny, nz, dist;
-    missile_guidance(m, pr, tg.f, ny, nz, dist);
-    m.consec = (dist > m.d_prev) ? m.consec + 1 : 0;
-    m.d_prev = dist;
-    const int order = MI(v, MI_ORDER, mid);
-    const bool target_alive = (tg.status == ST_ALIVE) && !(sWin[L.gbase + m.target] < order);
-    if (dist < pr.Rc && target_alive && m.status != MS_MISS) {
-      m.status = MS_HIT;
-      sShot[L.gbase + m.target] = 1;
-    } else if (m.t > pr.t_max || sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu) < pr.v_min || m.consec >= maxlen || !target_alive) {
-      m.status = MS_MISS;
-    } else {
-      missile_state_trans(m, pr, org, ny, nz, dt);
-    }
-    missile_store(v, mid, m);
+  for (unsigned long long m = live; m; m &= m - 1) {
+    const int mid = L.row * v.S + (__ffsll((long long)m) - 1);
+    const int target = MI(v, MI_TARGET, mid);
+    const Feat& tg = sP[L.gbase + target].f;
+    const double ax = MD(v, MD_POS_N, mid) - tg.n, ay = MD(v, MD_POS_E, mid) - tg.e, az = tg.u - MD(v, MD_POS_U, mid);
+    const double d = sqrt(ax * ax + ay * ay + az * az);
+    if (d < missile_params(MI(v, MI_KIND, mid)).Rc && MI(v, MI_STATUS, mid) != MS_MISS) atomicMin(&sWin[L.gbase + target], MI(v, MI_ORDER, mid));
   }
   // ---- chaff run() (:377-381) and publication
   {
@@ -158,27 +161,52 @@ __device__ __noinline__ void missile_phase(const EnvView& v, const AcsTaskConfig
     }
     sCh[L.tid] = c;
   }
-  __syncwarp(L.gmask);
-  // ---- chaff x missile (E/envs/env_base.py:146-154): every live missile against every effective chaff
-  for (int s = 0; s < nl; s++) {
-    const int mid = L.row * v.S + s;
-    if (MI(v, MI_DETACHED, mid)) continue;
-    const int st = MI(v, MI_STATUS, mid);
-    if (st == MS_HIT || st == MS_MISS) continue;
-    const double pn = MD(v, MD_POS_N, mid), pe = MD(v, MD_POS_E, mid), pu = MD(v, MD_POS_U, mid);
-    const int keyn = MI(v, MI_KEYN, mid);
-    bool missed = false;
-    for (int j = 0; j < v.A; j++) {
-      const PubChaff& c = sCh[L.gbase + j];
-      if (c.state != CH_ACTIVE) continue;
-      const double dx = c.n - pn, dy = c.e - pe, dz = c.u - pu;
-      if (sqrt(dx * dx + dy * dy + dz * dz) <= 300.0) {
-        for (int q = 0; q < c.count; q++)
-          if (env_u01(cfg.seed, cfg.env_offset + L.env, RNG_CHAFF, substep_count, L.lane * 64 + keyn, j * 64 + q) < 0.85) missed = true;
-      }
+  __syncwarp(L.gmask);                              // sWin and sCh of the whole env are complete
+  const bool any_chaff = (__ballot_sync(L.gmask, sCh[L.tid].state == CH_ACTIVE) & L.gmask) != 0;
+  // ---- phase 2: MissileSimulator.run() (:520-533), then this missile against every effective chaff (E/envs/env_base.py:146-154)
+  for (unsigned long long mm = live; mm; mm &= mm - 1) {
+    const int slot = __ffsll((long long)mm) - 1;
+    const int mid = L.row * v.S + slot;
+    Missile m;
+    missile_load(v, mid, m);
+    const MissileParams pr = missile_params(m.kind);
+    const PubAc& tg = sP[L.gbase + m.target];
+    m.t += dt;
+    double ny, nz, dist;
+    missile_guidance(m, pr, tg.f, ny, nz, dist);
+    m.consec = (dist > m.d_prev) ? m.consec + 1 : 0;
+    m.d_prev = dist;
+    const int order = MI(v, MI_ORDER, mid);
+    const bool target_alive = (tg.status == ST_ALIVE) && !(sWin[L.gbase + m.target] < order);
+    if (dist < pr.Rc && target_alive && m.status != MS_MISS) {
+      m.status = MS_HIT;
+      sShot[L.gbase + m.target] = 1;
+    } else if (m.t > pr.t_max || sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu) < pr.v_min || m.consec >= maxlen || !target_alive) {
+      // inert from here on (see missile_inert); `consec >= maxlen` alone is not permanent
+      if (m.status == MS_MISS && (m.t > pr.t_max || !target_alive || sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu) < pr.v_min)) live &= ~(1ull << slot);
+      m.status = MS_MISS;
+    } else {
+      missile_state_trans(m, pr, org, ny, nz, dt);
     }
-    if (missed) MI(v, MI_STATUS, mid) = MS_MISS;
+    if (any_chaff && m.status == MS_LAUNCHED) {
+      const int keyn = MI(v, MI_KEYN, mid);
+      // the episode is part of the key: substep counters restart at every reset
+      const int64_t when = ((int64_t)EI(v, EI_EPISODE, L.env) << 20) + substep_count;
+      bool missed = false;
+      for (int j = 0; j < v.A; j++) {
+        const PubChaff& c = sCh[L.gbase + j];
+        if (c.state != CH_ACTIVE) continue;
+        const double dx = c.n - m.pn, dy = c.e - m.pe, dz = c.u - m.pu;
+        if (sqrt(dx * dx + dy * dy + dz * dz) <= 300.0) {
+          for (int q = 0; q < c.count; q++)
+            if (env_u01(cfg.seed, cfg.env_offset + L.env, RNG_CHAFF, when, L.lane * 64 + keyn, j * 64 + q) < 0.85) missed = true;
+        }
+      }
+      if (missed) m.status = MS_MISS;
+    }
+    missile_store(v, mid, m);
   }
+  live_io = live;
 }
 
 // ---------------------------------------------------------------------------------------------- shared by the substep kernels
@@ -234,19 +262,21 @@ struct EomLane {
   double v_mps, w_mps, vc_mps;
   int status, sc0;
   bool has_ms, was_alive;
+  unsigned long long live;     // slots of this aircraft whose missile still runs (live_missiles)
   AcOut o;
 };
 ENV_DEV void eom_begin(const EnvView& v, const Lane& L, EomLane& E) {
   E.v_mps = E.w_mps = E.vc_mps = 0;
-  E.status = ST_CRASH; E.has_ms = false;
+  E.status = ST_CRASH; E.has_ms = false; E.live = 0;
   E.me.status = ST_CRASH; E.me.bloods = 0; E.me.h = 0; E.me.u_mps = 0;
   E.me.f.n = E.me.f.e = E.me.f.u = E.me.f.vn = E.me.f.ve = E.me.f.vd = 0;
   if (L.valid) {
     load_pub(v, L.row, E.me);
     E.status = E.me.status;
-    E.has_ms = (AI(v, AI_N_LAUNCHED, L.row) > 0) || (AI(v, AI_CH_STATE, L.row) == CH_ACTIVE);
+    E.live = live_missiles(v, L);
+    E.has_ms = (E.live != 0) || (AI(v, AI_CH_STATE, L.row) == CH_ACTIVE);
   }
-  // an env needs the per-substep exchange only while it has missiles or chaff in the air
+  // an env needs the per-substep exchange only while it has missiles that still run or an effective chaff cloud
   const unsigned b = __ballot_sync(L.gmask, E.has_ms);
   E.has_ms = (b & L.gmask) != 0;
   E.was_alive = L.valid && E.status == ST_ALIVE;
@@ -272,7 +302,7 @@ ENV_DEV void eom_after_frame(const EnvView& v, const AcsTaskConfig& cfg, const L
     sWin[L.tid] = 0x7fffffff;
     sShot[L.tid] = 0;
     __syncwarp(L.gmask);
-    missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, E.sc0 + k);
+    missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, E.sc0 + k, E.live);
     __syncwarp(L.gmask);
     if (sShot[L.tid] && E.status == ST_ALIVE) E.status = ST_SHOTDOWN;   // target_aircraft.shotdown() (simulatior.py:527)
     __syncwarp(L.gmask);
@@ -304,6 +334,9 @@ ENV_DEV void eom_propulsion(AcCore& a, const Props& p, Frame& f, const double* _
   a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
 }
 
+#ifndef ACS_LEAN_FRAME
+#define ACS_LEAN_FRAME 1
+#endif
 __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
                                                            const int32_t* __restrict__ actions) {
   __shared__ double sT[F16_NTAB];
@@ -316,15 +349,55 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
   const int K = cfg.substeps;
   const double dt = cfg.sim_dt, fcs_dt = cfg.fcs_dt;
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
-  AcCore a; Props p; FcsState s; Frame f;
+  AcCore a; Props p; FcsState s;
   EomLane E;
   eom_begin(v, L, E);
   if (L.valid) load_commanded(v, cfg, L, actions, E.status == ST_ALIVE, a, p, s);
+#if ACS_LEAN_FRAME
+  // Lean frame (fdm_core.cuh): nothing of a frame's scratch outlives it.  The publication the other lanes' missiles read is
+  // written to shared memory from inside the frame (the previous substep's readers are behind the __syncwarp that ended
+  // their missile phase); the property read-back (_update_properties, simulatior.py:238-257) is materialised once, from
+  // the state the aircraft's last frame left, after the K loop.
+  FrameKeep keep;
+  keep.pilot_nx = keep.vcas = keep.beta = keep.thrust = 0.0;
+  const bool has_ms = E.has_ms;
+  const double bloods = E.me.bloods;
+  int status = E.status;
+  if (has_ms) sP[L.tid] = E.me;          // dead aircraft stay where the arena has them
+  for (int k = 0; k < K; k++) {
+    const bool ran = L.valid && status == ST_ALIVE;
+    if (ran) {
+      if (bloods <= 0) status = ST_SHOTDOWN;     // AircraftSimulator.run's gate (simulatior.py:220-226): still integrates this frame
+      fdm_frame_lean(a, p, s, keep, sT, g_atmo, dt, fcs_dt, [&](const Frame& f) {
+        if (has_ms) { PubAc pub; publish_from_frame(f, org, pub); sP[L.tid].f = pub.f; sP[L.tid].h = pub.h; sP[L.tid].u_mps = pub.u_mps; }
+      });
+    }
+    if (has_ms) {
+      sP[L.tid].status = status;
+      sWin[L.tid] = 0x7fffffff;
+      sShot[L.tid] = 0;
+      __syncwarp(L.gmask);
+      missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, E.sc0 + k, E.live);
+      __syncwarp(L.gmask);
+      if (sShot[L.tid] && status == ST_ALIVE) status = ST_SHOTDOWN;   // target_aircraft.shotdown() (simulatior.py:527)
+      __syncwarp(L.gmask);
+    }
+  }
+  E.status = status;
+  if (E.was_alive) {
+    Frame f;
+    fdm_refresh(a, p, keep, f);
+    fdm_outputs(a, f, E.o);
+    derive_aircraft(E.o, org, E.me, E.v_mps, E.w_mps, E.vc_mps);
+  }
+#else
+  Frame f;
   for (int k = 0; k < K; k++) {
     const bool ran = eom_runs(L, E);
     if (ran) fdm_frame(a, p, s, f, sT, g_atmo, dt, fcs_dt, false);
     eom_after_frame(v, cfg, L, org, E, a, f, ran, k, K, sP, sWin, sShot, sCh);
   }
+#endif
   eom_end<true>(v, L, E, a, p, s, K);
 }
 
@@ -350,6 +423,9 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
 // (64 threads), so pairs never wait for each other.  Buffer reuse: EARLY aliases SURF and the axis sums alias AUX --
 // in both cases the reader of the first finishes (same thread) before it writes the second, and the next writer of
 // the first is behind a later barrier.
+#ifndef ACS_S2_MIN_BLOCKS
+#define ACS_S2_MIN_BLOCKS 1
+#endif
 constexpr int SPLIT_N_BUF1 = F16_N_X_SURF > F16_N_X_EARLY ? F16_N_X_SURF : F16_N_X_EARLY;
 constexpr int SPLIT_N_BUF2 = (F16_N_X_AUX + 1) > 6 ? (F16_N_X_AUX + 1) : 6;
 
@@ -372,7 +448,7 @@ __device__ long long g_split_prof[2][8];
 ENV_DEV void pair_barrier(const int id) { __syncwarp(); asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 #endif
 
-__global__ void __launch_bounds__(2 * SPLIT_SLOTS, 1) k_env_substeps_split(const EnvView v, const __grid_constant__ AcsTaskConfig cfg,
+__global__ void __launch_bounds__(2 * SPLIT_SLOTS, ACS_S2_MIN_BLOCKS) k_env_substeps_split(const EnvView v, const __grid_constant__ AcsTaskConfig cfg,
                                                                           const int lg, const int32_t* __restrict__ actions) {
   __shared__ double sT[F16_NTAB];
   __shared__ PubAc sP[SPLIT_SLOTS];
@@ -562,11 +638,14 @@ ENV_DEV void role_fcs_axes(const EnvView& v, const AcsTaskConfig& cfg, const Lan
 #define ACS_SPLIT3_SLOTS 64     // measured: 64 slots (two warps per role share an instruction stream) 0.087 ms, 32 slots 0.093 ms
 #endif
 constexpr int S3 = ACS_SPLIT3_SLOTS;
+#ifndef ACS_S3_MIN_BLOCKS
+#define ACS_S3_MIN_BLOCKS 1
+#endif
 static_assert(S3 % 32 == 0 && S3 >= 32 && 3 * S3 <= 384, "whole warps, at most 4 triples per block");
 
 #define TRIPLE_BARRIER(id) { __syncwarp(); asm volatile("bar.sync %0, 96;" ::"r"(id) : "memory"); }
 
-__global__ void __launch_bounds__(3 * S3, 1) k_env_substeps_split3(const EnvView v, const __grid_constant__ AcsTaskConfig cfg,
+__global__ void __launch_bounds__(3 * S3, ACS_S3_MIN_BLOCKS) k_env_substeps_split3(const EnvView v, const __grid_constant__ AcsTaskConfig cfg,
                                                                   const int lg, const int32_t* __restrict__ actions) {
   __shared__ double sT[F16_NTAB];
   __shared__ PubAc sP[S3];

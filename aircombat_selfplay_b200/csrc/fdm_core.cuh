@@ -748,6 +748,161 @@ FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
   FPROF(13)
 }
 
+// ============================================================== lean frame (throughput kernel)
+// fdm_frame keeps its whole scratch (three 3x3 matrices, the inertia tensor and its inverse, the geodetic quantities, the
+// local-frame velocities ...) alive until the frame ends, because its caller reads outputs from it afterwards: ~145
+// doubles live through the flight-control / engine / aerodynamics stages, i.e. 290 registers for a 255-register thread
+// (ncu: 73 STL + 90 LDL per frame, 15 % long-scoreboard stalls).  The lean frame evaluates the SAME expressions in the same
+// order but hands nothing back except the handful of scalars that cannot be recomputed from the carried state
+// (FrameKeep); what the per-step logic reads is recomputed ONCE per interaction step from the final state by
+// fdm_refresh (position and attitude do not change between Propagate and the end of a frame):
+//   * body / local matrices, geodetic quantities, velocities: recomputed after the K loop (fdm_refresh);
+//   * the inertia tensor and its inverse: built where Accelerations consumes them (from the tank contents and the
+//     previous frame's cg, as MassBalance does), not held from MassBalance through the aerodynamics;
+//   * Ti2b: rebuilt from the quaternion in Accelerations; gravity: rotated to the inertial frame at once (3 doubles
+//     instead of gravity + sin / cos of the earth rotation angle).
+// opaque(): the optimiser must not merge a recomputation with the original (that would re-create the long live range).
+FDM_DEV double opaque(double x) { asm volatile("" : "+d"(x)); return x; }
+
+struct FrameKeep { double pilot_nx, vcas, beta, thrust; };
+
+// MassBalance, first half: weight, mass, cg (J/models/FGMassBalance.cpp:181-260); the inertia half is fdm_inertia
+FDM_DEV void fdm_mass_cg(const AcCore& a, double& Mass, V3& cg) {
+  const double tw = ((a.tank0 + a.tank1) + a.tank2) + a.tank3;
+  V3 tm = v3(0, 0, 0);
+  tm = tm + a.tank0 * v3(K_TANK0_X, K_TANK0_Y, K_TANK0_Z);
+  tm = tm + a.tank1 * v3(K_TANK1_X, K_TANK1_Y, K_TANK1_Z);
+  tm = tm + a.tank2 * v3(K_TANK2_X, K_TANK2_Y, K_TANK2_Z);
+  tm = tm + a.tank3 * v3(K_TANK3_X, K_TANK3_Y, K_TANK3_Z);
+  const double pmw = K_PM0_W + K_PM1_W;
+  const double Weight = K_emptywt + tw + pmw;
+  Mass = LBTOSLUG * Weight;
+  V3 pm = v3(0, 0, 0);
+  pm = pm + K_PM0_W * v3(K_PM0_X, K_PM0_Y, K_PM0_Z);
+  pm = pm + K_PM1_W * v3(K_PM1_X, K_PM1_Y, K_PM1_Z);
+  const V3 num = (K_emptywt * v3(K_CG_X, K_CG_Y, K_CG_Z) + pm) + tm;
+  const double rw = 1.0 / Weight;
+  cg = v3(num.x * rw, num.y * rw, num.z * rw);
+}
+// MassBalance, second half: inertia tensor about the cg and its inverse.  tanks = the contents MassBalance saw (before this
+// frame's fuel burn), cg_prev = the previous frame's cg (tank inertia lags, J/FGFDMExec.cpp:563-571), cg = this frame's
+FDM_DEV void fdm_inertia(const double t0, const double t1, const double t2, const double t3, const V3& cg_prev, const V3& cg, M33& Jout, M33& Jinv) {
+  M33 tankJ;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) tankJ.m[i][j] = 0.0;
+  add_pointmass_inertia(tankJ, cg_prev, LBTOSLUG * t0, K_TANK0_X, K_TANK0_Y, K_TANK0_Z);
+  add_pointmass_inertia(tankJ, cg_prev, LBTOSLUG * t1, K_TANK1_X, K_TANK1_Y, K_TANK1_Z);
+  add_pointmass_inertia(tankJ, cg_prev, LBTOSLUG * t2, K_TANK2_X, K_TANK2_Y, K_TANK2_Z);
+  add_pointmass_inertia(tankJ, cg_prev, LBTOSLUG * t3, K_TANK3_X, K_TANK3_Y, K_TANK3_Z);
+  M33 J;
+  if (!K_negated_crossproduct_inertia) {
+    J.m[0][0] = K_ixx; J.m[0][1] = K_ixy; J.m[0][2] = -K_ixz; J.m[1][0] = K_ixy; J.m[1][1] = K_iyy; J.m[1][2] = K_iyz;
+    J.m[2][0] = -K_ixz; J.m[2][1] = K_iyz; J.m[2][2] = K_izz;
+  } else {
+    J.m[0][0] = K_ixx; J.m[0][1] = -K_ixy; J.m[0][2] = K_ixz; J.m[1][0] = -K_ixy; J.m[1][1] = K_iyy; J.m[1][2] = -K_iyz;
+    J.m[2][0] = K_ixz; J.m[2][1] = -K_iyz; J.m[2][2] = K_izz;
+  }
+  add_pointmass_inertia(J, cg, LBTOSLUG * K_emptywt, K_CG_X, K_CG_Y, K_CG_Z);
+  M33 pmJ;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) pmJ.m[i][j] = 0.0;
+  add_pointmass_inertia(pmJ, cg, LBTOSLUG * K_PM0_W, K_PM0_X, K_PM0_Y, K_PM0_Z);
+  add_pointmass_inertia(pmJ, cg, LBTOSLUG * K_PM1_W, K_PM1_X, K_PM1_Y, K_PM1_Z);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) J.m[i][j] = (J.m[i][j] + pmJ.m[i][j]) + tankJ.m[i][j];
+  Jout = J;
+  const double Ixx = J.m[0][0], Iyy = J.m[1][1], Izz = J.m[2][2], Ixy = -J.m[0][1], Ixz = -J.m[0][2], Iyz = -J.m[1][2];
+  double k1 = (Iyy * Izz - Iyz * Iyz), k2 = (Iyz * Ixz + Ixy * Izz), k3 = (Ixy * Iyz + Iyy * Ixz);
+  const double denom = 1.0 / (Ixx * k1 - Ixy * k2 - Ixz * k3);
+  k1 = k1 * denom; k2 = k2 * denom; k3 = k3 * denom;
+  const double k4 = (Izz * Ixx - Ixz * Ixz) * denom, k5 = (Ixy * Ixz + Iyz * Ixx) * denom, k6 = (Ixx * Iyy - Ixy * Ixy) * denom;
+  Jinv.m[0][0] = k1; Jinv.m[0][1] = k2; Jinv.m[0][2] = k3;
+  Jinv.m[1][0] = k2; Jinv.m[1][1] = k4; Jinv.m[1][2] = k5;
+  Jinv.m[2][0] = k3; Jinv.m[2][1] = k5; Jinv.m[2][2] = k6;
+}
+
+// AFTER_PROPAGATE: called with the frame scratch once Propagate and Atmosphere are done (the env layer publishes position / velocity to
+// the other lanes' missiles from there); everything it does not consume dies at that point.
+template <class AfterPropagate>
+FDM_DEV void fdm_frame_lean(AcCore& a, Props& p, FcsState& s, FrameKeep& keep, const double* __restrict__ T, const AtmoConst& ac,
+                            const double dt, const double fcs_dt, AfterPropagate after_propagate) {
+  V3 gi;
+  double twoVt, Mass, qbar;
+  V3 cg, cg_prev;
+  double tk0, tk1, tk2, tk3;
+  WindAxes w;
+  Atmo atm;
+  {
+    Frame f;
+    fdm_stage_propagate(a, p, f, dt);
+    fdm_stage_gravity(f);
+    // Tec2i * gravity, formed here so that neither the ECEF gravity nor sin / cos(epa) outlive this block
+    gi = v3(f.cos_epa * f.grav.x - f.sin_epa * f.grav.y, f.sin_epa * f.grav.x + f.cos_epa * f.grav.y, f.grav.z);
+    fdm_stage_atmosphere(p, f, ac);
+    after_propagate(f);           // position, velocities and h_asl of this frame are final
+    f16_fcs(p, s, T, fcs_dt);
+    tk0 = a.tank0; tk1 = a.tank1; tk2 = a.tank2; tk3 = a.tank3;
+    cg_prev = a.cg;
+    fdm_mass_cg(a, Mass, cg);
+    a.cg = cg; f.cg = cg;
+    fdm_stage_auxiliary(a, p, f, ac, w);
+    twoVt = 2 * f.Vt; qbar = f.qbar; atm = f.atm;
+    keep.pilot_nx = f.pilotN.x; keep.vcas = f.vcas; keep.beta = f.beta;
+  }
+  double thrust;
+  {
+    const int flags = (int)a.engflags;
+    bool augmentation = flags & 2;
+    thrust = fdm_stage_engine(a, p, atm, qbar, T, ac, dt, flags & 1, augmentation);
+    const bool starved_next = fdm_stage_consume_fuel(a, dt, flags & 1, false);
+    a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
+  }
+  keep.thrust = thrust;
+  double c[6];
+  f16_aero<63>(p, T, twoVt, c);
+  {
+    // FGAerodynamics wind->body + FGAircraft sums + FGAccelerations, as fdm_stage_accelerations
+    const double sa = w.sa, ca = w.ca, sb = w.sb, cb = w.cb;
+    const double fw0 = -c[0], fw1 = c[1], fw2 = -c[2];
+    V3 Fa;
+    Fa.x = (ca * cb) * fw0 + (-ca * sb) * fw1 + (-sa) * fw2;
+    Fa.y = sb * fw0 + cb * fw1 + 0.0 * fw2;
+    Fa.z = (sa * cb) * fw0 + (-sa * sb) * fw1 + ca * fw2;
+    const V3 rp = structural_to_body(cg, K_AERORP_X, K_AERORP_Y, K_AERORP_Z);
+    const V3 Ma = v3(c[3], c[4], c[5]) + cross(rp, Fa);
+    const V3 Fp = v3(thrust, 0.0, 0.0);
+    const V3 Mp = cross(structural_to_body(cg, K_THRUSTER_X, K_THRUSTER_Y, K_THRUSTER_Z), Fp);
+    const V3 F = Fa + Fp, M = Ma + Mp;
+    M33 J, Jinv;
+    fdm_inertia(tk0, tk1, tk2, tk3, cg_prev, cg, J, Jinv);
+    a.pqridot = mul(Jinv, M - cross(a.wi, mul(J, a.wi)));
+    const double rm = 1.0 / Mass;
+    a.bodyaccel = v3(F.x * rm, F.y * rm, F.z * rm);
+    const M33 Ti2b = quat_T(opaque(a.q0), opaque(a.q1), opaque(a.q2), opaque(a.q3));
+    a.uvwidot = mulT(Ti2b, a.bodyaccel) + gi;
+  }
+}
+
+// The frame scratch the outputs and the publication need, recomputed from the state a frame left behind (position,
+// attitude and velocities do not change after Propagate; dt = 0 evaluates the derived quantities without integrating).
+FDM_DEV void fdm_refresh(const AcCore& a, const Props& p, const FrameKeep& keep, Frame& f) {
+  AcCore t = a;                 // fdm_propagate_pos adds EARTH_OMEGA * 0 to epa: exact
+  Props pp = p;
+  fdm_propagate_pos(t, f, t.vi, 0.0);
+  fdm_propagate_combine(t, pp, f, t.ri.x, t.ri.y);
+  const double ecr = EARTH_B / EARTH_A;
+  const double slr = EARTH_A * ecr / sqrt(1.0 - (1.0 - ecr * ecr) * f.cosLatGc * f.cosLatGc);
+  f.h_asl = f.radius - slr;
+  f.vcas = keep.vcas; f.pilotN = v3(keep.pilot_nx, p.accelerations_n_pilot_y_norm, p.accelerations_n_pilot_z_norm);
+  f.alpha = p.aero_alpha_rad; f.beta = keep.beta; f.mach = p.velocities_mach; f.thrust = keep.thrust;
+}
+
 // outputs of the frame that has just run (what the reference reads back through get_property_value)
 FDM_DEV void fdm_outputs(const AcCore& a, const Frame& f, AcOut& o) {
   const double lon = (f.rxy == 0.0) ? 0.0 : atan2(f.ecef.y, f.ecef.x);

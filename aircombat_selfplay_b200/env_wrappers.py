@@ -76,9 +76,10 @@ class BatchedVecEnv(VecEnv):
 
     def __init__(self, config_name: str, num_envs: int, device: int = 0, seed: int = 0, env_offset: int = 0,
                  config_dir: Optional[str] = None, substeps: Optional[int] = None, controller_path: Optional[str] = None,
-                 copy: bool = True):
+                 copy: bool = True, allow_random_controller: bool = False):
         self.core = BatchedEnv(config_name, num_envs, device=device, seed=seed, env_offset=env_offset, config_dir=config_dir,
-                               substeps=substeps, controller_path=controller_path, auto_reset=True)
+                               substeps=substeps, controller_path=controller_path, auto_reset=True,
+                               allow_random_controller=allow_random_controller)
         if self.share:
             ShareVecEnv.__init__(self, num_envs, self.core.observation_space, self.core.share_observation_space,
                                  self.core.action_space)

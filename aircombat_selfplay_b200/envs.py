@@ -54,15 +54,15 @@ class BatchedEnv:
 
     def __init__(self, config_name: str, n_envs: int, device: int = 0, seed: int = 0, env_offset: int = 0,
                  config_dir: Optional[str] = None, substeps: Optional[int] = None, controller_path: Optional[str] = None,
-                 auto_reset: bool = True, use_cuda_graph: Optional[bool] = None):
+                 auto_reset: bool = True, use_cuda_graph: Optional[bool] = None, allow_random_controller: bool = False):
         if not torch.cuda.is_available():
             raise AcsError("CUDA is not available; the simulator has no CPU fallback")
         self.config_name = config_name
         self.config = parse_config(config_name, config_dir)
         self.spec = load_spec(config_name, config_dir, substeps)
         self.task_name = self.spec.name
-        self.task = TASKS[self.task_name]
-        if self.spec.use_baseline and not self.task["hier"]:
+        self.task_desc = TASKS[self.task_name]
+        if self.spec.use_baseline and not self.task_desc["hier"]:
             raise NotImplementedError("use_baseline is wired for the hierarchical task families this fork ships (scenario1/2/3, "
                                       "wvr, maneuver_curriculum); the LAG-style SingleCombatTask path calls "
                                       "baseline_agent.get_action with a signature the fork's agents no longer have")
@@ -72,7 +72,7 @@ class BatchedEnv:
         self.seed_value = int(seed)
         with torch.cuda.device(self.device):
             self.batch = EnvBatch(self.spec, n_envs, seed=seed, device=device, env_offset=env_offset)
-        self.hier = bool(self.task["hier"])
+        self.hier = bool(self.task_desc["hier"])
         self.high_dim = 3 if self.hier else 4
         self.act_dim = self.high_dim + self.spec.shoot_dim
         self.observation_space = spaces.Box(low=-10, high=10.0, shape=(self.spec.obs_dim,))
@@ -83,15 +83,15 @@ class BatchedEnv:
         self.enm_ids = [u for u in uids if u[0] != uids[0][0]]
         self._low = torch.zeros((n_envs, self.n_agents, 4 + self.spec.shoot_dim), dtype=torch.int32, device=self.device)
         if self.hier:
-            self.controller = make_controller(self.device, controller_path)
+            self.controller = make_controller(self.device, controller_path, config_dir=config_dir, allow_random=allow_random_controller)
             self._luts = hierarchical_luts(self.device)
             self.rnn = torch.zeros((n_envs * self.n_agents, 128), dtype=torch.float32, device=self.device)
             # 1v1 hierarchical tasks force a climb below 3500 m (E/tasks/singlecombat_task.py:235-237)
-            self._climb_below = 3500.0 if self.task["env"] == "1v1" else None
+            self._climb_below = 3500.0 if self.task_desc["env"] == "1v1" else None
         self.opponents = None
         if self.spec.use_baseline:
             from .opponents import DeviceState, RuleOpponents
-            self.opponents = RuleOpponents(self.spec.baseline_type, self.task["env"], self.spec.n_ego, self.spec.n_enm,
+            self.opponents = RuleOpponents(self.spec.baseline_type, self.task_desc["env"], self.spec.n_ego, self.spec.n_enm,
                                            self.spec.substeps / self.spec.sim_freq, DeviceState(self.batch), n_envs, self.device)
         self._was_reset = False
         # hierarchical tasks: the whole step -- controller (~40 small PyTorch kernels) + the env kernels -- is captured once
@@ -102,6 +102,9 @@ class BatchedEnv:
         self._epoch = 0             # bumped whenever a captured step goes stale (host wrappers hold graphs of their own)
         self._act_in = torch.zeros((n_envs, self.n_agents, self.act_dim), dtype=torch.int32, device=self.device)
         self._timing = False
+        self.curriculum_angle = 0
+        from .task_api import Task
+        self.task = Task(self, single=False)       # the reference's Task plugin surface as a view of the device state
 
     # ------------------------------------------------------------------ reference-shaped properties
     @property
@@ -382,10 +385,12 @@ class _SingleEnvBase:
     ENV_KIND = None
 
     def __init__(self, config_name: str, device: int = 0, config_dir: Optional[str] = None, substeps: Optional[int] = None,
-                 controller_path: Optional[str] = None):
+                 controller_path: Optional[str] = None, allow_random_controller: bool = False):
         self.core = BatchedEnv(config_name, 1, device=device, config_dir=config_dir, substeps=substeps,
-                               controller_path=controller_path, auto_reset=False)
-        kind = self.core.task["env"]
+                               controller_path=controller_path, auto_reset=False, allow_random_controller=allow_random_controller)
+        kind = self.core.task_desc["env"]
+        from .task_api import Task
+        self.task = Task(self.core, single=True)
         if self.ENV_KIND is not None and kind != self.ENV_KIND:
             raise NotImplementedError(f"Unknown taskname: {self.core.task_name}")   # load_task of the reference env classes
         self.config_name = config_name

@@ -198,7 +198,7 @@ def synthetic_actions(rng, spec, high_dim, n_envs, n_steps):
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
 def _cpu_worker(args):
-    config, n_envs, warm_rounds, n_rounds, seed, budget_s = args
+    config, n_envs, warm_rounds, n_rounds, seed, budget_s, min_s = args
     import numpy as np
     from aircombat_selfplay_b200.tasks import load_spec
     from oracle.env_oracle import OracleEnv
@@ -218,33 +218,150 @@ def _cpu_worker(args):
         one_round(t)
     t0 = time.perf_counter()
     done = 0
-    for t in range(n_rounds):
-        one_round(warm_rounds + t)
+    while True:
+        one_round(warm_rounds + done)
         done += 1
-        if time.perf_counter() - t0 > budget_s:
+        el = time.perf_counter() - t0
+        if el > budget_s or (done >= n_rounds and el >= min_s):
             break
     return n_envs * spec.n_agents * done, time.perf_counter() - t0
 
 
-def cpu_env_baseline(config: str, rounds: int, warm_rounds: int = 2, budget_s: float = 20.0, envs_per_core: int = 2):
+def cpu_env_baseline(config: str, rounds: int, warm_rounds: int = 2, budget_s: float = 20.0, envs_per_core: int = 2, min_s: float = 0.0):
     """The oracle port of the same workload on every host core: one process per core, ``envs_per_core`` envs each (the
     reference's SubprocVecEnv layout), synthetic actions of the same distribution, K = 12.  Each worker times its own
-    step loop (env construction and the first reset are outside); the rate is total agent-steps / slowest worker."""
+    step loop (env construction and the first reset are outside) for at least ``min_s`` seconds and ``rounds`` env-steps,
+    at most ``budget_s`` seconds; the rate is total agent-steps / slowest worker."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(config, envs_per_core, warm_rounds, rounds, 100 + k, budget_s) for k in range(cores)])
+        res = pool.map(_cpu_worker, [(config, envs_per_core, warm_rounds, rounds, 100 + k, budget_s, min_s) for k in range(cores)])
     agent_steps = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
+    rates = sorted(r[0] / r[1] for r in res)
     return {"value": agent_steps / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "per_worker_agent_steps_per_s": {"min": rates[0], "median": rates[len(rates) // 2], "max": rates[-1]},
             "sample": f"{cores} worker processes x {envs_per_core} envs of {config}, {agent_steps} agent-steps in {wall:.1f} s, K={SUBSTEPS}; "
                       "restated Python env layer over the restated C++ F-16 FDM (not JSBSim itself, which cannot run here)"}
 
 
 # ----------------------------------------------------------------------------- B200 arm
-def run_b200(args):
+KERNELS = ("k_env_substeps", "k_env_substeps_split", "k_env_substeps_split3", "k_env_substeps_split4")
+# Algorithmic fp64 work of one aircraft substep: 2*DFMA + DMUL + DADD thread instructions of the FDM frame in the committed
+# ncu capture (profiles/r1_k_env_substeps_split3_4096envs_final.txt: 24 770 per aircraft per 12-substep step).  It is a
+# property of the physics, kept fixed across kernel versions; missile / chaff arithmetic is NOT counted (conservative).
+FLOPS_PER_SUBSTEP = 2064.0
+MISSILE_SLOT_BYTES = 2 * 16 * 8 + 8 * 4 + 2 * 4     # 16 doubles read + written, 8 ints read, 2 ints written per live slot
+
+
+def workload_config(desc, config, n_envs, A, hier):
+    return {"workload": desc, "scenario": config, "envs_per_gpu": n_envs, "agents_per_env": A, "substeps": SUBSTEPS,
+            "sim_freq": 60, "auto_reset": True, "l2": "flushed between timed steps (256 MB fill)",
+            "controller": ("batched GRU low-level controller in PyTorch, random-init weights of the reference architecture"
+                           if hier else "none (direct stick/throttle classes)")}
+
+
+def measure(config, n_envs, steps, warmup, seed, world, rank, local, dev, flush, fp64_peak, e2e_views=True):
+    """One workload on this rank's GPU: device-resident rate, per-kernel times, end-to-end rate through the VecEnv API
+    (host numpy in / out), both rooflines of the substep kernel.  Every timing is the max over ranks."""
     import numpy as np
+    import torch
+    from aircombat_selfplay_b200 import capi
+    from aircombat_selfplay_b200.env_wrappers import BatchedVecEnv, ShareBatchedVecEnv
+    from aircombat_selfplay_b200.tasks import load_spec
+    cls = ShareBatchedVecEnv if load_spec(config).share_obs else BatchedVecEnv
+    # one env slice per GPU: rank r owns envs [r*n_envs, (r+1)*n_envs) of the job (RNG streams keyed by global env index)
+    ve = cls(config, n_envs, device=local, seed=seed, env_offset=rank * n_envs, substeps=SUBSTEPS,
+             allow_random_controller=True)     # synthetic weights of the reference's architecture (no checkpoint travels)
+    core, batch, spec = ve.core, ve.core.batch, ve.core.spec
+    A = spec.n_agents
+    rng = np.random.default_rng(seed + rank)
+    total = warmup + steps
+    acts_host = synthetic_actions(rng, spec, core.high_dim, n_envs, total)
+    acts_dev = torch.from_numpy(acts_host).to(dev)
+
+    # ---- device-resident arm: the step (controller + env kernels) replays as one CUDA graph
+    core.reset()
+    for t in range(warmup):
+        core.step(acts_dev[t])
+    torch.cuda.synchronize(); _barrier(world)
+    sampler = ClockSampler(local); sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record(); core.step(acts_dev[warmup + k]); ev[k][1].record()
+    sampler.poll_once()                     # the launches above run ahead of the device: this sample is under load
+    torch.cuda.synchronize(); _barrier(world)
+    clocks = sampler.stop()
+    ms = _max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), world, dev)
+    value = world * n_envs * A * steps / (ms * 1e-3)
+    # ---- per-kernel breakdown of the same step (eager launches bracketed by CUDA events on the launching stream)
+    core.set_timing(True)
+    nk = min(steps, 50)
+    for k in range(nk):
+        flush.fill_(k & 0xFF)
+        core.step(acts_dev[warmup + k])
+    kms, ksteps = batch.get_timing()
+    core.set_timing(False)
+    live_frac, n_slots = 0.0, 0
+    if spec.n_missile_slots and spec.launch_kind:
+        names, mi = batch.arena("ms_i")
+        live_frac = float((mi[names.index("status")] == 0).float().mean())
+        n_slots = int(spec.n_missile_slots)
+
+    # ---- end to end through the VecEnv contract (host numpy in / out, the default API: fresh arrays every step)
+    def run_e2e(v):
+        v.reset()
+        for t in range(warmup):
+            v.step(acts_host[t])
+        torch.cuda.synchronize(); _barrier(world)
+        done = 0
+        t0 = time.perf_counter()
+        for k in range(steps):
+            out = v.step(acts_host[warmup + k])
+            done += int(out[-2].all(axis=1).sum())
+        _barrier(world)
+        s_ = _max_over_ranks(time.perf_counter() - t0, world, dev)
+        return {"value": world * n_envs * A * steps / s_, "unit": UNIT, "h2d_bytes_per_step": v.h2d_bytes_per_step,
+                "d2h_bytes_per_step": v.d2h_bytes_per_step, "ms_per_step": s_ / steps * 1e3}, done
+    e2e, done_envs = run_e2e(ve)
+    e2e["api"] = "VecEnv.step(numpy) with the default copy=True: obs / rewards / dones are fresh host arrays every step"
+    if e2e_views:
+        ve.copy = False
+        e2e["views"], _ = run_e2e(ve)
+        e2e["views"]["api"] = "copy=False: the returned arrays are views of the pinned D2H buffer, valid until the next step"
+        ve.copy = True
+
+    # ---- rooflines of the dominant kernel (k_env_substeps*): DESIGN.md section 5
+    peak, peak_src = _peaks()
+    n_state, n_out = len(capi.state_field_names()), len(capi.output_field_names())
+    base_bytes = (2 * n_state + n_out + 11 + 11) * 8 + 2 * 4 + (4 + spec.shoot_dim) * 4
+    bytes_per_agent_step = base_bytes + n_slots * live_frac * MISSILE_SLOT_BYTES
+    k_ms = kms["substeps"] / max(ksteps, 1)
+    kname = KERNELS[batch.get_option("frame_split_effective")]
+    flops = FLOPS_PER_SUBSTEP * SUBSTEPS
+    ach_tf = n_envs * A * flops / (k_ms * 1e-3) / 1e12
+    ach_gb = n_envs * A * bytes_per_agent_step / (k_ms * 1e-3) / 1e9
+    roof = {"bound": "fp64", "kernel": kname, "achieved": ach_tf, "peak": (fp64_peak or 0.0) / 1e12, "unit": "TFLOP/s",
+            "frac": (ach_tf / (fp64_peak / 1e12)) if fp64_peak else None,
+            "peak_source": "measured live (acs_bench_fp64_peak: dependent-free DFMA loop on every SM; MEASURED_PEAKS.json has no fp64 figure)",
+            "flops_per_agent_step": flops, "flops_note": "algorithmic FDM flops only (2*DFMA + DMUL + DADD of one frame x 12); missile arithmetic not counted",
+            "traffic": _ncu_traffic(kname, config, n_envs), "kernel_ms": k_ms,
+            "kernel_share_of_step": kms["substeps"] / max(sum(kms.values()), 1e-12),
+            "post_ms": kms["post"] / max(ksteps, 1), "reset_ms": kms["reset"] / max(ksteps, 1),
+            "hbm": {"achieved": ach_gb, "peak": peak, "unit": "GB/s", "frac": ach_gb / peak, "peak_source": peak_src,
+                    "algorithmic_bytes_per_agent_step": bytes_per_agent_step, "missile_slots": n_slots,
+                    "missile_live_fraction": live_frac,
+                    "note": "secondary view: fusing the K substeps leaves the kernel fp64-pipe / issue bound, not HBM bound"}}
+    res = {"value": value, "ms_per_step": ms / steps, "e2e": e2e, "roofline": roof, "clocks": clocks, "A": A, "hier": bool(core.hier),
+           "gpu_launches": batch.get_option("launches_per_step") * steps, "episodes_finished_in_e2e": done_envs,
+           "missile_live_fraction": live_frac}
+    ve.close()
+    return res
+
+
+def run_b200(args):
     import torch
     world, rank, local = _dist_init("nccl")
     if not torch.cuda.is_available():
@@ -252,97 +369,47 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from aircombat_selfplay_b200 import capi
-    from aircombat_selfplay_b200.env_wrappers import BatchedVecEnv, ShareBatchedVecEnv
     config, n_envs, desc = WORKLOADS[args.workload]
     if args.envs:
         n_envs = args.envs
-    from aircombat_selfplay_b200.tasks import load_spec
-    cls = ShareBatchedVecEnv if load_spec(config).share_obs else BatchedVecEnv
-    # one env slice per GPU: rank r owns envs [r*n_envs, (r+1)*n_envs) of the job (RNG streams keyed by global env index)
-    ve = cls(config, n_envs, device=local, seed=args.seed, env_offset=rank * n_envs, substeps=SUBSTEPS, copy=False)
-    core, batch, spec = ve.core, ve.core.batch, ve.core.spec
-    A = spec.n_agents
-    rng = np.random.default_rng(args.seed + rank)
-    total = args.warmup + args.steps
-    acts_host = synthetic_actions(rng, spec, core.high_dim, n_envs, total)
-    acts_dev = torch.from_numpy(acts_host).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
-    # ---- device-resident arm: the step (controller + env kernels) replays as one CUDA graph
-    core.reset()
-    for t in range(args.warmup):
-        core.step(acts_dev[t])
-    torch.cuda.synchronize(); _barrier(world)
-    sampler = ClockSampler(local); sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    done_envs = 0
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
-        ev[k][0].record(); core.step(acts_dev[args.warmup + k]); ev[k][1].record()
-    sampler.poll_once()                     # the launches above run ahead of the device: this sample is under load
-    torch.cuda.synchronize(); _barrier(world)
-    clocks = sampler.stop()
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    ms = _max_over_ranks(ms, world, dev)
-    value = world * n_envs * A * args.steps / (ms * 1e-3)
-    # ---- per-kernel breakdown of the same step (eager launches bracketed by CUDA events on the launching stream)
-    core.set_timing(True)
-    nk = min(args.steps, 50)
-    for k in range(nk):
-        flush.fill_(k & 0xFF)
-        core.step(acts_dev[args.warmup + k])
-    kms, ksteps = batch.get_timing()
-    core.set_timing(False)
-
-    # ---- end to end through the VecEnv contract (host numpy in / out)
-    ve.reset()
-    for t in range(args.warmup):
-        ve.step(acts_host[t])
-    torch.cuda.synchronize(); _barrier(world)
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        out = ve.step(acts_host[args.warmup + k])
-        done_envs += int(out[-2].all(axis=1).sum())
-    _barrier(world)
-    e2e_s = _max_over_ranks(time.perf_counter() - t0, world, dev)
-    e2e = {"value": world * n_envs * A * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ve.h2d_bytes_per_step,
-           "d2h_bytes_per_step": ve.d2h_bytes_per_step, "ms_per_step": e2e_s / args.steps * 1e3}
-
-    # ---- roofline of the dominant kernel (k_env_substeps): algorithmic bytes per agent-step
-    peak, peak_src = _peaks()
-    n_state, n_out = len(capi.state_field_names()), len(capi.output_field_names())
-    bytes_per_agent_step = (2 * n_state + n_out + 11 + 11) * 8 + 2 * 4 + (4 + spec.shoot_dim) * 4
-    k_ms = kms["substeps"] / max(ksteps, 1)
-    ach = n_envs * A * bytes_per_agent_step / (k_ms * 1e-3) / 1e9
-    kname = ("k_env_substeps", "k_env_substeps_split", "k_env_substeps_split3", "k_env_substeps_split4")[batch.get_option("frame_split_effective")]
-    roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": _ncu_traffic(kname, config, n_envs), "peak_source": peak_src, "algorithmic_bytes_per_agent_step": bytes_per_agent_step,
-            "kernel_ms": k_ms, "kernel_share_of_step": kms["substeps"] / max(sum(kms.values()), 1e-12),
-            "post_ms": kms["post"] / max(ksteps, 1), "reset_ms": kms["reset"] / max(ksteps, 1),
-            "note": "the fused K-substep kernel is fp64-pipe/latency bound, not HBM bound (DESIGN.md section 5); fp64 view below"}
-    if rank == 0 and not args.no_fp64_peak:
+    fp64_peak = None
+    if not args.no_fp64_peak:
         try:
             fp64_peak = capi.fp64_peak_flops(local)
-            flops_per_agent_step = args.flops_per_substep * SUBSTEPS
-            roof["fp64"] = {"achieved_tflops": n_envs * A * flops_per_agent_step / (k_ms * 1e-3) / 1e12,
-                            "peak_tflops": fp64_peak / 1e12, "peak_source": "measured live (acs_bench_fp64_peak: dependent-free DFMA loop)",
-                            "flops_per_agent_step": flops_per_agent_step}
-            roof["fp64"]["frac"] = roof["fp64"]["achieved_tflops"] / roof["fp64"]["peak_tflops"]
-        except Exception as exc:   # measurement helper only
-            roof["fp64"] = {"error": str(exc)}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": desc, "scenario": config, "envs_per_gpu": n_envs, "agents_per_env": A, "substeps": SUBSTEPS,
-                       "sim_freq": 60, "auto_reset": True, "l2": "flushed between timed steps (256 MB fill)",
-                       "controller": ("batched GRU low-level controller in PyTorch" if core.hier else "none (direct stick/throttle classes)")},
-            "e2e": e2e, "gpu_launches": batch.get_option("launches_per_step") * args.steps, "clocks": clocks, "roofline": roof,
-            "episodes_finished_in_e2e": done_envs}
+        except Exception:          # measurement helper only
+            fp64_peak = None
+    m = measure(config, n_envs, args.steps, args.warmup, args.seed, world, rank, local, dev, flush, fp64_peak)
+    line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(desc, config, n_envs, m["A"], m["hier"]),
+            "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"], "roofline": m["roofline"],
+            "episodes_finished_in_e2e": m["episodes_finished_in_e2e"],
+            "parity": "FDM parity is against the restated CPU oracle (unpinned: no runnable JSBSim here); the env layer is pinned "
+                      "by golden trajectories of the reference's own Python (DESIGN.md section 3)"}
+    # ---- the other BASELINE.json configurations, short samples of the same measurement (headline stays configs[1])
+    if not args.no_workloads and args.workload == "1v1_noweapon" and not args.envs:
+        extra = {}
+        for name, (cfg_w, n_w, desc_w) in [("1v1_noweapon_65536", ("1v1/NoWeapon/Selfplay", 65536, "configs[1] at 65536 envs per GPU")),
+                                            ("1v1_shoot", WORKLOADS["1v1_shoot"]), ("2v2_shoot", WORKLOADS["2v2_shoot"]),
+                                            ("4v4", WORKLOADS["4v4"])]:
+            try:
+                w = measure(cfg_w, n_w, args.extra_steps, args.extra_warmup, args.seed, world, rank, local, dev, flush, fp64_peak,
+                            e2e_views=False)
+                r = w["roofline"]
+                extra[name] = {"config": workload_config(desc_w, cfg_w, n_w, w["A"], w["hier"]), "value": w["value"],
+                               "ms_per_step": w["ms_per_step"], "e2e": w["e2e"], "kernel": r["kernel"], "kernel_ms": r["kernel_ms"],
+                               "post_ms": r["post_ms"], "reset_ms": r["reset_ms"], "roofline_fp64_frac": r["frac"],
+                               "roofline_hbm_frac": r["hbm"]["frac"], "missile_live_fraction": w["missile_live_fraction"],
+                               "steps": args.extra_steps, "warmup": args.extra_warmup}
+            except Exception as exc:
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+        extra["north_star"] = "2v2_shoot"
+        line["workloads"] = extra
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_env_baseline(config, rounds=10 ** 9, budget_s=args.cpu_seconds)
         print(json.dumps(line), flush=True)
-    ve.close()
 
 
 def run_reference(args):
@@ -350,13 +417,19 @@ def run_reference(args):
     if rank != 0:
         return
     config, n_envs, desc = WORKLOADS[args.workload]
+    if args.envs:
+        n_envs = args.envs
+    from aircombat_selfplay_b200.tasks import TASKS, load_spec
+    spec = load_spec(config)
     # every "step" of this arm is a bounded sample of the workload: `ref_rounds` env-steps of (host cores x 2) envs;
-    # W warm-up steps untimed, K steps timed, the whole run capped at 150 s of wall clock
-    b = cpu_env_baseline(config, rounds=args.steps * args.ref_rounds, warm_rounds=args.warmup * args.ref_rounds, budget_s=150.0)
+    # W warm-up steps untimed, then at least K steps AND at least `ref_min_seconds` of wall clock timed (a 0.3 s sample
+    # moved the rate by +-30 %), the whole run capped at 150 s
+    b = cpu_env_baseline(config, rounds=args.steps * args.ref_rounds, warm_rounds=args.warmup * args.ref_rounds, budget_s=150.0,
+                         min_s=args.ref_min_seconds)
+    hier = bool(TASKS[spec.name]["hier"])
     line = {"impl": "reference", "metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "scenario": config, "substeps": SUBSTEPS, "sim_freq": 60},
+            "dtype": "f64", "data": "synthetic", "config": workload_config(desc, config, n_envs, spec.n_agents, hier),
             "cpu_baseline": b, "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -374,9 +447,10 @@ def main():
     ap.add_argument("--no-fp64-peak", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="wall budget of the CPU baseline sample")
     ap.add_argument("--ref-rounds", type=int, default=10, help="--impl reference: env-steps per bench step")
-    ap.add_argument("--flops-per-substep", type=float, default=2064.0,
-                    help="fp64 FLOPs per aircraft per substep: 2*DFMA + DMUL + DADD thread instructions of the committed ncu "
-                         "capture (profiles/r1_k_env_substeps_split3_4096envs_final.txt: 24 770 per aircraft per 12-substep step)")
+    ap.add_argument("--ref-min-seconds", type=float, default=8.0, help="--impl reference: minimum timed wall clock per worker")
+    ap.add_argument("--no-workloads", action="store_true", help="headline workload only (skip the `workloads` samples)")
+    ap.add_argument("--extra-steps", type=int, default=40, help="timed steps of each `workloads` sample")
+    ap.add_argument("--extra-warmup", type=int, default=60, help="warm-up steps of each `workloads` sample (missiles in flight)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

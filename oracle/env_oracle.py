@@ -426,7 +426,9 @@ class OracleEnv:
                         continue
                     if float(np.linalg.norm(c.position - m.position)) <= 300:
                         for j in range(c.count):
-                            if u01(self.seed, self.env_index, RNG_CHAFF, self.substep_count, key[0] * 64 + key[1], c.parent.idx * 64 + j) < 0.85:
+                            # the episode is part of the key: substep counters restart at every reset
+                            if u01(self.seed, self.env_index, RNG_CHAFF, (self.episode << 20) + self.substep_count, key[0] * 64 + key[1],
+                                   c.parent.idx * 64 + j) < 0.85:
                                 m.status = M_MISS
             self.substep_count += 1
         self._task_step()

@@ -982,6 +982,8 @@ static const char* SNAP_NAMES[] = {
     // diagnostics
     "alpha_rad", "beta_rad", "mach", "qbar", "vt_fps", "thrust_lbs", "mass_slugs", "geod_alt_ft",
     "fx", "fy", "fz", "mx", "my", "mz", "temperature_R", "pressure_psf", "density", "density_altitude",
+    // turbine flags as the CUDA state packs them: bit 0 Starved, bit 1 Augmentation
+    "engflags",
 };
 static const int N_SNAP = sizeof(SNAP_NAMES) / sizeof(SNAP_NAMES[0]);
 
@@ -1022,6 +1024,7 @@ void orc_fdm_snapshot(void* h, double* o) {
   o[k++] = f->alpha; o[k++] = f->beta; o[k++] = f->Mach; o[k++] = f->qbar; o[k++] = f->Vt; o[k++] = f->Thrust; o[k++] = f->Mass; o[k++] = f->loc.geodAlt;
   o[k++] = f->acForces.x; o[k++] = f->acForces.y; o[k++] = f->acForces.z; o[k++] = f->acMoments.x; o[k++] = f->acMoments.y; o[k++] = f->acMoments.z;
   o[k++] = f->atm.Temperature; o[k++] = f->atm.Pressure; o[k++] = f->atm.Density; o[k++] = f->atm.DensityAltitude;
+  o[k++] = (double)((f->Starved ? 1 : 0) | (f->Augmentation ? 2 : 0));
   if (k != N_SNAP) { std::fprintf(stderr, "oracle: snapshot size mismatch %d vs %d\n", k, N_SNAP); std::abort(); }
 }
 int orc_fdm_n_props() { return orc::N_PROPS; }

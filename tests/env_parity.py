@@ -32,24 +32,33 @@ def random_actions(rng, spec, n_envs, shoot_p=0.3, mode="random"):
 class Pair:
     """n_envs CUDA envs + n_envs oracle envs of one TaskSpec, same seed."""
 
-    def __init__(self, spec, n_envs, seed=0, init_states=None):
+    def __init__(self, spec, n_envs, seed=0, init_states=None, sample=None):
+        """``sample``: env indices that get an oracle (default: all of them).  The GPU batch always has ``n_envs`` envs
+        and is stepped with one distinct action row per env; the comparison then covers the sampled rows only -- this is
+        how BASELINE-size batches are checked against the oracle (row-indexed action reads, per-env RNG keys, block and
+        warp boundaries) without stepping tens of thousands of Python oracles."""
         import torch
         from aircombat_selfplay_b200.capi import EnvBatch
         from oracle.env_oracle import OracleEnv
         self.spec, self.n = spec, n_envs
-        self.gpu = EnvBatch(spec, n_envs, seed=seed)
-        self.cpu = [OracleEnv(spec, seed=seed, env_index=i) for i in range(n_envs)]
+        self.sample = list(range(n_envs)) if sample is None else [int(i) for i in sample]
+        # device_share_obs: share_obs is what the kernel wrote, not the host layer's stride-0 view of obs
+        self.gpu = EnvBatch(spec, n_envs, seed=seed, device_share_obs=True)
+        self.cpu = [OracleEnv(spec, seed=seed, env_index=i) for i in self.sample]
         if init_states is not None:
             self.gpu.set_init_states(init_states)
             for e in self.cpu:
                 e.init_states = [list(r) for r in init_states]
         self.torch = torch
-        self.alive_oracle = [True] * n_envs   # envs whose oracle is still being stepped (no auto reset in this harness)
+        self._idx = torch.tensor(self.sample, device="cuda", dtype=torch.long)
+
+    def _rows(self, t):
+        return None if t is None else t.index_select(0, self._idx).cpu().numpy()
 
     def reset(self):
         obs, share = self.gpu.reset()
-        g_obs = obs.cpu().numpy()
-        g_share = None if share is None else share.cpu().numpy()
+        g_obs = self._rows(obs)
+        g_share = self._rows(share)
         c = [e.reset() for e in self.cpu]
         c_obs = np.stack([x[0] for x in c])
         c_share = None if g_share is None else np.stack([x[1] for x in c])
@@ -57,9 +66,13 @@ class Pair:
 
     def step(self, act):
         t = self.torch
-        obs, share, rew, done, info = self.gpu.step(t.tensor(act, device="cuda"))
-        g = dict(obs=obs.cpu().numpy(), share=None if share is None else share.cpu().numpy(), rew=rew.cpu().numpy(),
-                 done=done.cpu().numpy().astype(bool), info=info.cpu().numpy())
+        obs, share, rew, done, info = self.gpu.step(act if isinstance(act, t.Tensor) else t.tensor(act, device="cuda"))
+        g = dict(obs=self._rows(obs), share=self._rows(share), rew=self._rows(rew), done=self._rows(done).astype(bool),
+                 info=self._rows(info))
+        if isinstance(act, t.Tensor):
+            act = act.index_select(0, self._idx).cpu().numpy()
+        else:
+            act = act[self.sample]
         c = [e.step(act[i]) for i, e in enumerate(self.cpu)]
         cc = dict(obs=np.stack([x[0] for x in c]), share=None if g["share"] is None else np.stack([x[1] for x in c]),
                   rew=np.stack([x[2] for x in c]), done=np.stack([x[3] for x in c]).astype(bool),
@@ -126,16 +139,25 @@ def obs_tolerance(spec, c_obs, base=1e-9, missile_tol=1e-5):
     return tol
 
 
-def compare_step(g, c, spec, rew_tol=1e-6, envs=None):
-    """Returns a list of human-readable mismatches (empty = parity)."""
+def compare_step(g, c, spec, rew_tol=1e-6, envs=None, missile_tol=1e-5):
+    """Returns a list of human-readable mismatches (empty = parity).  ``g["share"]`` -- when the batch materialises
+    share_obs on the device (``device_share_obs=True``) it is what the KERNEL wrote, and is compared with the oracle's
+    get_state() row by row; otherwise it is the stride-0 view of ``obs`` the host layer exposes."""
     bad = []
     if envs is not None:
         g = dict(g)
         g["obs"] = mask_degenerate_sides(g["obs"], c["obs"], envs)
         if g["share"] is not None:
-            A = g["obs"].shape[1]
-            g["share"] = np.repeat(g["obs"].reshape(g["obs"].shape[0], 1, -1), A, axis=1)
-    tol = obs_tolerance(spec, c["obs"])
+            # the same masking on every agent's copy of the concatenated observations (noise columns only)
+            B, A, D = c["obs"].shape
+            deg = degenerate_side(envs)
+            cols = side_columns(D)
+            sh = g["share"].copy().reshape(B, A, A, D)
+            csh = c["share"].reshape(B, A, A, D)
+            for i, a in zip(*np.nonzero(deg)):
+                sh[i, :, a, cols] = csh[i, :, a, cols]
+            g["share"] = sh.reshape(B, A, A * D)
+    tol = obs_tolerance(spec, c["obs"], missile_tol=missile_tol)
     e = np.abs(g["obs"] - c["obs"]) / np.maximum(1.0, np.abs(c["obs"]))
     if not np.all(e <= tol):
         k = np.unravel_index(np.nanargmax(np.where(np.isnan(e), np.inf, e / tol)), e.shape)
@@ -190,3 +212,83 @@ def low_init_states(spec, h_ft=9200.0):
     for r in rows:
         r[2] = h_ft
     return rows
+
+
+def inject_oracle_state(pair):
+    """Overwrites the continuous state of the CUDA batch with the oracles' (every env of ``pair`` must have an oracle), so
+    that the next step starts from IDENTICAL states on both sides and the comparison measures single-step deltas
+    (north_star: <= 1e-9 on positions, attitudes, velocities from identical states).  Integer state (status, counters,
+    missile bookkeeping) is compared bit-exactly every step and therefore already identical."""
+    import math
+    import torch
+    from tests.fdm_parity import oracle_named_state
+    gpu, envs = pair.gpu, pair.cpu
+    assert len(envs) == gpu.n_envs
+    A, S = gpu.n_agents, None
+
+    def put(arena, fill):
+        names, t = gpu.arena(arena)
+        h = t.cpu().numpy()
+        fill({n: k for k, n in enumerate(names)}, h)
+        gpu.set_arena(arena, torch.tensor(h, device="cuda"))
+
+    states = [[oracle_named_state(s.fdm) for s in e.sims] for e in envs]
+
+    def fill_named(ix, h):
+        for i, e in enumerate(envs):
+            for a in range(A):
+                d = states[i][a]
+                for n, k in ix.items():
+                    if n in d:
+                        h[k, i * A + a] = d[n]
+    put("fdm", fill_named)
+    put("out", fill_named)
+
+    def fill_ac(ix, h):
+        for i, e in enumerate(envs):
+            for a, s in enumerate(e.sims):
+                r = i * A + a
+                h[ix["pos_n"], r], h[ix["pos_e"], r], h[ix["pos_u"], r] = s.position
+                h[ix["vel_n"], r], h[ix["vel_e"], r], h[ix["vel_d"], r] = s.velocity
+                h[ix["h_sl_m"], r] = s.h_sl_m
+                h[ix["u_mps"], r], h[ix["v_mps"], r], h[ix["w_mps"], r] = s.uvw_mps
+                h[ix["vc_mps"], r] = s.vc_mps
+                h[ix["bloods"], r] = s.bloods
+                if e.hr_last[a] is not None:
+                    h[ix["hr_roll"], r], h[ix["hr_p"], r], h[ix["hr_q"], r] = e.hr_last[a]
+                c = e.last_shot_chaff[a]
+                if c is not None:
+                    h[ix["chaff_n"], r], h[ix["chaff_e"], r], h[ix["chaff_u"], r] = c.position
+                    h[ix["chaff_t"], r] = c.t
+                for ri in range(len(e.spec.rewards)):
+                    h[ix[f"pre_reward{ri}"], r] = e.pre_rewards[ri][a]
+    put("ac_d", fill_ac)
+
+    def fill_env(ix, h):
+        for i, e in enumerate(envs):
+            if e.spec.obs_kind == 0:
+                h[ix["tgt_heading_deg"], i] = e.target_heading_deg
+                h[ix["tgt_altitude_ft"], i] = e.target_altitude_ft
+                h[ix["tgt_velocity_mps"], i] = e.target_velocities_u_mps
+                h[ix["check_time"], i] = e.heading_check_time
+            if e.cg_prev is not None:
+                h[ix["cg_prev_ao"], i], h[ix["cg_prev_ta"], i] = e.cg_prev
+            for nm, prev in (("tt_prev", e.tt_prev), ("wd_prev", e.wd_prev)):
+                if prev is not None:
+                    for j, x in enumerate(prev):
+                        h[ix[f"{nm}{j}"], i] = x
+    put("env_d", fill_env)
+
+    def fill_ms(ix, h):
+        S = h.shape[1] // (len(envs) * A)
+        for i, e in enumerate(envs):
+            for a, s in enumerate(e.sims):
+                for k, m in enumerate(s.launch_missiles):
+                    c = (i * A + a) * S + k
+                    h[ix["pos_n"], c], h[ix["pos_e"], c], h[ix["pos_u"], c] = m.position
+                    h[ix["vel_n"], c], h[ix["vel_e"], c], h[ix["vel_u"], c] = m.velocity
+                    h[ix["theta"], c], h[ix["phi"], c] = m.posture[1], m.posture[2]
+                    h[ix["alt"], c], h[ix["t"], c], h[ix["m"], c] = m.alt, m.t, m.m
+                    h[ix["dtheta"], c], h[ix["dphi"], c], h[ix["d_prev"], c] = m.dtheta, m.dphi, m.distance_pre
+                    h[ix["sin_theta"], c], h[ix["cos_theta"], c] = math.sin(m.posture[1]), math.cos(m.posture[1])
+    put("ms_d", fill_ms)

@@ -8,7 +8,8 @@ import pytest
 import torch
 
 from aircombat_selfplay_b200.tasks import load_spec
-from tests.env_parity import CONFIGS, Pair, close_init_states, compare_reset, compare_step, low_init_states, random_actions
+from tests.env_parity import (CONFIGS, Pair, close_init_states, compare_reset, compare_step, inject_oracle_state, low_init_states,
+                              random_actions)
 
 pytestmark = pytest.mark.gpu
 
@@ -277,3 +278,64 @@ def test_full_size_batches_are_replicas(name, n, frame_split):
     names, ei = b.arena("env_i")
     assert int(ei[names.index("episode")].min()) == int(ei[names.index("episode")].max()) == 1
     b.close()
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE sizes vs the oracle
+FULL_SIZE = [("1v1/NoWeapon/Selfplay", 4096), ("1v1/NoWeapon/Selfplay", 65536), ("1v1/ShootMissile/Selfplay", 16384),
+             ("2v2/ShootMissile/HierarchySelfplay", 8192), ("scenario3/scenario3", 4096)]
+
+
+@pytest.mark.parametrize("name,n", FULL_SIZE)
+def test_full_size_batches_match_sampled_oracles(name, n, frame_split):
+    """Every BASELINE.json batch size with DISTINCT random action rows per env (close-engagement geometry so the weapon
+    configs launch): 20 sampled envs -- first, last, warp / block boundaries, random -- are compared step by step with
+    their own oracle (env index keys the RNG streams, the action read is row-indexed), on every substep kernel."""
+    spec = load_spec(name, substeps_override=12)
+    rng = np.random.default_rng(17)
+    init = close_init_states(spec, rng)
+    edge = [0, 1, 15, 16, 31, 32, 63, 64, 127, 128, n // 2 - 1, n // 2, n - 129, n - 128, n - 2, n - 1]
+    sample = sorted(set(edge) | set(int(x) for x in rng.integers(0, n, 6)))
+    p = Pair(spec, n, seed=5, init_states=init, sample=sample)
+    (g_obs, _), (c_obs, _) = p.reset()
+    assert not compare_reset(g_obs, c_obs, spec, p.cpu)
+    launched = False
+    for t in range(24):
+        g, c = p.step(random_actions(rng, spec, n, mode="smooth", shoot_p=0.3))
+        bad = compare_step(g, c, spec, envs=p.cpu)
+        assert not bad, (name, n, t, bad)
+        launched = launched or any(e.missiles for e in p.cpu)
+    if spec.launch_kind in (1, 2, 3, 4):
+        assert launched
+    names, faults = p.gpu.arena("env_i")
+    assert int(faults[names.index("faults")].sum()) == 0
+    p.gpu.close()
+
+
+@pytest.mark.parametrize("name", ["1v1/NoWeapon/Selfplay", "1v1/ShootMissile/Selfplay", "1v1/DodgeMissile/Selfplay",
+                                  "2v2/ShootMissile/HierarchySelfplay", "scenario2/scenario2", "scenario3/scenario3_nvn",
+                                  "singlecontrol/heading"])
+def test_single_step_deltas_from_identical_states(name):
+    """north_star: single-step deltas from IDENTICAL states.  After every step the oracles' continuous state (FDM, derived
+    aircraft properties, missiles, chaff, reward memories) is copied into the CUDA arenas (acs_env_set_arena), so each
+    comparison measures one interaction step (K substeps) from a common state: the missile block then holds the same
+    1e-9 as everything else -- the 1e-5 drift bound of the free-running tests is proportional-navigation chaos
+    accumulated over a fly-by, not a per-step error."""
+    spec = load_spec(name)
+    rng = np.random.default_rng(23)
+    init = None if name.startswith("singlecontrol/") else close_init_states(spec, rng)
+    n = 6
+    p = Pair(spec, n, seed=4, init_states=init)
+    (g_obs, _), (c_obs, _) = p.reset()
+    assert not compare_reset(g_obs, c_obs, spec, p.cpu)
+    inject_oracle_state(p)
+    ev = set()
+    for t in range(70):
+        g, c = p.step(random_actions(rng, spec, n, mode="smooth", shoot_p=0.3))
+        bad = compare_step(g, c, spec, envs=p.cpu, missile_tol=1e-9)
+        assert not bad, (name, t, bad)
+        inject_oracle_state(p)
+        for e in p.cpu:
+            ev.update({0: "launched", 1: "hit", 2: "miss"}[m.status] for m in e.missiles.values())
+    if spec.launch_kind in (1, 2, 3, 4):
+        assert "launched" in ev and "miss" in ev
+    p.gpu.close()

@@ -122,3 +122,31 @@ def test_every_shipped_config_resolves():
     for n in names:
         sp = load_spec(n)
         assert sp.obs_dim > 0 and len(sp.rewards) > 0 and len(sp.terminations) >= 4
+
+
+def test_missing_controller_checkpoint_is_loud(monkeypatch, tmp_path):
+    """No baseline_model.pt -> AcsError (the reference's torch.load raises too); a named but missing file -> FileNotFoundError;
+    random-init weights only behind the explicit opt-in."""
+    import pytest
+    from aircombat_selfplay_b200 import controller
+    from aircombat_selfplay_b200.capi import AcsError
+    monkeypatch.delenv("ACS_ALLOW_RANDOM_CONTROLLER", raising=False)
+    monkeypatch.delenv("ACS_BASELINE_MODEL", raising=False)
+    if controller.find_checkpoint() is None:
+        with pytest.raises(AcsError):
+            controller.make_controller("cpu")
+        assert controller.make_controller("cpu", allow_random=True).checkpoint is None
+    with pytest.raises(FileNotFoundError):
+        controller.make_controller("cpu", path=str(tmp_path / "nope.pt"))
+    monkeypatch.setenv("ACS_BASELINE_MODEL", str(tmp_path / "nope.pt"))
+    with pytest.raises(FileNotFoundError):
+        controller.make_controller("cpu")
+    # a reference checkout next to the yaml files is found through config_dir
+    g = np.load(GOLDEN / "controller.npz")
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd:")}
+    (tmp_path / "model").mkdir()
+    (tmp_path / "configs").mkdir()
+    torch.save(sd, tmp_path / "model" / "baseline_model.pt")
+    monkeypatch.delenv("ACS_BASELINE_MODEL")
+    ctl = controller.make_controller("cpu", config_dir=str(tmp_path / "configs"))
+    assert ctl.checkpoint == str(tmp_path / "model" / "baseline_model.pt")

@@ -1,4 +1,5 @@
 """Tuning experiment: where the end-to-end VecEnv.step time goes (host wall clock per stage, 4096-env headline config)."""
+import os as _os; _os.environ.setdefault("ACS_ALLOW_RANDOM_CONTROLLER", "1")   # synthetic controller weights: timing / soak only
 import sys, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
