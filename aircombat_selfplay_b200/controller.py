@@ -40,18 +40,34 @@ class LowLevelController(nn.Module):
         self.norm = nn.LayerNorm(HIDDEN)
         self.heads = nn.Linear(HIDDEN, sum(HEAD_DIMS))   # the four logits_net layers stacked row-wise
 
+    def _padded_heads(self):
+        """The four logit heads as one [4 * 41, 128] weight: head k occupies rows [41 k, 41 k + HEAD_DIMS[k]), the padding
+        rows have zero weight and a -1e30 bias, so ONE arg-max over a [N, 4, 41] view picks the four classes (the
+        throttle head has 30 classes) instead of four reduction kernels over slices."""
+        w, b = self.heads.weight, self.heads.bias
+        key = (w.data_ptr(), w._version, b._version, w.device)
+        if getattr(self, "_hp_key", None) != key:
+            m = max(HEAD_DIMS)
+            wp = torch.zeros((len(HEAD_DIMS) * m, HIDDEN), dtype=w.dtype, device=w.device)
+            bp = torch.full((len(HEAD_DIMS) * m,), -1e30, dtype=b.dtype, device=b.device)
+            o = 0
+            for k, d in enumerate(HEAD_DIMS):
+                wp[k * m:k * m + d] = w[o:o + d]
+                bp[k * m:k * m + d] = b[o:o + d]
+                o += d
+            self._hp, self._hp_key = (wp, bp), key
+        return self._hp
+
     @torch.no_grad()
     def forward(self, obs12: torch.Tensor, h: torch.Tensor):
         """obs12 [N, 12] float32, h [N, 128] float32 -> (actions [N, 4] int32, h' [N, 128])."""
-        x = self.ln1(F.relu(self.fc1(obs12)))
-        x = self.ln2(F.relu(self.fc2(x)))
+        x = self.ln1(F.relu_(self.fc1(obs12)))
+        x = self.ln2(F.relu_(self.fc2(x)))
         h = self.gru(x, h)
-        logits = self.heads(self.norm(h))
-        acts, o = [], 0
-        for d in HEAD_DIMS:
-            acts.append(logits[:, o:o + d].argmax(dim=-1))     # Categorical(logits).probs.argmax == logits.argmax
-            o += d
-        return torch.stack(acts, dim=-1).to(torch.int32), h
+        wp, bp = self._padded_heads()
+        logits = torch.addmm(bp, self.norm(h), wp.t())               # same dot products as the four logits_net layers
+        # Categorical(logits).probs.argmax == logits.argmax (first maximum on ties, as torch.argmax)
+        return logits.view(-1, len(HEAD_DIMS), max(HEAD_DIMS)).argmax(dim=-1).to(torch.int32), h
 
     def load_reference_state_dict(self, sd: dict):
         """Maps ``BaselineActor.state_dict()`` keys (reference envs/JSBSim/model/baseline_actor.py) onto this module."""
@@ -121,21 +137,21 @@ def make_controller(device, path=None, seed: int = 0, config_dir=None, allow_ran
 
 
 def hierarchical_luts(device):
-    """The three class -> delta lookup tables as device tensors (created once: building them inside a step would be a
-    pageable H2D copy, which a CUDA-graph capture forbids)."""
-    kw = dict(dtype=torch.float64, device=device)
-    return (torch.tensor(NORM_DELTA_ALTITUDE, **kw), torch.tensor(NORM_DELTA_HEADING, **kw), torch.tensor(NORM_DELTA_VELOCITY, **kw))
+    """The three class -> delta lookup tables as ONE device tensor of 11 entries plus the per-column offsets (created once:
+    building them inside a step would be a pageable H2D copy, which a CUDA-graph capture forbids)."""
+    lut = torch.tensor(NORM_DELTA_ALTITUDE + NORM_DELTA_HEADING + NORM_DELTA_VELOCITY, dtype=torch.float64, device=device)
+    off = torch.tensor([0, len(NORM_DELTA_ALTITUDE), len(NORM_DELTA_ALTITUDE) + len(NORM_DELTA_HEADING)], dtype=torch.int64, device=device)
+    return lut, off
 
 
 def hierarchical_input(high: torch.Tensor, obs: torch.Tensor, force_climb_below_m=None, luts=None) -> torch.Tensor:
     """input_obs of the reference (singlecombat_task.py:234-246 / multiplecombat_task.py:171-178).
 
     high [N, 3] integer classes; obs [N, D] float64 current observations (obs[:, 0] = altitude / 5000).  The 1v1 task
-    forces the "climb" class below 3500 m (singlecombat_task.py:235-237)."""
-    lut_a, lut_h, lut_v = luts if luts is not None else hierarchical_luts(obs.device)
-    da = lut_a[high[:, 0].long()]
+    forces the "climb" class below 3500 m (singlecombat_task.py:235-237).  One gather for the three deltas, one
+    concatenation, one cast."""
+    lut, off = luts if luts is not None else hierarchical_luts(obs.device)
+    idx = high.to(torch.int64) + off
     if force_climb_below_m is not None:
-        da = torch.where(obs[:, 0] * 5000.0 < force_climb_below_m, lut_a[0], da)
-    dh = lut_h[high[:, 1].long()]
-    dv = lut_v[high[:, 2].long()]
-    return torch.cat([torch.stack([da, dh, dv], dim=-1), obs[:, :9]], dim=-1).to(torch.float32)
+        idx[:, 0] = torch.where(obs[:, 0] * 5000.0 < force_climb_below_m, 0, idx[:, 0])
+    return torch.cat([lut[idx], obs[:, :9]], dim=-1).to(torch.float32)

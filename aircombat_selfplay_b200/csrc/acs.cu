@@ -294,6 +294,9 @@ struct AcsEnv {
   int tpl_mode = 2;              // 0 none, 1 FDM reload only, 2 whole reset (ACS_RESET_TEMPLATE)
   bool fused_reset = true;       // auto-reset inside k_env_post (needs the template)
   bool post_split = true;        // get_obs on its own warps in k_env_post where that is legal (ACS_POST_SPLIT)
+  PostKernel post = nullptr;     // k_env_post instantiation of this task's family (post_kernel_for)
+  int post_family = -1;          // its index in ACS_POST_FAMILIES, -1 = the generic kernel
+  bool defer_missiles = true;    // one-thread frame: missiles of decoupled envs run in k_env_missiles (ACS_DEFER_MISSILES)
   int frame_split = -1;          // substep kernel: 0 one thread per aircraft, 1 two-warp frame, -1 by batch size
   int split_max_threads = 0;     // auto: use the two-warp frame up to this many aircraft lanes
   int n_sms = 0;
@@ -386,9 +389,17 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
   if (const char* s = std::getenv("ACS_RESET_TEMPLATE")) e->tpl_mode = std::atoi(s);
   if (const char* s = std::getenv("ACS_FUSED_RESET")) e->fused_reset = std::atoi(s) != 0;
   if (const char* s = std::getenv("ACS_POST_SPLIT")) e->post_split = std::atoi(s) != 0;
+  if (const char* s = std::getenv("ACS_DEFER_MISSILES")) e->defer_missiles = std::atoi(s) != 0;
+  e->post = post_kernel_for(e->cfg, &e->post_family);
+  if (const char* s = std::getenv("ACS_POST_GENERIC")) if (std::atoi(s) != 0) { e->post = k_env_post<PostGeneric>; e->post_family = -1; }
+  v.traj = nullptr;
+  if (cfg->launch_kind != ACS_L_NONE && cfg->launch_kind != ACS_L_AUTO_GUN) {     // tasks that fly missiles
+    CUDA_TRY(cudaMalloc(&v.traj, sizeof(double) * 6 * (size_t)cfg->substeps * rows));
+    CUDA_TRY(cudaMemset(v.traj, 0, sizeof(double) * 6 * (size_t)cfg->substeps * rows));
+  }
   if (cfg->obs_kind != ACS_OBS_HEADING && e->tpl_mode > 0) {
     EnvView& t = e->tpl.t;
-    t.B = 1; t.A = A; t.S = v.S; t.rows = A;
+    t.B = 1; t.A = A; t.S = v.S; t.rows = A; t.traj = nullptr;
     // one contiguous block (256-byte aligned pieces): arenas of one env, reset observation, field lists
     const size_t n64max = (size_t)(N_STATE + FDM_N_OUT + N_AD) * A + (size_t)N_MD * A * v.S + N_ED;
     const size_t n32max = (size_t)N_AI * A + (size_t)N_MI * A * v.S + N_EI;
@@ -515,9 +526,11 @@ int acs_env_get_option(const AcsEnv* e, const char* name, int* value) {
     *value = frame_split_effective(e);
     return 0;
   }
+  if (!std::strcmp(name, "post_family")) { *value = e->post_family; return 0; }
   if (!std::strcmp(name, "reset_template")) { *value = e->tpl.t.fdm == nullptr ? 0 : (e->tpl.full ? 2 : 1); return 0; }
   if (!std::strcmp(name, "launches_per_step")) {       // kernels one auto-resetting acs_env_step launches
-    *value = (e->tpl.t.fdm != nullptr && e->fused_reset) ? 2 : ((e->tpl.t.fdm != nullptr) ? 3 : 4);
+    *value = (e->tpl.t.fdm != nullptr && e->tpl.full && e->fused_reset) ? 2 : ((e->tpl.t.fdm != nullptr) ? 3 : 4);
+    if (frame_split_effective(e) == 0 && e->defer_missiles && e->v.traj != nullptr) *value += 1;     // k_env_missiles
     return 0;
   }
   return fail(std::string("acs_env_get_option: unknown option ") + name);
@@ -527,6 +540,7 @@ int acs_env_destroy(AcsEnv* e) {
   if (!e) return 0;
   cudaSetDevice(e->fdm->device);
   cudaFree(e->v.ad); cudaFree(e->v.ai); cudaFree(e->v.ed); cudaFree(e->v.ei); cudaFree(e->v.md); cudaFree(e->v.mi);
+  if (e->v.traj) cudaFree(e->v.traj);
   if (e->tpl_block) cudaFree(e->tpl_block);
   for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
   acs_destroy(e->fdm);
@@ -573,14 +587,19 @@ int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double*
   if (split == 3) k_env_substeps_split4<<<(threads + S4 - 1) / S4, 4 * S4, S4_DYN_SMEM, st>>>(e->v, e->cfg, e->lg, actions_dev);
   else if (split == 2) k_env_substeps_split3<<<(threads + S3 - 1) / S3, 3 * S3, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   else if (split == 1) k_env_substeps_split<<<(threads + SPLIT_SLOTS - 1) / SPLIT_SLOTS, 2 * SPLIT_SLOTS, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
-  else k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
+  else {
+    const int defer = (e->defer_missiles && e->v.traj != nullptr) ? 1 : 0;
+    k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev, defer);
+    CUDA_TRY(cudaGetLastError());
+    if (defer) k_env_missiles<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg);
+  }
   CUDA_TRY(cudaGetLastError());
   if (e->timing) timing_event(e, st);
-  const int fuse = (auto_reset && e->tpl.t.fdm != nullptr && e->fused_reset) ? 1 : 0;
+  const int fuse = (auto_reset && e->tpl.t.fdm != nullptr && e->tpl.full && e->fused_reset) ? 1 : 0;
   const int obs_split = (e->post_split && e->cfg.launch_kind == ACS_L_NONE && !e->cfg.use_artillery &&
                          e->cfg.obs_kind != ACS_OBS_HEADING) ? 1 : 0;
-  k_env_post<<<(threads + 127) / 128, obs_split ? 256 : 128, 0, st>>>(e->v, e->cfg, e->lg, obs_dev, share_obs_dev, rewards_dev, dones_dev,
-                                                                      info_dev, env_done_dev, fuse, e->tpl, obs_split);
+  e->post<<<(threads + 127) / 128, obs_split ? 256 : 128, 0, st>>>(e->v, e->cfg, e->lg, obs_dev, share_obs_dev, rewards_dev, dones_dev,
+                                                                   info_dev, env_done_dev, fuse, e->tpl, obs_split);
   CUDA_TRY(cudaGetLastError());
   if (e->timing) timing_event(e, st);
   int rc = 0;

@@ -36,7 +36,7 @@ enum {
 };
 // per env ints
 enum { EI_CURRENT_STEP, EI_EPISODE, EI_SUBSTEP_COUNT, EI_TURN_COUNTS, EI_PMV_REF, EI_CG_VALID, EI_TT_VALID, EI_WD_VALID,
-       EI_ORDER_SEQ, EI_BORN_SEQ, EI_FAULTS, N_EI };
+       EI_ORDER_SEQ, EI_BORN_SEQ, EI_FAULTS, EI_DEFERRED, N_EI };
 // per missile slot doubles / ints
 enum { MD_POS_N, MD_POS_E, MD_POS_U, MD_VEL_N, MD_VEL_E, MD_VEL_U, MD_THETA, MD_PHI, MD_ALT, MD_T, MD_M, MD_DTHETA,
        MD_DPHI, MD_D_PREV, MD_SIN_THETA, MD_COS_THETA, N_MD };
@@ -53,7 +53,7 @@ static const char* const ED_NAMES[] = {"tgt_heading_deg", "tgt_altitude_ft", "tg
   "cg_prev_ta", "tt_prev0", "tt_prev1", "tt_prev2", "tt_prev3", "tt_prev4", "tt_prev5", "tt_prev6", "tt_prev7", "wd_prev0",
   "wd_prev1", "wd_prev2", "wd_prev3", "wd_prev4", "wd_prev5", "wd_prev6", "wd_prev7"};
 static const char* const EI_NAMES[] = {"current_step", "episode", "substep_count", "turn_counts", "pmv_ref", "cg_valid", "tt_valid",
-  "wd_valid", "order_seq", "born_seq", "faults"};
+  "wd_valid", "order_seq", "born_seq", "faults", "deferred"};
 static const char* const MD_NAMES[] = {"pos_n", "pos_e", "pos_u", "vel_n", "vel_e", "vel_u", "theta", "phi", "alt", "t", "m",
   "dtheta", "dphi", "d_prev", "sin_theta", "cos_theta"};
 static const char* const MI_NAMES[] = {"status", "kind", "target", "consec", "order", "born", "keyn", "detached"};
@@ -76,6 +76,8 @@ struct EnvView {
   double* ed; int* ei;     // [N_ED][B],   [N_EI][B]
   double* md; int* mi;     // [N_MD][rows*S], [N_MI][rows*S]
   int B, A, S, rows;
+  double* traj;  // [K][6][rows] position / velocity every aircraft published after each substep of the current step, for
+                 // the envs whose missiles are integrated by k_env_missiles (nullptr: the task has no missiles)
 };
 // Reset template of a handle (acs.cu, build_reset_template).  Every task but the heading task resets an env to the same
 // state each time (fixed per-lane initial conditions, no random draw), so reset() is run once on a one-env arena `t`.

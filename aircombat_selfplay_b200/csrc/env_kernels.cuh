@@ -262,25 +262,68 @@ struct EomLane {
   double v_mps, w_mps, vc_mps;
   int status, sc0;
   bool has_ms, was_alive;
+  bool deferred;               // the env's missiles are integrated after the K loop by k_env_missiles (this kernel only records
+                               // every aircraft's position / velocity per substep in v.traj)
   unsigned long long live;     // slots of this aircraft whose missile still runs (live_missiles)
   AcOut o;
 };
-ENV_DEV void eom_begin(const EnvView& v, const Lane& L, EomLane& E) {
+// Can a missile of this aircraft reach its target's fuze radius within this interaction step?  Conservative bound on the
+// closing distance over K substeps: the missile's speed now + the most its motor can add (753 m/s^2 for the AIM-120B
+// numbers, simulatior.py:700-712) + 1500 m/s for the target (an F-16 stays below half of that), plus a margin.
+ENV_DEV bool missile_threatens(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const unsigned long long live) {
+  const double T = cfg.substeps * cfg.sim_dt;
+  for (unsigned long long m = live; m; m &= m - 1) {
+    const int mid = L.row * v.S + (__ffsll((long long)m) - 1);
+    if (MI(v, MI_STATUS, mid) != MS_LAUNCHED) continue;          // HIT / MISS missiles never score again
+    const int trow = L.env * v.A + MI(v, MI_TARGET, mid);
+    const double dx = MD(v, MD_POS_N, mid) - AD(v, AD_POS_N, trow), dy = MD(v, MD_POS_E, mid) - AD(v, AD_POS_E, trow),
+                 dz = MD(v, MD_POS_U, mid) - AD(v, AD_POS_U, trow);
+    const double vn = MD(v, MD_VEL_N, mid), ve = MD(v, MD_VEL_E, mid), vu = MD(v, MD_VEL_U, mid);
+    const double reach = missile_params(MI(v, MI_KIND, mid)).Rc + (sqrt(vn * vn + ve * ve + vu * vu) + 800.0 * T + 1500.0) * T + 50.0;
+    if (dx * dx + dy * dy + dz * dz < reach * reach) return true;
+  }
+  return false;
+}
+// allow_defer: this launch is followed by k_env_missiles.  An env is COUPLED when something in its missile phase can feed
+// back into the aircraft or needs the per-substep lockstep of its lanes: a missile close enough to score within this
+// step (the hit stops the target's integration at that substep), or an effective chaff cloud (timers, decoy draws).
+// Every other env with live missiles is DEFERRED: no hit can happen, so aircraft statuses are constant over the step, the
+// missiles are independent of each other and of everything but their target's trajectory -- this kernel integrates the
+// aircraft without stopping and records their position / velocity per substep, k_env_missiles then integrates each
+// missile over the K substeps with its state in registers (same expressions, same per-missile order).
+ENV_DEV void eom_begin(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, EomLane& E, const bool allow_defer) {
   E.v_mps = E.w_mps = E.vc_mps = 0;
-  E.status = ST_CRASH; E.has_ms = false; E.live = 0;
+  E.status = ST_CRASH; E.has_ms = false; E.live = 0; E.deferred = false;
   E.me.status = ST_CRASH; E.me.bloods = 0; E.me.h = 0; E.me.u_mps = 0;
   E.me.f.n = E.me.f.e = E.me.f.u = E.me.f.vn = E.me.f.ve = E.me.f.vd = 0;
+  bool chaff = false, threat = false;
   if (L.valid) {
     load_pub(v, L.row, E.me);
     E.status = E.me.status;
     E.live = live_missiles(v, L);
-    E.has_ms = (E.live != 0) || (AI(v, AI_CH_STATE, L.row) == CH_ACTIVE);
+    chaff = AI(v, AI_CH_STATE, L.row) == CH_ACTIVE;
+    if (allow_defer && v.traj != nullptr) threat = missile_threatens(v, cfg, L, E.live);
   }
+  const bool any_live = (__ballot_sync(L.gmask, E.live != 0) & L.gmask) != 0;
+  const bool any_chaff = (__ballot_sync(L.gmask, chaff) & L.gmask) != 0;
+  const bool any_threat = (__ballot_sync(L.gmask, threat) & L.gmask) != 0;
+  E.deferred = allow_defer && v.traj != nullptr && any_live && !any_chaff && !any_threat;
   // an env needs the per-substep exchange only while it has missiles that still run or an effective chaff cloud
-  const unsigned b = __ballot_sync(L.gmask, E.has_ms);
-  E.has_ms = (b & L.gmask) != 0;
+  E.has_ms = !E.deferred && (any_live || any_chaff);
   E.was_alive = L.valid && E.status == ST_ALIVE;
   E.sc0 = (L.env < v.B) ? EI(v, EI_SUBSTEP_COUNT, L.env) : 0;
+  if (L.valid && L.lane == 0) EI(v, EI_DEFERRED, L.env) = E.deferred;
+}
+// the record k_env_missiles reads: what the aircraft of `row` published after substep k
+ENV_DEV void traj_store(const EnvView& v, const int k, const int row, const Feat& f) {
+  double* t = v.traj + (size_t)k * 6 * v.rows + row;
+  t[0] = f.n; t[(size_t)v.rows] = f.e; t[(size_t)2 * v.rows] = f.u;
+  t[(size_t)3 * v.rows] = f.vn; t[(size_t)4 * v.rows] = f.ve; t[(size_t)5 * v.rows] = f.vd;
+}
+ENV_DEV void traj_load(const EnvView& v, const int k, const int row, Feat& f) {
+  const double* t = v.traj + (size_t)k * 6 * v.rows + row;
+  f.n = t[0]; f.e = t[(size_t)v.rows]; f.u = t[(size_t)2 * v.rows];
+  f.vn = t[(size_t)3 * v.rows]; f.ve = t[(size_t)4 * v.rows]; f.vd = t[(size_t)5 * v.rows];
 }
 // AircraftSimulator.run's gate (simulatior.py:210-229): an aircraft whose bloods ran out turns SHOTDOWN and still
 // integrates this frame
@@ -338,7 +381,7 @@ ENV_DEV void eom_propulsion(AcCore& a, const Props& p, Frame& f, const double* _
 #define ACS_LEAN_FRAME 1
 #endif
 __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
-                                                           const int32_t* __restrict__ actions) {
+                                                           const int32_t* __restrict__ actions, const int allow_defer) {
   __shared__ double sT[F16_NTAB];
   __shared__ PubAc sP[FDM_BLOCK];
   __shared__ int sWin[FDM_BLOCK];
@@ -351,7 +394,11 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
   AcCore a; Props p; FcsState s;
   EomLane E;
-  eom_begin(v, L, E);
+#if ACS_LEAN_FRAME
+  eom_begin(v, cfg, L, E, allow_defer != 0);
+#else
+  eom_begin(v, cfg, L, E, false);
+#endif
   if (L.valid) load_commanded(v, cfg, L, actions, E.status == ST_ALIVE, a, p, s);
 #if ACS_LEAN_FRAME
   // Lean frame (fdm_core.cuh): nothing of a frame's scratch outlives it.  The publication the other lanes' missiles read is
@@ -360,7 +407,7 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
   // the state the aircraft's last frame left, after the K loop.
   FrameKeep keep;
   keep.pilot_nx = keep.vcas = keep.beta = keep.thrust = 0.0;
-  const bool has_ms = E.has_ms;
+  const bool has_ms = E.has_ms, deferred = E.deferred;
   const double bloods = E.me.bloods;
   int status = E.status;
   if (has_ms) sP[L.tid] = E.me;          // dead aircraft stay where the arena has them
@@ -370,7 +417,14 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
       if (bloods <= 0) status = ST_SHOTDOWN;     // AircraftSimulator.run's gate (simulatior.py:220-226): still integrates this frame
       fdm_frame_lean(a, p, s, keep, sT, g_atmo, dt, fcs_dt, [&](const Frame& f) {
         if (has_ms) { PubAc pub; publish_from_frame(f, org, pub); sP[L.tid].f = pub.f; sP[L.tid].h = pub.h; sP[L.tid].u_mps = pub.u_mps; }
+        if (deferred) { PubAc pub; publish_from_frame(f, org, pub); traj_store(v, k, L.row, pub.f); }
       });
+    } else if (deferred && L.valid) {
+      // an aircraft that does not run this substep stays where it stopped: the arena's position before its first frame of
+      // the step, its own last record afterwards (only a gun kill -- bloods <= 0 -- stops an aircraft of a deferred env)
+      Feat f = E.me.f;
+      if (k > 0) traj_load(v, k - 1, L.row, f);
+      traj_store(v, k, L.row, f);
     }
     if (has_ms) {
       sP[L.tid].status = status;
@@ -399,6 +453,56 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
   }
 #endif
   eom_end<true>(v, L, E, a, p, s, K);
+}
+
+// ---------------------------------------------------------------------------------------------- deferred missiles
+// The missiles of the envs k_env_substeps marked DEFERRED (eom_begin): no missile of the env can score within this step, so
+// target statuses are constant, nothing feeds back into the aircraft and the missiles do not interact.  One thread per
+// shooter walks its live slots; each missile is loaded once, run() K times against the target's recorded trajectory with
+// its state in registers, and stored once -- instead of K x (load, run, store) between the frames of a 255-register
+// thread.  Same expressions as missile_phase.  A fuze condition met here would mean the reach bound of
+// missile_threatens was wrong: it is counted in the env's fault counter (asserted zero by every parity test).
+__global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg) {
+  const Lane L = lane_setup(v, lg);
+  if (!L.valid || !EI(v, EI_DEFERRED, L.env)) return;
+  const int K = cfg.substeps;
+  const double dt = cfg.sim_dt;
+  const int maxlen = (int)(5.0 / dt);
+  const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
+  const int nl = AI(v, AI_N_LAUNCHED, L.row);
+  for (int slot = 0; slot < nl; slot++) {
+    const int mid = L.row * v.S + slot;
+    if (MI(v, MI_DETACHED, mid) || missile_inert(v, mid, L.env)) continue;
+    Missile m;
+    missile_load(v, mid, m);
+    const MissileParams pr = missile_params(m.kind);
+    const int trow = L.env * v.A + m.target;
+    const bool target_alive = AI(v, AI_STATUS, trow) == ST_ALIVE;     // constant over the step in a deferred env
+    Feat tg;
+    traj_load(v, 0, trow, tg);
+    for (int k = 0; k < K; k++) {
+      Feat nxt = tg;
+      if (k + 1 < K) traj_load(v, k + 1, trow, nxt);                  // in flight while this substep computes
+      m.t += dt;
+      double ny, nz, dist;
+      missile_guidance(m, pr, tg, ny, nz, dist);
+      m.consec = (dist > m.d_prev) ? m.consec + 1 : 0;
+      m.d_prev = dist;
+      const double speed = sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
+      if (dist < pr.Rc && target_alive && m.status != MS_MISS) {
+        atomicAdd(&EI(v, EI_FAULTS, L.env), 1);                       // cannot happen (missile_threatens)
+        m.status = MS_HIT;
+      } else if (m.t > pr.t_max || speed < pr.v_min || m.consec >= maxlen || !target_alive) {
+        const bool inert = m.status == MS_MISS && (m.t > pr.t_max || !target_alive || speed < pr.v_min);
+        m.status = MS_MISS;
+        if (inert) break;             // every later run() is the same no-op (missile_inert)
+      } else {
+        missile_state_trans(m, pr, org, ny, nz, dt);
+      }
+      tg = nxt;
+    }
+    missile_store(v, mid, m);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- two-warp frame
@@ -504,7 +608,7 @@ __global__ void __launch_bounds__(2 * SPLIT_SLOTS, ACS_S2_MIN_BLOCKS) k_env_subs
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
   AcCore a; Props p; FcsState s; Frame f;
   EomLane E;
-  eom_begin(v, L, E);
+  eom_begin(v, cfg, L, E, false);
   if (E.was_alive) { f16_props_init(p, s); load_state(v.fdm, v.rows, L.row, a, p, s); }
   PROF_DECL
   for (int k = 0; k < K; k++) {
@@ -709,7 +813,7 @@ __global__ void __launch_bounds__(3 * S3, ACS_S3_MIN_BLOCKS) k_env_substeps_spli
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
   AcCore a; Props p; FcsState s; Frame f;
   EomLane E;
-  eom_begin(v, L, E);
+  eom_begin(v, cfg, L, E, false);
   if (E.was_alive) { f16_props_init(p, s); load_state(v.fdm, v.rows, L.row, a, p, s); }
   for (int k = 0; k < K; k++) {
     const bool ran = eom_runs(L, E);
@@ -901,7 +1005,7 @@ __global__ void __launch_bounds__(4 * S4, 1) k_env_substeps_split4(const EnvView
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
   AcCore a; Props p; FcsState s; Frame f;
   EomLane E;
-  eom_begin(v, L, E);
+  eom_begin(v, cfg, L, E, false);
   if (E.was_alive) { f16_props_init(p, s); load_state(v.fdm, v.rows, L.row, a, p, s); }
   QUAD_BARRIER_ALL(quad)                                 // 0
   for (int k = 0; k < K; k++) {
@@ -963,6 +1067,22 @@ __global__ void __launch_bounds__(4 * S4, 1) k_env_substeps_split4(const EnvView
 #undef XR_L
 
 // ============================================================================================== per-step logic
+// k_env_post executes every instruction once per launch, so its time is the fetch of its own instruction stream -- and a
+// kernel that carries all 8 observation packers x 6 launch rules x 12 reward classes streams 57 k SASS instructions to
+// execute ~3 k of them (ncu: stall_no_inst on top).  The per-step logic is therefore compiled per TASK FAMILY: the
+// observation packer, the launch rule and the set of reward classes are template constants (PostSpec), acs_env_create
+// picks the instantiation that covers the task (same expressions, dead branches removed) and falls back to the generic
+// one (all three read from AcsTaskConfig at run time) for a combination that has none.
+template <int OBS, int LAUNCH, unsigned RMASK>
+struct PostSpec {
+  static constexpr int obs = OBS, launch = LAUNCH;
+  static constexpr unsigned rmask = RMASK;
+  static ENV_DEV int obs_kind(const AcsTaskConfig& c) { return OBS >= 0 ? OBS : c.obs_kind; }
+  static ENV_DEV int launch_kind(const AcsTaskConfig& c) { return LAUNCH >= 0 ? LAUNCH : c.launch_kind; }
+  static ENV_DEV bool has(const int kind) { return (RMASK >> kind) & 1u; }      // folds: `kind` is a literal at every use
+};
+using PostGeneric = PostSpec<-1, -1, 0xfffu>;
+
 struct StepCtx {
   const EnvView& v;
   const AcsTaskConfig& cfg;
@@ -1062,6 +1182,7 @@ ENV_DEV void a2a_available(const StepCtx& c, int a, bool ret[3], int& enemy) {
 }
 
 // task.step for agent a (executed by lane a while the other lanes of the env wait)
+template <class S>
 ENV_DEV void task_step_agent(const StepCtx& c, int a) {
   const EnvView& v = c.v;
   const AcsTaskConfig& cfg = c.cfg;
@@ -1069,7 +1190,7 @@ ENV_DEV void task_step_agent(const StepCtx& c, int a) {
   PubAc* sP = c.sP + c.L.gbase;
   const bool alive = sP[a].status == ST_ALIVE;
   const int shoot = AI(v, AI_SHOOT, row);
-  if (cfg.launch_kind == ACS_L_RULE_LOCK) {          // E/tasks/singlecombat_with_missile_task.py:109-127
+  if (S::launch_kind(cfg) == ACS_L_RULE_LOCK) {          // E/tasks/singlecombat_with_missile_task.py:109-127
     int e0 = -1;
     for (int j = 0; j < v.A && e0 < 0; j++) if (!same_team(cfg, a, j)) e0 = j;
     double distance, ang;
@@ -1090,7 +1211,7 @@ ENV_DEV void task_step_agent(const StepCtx& c, int a) {
       AI(v, AI_REM_MISSILES, row) = rem - 1;
       AI(v, AI_LAST_SHOOT_TIME, row) = c.cs;
     }
-  } else if (cfg.launch_kind == ACS_L_RL_SINGLE) {   // E/tasks/singlecombat_with_missile_task.py:194-204
+  } else if (S::launch_kind(cfg) == ACS_L_RL_SINGLE) {   // E/tasks/singlecombat_with_missile_task.py:194-204
     int e0 = -1;
     for (int j = 0; j < v.A && e0 < 0; j++) if (!same_team(cfg, a, j)) e0 = j;
     const int rem = AI(v, AI_REM_MISSILES, row);
@@ -1098,7 +1219,7 @@ ENV_DEV void task_step_agent(const StepCtx& c, int a) {
       AI(v, AI_LAST_SHOT_SLOT, row) = launch_missile(c, a, e0, 0, rem);
       AI(v, AI_REM_MISSILES, row) = rem - 1;
     }
-  } else if (cfg.launch_kind == ACS_L_RL_NEAREST) {  // E/tasks/multiplecombat_task.py:278-299
+  } else if (S::launch_kind(cfg) == ACS_L_RL_NEAREST) {  // E/tasks/multiplecombat_task.py:278-299
     int ti = -1; double bd = INFINITY;
     for (int j = 0; j < v.A; j++) {
       if (same_team(cfg, a, j)) continue;
@@ -1116,12 +1237,12 @@ ENV_DEV void task_step_agent(const StepCtx& c, int a) {
       AI(v, AI_REM_MISSILES, row) = rem - 1;
       AI(v, AI_LAST_SHOOT_TIME, row) = c.cs;
     }
-  } else if (cfg.launch_kind == ACS_L_AUTO_GUN) {    // E/tasks/WVR_task.py:67-81, singlecombat_task.py:290-297
+  } else if (S::launch_kind(cfg) == ACS_L_AUTO_GUN) {    // E/tasks/WVR_task.py:67-81, singlecombat_task.py:290-297
     const int enemy = scenario_target(c, a);          // farthest enemy; no ammunition, no alive checks on either side
     double distance, ang;
     attack_geometry(sP[a], sP[enemy], distance, ang);
     if (distance / 1000 < 3 && ang < 5) sP[enemy].bloods -= 5;
-  } else if (cfg.launch_kind == ACS_L_SCENARIO) {    // E/tasks/scenario2_task.py:73-114
+  } else if (S::launch_kind(cfg) == ACS_L_SCENARIO) {    // E/tasks/scenario2_task.py:73-114
     const bool f_gun = alive && (shoot & 1) && AI(v, AI_REM_GUN, row) > 0;
     const bool f_9m = alive && (shoot & 2) && AI(v, AI_REM_9M, row) > 0;
     const bool f_120 = alive && (shoot & 4) && AI(v, AI_REM_120B, row) > 0;
@@ -1196,13 +1317,14 @@ ENV_DEV bool obs_missile6(const StepCtx& c, int a, double* o) {
   return true;
 }
 // get_obs for agent a into o[obs_dim] (global memory); citations per branch in taskspec.py
+template <class S>
 ENV_DEV void write_obs(const StepCtx& c, int a, double* __restrict__ o) {
   const EnvView& v = c.v;
   const AcsTaskConfig& cfg = c.cfg;
   const int row = c.L.env * v.A + a;
   const PubAc* sP = c.sP + c.L.gbase;
   const PubAc& s = sP[a];
-  const int D = cfg.obs_dim, k = cfg.obs_kind;
+  const int D = cfg.obs_dim, k = S::obs_kind(cfg);
   double t[9];
   for (int i = 0; i < D; i++) o[i] = 0.0;
   if (k == ACS_OBS_HEADING) {                      // E/tasks/heading_task.py:67-100
@@ -1278,6 +1400,7 @@ ENV_DEV double reward_process(const StepCtx& c, int ri, int row, double new_rewa
 }
 // geo[0..n) = get_AO_TA_R of agent a against each enemy in enemy order, computed once per agent per step (the reference
 // recomputes it inside every reward class)
+template <class S>
 ENV_DEV double reward_one(const StepCtx& c, int ri, int a, const AoTaR* geo, int n) {
   const EnvView& v = c.v;
   const AcsTaskConfig& cfg = c.cfg;
@@ -1286,27 +1409,27 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a, const AoTaR* geo, int
   const PubAc* sP = c.sP + c.L.gbase;
   const PubAc& s = sP[a];
   const double FT = 1 / 3.28084, PI = 3.14159265358979323846;
-  switch (r.kind) {
-    case ACS_R_ALTITUDE: {            // altitude_reward.py:20-40
+  const int kind = r.kind;
+  if (S::has(ACS_R_ALTITUDE) && kind == ACS_R_ALTITUDE) {            // altitude_reward.py:20-40
       const double ego_z = s.f.u / 1000, ego_vz = s.f.vd / 340;
       double Pv = 0., PH = 0.;
       if (ego_z <= r.p0) Pv = -env_clip(ego_vz / r.p2 * (r.p0 - ego_z) / r.p0, 0., 1.);
       if (ego_z <= r.p1) PH = env_clip(ego_z / r.p1, 0., 1.) - 1. - 1.;
       return reward_process(c, ri, row, Pv + PH);
     }
-    case ACS_R_POSTURE: {             // posture_reward.py:26-75
+  if (S::has(ACS_R_POSTURE) && kind == ACS_R_POSTURE) {             // posture_reward.py:26-75
       double nr = 0;
       for (int i = 0; i < n; i++) nr += posture_orientation((int)r.p0, geo[i].AO, geo[i].TA) * posture_range((int)r.p1, geo[i].R / 1000, r.p2);
       return reward_process(c, ri, row, nr);
     }
-    case ACS_R_EVENT: {               // event_driven_reward.py:15-34
+  if (S::has(ACS_R_EVENT) && kind == ACS_R_EVENT) {               // event_driven_reward.py:15-34
       double rew = 0;
       if (s.status == ST_SHOTDOWN) rew -= 200; else if (s.status == ST_CRASH) rew -= 200;
       const int nl = AI(v, AI_N_LAUNCHED, row);
       for (int q = 0; q < nl; q++) if (MI(v, MI_STATUS, row * v.S + q) == MS_HIT) rew += 200;
       return reward_process(c, ri, row, rew);
     }
-    case ACS_R_MISSILE_POSTURE: {     // missile_posture_reward.py:18-46 (bypasses _process; previous_missile_v aliases a live array)
+  if (S::has(ACS_R_MISSILE_POSTURE) && kind == ACS_R_MISSILE_POSTURE) {     // missile_posture_reward.py:18-46 (bypasses _process; previous_missile_v aliases a live array)
       double rew = 0;
       const int mid = missile_warning(c, a);
       if (mid >= 0) {
@@ -1324,14 +1447,14 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a, const AoTaR* geo, int
       }
       return rew;
     }
-    case ACS_R_SHOOT_PENALTY: {       // shoot_penalty_reward.py:17-32
+  if (S::has(ACS_R_SHOOT_PENALTY) && kind == ACS_R_SHOOT_PENALTY) {       // shoot_penalty_reward.py:17-32
       double rew = 0;
       const int rem = AI(v, AI_REM_MISSILES, row);
       if (rem == AI(v, AI_PRE_REMAINING, row) - 1) rew -= 30;
       AI(v, AI_PRE_REMAINING, row) = rem;
       return reward_process(c, ri, row, rew);
     }
-    case ACS_R_HEADING: {             // heading_reward.py:18-71
+  if (S::has(ACS_R_HEADING) && kind == ACS_R_HEADING) {             // heading_reward.py:18-71
       const double roll = OUTF(v, O_ROLL, row), p = OUTF(v, O_P, row), q = OUTF(v, O_Q, row);
       const double psi_deg = OUTF(v, O_HEADING, row) * RADTODEG;
       const double d_head = delta_heading_deg(ED(v, ED_TGT_HEADING, env), psi_deg);
@@ -1346,27 +1469,25 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a, const AoTaR* geo, int
       AD(v, AD_HR_ROLL, row) = roll; AD(v, AD_HR_P, row) = p; AD(v, AD_HR_Q, row) = q;
       return reward_process(c, ri, row, rew);
     }
-    case ACS_R_RELATIVE_ALTITUDE: {   // relative_altitude_reward.py:18-32
+  if (S::has(ACS_R_RELATIVE_ALTITUDE) && kind == ACS_R_RELATIVE_ALTITUDE) {   // relative_altitude_reward.py:18-32
       int e0 = -1;
       for (int j = 0; j < v.A && e0 < 0; j++) if (!same_team(cfg, a, j)) e0 = j;
       const double ego_z = s.f.u / 1000, enm_z = sP[e0].f.u / 1000;
       return reward_process(c, ri, row, fmin(r.p0 - fabs(ego_z - enm_z), 0.0));
     }
-    default: break;
-  }
   // per-enemy geometry rewards share the (AO, TA, R) list
   double nr = 0;
-  if (r.kind == ACS_R_COMBAT_GEOMETRY) {          // combat_geometry_reward.py:28-68 (index never advances; prev list only grows)
+  if (S::has(ACS_R_COMBAT_GEOMETRY) && kind == ACS_R_COMBAT_GEOMETRY) {          // combat_geometry_reward.py:28-68 (index never advances; prev list only grows)
     if (!EI(v, EI_CG_VALID, env)) { ED(v, ED_CG_PREV0, env) = geo[0].AO; ED(v, ED_CG_PREV1, env) = geo[0].TA; EI(v, EI_CG_VALID, env) = 1; }
     const double p0 = ED(v, ED_CG_PREV0, env), p1 = ED(v, ED_CG_PREV1, env);
     for (int i = 0; i < n; i++) nr += -(geo[0].AO - p0) - (geo[0].TA - p1);
-  } else if (r.kind == ACS_R_GUN_BEHIT) {         // gun_behit_reward.py:27-54
+  } else if (S::has(ACS_R_GUN_BEHIT) && kind == ACS_R_GUN_BEHIT) {         // gun_behit_reward.py:27-54
     for (int i = 0; i < n; i++) if (geo[i].R >= 500 * FT && geo[i].R <= 3000 * FT && geo[i].AO >= 179 * PI / 180) nr += -5;
-  } else if (r.kind == ACS_R_GUN_WEZ) {           // gun_WEZ_reward.py:28-55
+  } else if (S::has(ACS_R_GUN_WEZ) && kind == ACS_R_GUN_WEZ) {           // gun_WEZ_reward.py:28-55
     for (int i = 0; i < n; i++)
       if (geo[i].R >= 500 * FT && geo[i].R <= 3000 * FT && geo[i].AO <= 1 * PI / 180) nr += 5 + 5 * (3000 * FT - geo[i].R) / (2500 * FT);
-  } else if (r.kind == ACS_R_GUN_TARGETTAIL || r.kind == ACS_R_GUN_WEZDOT) {   // gun_targettail_reward.py:28-78; gun_WEZDOT_reward.py:29-77
-    const bool tt = r.kind == ACS_R_GUN_TARGETTAIL;
+  } else if ((S::has(ACS_R_GUN_TARGETTAIL) && kind == ACS_R_GUN_TARGETTAIL) || (S::has(ACS_R_GUN_WEZDOT) && kind == ACS_R_GUN_WEZDOT)) {   // gun_targettail_reward.py:28-78; gun_WEZDOT_reward.py:29-77
+    const bool tt = kind == ACS_R_GUN_TARGETTAIL;
     double d[ACS_MAX_AGENTS];
     for (int i = 0; i < n; i++) {
       const double R = geo[i].R;
@@ -1421,6 +1542,7 @@ ENV_DEV bool reward_gated(const StepCtx& c, int a) {
 // All agents' rewards of one env.  The reference evaluates agent by agent, reward class by reward class; the classes
 // without cross-agent state are evaluated by all lanes at once, the order-dependent ones lane after lane, and the
 // per-agent total is summed in the reference's class order.
+template <class S>
 ENV_DEV double env_rewards(const StepCtx& c, bool valid) {
   const Lane& L = c.L;
   const int nr = c.cfg.n_rewards;
@@ -1432,18 +1554,18 @@ ENV_DEV double env_rewards(const StepCtx& c, bool valid) {
   if (valid) {
     gated = reward_gated(c, L.lane);
     for (int ri = 0; ri < nr; ri++) if (reward_is_order_dependent(c, c.cfg.rewards[ri].kind)) serial |= 1u << ri;
-    if (!gated) {
-      n = enemy_geometry(c, L.lane, geo);
-      for (int ri = 0; ri < nr; ri++) if (!(serial >> ri & 1)) vals[ri] = reward_one(c, ri, L.lane, geo, n);
-    }
+    if (!gated) n = enemy_geometry(c, L.lane, geo);
   }
   serial = __reduce_or_sync(L.gmask, serial);
-  if (serial) {
-    for (int a = 0; a < c.v.A; a++) {
-      if (valid && L.lane == a && !gated)
-        for (int ri = 0; ri < nr; ri++) if (serial >> ri & 1) vals[ri] = reward_one(c, ri, a, geo, n);
-      __syncwarp(L.gmask);
+  // pass 0: every lane evaluates the classes without cross-agent state; passes 1 .. A (only when some class is
+  // order-dependent this step): lane pass-1 evaluates those -- one call site of the reward code
+  const int passes = serial ? c.v.A + 1 : 1;
+  for (int pass = 0; pass < passes; pass++) {
+    if (valid && !gated && (pass == 0 || L.lane == pass - 1)) {
+      const unsigned sel = pass == 0 ? ~serial : serial;
+      for (int ri = 0; ri < nr; ri++) if (sel >> ri & 1) vals[ri] = reward_one<S>(c, ri, L.lane, geo, n);
     }
+    if (pass > 0) __syncwarp(L.gmask);
   }
   double tot = 0.0;
   if (valid && !gated) for (int ri = 0; ri < nr; ri++) tot += vals[ri];
@@ -1453,6 +1575,7 @@ ENV_DEV double env_rewards(const StepCtx& c, bool valid) {
 // ---------------------------------------------------------------------------------------------- terminations
 // task.get_termination for agent a: conditions in order, first done short-circuits (E/tasks/task_base.py:90-112).
 // Returns the cause (ACS_T_*) or -1.  crash() side effects go to sP[a].status.
+template <class S>
 ENV_DEV int agent_termination(const StepCtx& c, int a) {
   const EnvView& v = c.v;
   const AcsTaskConfig& cfg = c.cfg;
@@ -1461,7 +1584,7 @@ ENV_DEV int agent_termination(const StepCtx& c, int a) {
   for (int ti = 0; ti < cfg.n_terms; ti++) {
     const int t = cfg.terms[ti];
     bool done = false;
-    if (t == ACS_T_UNREACH_HEADING) {              // unreach_heading.py:22-65
+    if ((S::obs < 0 || S::obs == ACS_OBS_HEADING) && t == ACS_T_UNREACH_HEADING) {              // unreach_heading.py:22-65 (heading task only)
       const double sim_time = v.fdm[(size_t)F_SIM_TIME * v.rows + row];
       const double check_time = ED(v, ED_CHECK_TIME, env);
       if (sim_time >= check_time) {
@@ -1519,8 +1642,8 @@ ENV_DEV int agent_termination(const StepCtx& c, int a) {
   return -1;
 }
 
-__device__ __noinline__ void reset_task_lanes(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const bool on, PubAc* sP,
-                                              double* __restrict__ obs, double* __restrict__ share_obs, const ResetTpl& tp);
+ENV_DEV void reset_copy_warp(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const bool on, double* __restrict__ obs,
+                             double* __restrict__ share_obs, const ResetTpl& tp);
 
 // fuse_reset != 0 (auto-reset with a reset template, i.e. every task but the heading task): an env whose agents are all
 // done is reset right here -- rewards / dones / info of the terminal step are already written, the reset observation
@@ -1532,6 +1655,7 @@ __device__ __noinline__ void reset_task_lanes(const EnvView& v, const AcsTaskCon
 // parallel.  Legal when nothing the step logic writes is read by get_obs: no weapons (task.step is empty) and not the
 // heading task (UnreachHeading re-targets what the observation shows); get_obs precedes terminations and rewards in the
 // reference (E/envs/env_base.py:155-171), and here it reads its own copy of the pre-termination aircraft state.
+template <class S>
 __global__ void __launch_bounds__(256) k_env_post(const __grid_constant__ EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg, double* __restrict__ obs,
                                                   double* __restrict__ share_obs, double* __restrict__ rewards,
                                                   uint8_t* __restrict__ dones, int32_t* __restrict__ info, uint8_t* __restrict__ env_done,
@@ -1551,50 +1675,52 @@ __global__ void __launch_bounds__(256) k_env_post(const __grid_constant__ EnvVie
   const int cs = (L.env < v.B) ? EI(v, EI_CURRENT_STEP, L.env) + 1 : 0;
   __syncwarp(L.gmask);
   const StepCtx c{v, cfg, L, sP, cs};
+  if (!obs_role) {
+    sRew[L.tid] = 0.0;
+    sDone[L.tid] = 1;
+    // ---- task.step: artillery (E/tasks/singlecombat_task.py:163-188), then the launch rules, agents in dict order
+    if (cfg.use_artillery) {
+      for (int a = 0; a < A; a++) {
+        if (L.valid && L.lane == a) {
+          for (int j = 0; j < A; j++) {
+            if (same_team(cfg, a, j) || sP[L.gbase + j].status != ST_ALIVE) continue;
+            const AoTaR g = get_ao_ta_r(sP[L.gbase + a].f, sP[L.gbase + j].f, false);
+            double of = 0.0;
+            if (g.AO >= 0 && g.AO <= 0.5236) of = 1 - g.AO / 0.5236; else if (g.AO >= -0.5236 && g.AO <= 0) of = 1 + g.AO / 0.5236;
+            const double Rk = g.R / 1000;
+            const double df = Rk <= 1 ? 1.0 : (Rk <= 3 ? (3 - Rk) / 2. : 0.0);
+            sP[L.gbase + j].bloods -= of * df;
+          }
+        }
+        __syncwarp(L.gmask);
+      }
+    }
+    if (S::launch_kind(cfg) != ACS_L_NONE) {
+      for (int a = 0; a < A; a++) {
+        if (L.valid && L.lane == a) task_step_agent<S>(c, a);
+        __syncwarp(L.gmask);
+      }
+    }
+  }
+  // ---- get_obs (every agent, before terminations / rewards): by the observation warps when there are any (the one call
+  // site of the packer in this kernel; task.step above is empty whenever obs_split is legal)
+  if ((obs_role || !obs_split) && L.valid) write_obs<S>(c, L.lane, obs + ((size_t)L.env * A + L.lane) * cfg.obs_dim);
   if (obs_role) {
-    if (L.valid) write_obs(c, L.lane, obs + ((size_t)L.env * A + L.lane) * cfg.obs_dim);
     __syncthreads();        // pairs with the one below: the observations are complete
     return;
   }
-  sRew[L.tid] = 0.0;
-  sDone[L.tid] = 1;
-  // ---- task.step: artillery (E/tasks/singlecombat_task.py:163-188), then the launch rules, agents in dict order
-  if (cfg.use_artillery) {
-    for (int a = 0; a < A; a++) {
-      if (L.valid && L.lane == a) {
-        for (int j = 0; j < A; j++) {
-          if (same_team(cfg, a, j) || sP[L.gbase + j].status != ST_ALIVE) continue;
-          const AoTaR g = get_ao_ta_r(sP[L.gbase + a].f, sP[L.gbase + j].f, false);
-          double of = 0.0;
-          if (g.AO >= 0 && g.AO <= 0.5236) of = 1 - g.AO / 0.5236; else if (g.AO >= -0.5236 && g.AO <= 0) of = 1 + g.AO / 0.5236;
-          const double Rk = g.R / 1000;
-          const double df = Rk <= 1 ? 1.0 : (Rk <= 3 ? (3 - Rk) / 2. : 0.0);
-          sP[L.gbase + j].bloods -= of * df;
-        }
-      }
-      __syncwarp(L.gmask);
-    }
-  }
-  if (cfg.launch_kind != ACS_L_NONE) {
-    for (int a = 0; a < A; a++) {
-      if (L.valid && L.lane == a) task_step_agent(c, a);
-      __syncwarp(L.gmask);
-    }
-  }
-  // ---- get_obs (every agent, before terminations / rewards)
-  if (!obs_split && L.valid) write_obs(c, L.lane, obs + ((size_t)L.env * A + L.lane) * cfg.obs_dim);
   __syncwarp(L.gmask);
   // ---- dones and rewards in the reference's order
   int cause = -1;
   if (cfg.dones_before_rewards) {
     for (int a = 0; a < A; a++) {
-      if (L.valid && L.lane == a) cause = agent_termination(c, a);
+      if (L.valid && L.lane == a) cause = agent_termination<S>(c, a);
       __syncwarp(L.gmask);
     }
-    sRew[L.tid] = env_rewards(c, L.valid);
+    sRew[L.tid] = env_rewards<S>(c, L.valid);
     __syncwarp(L.gmask);
   } else {
-    sRew[L.tid] = env_rewards(c, L.valid);
+    sRew[L.tid] = env_rewards<S>(c, L.valid);
     __syncwarp(L.gmask);
     if (cfg.team_mean) {                            // E/envs/multiplecombat_env.py:170-175
       double ego = 0.0, enm = 0.0;
@@ -1605,7 +1731,7 @@ __global__ void __launch_bounds__(256) k_env_post(const __grid_constant__ EnvVie
       sRew[L.tid] = L.lane < cfg.n_ego ? ego : enm;
     }
     for (int a = 0; a < A; a++) {
-      if (L.valid && L.lane == a) cause = agent_termination(c, a);
+      if (L.valid && L.lane == a) cause = agent_termination<S>(c, a);
       __syncwarp(L.gmask);
     }
   }
@@ -1639,7 +1765,7 @@ __global__ void __launch_bounds__(256) k_env_post(const __grid_constant__ EnvVie
     bool all = L.valid;
     for (int j = 0; j < A; j++) all = all && sDone[L.gbase + j];
     // the reset synchronises the lanes of each env on their mask: the whole warp takes the call together
-    if (__any_sync(0xffffffffu, all)) reset_task_lanes(v, cfg, L, all, sP, obs, share_obs, tpl);
+    if (__any_sync(0xffffffffu, all)) reset_copy_warp(v, cfg, L, all, obs, share_obs, tpl);     // fuse_reset implies tpl.full (acs_env_step)
   }
 }
 
@@ -1737,6 +1863,7 @@ ENV_DEV void reset_copy_warp(const EnvView& v, const AcsTaskConfig& cfg, const L
   }
 }
 
+template <class S>
 __device__ __noinline__ void reset_task_lanes(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const bool on, PubAc* sP,
                                               double* __restrict__ obs, double* __restrict__ share_obs, const ResetTpl& tp) {
   if (tp.full) { reset_copy_warp(v, cfg, L, on, obs, share_obs, tp); return; }
@@ -1812,13 +1939,13 @@ __device__ __noinline__ void reset_task_lanes(const EnvView& v, const AcsTaskCon
     if (!cfg.rewards[ri].potential) continue;
     for (int a = 0; a < A; a++) {
       if (on && L.lane == a) {
-        const double r0 = reward_one(c, ri, a, geo, n_geo);
+        const double r0 = reward_one<S>(c, ri, a, geo, n_geo);
         AD(v, AD_PRE_REWARD0 + ri, L.row) = r0;
       }
       __syncwarp(L.gmask);
     }
   }
-  if (on) write_obs(c, L.lane, obs + ((size_t)L.env * A + L.lane) * cfg.obs_dim);
+  if (on) write_obs<S>(c, L.lane, obs + ((size_t)L.env * A + L.lane) * cfg.obs_dim);
   __syncwarp(L.gmask);
   if (on && share_obs) {
     const int D = cfg.obs_dim;
@@ -1836,5 +1963,41 @@ __global__ void __launch_bounds__(128) k_env_reset_task(const __grid_constant__ 
   const bool on = L.valid && (env_mask == nullptr || env_mask[L.env]);
   if (!__syncthreads_or(on)) return;
   if (tpl.full) tpl_prefetch(tpl);
-  reset_task_lanes(v, cfg, L, on, sP, obs, share_obs, tpl);
+  reset_task_lanes<PostGeneric>(v, cfg, L, on, sP, obs, share_obs, tpl);
 }
+
+// ---------------------------------------------------------------------------------------------- k_env_post instantiations
+// (observation packer, launch rule, reward classes) of the task families the shipped yamls resolve to (tasks.py);
+// post_kernel_for() returns the first entry that covers a config, the generic kernel otherwise.
+#define RM(x) (1u << (x))
+constexpr unsigned RM_BASE = RM(ACS_R_ALTITUDE) | RM(ACS_R_POSTURE) | RM(ACS_R_EVENT);
+constexpr unsigned RM_SCENARIO = RM_BASE | RM(ACS_R_COMBAT_GEOMETRY) | RM(ACS_R_GUN_BEHIT) | RM(ACS_R_GUN_TARGETTAIL) | RM(ACS_R_GUN_WEZDOT) |
+                                 RM(ACS_R_GUN_WEZ) | RM(ACS_R_RELATIVE_ALTITUDE) | RM(ACS_R_MISSILE_POSTURE) | RM(ACS_R_SHOOT_PENALTY);
+constexpr unsigned RM_GUNS = RM_BASE | RM(ACS_R_COMBAT_GEOMETRY) | RM(ACS_R_GUN_BEHIT) | RM(ACS_R_GUN_TARGETTAIL) | RM(ACS_R_GUN_WEZDOT) |
+                             RM(ACS_R_GUN_WEZ) | RM(ACS_R_RELATIVE_ALTITUDE);
+#define ACS_POST_FAMILIES(X) \
+  X(ACS_OBS_HEADING, ACS_L_NONE, RM(ACS_R_HEADING) | RM(ACS_R_ALTITUDE))            /* heading, approach */ \
+  X(ACS_OBS_1V1, ACS_L_NONE, RM_BASE)                                               /* 1v1 NoWeapon */ \
+  X(ACS_OBS_1V1_MISSILE, ACS_L_RL_SINGLE, RM_BASE | RM(ACS_R_SHOOT_PENALTY))        /* 1v1 ShootMissile */ \
+  X(ACS_OBS_1V1_MISSILE, ACS_L_RULE_LOCK, RM_BASE | RM(ACS_R_MISSILE_POSTURE))      /* 1v1 DodgeMissile */ \
+  X(ACS_OBS_MULTI, ACS_L_NONE, RM_BASE)                                             /* 2v2 NoWeapon */ \
+  X(ACS_OBS_MULTI_MISSILE, ACS_L_RL_NEAREST, RM_BASE | RM(ACS_R_MISSILE_POSTURE))   /* 2v2 ShootMissile (shoot nearest) */ \
+  X(ACS_OBS_NV_MISSILE, ACS_L_SCENARIO, RM_SCENARIO)                                /* scenario2, scenario3 */ \
+  X(ACS_OBS_1V1_MISSILE, ACS_L_SCENARIO, RM_SCENARIO)                               /* scenario1 */ \
+  X(ACS_OBS_NVN, ACS_L_SCENARIO, RM_SCENARIO)                                       /* scenario2/3 _nvn, _rwr */ \
+  X(ACS_OBS_1V1, ACS_L_AUTO_GUN, RM_GUNS)                                           /* wvr, maneuver_curriculum */
+typedef void (*PostKernel)(const EnvView, const AcsTaskConfig, const int, double*, double*, double*, uint8_t*, int32_t*, uint8_t*, const int,
+                           const ResetTpl, const int);
+static PostKernel post_kernel_for(const AcsTaskConfig& cfg, int* family) {
+  unsigned need = 0;
+  for (int i = 0; i < cfg.n_rewards; i++) need |= 1u << cfg.rewards[i].kind;
+  int k = 0;
+#define X(OBS, LAUNCH, MASK) \
+  if (cfg.obs_kind == (OBS) && cfg.launch_kind == (LAUNCH) && (need & ~(unsigned)(MASK)) == 0) { *family = k; return k_env_post<PostSpec<OBS, LAUNCH, (MASK)>>; } \
+  k++;
+  ACS_POST_FAMILIES(X)
+#undef X
+  *family = -1;
+  return k_env_post<PostGeneric>;
+}
+#undef RM

@@ -82,9 +82,12 @@ class TerminationCondition:
         """(done, success, info): done iff THIS condition ended the agent's episode in the last step (conditions are
         evaluated in order and the first hit short-circuits, task_base.py:104-110)."""
         info = {} if info is None else info
-        cause = self._task._info_row(agent_id)[..., 0]
+        row = self._task._info_row(agent_id)
+        cause = row[..., 0]
         done = cause == self.kind
-        success = done & (self.kind in (ts.T_TIMEOUT, ts.T_SAFE_RETURN)) & (self._task._info_row(agent_id)[..., 1] == 0)
+        # the reference's aggregate `success` survives only when the agent ends ALIVE through SafeReturn (safe_return.py:41-47:
+        # every enemy down, no missile inbound); every other ending reports success False (timeout.py:31, low_altitude.py:33 ...)
+        success = done & (self.kind == ts.T_SAFE_RETURN) & (row[..., 1] == 0)
         if self._task._single:
             done, success = bool(done), bool(success)
             if done:

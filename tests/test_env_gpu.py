@@ -339,3 +339,76 @@ def test_single_step_deltas_from_identical_states(name):
     if spec.launch_kind in (1, 2, 3, 4):
         assert "launched" in ev and "miss" in ev
     p.gpu.close()
+
+
+@pytest.mark.parametrize("name", ["1v1/ShootMissile/Selfplay", "2v2/ShootMissile/HierarchySelfplay", "scenario2/scenario2",
+                                  "1v1/DodgeMissile/Selfplay"])
+def test_deferred_missiles_equal_the_lockstep_missile_phase(name, monkeypatch):
+    """One-thread frame: envs in which no missile can score within the step hand their missiles to k_env_missiles (K substeps
+    per missile in registers, against the recorded target trajectory); envs with a missile in reach or an effective chaff
+    cloud keep the per-substep lockstep phase.  Both give the same flags bit for bit and the same numbers to rounding
+    (same expressions, compiled in two contexts), through launches, fly-bys, hits, chaff and auto-resets."""
+    from aircombat_selfplay_b200.capi import EnvBatch
+    monkeypatch.setenv("ACS_FRAME_SPLIT", "0")
+    spec = load_spec(name)
+    spec.max_steps = 120
+    n = 300
+    bs = []
+    for on in ("1", "0"):
+        monkeypatch.setenv("ACS_DEFER_MISSILES", on)
+        b = EnvBatch(spec, n, seed=3)
+        assert b.get_option("launches_per_step") == (3 if on == "1" else 2)
+        b.set_init_states(close_init_states(spec, np.random.default_rng(2)))
+        b.reset()
+        bs.append(b)
+    rng = np.random.default_rng(9)
+    deferred_seen = coupled_seen = hits = 0
+    for t in range(150):
+        act = torch.tensor(random_actions(rng, spec, n, mode="smooth", shoot_p=0.3), device="cuda")
+        ra = [None if x is None else x.clone() for x in bs[0].step(act, auto_reset=True)]
+        rb = bs[1].step(act, auto_reset=True)
+        assert torch.equal(ra[3], rb[3]) and torch.equal(ra[4], rb[4]), t                         # dones, info (cause, status, step)
+        assert torch.allclose(ra[0], rb[0], rtol=0, atol=1e-9) and torch.allclose(ra[2], rb[2], rtol=0, atol=1e-9), t
+        names, ei = bs[0].arena("env_i")
+        d = ei[names.index("deferred")]
+        deferred_seen += int(d.sum()); coupled_seen += int((d == 0).sum())
+        mn, mi = bs[0].arena("ms_i")
+        assert torch.equal(mi, bs[1].arena("ms_i")[1]), t                                        # missile status / bookkeeping
+        hits += int((mi[mn.index("status")] == 1).sum())
+        assert int(ei[names.index("faults")].sum()) == 0
+    md0, md1 = bs[0].arena("ms_d")[1], bs[1].arena("ms_d")[1]
+    fin = torch.isfinite(md0)
+    assert torch.equal(fin, torch.isfinite(md1)) and torch.allclose(md0[fin], md1[fin], rtol=1e-9, atol=1e-9)
+    assert deferred_seen > 0 and coupled_seen > 0
+    if spec.launch_kind != 4:            # the AIM-9L tasks score hits in this geometry (300 m fuze)
+        assert hits > 0
+
+
+@pytest.mark.parametrize("name", ["singlecontrol/heading", "1v1/NoWeapon/Selfplay", "1v1/ShootMissile/Selfplay", "1v1/DodgeMissile/Selfplay",
+                                  "2v2/NoWeapon/Selfplay", "2v2/ShootMissile/HierarchySelfplay", "scenario1/scenario1", "scenario2/scenario2",
+                                  "scenario3/scenario3_nvn", "scenario1/WVR_selfplay"])
+def test_specialised_post_kernel_equals_the_generic_one(name, monkeypatch):
+    """k_env_post is compiled per task family (observation packer, launch rule, reward classes as template constants); the
+    instantiation acs_env_create picks returns the bits of the generic kernel that reads all three from the config."""
+    from aircombat_selfplay_b200.capi import EnvBatch
+    monkeypatch.setenv("ACS_FRAME_SPLIT", "0")
+    spec = load_spec(name)
+    spec.max_steps = 40
+    n = 200
+    bs = []
+    for generic in ("0", "1"):
+        monkeypatch.setenv("ACS_POST_GENERIC", generic)
+        b = EnvBatch(spec, n, seed=6, device_share_obs=True)
+        assert (b.get_option("post_family") >= 0) == (generic == "0")
+        if not name.startswith("singlecontrol/"):
+            b.set_init_states(close_init_states(spec, np.random.default_rng(3)))
+        b.reset()
+        bs.append(b)
+    rng = np.random.default_rng(10)
+    for t in range(90):
+        act = torch.tensor(random_actions(rng, spec, n, mode="smooth" if t % 3 else "random", shoot_p=0.3), device="cuda")
+        for b in bs:
+            b.step(act, auto_reset=True)
+        assert torch.equal(bs[0].out_buf, bs[1].out_buf), t
+    for arena in ("ac_d", "ac_i", "env_d", "env_i", "ms_d", "ms_i"):
+        assert torch.equal(bs[0].arena(arena)[1], bs[1].arena(arena)[1]), arena

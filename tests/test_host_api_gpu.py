@@ -1,6 +1,7 @@
 """GPU tests of the reference-facing Python API, modelled on the reference's own tests (reference tests/test_jsbsim.py):
 env classes (shapes, same seed => same trajectory, crash semantics) and the VecEnv contract (shapes, infos, auto reset)."""
 import numpy as np
+from pathlib import Path
 import pytest
 import torch
 
@@ -301,3 +302,87 @@ def test_env_state_checkpoint_resumes_bit_exactly(config):
     second = [other.step(a)[0].clone() for a in acts[12:]]
     for x, y in zip(first, second):
         assert torch.equal(x, y)
+
+
+def test_task_plugin_surface():
+    """env.task keeps the reference's Task surface (reference envs/JSBSim/tasks/task_base.py:8-122) as a view of what the
+    device computed: reward / termination descriptors in evaluation order, get_obs, normalize_action, get_reward,
+    get_termination, _check_missile_warning -- the calls the reference's render scripts make (render_vs_pursue.py:65)."""
+    env = SingleCombatEnv("1v1/ShootMissile/Selfplay")
+    task = env.task
+    assert task.num_agents == 2 and task.observation_space.shape == (21,)
+    assert [r.name for r in task.reward_functions] == ["PostureReward", "AltitudeReward", "EventDrivenReward", "ShootPenaltyReward"]
+    assert [t.name for t in task.termination_conditions] == ["LowAltitude", "ExtremeState", "Overload", "SafeReturn", "Timeout"]
+    alt = task.reward_functions[1]
+    assert alt.params == {"safe_altitude": 4.0, "danger_altitude": 3.5, "Kv": 0.2} and not alt.is_potential
+    assert task.reward_functions[0].is_potential and task.reward_functions[0].params["orientation_version"] == "v2"
+    obs = env.reset()
+    assert np.array_equal(task.get_obs(env, "A0100"), obs[0]) and np.array_equal(task.get_obs(env, 1), obs[1])
+    np.testing.assert_allclose(task.normalize_action(env, "A0100", [20, 19, 20, 0, 1]), [0.0, -0.05, 0.0, 0.4], atol=1e-15)
+    np.testing.assert_allclose(task.normalize_action(env, "B0100", [0, 40, 41, 29, 0]), [-1.0, 1.0, 1.0, 0.9], atol=1e-15)
+    assert task._check_missile_warning(env, "B0100") is None
+    obs, rew, done, info = env.step(np.array([[20, 19, 20, 10, 1], [20, 19, 20, 10, 0]]))      # A0100 shoots
+    w = task._check_missile_warning(env, "B0100")
+    assert w is not None and w["shooter"] == 0 and task._check_missile_warning(env, "A0100") is None
+    np.testing.assert_allclose(w["position"], env.agents["A0100"].get_position(), atol=300.0)     # one step after launch
+    r, _ = task.get_reward(env, "A0100", {})
+    assert r == float(rew[0, 0]) and task.get_termination(env, "A0100", {}) == (False, {})
+    assert float(task.reward_functions[0].pre_rewards()[0, 0]) != 0.0                            # PostureReward is potential-based
+    env.close()
+    # a crash: the LowAltitude condition reports it, the aggregate carries the done_condition
+    env = SingleCombatEnv("1v1/NoWeapon/Selfplay")
+    env.core.set_init_states([[120.0, 60.0, 8400.0, 0.0, 800.0] + [0.0] * 7, [120.0, 60.1, 20000.0, 180.0, 800.0] + [0.0] * 7])
+    env.reset()
+    for _ in range(40):
+        obs, rew, done, info = env.step(np.array([[20, 40, 20, 29], [20, 19, 20, 10]]))
+        if done[0]:
+            break
+    assert done[0] and not done[1]
+    d, inf = env.task.get_termination(env, "A0100", {})
+    assert d and inf["done_condition"] == "low_altitude" == info["done_condition"][0]
+    low = env.task.termination_conditions[0]
+    assert low.get_termination(env.task, env, "A0100", {})[:2] == (True, False)
+    assert env.task.termination_conditions[3].get_termination(env.task, env, "A0100", {})[:2] == (False, False)
+    env.close()
+    # hierarchical task: normalize_action previews the controller without advancing its recurrent state
+    env = MultipleCombatEnv("scenario2/scenario2")
+    env.reset()
+    env.step([(np.array([1, 2, 1]), np.array([0, 0, 0, 0]))] * 4)
+    h0 = env.core.rnn.clone()
+    u = env.task.normalize_action(env, "A0200", np.array([0, 4, 2, 0, 0, 0, 0]))
+    assert u.shape == (4,) and (-1 <= u[:3]).all() and (u[:3] <= 1).all() and 0.4 <= u[3] <= 0.9
+    assert torch.equal(h0, env.core.rnn) and env.task["hier"] and env.task.descriptor["env"] == "nvn"
+    assert len(env.task.reward_functions) == 11 and env.task.reward_functions[-1].name == "ShootPenaltyReward"
+    env.close()
+
+
+def test_render_vs_pursue_style_episode():
+    """The loop of the reference's render_vs_pursue.py:47-80 against this package: a scripted PursueAgent red team
+    (use_baseline yaml), the ego policy's actions from outside, bloods and infos read back per step, until all done."""
+    import yaml
+    from aircombat_selfplay_b200.tasks import parse_config
+    import tempfile
+    cfg = parse_config("scenario1/scenario1_curriculum_vs_pursue")
+    cfg["max_steps"] = 60
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "vs.yaml").write_text(yaml.safe_dump(cfg, sort_keys=False))
+        env = SingleCombatEnv("vs", config_dir=d)
+    num_agents = env.num_agents
+    for angle in (0, 60):
+        env.core.set_curriculum_angle(angle)          # env.reset_simulators_curriculum(i) of the reference script
+        obs = env.reset()
+        steps = 0
+        while True:
+            ego_obs = obs[:num_agents // 2]
+            assert np.array_equal(ego_obs[0], env.task.get_obs(env, env.ego_ids[0]))
+            ego_actions = np.array([[1, 2, 1, 0, 0, 0, 0]])
+            enm_actions = np.zeros((1, 7), dtype=np.int64)           # ignored: the scripted agent flies the red aircraft
+            obs, rewards, dones, infos = env.step(np.concatenate([ego_actions, enm_actions], axis=0))
+            steps += 1
+            bloods = [env.agents[a].bloods for a in env.agents]
+            assert len(bloods) == 2 and infos["current_step"] == steps
+            if dones.all():
+                assert "done_condition" in infos
+                break
+        assert steps <= 60
+    env.close()

@@ -30,3 +30,20 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)[:14]
 for r in rows: print("  %-70s n=%3d  %.1f us each" % (r.key[:70], r.count, r.device_time_total / max(r.count, 1)))
+
+# ---- micro-benchmarks of the pieces (alternatives for the LayerNorms and the K = 12 input layer)
+import torch.nn.functional as F
+N = n * A
+x = torch.randn(N, 128, device="cuda"); w = torch.ones(128, device="cuda"); b = torch.zeros(128, device="cuda")
+def ln_manual(x):
+    var, mean = torch.var_mean(x, dim=-1, correction=0, keepdim=True)
+    return torch.addcmul(b, (x - mean) * torch.rsqrt(var + 1e-5), w)
+for name, fn in (("F.layer_norm", lambda: F.layer_norm(x, (128,), w, b)), ("var_mean + addcmul", lambda: ln_manual(x)),
+                 ("native_layer_norm [N/8, 8, 128]", lambda: F.layer_norm(x.view(-1, 8, 128), (128,), w, b))):
+    fn(); print("  %-34s %.1f us" % (name, 1e3 * timed(fn, 100)))
+print("  max |F.layer_norm - manual| = %.2e" % float((F.layer_norm(x, (128,), w, b) - ln_manual(x)).abs().max()))
+x12 = torch.randn(N, 12, device="cuda"); w1 = torch.randn(128, 12, device="cuda"); b1 = torch.randn(128, device="cuda")
+x16 = F.pad(x12, (0, 4)); w16 = F.pad(w1, (0, 4))
+for name, fn in (("linear K=12", lambda: F.linear(x12, w1, b1)), ("linear K=16 (padded)", lambda: F.linear(x16, w16, b1)),
+                 ("addmm K=12", lambda: torch.addmm(b1, x12, w1.t()))):
+    fn(); print("  %-34s %.1f us" % (name, 1e3 * timed(fn, 100)))

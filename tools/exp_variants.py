@@ -68,11 +68,14 @@ def main() -> None:
             for case, n in cases:
                 for split in splits:
                     env = dict(os.environ)
-                    if lib != "default":
-                        env["ACS_LIB"] = str(Path(lib).resolve())
+                    path, *kv = lib.split("@")          # "lib.so@KEY=VAL@KEY2=VAL2": environment of that variant
+                    for x in kv:
+                        env[x.split("=")[0]] = x.split("=", 1)[1]
+                    if path != "default":
+                        env["ACS_LIB"] = str(Path(path).resolve())
                     r = subprocess.run([sys.executable, __file__, "--steps", str(a.steps), "--warm", str(a.warm), "--child", case, str(n), str(split)],
                                        env=env, capture_output=True, text=True, timeout=600)
-                    key = (Path(lib).name, case, n, split)
+                    key = (lib.split("/")[-1], case, n, split)
                     if r.returncode != 0:
                         best[key] = {"error": r.stderr.strip().splitlines()[-1:]}
                         continue
