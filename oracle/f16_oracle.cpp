@@ -373,6 +373,44 @@ struct Location {
 // ---------------------------------------------------------------- the F-16 FDM
 struct PidState { double Input_prev, Input_prev2, I_out_total; };
 
+// ---- FCS component steps as free functions: the F-16's component list (fcs_run) and the known-answer tests ported from
+// JSBSim's own test-suite (tests/test_oracle_fdm.py <- envs/JSBSim/data/tests/TestKinematic.py, TestIntegrators.py) run the
+// SAME code.
+// J/models/flight_control/FGPID.cpp:154-214 (non-"standard" form, no pvdot)
+inline double pid_step(PidState& s, double Input, double test, double kp, double ki, double kd, int int_type, double dt) {
+  double I_out_delta = 0.0;
+  double Dval = (Input - s.Input_prev) / dt;
+  if (std::fabs(test) < 0.000001) {
+    switch (int_type) { case 1: I_out_delta = Input; break; case 2: I_out_delta = 0.5 * (Input + s.Input_prev); break;
+      case 3: I_out_delta = 1.5 * Input - 0.5 * s.Input_prev; break; case 4: I_out_delta = (23.0 * Input - 16.0 * s.Input_prev + 5.0 * s.Input_prev2) / 12.0; break; default: I_out_delta = 0.0; }
+  }
+  if (test < 0.0) s.I_out_total = 0.0;
+  s.I_out_total += ki * dt * I_out_delta;
+  const double Output = kp * Input + s.I_out_total + kd * Dval;
+  s.Input_prev2 = test < 0.0 ? 0.0 : s.Input_prev; s.Input_prev = Input;
+  return Output;
+}
+// J/models/flight_control/FGKinemat.cpp:99-157; Input is the (signed) input property, Output the component's current output
+inline double kinemat_step(const double* detents, const double* times, int ndet, bool noscale, bool trim_status, double Input, double Output, double dt) {
+  double dt0 = dt;
+  if (!noscale) Input *= detents[ndet - 1];
+  Input = Constrain(detents[0], Input, detents[ndet - 1]);
+  if (trim_status) return Input;
+  while (dt0 > 0.0 && !EqualToRoundoff(Input, Output)) {
+    int ind;
+    for (ind = 1; ind < ndet && ((Input < Output) ? detents[ind] < Output : detents[ind] <= Output); ++ind) {}
+    if (ind >= ndet) ind = ndet - 1;  // upstream reads past the end here; unreachable while Output stays inside the detents
+    if (times[ind] <= 0.0) { Output = Input; break; }
+    double Rate = (detents[ind] - detents[ind - 1]) / times[ind];
+    double ThisInput = Constrain(detents[ind - 1], Input, detents[ind]);
+    double ThisDt = std::fabs((ThisInput - Output) / Rate);
+    if (dt0 < ThisDt) { ThisDt = dt0; if (Output < Input) Output += ThisDt * Rate; else Output -= ThisDt * Rate; }
+    else Output = ThisInput;
+    dt0 -= ThisDt;
+  }
+  return Output;
+}
+
 struct F16 {
   // ---- executive (J/FGFDMExec.cpp)
   double dT, saved_dT, sim_time;
@@ -683,39 +721,15 @@ struct F16 {
           Output *= c.gain;
           break;
         case C_SUMMER: Output = 0.0; for (int k = 0; k < c.n_in; k++) Output += c.in_sign[k] * P[c.in_prop[k]]; Output += c.bias; break;  // FGSummer.cpp:72-84
-        case C_PID: {  // J/models/flight_control/FGPID.cpp:154-214
-          PidState& s = pid[ci];
-          double I_out_delta = 0.0; Input = c.in_sign[0] * P[c.in_prop[0]];
-          double Dval = (Input - s.Input_prev) / dt;
+        case C_PID: {  // pid_step above
+          Input = c.in_sign[0] * P[c.in_prop[0]];
           double test = 0.0; if (c.has_trigger) test = c.trig_sign * P[c.trig_prop];
-          if (std::fabs(test) < 0.000001) {
-            switch (c.int_type) { case 1: I_out_delta = Input; break; case 2: I_out_delta = 0.5 * (Input + s.Input_prev); break;
-              case 3: I_out_delta = 1.5 * Input - 0.5 * s.Input_prev; break; case 4: I_out_delta = (23.0 * Input - 16.0 * s.Input_prev + 5.0 * s.Input_prev2) / 12.0; break; default: I_out_delta = 0.0; }
-          }
-          if (test < 0.0) s.I_out_total = 0.0;
-          s.I_out_total += c.ki * dt * I_out_delta;
-          Output = c.kp * Input + s.I_out_total + c.kd * Dval;
-          s.Input_prev2 = test < 0.0 ? 0.0 : s.Input_prev; s.Input_prev = Input;
+          Output = pid_step(pid[ci], Input, test, c.kp, c.ki, c.kd, c.int_type, dt);
         } break;
-        case C_KINEMATIC: {  // J/models/flight_control/FGKinemat.cpp:99-157
-          double dt0 = dt; Input = c.in_sign[0] * P[c.in_prop[0]];
-          if (!c.noscale) Input *= c.detents[c.ndet - 1];
-          Output = P[c.out_prop[0]];
-          Input = Constrain(c.detents[0], Input, c.detents[c.ndet - 1]);
-          if (trim_status) Output = Input;
-          else while (dt0 > 0.0 && !EqualToRoundoff(Input, Output)) {
-            int ind;
-            for (ind = 1; ind < c.ndet && ((Input < Output) ? c.detents[ind] < Output : c.detents[ind] <= Output); ++ind) {}
-            if (ind >= c.ndet) ind = c.ndet - 1;  // upstream reads past the end here; unreachable while Output stays inside the detents
-            if (c.times[ind] <= 0.0) { Output = Input; break; }
-            double Rate = (c.detents[ind] - c.detents[ind - 1]) / c.times[ind];
-            double ThisInput = Constrain(c.detents[ind - 1], Input, c.detents[ind]);
-            double ThisDt = std::fabs((ThisInput - Output) / Rate);
-            if (dt0 < ThisDt) { ThisDt = dt0; if (Output < Input) Output += ThisDt * Rate; else Output -= ThisDt * Rate; }
-            else Output = ThisInput;
-            dt0 -= ThisDt;
-          }
-        } break;
+        case C_KINEMATIC:  // kinemat_step above
+          Input = c.in_sign[0] * P[c.in_prop[0]];
+          Output = kinemat_step(c.detents, c.times, c.ndet, c.noscale, trim_status, Input, P[c.out_prop[0]], dt);
+          break;
         case C_FCSFUNC: Output = eval_factors(c.factors, c.nfac); if (c.n_in > 0) { Input = c.in_sign[0] * P[c.in_prop[0]]; Output *= Input; } break;  // FGFCSFunction.cpp:73-84
       }
       if (c.has_clip) Output = Constrain(c.clip_min, Output, c.clip_max);  // FGFCSComponent::Clip :266-290
@@ -1039,5 +1053,30 @@ void orc_fdm_get_pid(void* h, double* o) { F16* f = (F16*)h; for (int i = 0; i <
 // standalone closed-form helpers (used by the known-answer tests)
 void orc_atmosphere(double h_ft, double* out) { orc::StdAtmosphere a; a.Calculate(h_ft); out[0] = a.Temperature; out[1] = a.Pressure; out[2] = a.Density; out[3] = a.Soundspeed; out[4] = a.DensityAltitude; out[5] = a.PressureAltitude; }
 double orc_vcas_from_mach(double mach, double p) { orc::StdAtmosphere a; double qc = orc::PitotTotalPressure(mach, p) - p; return a.StdDaySLsoundspeed * orc::MachFromImpactPressure(qc, a.StdDaySLpressure); }
+double orc_kinemat(const double* detents, const double* times, int ndet, int noscale, double input, double output, double dt) {
+  return orc::kinemat_step(detents, times, ndet, noscale != 0, false, input, output, dt);
+}
+// state = {Input_prev, Input_prev2, I_out_total}, updated in place
+double orc_pid(double* state, double input, double test, double kp, double ki, double kd, int int_type, double dt) {
+  orc::PidState s{state[0], state[1], state[2]};
+  const double out = orc::pid_step(s, input, test, kp, ki, kd, int_type, dt);
+  state[0] = s.Input_prev; state[1] = s.Input_prev2; state[2] = s.I_out_total;
+  return out;
+}
+// J2 gravity in ECEF at an ECEF position (ft, ft/s^2): FGInertial::GetGravityJ2 (J/models/FGInertial.cpp:193-211)
+void orc_gravity(double x, double y, double z, double* out) {
+  F16 f(1.0 / 60.0, 1.0 / 120.0);
+  f.loc.ec = orc::V3(x, y, z); f.loc.ComputeDerived();
+  f.inertial_run();
+  out[0] = f.vGravAccel.x; out[1] = f.vGravAccel.y; out[2] = f.vGravAccel.z;
+}
+// mass properties of the last frame: out = {Weight lb, Mass slug, cg x y z (in), J[9], Jinv[9]}
+void orc_fdm_mass(void* h, double* out) {
+  F16* f = (F16*)h; int k = 0;
+  out[k++] = f->Weight; out[k++] = f->Mass; out[k++] = f->vXYZcg.x; out[k++] = f->vXYZcg.y; out[k++] = f->vXYZcg.z;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[k++] = f->mJ.m[i][j];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[k++] = f->mJinv.m[i][j];
+}
+void orc_fdm_set_tanks(void* h, const double* t) { F16* f = (F16*)h; for (int i = 0; i < f->ntanks; i++) f->tank[i] = t[i]; }
 void orc_geodetic(double x, double y, double z, double* out) { orc::Location l; l.SetEllipse(20925646.32546, 20855486.5951); l.ec = orc::V3(x, y, z); l.ComputeDerived(); out[0] = l.lon; out[1] = l.lat; out[2] = l.geodLat; out[3] = l.geodAlt; out[4] = l.radius; out[5] = l.GetSeaLevelRadius(); }
 }

@@ -51,6 +51,14 @@ def lib():
         L.orc_vcas_from_mach.restype = d
         L.orc_vcas_from_mach.argtypes = [d, d]
         L.orc_geodetic.argtypes = [d, d, d, ctypes.POINTER(d)]
+        pd = ctypes.POINTER(d)
+        L.orc_kinemat.restype = d
+        L.orc_kinemat.argtypes = [pd, pd, i, i, d, d, d]
+        L.orc_pid.restype = d
+        L.orc_pid.argtypes = [pd, d, d, d, d, d, i, d]
+        L.orc_gravity.argtypes = [d, d, d, pd]
+        L.orc_fdm_mass.argtypes = [vp, pd]
+        L.orc_fdm_set_tanks.argtypes = [vp, pd]
         _LIB = L
     return _LIB
 
@@ -134,3 +142,40 @@ def geodetic(x, y, z):
     out = (ctypes.c_double * 6)()
     lib().orc_geodetic(x, y, z, out)
     return dict(zip(["lon", "lat_gc", "lat_geod", "geod_alt", "radius", "slr"], list(out)))
+
+
+def kinemat(detents, times, input_, output, dt, noscale=False) -> float:
+    """One FGKinemat::Run (oracle restatement of J/models/flight_control/FGKinemat.cpp:99-157)."""
+    n = len(detents)
+    D = (ctypes.c_double * n)(*detents)
+    T = (ctypes.c_double * n)(*times)
+    return lib().orc_kinemat(D, T, n, int(noscale), input_, output, dt)
+
+
+class Pid:
+    """One FGPID component (oracle restatement of J/models/flight_control/FGPID.cpp:154-214); int_type 1 rect, 2 trap, 3 ab2, 4 ab3."""
+
+    def __init__(self, kp=0.0, ki=0.0, kd=0.0, int_type=4, dt=1.0 / 120.0):
+        self.kp, self.ki, self.kd, self.int_type, self.dt = kp, ki, kd, int_type, dt
+        self.state = (ctypes.c_double * 3)(0.0, 0.0, 0.0)
+
+    def run(self, input_, trigger=0.0) -> float:
+        return lib().orc_pid(self.state, input_, trigger, self.kp, self.ki, self.kd, self.int_type, self.dt)
+
+
+def gravity(x, y, z):
+    out = (ctypes.c_double * 3)()
+    lib().orc_gravity(x, y, z, out)
+    return np.array(list(out))
+
+
+def mass_properties(f: "OracleFdm"):
+    out = (ctypes.c_double * 23)()
+    lib().orc_fdm_mass(f._h, out)
+    o = np.array(list(out))
+    return {"weight": o[0], "mass": o[1], "cg": o[2:5], "J": o[5:14].reshape(3, 3), "Jinv": o[14:23].reshape(3, 3)}
+
+
+def set_tanks(f: "OracleFdm", contents):
+    t = (ctypes.c_double * 4)(*contents)
+    lib().orc_fdm_set_tanks(f._h, t)

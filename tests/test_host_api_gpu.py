@@ -337,12 +337,14 @@ def test_task_plugin_surface():
         obs, rew, done, info = env.step(np.array([[20, 40, 20, 29], [20, 19, 20, 10]]))
         if done[0]:
             break
-    assert done[0] and not done[1]
+    assert done[0] and done[1]                 # A0100 flew into the ground; B0100 is left without a live enemy: SafeReturn
     d, inf = env.task.get_termination(env, "A0100", {})
     assert d and inf["done_condition"] == "low_altitude" == info["done_condition"][0]
     low = env.task.termination_conditions[0]
     assert low.get_termination(env.task, env, "A0100", {})[:2] == (True, False)
     assert env.task.termination_conditions[3].get_termination(env.task, env, "A0100", {})[:2] == (False, False)
+    assert env.task.termination_conditions[3].get_termination(env.task, env, "B0100", {})[:2] == (True, True)     # the win
+    assert info["done_condition"][1] == "safe_return"
     env.close()
     # hierarchical task: normalize_action previews the controller without advancing its recurrent state
     env = MultipleCombatEnv("scenario2/scenario2")

@@ -21,9 +21,24 @@ GOLDEN = sorted(p for p in (Path(__file__).resolve().parent / "golden").glob("en
 
 @pytest.fixture()
 def chaff_draws_pinned(monkeypatch):
-    """The generator replaced np.random.rand() in the chaff test by 0.5; pin the oracle's keyed chaff draw likewise."""
+    """The generator replaced np.random.rand() in the chaff test (reference env_base.py:153) by a recorded sequence -- 0.5
+    everywhere in the older files, values on both sides of 0.85 in the *_chaff_mixed files (``chaff_draws``).  The
+    returned function pins the oracle's keyed chaff draw to replay that sequence in call order; a different number or
+    order of draws than the reference made shows up as a trajectory mismatch or as unconsumed draws."""
     real = eo.u01
-    monkeypatch.setattr(eo, "u01", lambda seed, env, purpose, a=0, b=0, c=0: 0.5 if purpose == eo.RNG_CHAFF else real(seed, env, purpose, a, b, c))
+    state = {"seq": None, "k": 0}
+
+    def u01(seed, env, purpose, a=0, b=0, c=0):
+        if purpose != eo.RNG_CHAFF:
+            return real(seed, env, purpose, a, b, c)
+        k = state["k"]
+        state["k"] += 1
+        if state["seq"] is None:
+            return 0.5
+        assert k < len(state["seq"]), "the oracle draws more chaff numbers than the reference did"
+        return float(state["seq"][k])
+    monkeypatch.setattr(eo, "u01", u01)
+    return state
 
 
 def test_golden_files_exist():
@@ -35,6 +50,8 @@ def test_oracle_reproduces_reference_trajectory(path, chaff_draws_pinned):
     g = np.load(path, allow_pickle=False)
     cfg = json.loads(str(g["config"]))
     spec = build_spec(cfg)
+    if "chaff_draws" in g.files:
+        chaff_draws_pinned["seq"] = g["chaff_draws"]
     env = eo.OracleEnv(spec, seed=int(g["seed"]), env_index=0)
     obs, share = env.reset()
     assert obs.shape == g["obs"][0].shape
@@ -53,3 +70,17 @@ def test_oracle_reproduces_reference_trajectory(path, chaff_draws_pinned):
         assert sum(c.count for c in env.chaffs) == int(g["n_chaffs"][t]), (path.stem, t)
     if "turn_counts" in g.files:
         assert env.heading_turn_counts == int(g["turn_counts"])
+    if "chaff_draws" in g.files:
+        assert chaff_draws_pinned["k"] == len(g["chaff_draws"]), (path.stem, chaff_draws_pinned["k"], len(g["chaff_draws"]))
+
+
+def test_chaff_golden_covers_both_sides_of_the_decoy_threshold():
+    """At least one reference trajectory has chaff draws below AND at / above 0.85 (a decoyed missile and a missile that
+    flies through the cloud), so the `< 0.85` comparison and the repeated per-substep draws are pinned."""
+    seen = False
+    for p in GOLDEN:
+        g = np.load(p, allow_pickle=False)
+        if "chaff_draws" in g.files and len(g["chaff_draws"]):
+            d = g["chaff_draws"]
+            seen = seen or ((d < 0.85).any() and (d >= 0.85).any() and (d == 0.85).any())
+    assert seen

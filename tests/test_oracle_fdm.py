@@ -147,3 +147,147 @@ def test_same_inputs_same_trajectory():
             f.set_controls(*u)
             f.run(12)
     assert np.array_equal(a.snapshot(), b.snapshot())
+
+
+# ---------------------------------------------------------------------------------------------- JSBSim's own known answers
+# Ported from the reference's copy of JSBSim's test-suite (envs/JSBSim/data/tests/*.py).  Those tests drive a full
+# jsbsim.FGFDMExec with other aircraft (c172r flaps, the "tripod" test systems); what they PIN is component semantics
+# with closed-form answers.  The oracle runs the same component code for the F-16's FCS (kinemat_step / pid_step are
+# the functions fcs_run calls), so the known answers pin the restatement of FGKinemat / FGPID / FGInertial / FGMassBalance.
+
+def test_kinematic_timing_known_answer():
+    """TestKinematic.testKinematicTiming (envs/JSBSim/data/tests/TestKinematic.py:27-83): the c172r flap kinematic --
+    detents 0 / 10 / 20 / 30 deg with traverse times 0 / 2 / 1 / 1 s, command scaled by the last detent and clamped."""
+    det, tim, dt = [0.0, 10.0, 20.0, 30.0], [0.0, 2.0, 1.0, 1.0], 1.0 / 120.0
+    pos, n = 0.0, 0
+
+    def run_until(t_end, cmd, expect):
+        nonlocal pos, n
+        while n * dt < t_end - 1e-12:
+            assert pos == pytest.approx(expect(n * dt), abs=1e-7), n * dt
+            pos = ofdm.kinemat(det, tim, cmd, pos, dt)
+            n += 1
+    run_until(2.0, 1.5, lambda t: 5.0 * t)                 # command 1.5 is clamped to the last detent
+    run_until(4.0, 1.5, lambda t: 10.0 * (t - 1.0))
+    run_until(5.0, 1.5, lambda t: 30.0)
+    run_until(7.0, 0.25, lambda t: 30.0 - 10.0 * (t - 5.0))   # up again, interrupted at 7.5 deg
+    run_until(7.5, 0.25, lambda t: 10.0 - 5.0 * (t - 7.0))
+    run_until(8.0, 0.25, lambda t: 7.5)
+    run_until(9.5, -1.0, lambda t: 10.0 - 5.0 * (t - 7.5))    # command -1 is clamped to the first detent
+    run_until(10.0, -1.0, lambda t: 0.0)
+
+
+def test_kinematic_noscale_known_answer():
+    """TestKinematic.testKinematicNoScale (:123-140): with <noscale/> the command is the position itself; 12 deg is reached
+    after 2 s + 0.2 s."""
+    det, tim, dt = [0.0, 10.0, 20.0, 30.0], [0.0, 2.0, 1.0, 1.0], 1.0 / 120.0
+    pos = 0.0
+    for _ in range(int(round(2.2 / dt)) + 1):
+        pos = ofdm.kinemat(det, tim, 12.0, pos, dt, noscale=True)
+    assert pos == pytest.approx(12.0, abs=1e-7)
+    # a zero traverse time moves instantly (FGKinemat.cpp:131-134)
+    assert ofdm.kinemat([0.0, 1.0], [0.0, 0.0], 0.7, 0.0, dt) == 0.7
+
+
+def test_pid_integrators_known_answer():
+    """TestIntegrators.test_integrators (envs/JSBSim/data/tests/TestIntegrators.py:38-105, integrators.xml): the four
+    integration schemes of FGPID on sin(8 pi t) at dt = 5 ms against the analytic integral, a positive trigger freezes
+    the integrator, a negative one resets it, zero restarts it."""
+    dt, k = 0.005, 8 * math.pi
+    pids = {name: ofdm.Pid(ki=1.0, int_type=it, dt=dt) for name, it in (("rect", 1), ("trap", 2), ("ab2", 3), ("ab3", 4))}
+    out = {name: 0.0 for name in pids}
+    t = 0.0
+    for i in range(100):
+        x = math.sin(k * t)
+        if i > 1:                                   # AB3 is not initialised before the third frame
+            assert out["ab3"] == pytest.approx((1.0 - math.cos(k * t)) / k, abs=1e-4)
+        for name, p in pids.items():
+            out[name] = p.run(x, 0.0)
+        t += dt
+    frozen = dict(out)
+    for _ in range(49):
+        for name, p in pids.items():
+            out[name] = p.run(math.sin(k * t), 1.0)
+        assert out == pytest.approx(frozen, abs=1e-15)
+    for name, p in pids.items():
+        out[name] = p.run(0.0, -1.0)
+        assert out[name] == 0.0
+    t0 = 0.0
+    for i in range(50):
+        x = math.sin(k * t0)
+        if i > 1:
+            assert out["ab3"] == pytest.approx((1.0 - math.cos(k * t0)) / k, abs=1e-4)
+        for name, p in pids.items():
+            out[name] = p.run(x, 0.0)
+        t0 += dt
+
+
+def test_pid_gains_known_answer():
+    """TestIntegrators.test_pid (:107-145): kp alone = kp sin, ki alone (default AB2) = ki (1 - cos) / k, kd alone ~ kd k cos,
+    and a pid with all three negated is minus their sum."""
+    dt, k, kp, ki, kd = 0.005, 2 * math.pi, 2.0, 0.5, -1.5
+    P, I, D = ofdm.Pid(kp=kp, dt=dt), ofdm.Pid(ki=ki, int_type=3, dt=dt), ofdm.Pid(kd=kd, dt=dt)
+    N = ofdm.Pid(kp=-kp, ki=-ki, kd=-kd, int_type=3, dt=dt)
+    oi = 0.0
+    for i in range(100):
+        t = i * dt
+        x = math.sin(k * t)
+        assert oi == pytest.approx(ki * (1.0 - math.cos(k * t)) / k, abs=1e-4)
+        op, oi, od, on = P.run(x), I.run(x), D.run(x), N.run(x)
+        assert -on == pytest.approx(op + oi + od, abs=1e-12)
+        assert op == pytest.approx(kp * math.sin(k * t), abs=1e-12)
+        if i > 1:
+            assert od == pytest.approx(kd * k * math.cos(k * t), abs=0.15)
+
+
+def test_gravity_known_answer():
+    """TestPlanet.py checks gravity-ft_sec2 and the terrain radius at the equator and the pole of a planet file; for the
+    earth model the reference loads (FGInertial.cpp:55-61: GM, J2, a, b) the J2 field gives the WGS-84 gravitation at the
+    surface: 9.8142 m/s^2 at the equator (normal gravity 9.78033 + centrifugal 0.03392), 9.8322 at the pole."""
+    a, b = 20925646.32546, 20855486.5951
+    ge, gp = ofdm.gravity(a, 0.0, 0.0), ofdm.gravity(0.0, 0.0, b)
+    assert ge[1] == 0.0 and ge[2] == 0.0 and gp[0] == 0.0 and gp[1] == 0.0
+    assert -ge[0] * 0.3048 == pytest.approx(9.7803253 + 0.00007292115 ** 2 * 6378137.0, abs=2e-4)
+    assert -gp[2] * 0.3048 == pytest.approx(9.8321849, abs=2e-4)
+    # sea-level (terrain) radius = a at the equator, b at the pole (FGLocation::GetSeaLevelRadius)
+    assert ofdm.geodetic(a, 0.0, 0.0)["slr"] == pytest.approx(a, rel=1e-15)
+    assert ofdm.geodetic(0.0, 1e-3, b)["slr"] == pytest.approx(b, rel=1e-12)
+
+
+def test_geocentric_vs_geodetic_latitude_known_answer():
+    """TestInitialConditions.py compares ic/lat-gc with ic/lat-geod: tan(lat_gc) = ((1 - e^2) N + h) / (N + h) tan(lat_geod)."""
+    a, b = 20925646.32546, 20855486.5951
+    e2 = 1 - (b / a) ** 2
+    for lat_deg, h in [(10.0, 0.0), (45.0, 20000.0), (60.0, 30000.0), (-75.0, 5000.0)]:
+        lat = math.radians(lat_deg)
+        N = a / math.sqrt(1 - e2 * math.sin(lat) ** 2)
+        x, z = (N + h) * math.cos(lat), ((1 - e2) * N + h) * math.sin(lat)
+        g = ofdm.geodetic(x, 0.0, z)
+        assert math.tan(g["lat_gc"]) == pytest.approx(((1 - e2) * N + h) / (N + h) * math.tan(lat), rel=1e-12)
+        assert g["radius"] == pytest.approx(math.hypot(x, z), rel=1e-15)
+
+
+def test_inertia_matrix_known_answer():
+    """TestPointMassInertia.testInertiaMatrix (envs/JSBSim/data/tests/TestPointMassInertia.py:96-128, run there on f16_test):
+    Jinv is the inverse of J; with the tanks empty the weight is empty weight + point masses; the point masses enter
+    through the parallel-axis tensor m (|r|^2 I - r r^T) about the cg (GetPointmassInertia, pinned here independently)."""
+    f = ofdm.OracleFdm()
+    f.reset()
+    m = ofdm.mass_properties(f)
+    np.testing.assert_allclose(m["J"] @ m["Jinv"], np.eye(3), atol=1e-12)
+    assert m["weight"] == pytest.approx(17400.0 + 6000.0 + 230.0)          # empty + 2 x 3000 lb fuel + the 230 lb pilot
+    ofdm.set_tanks(f, [0.0, 0.0, 0.0, 0.0])
+    f.run(1)
+    m0 = ofdm.mass_properties(f)
+    assert m0["weight"] == pytest.approx(17400.0 + 230.0)
+    # independent build-up about the new cg (structural frame inches -> body frame feet: x and z flip sign)
+    lb2slug = 1.0 / 32.174049
+    parts = [(17400.0, np.array([-193.0, 0.0, -5.1])), (230.0, np.array([-336.2, 0.0, 0.0]))]
+    cg = sum(w * r for w, r in parts) / sum(w for w, _ in parts)
+    np.testing.assert_allclose(m0["cg"], cg, rtol=1e-13)
+    J = np.array([[9496.0, 0.0, -982.0], [0.0, 55814.0, 0.0], [-982.0, 0.0, 63100.0]])    # f16.xml ixx iyy izz ixz (negated cross products)
+    for w, r in parts:
+        d = (r - cg) / 12.0 * np.array([-1.0, 1.0, -1.0])
+        J = J + w * lb2slug * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
+    np.testing.assert_allclose(m0["J"], J, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(m0["J"] @ m0["Jinv"], np.eye(3), atol=1e-12)

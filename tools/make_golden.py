@@ -341,7 +341,18 @@ CASES = [
     # guns (R < 3 km, AO < 5 deg: -5 blood per burst until SHOTDOWN by blood) and many chaff bursts
     ("scenario2_gun_chaff", "nvn", None, base_config("scenario2", 2, 6, missile=30, lat_gap=0.04, max_steps=9000), 120, "straight", 4, 0.8),
     ("scenario3_gun_chaff", "nvn", None, base_config("scenario3", 4, 6, missile=6, lat_gap=0.05, max_steps=9000), 100, "smooth", 4, 0.6),
+    # the chaff decoy draw on BOTH sides of 0.85 (CHAFF_DRAWS below): missiles that fly through a cloud unharmed for a
+    # while, some of them on to their target, and missiles that are decoyed
+    ("scenario2_chaff_mixed", "nvn", None, base_config("scenario2", 2, 6, missile=30, lat_gap=0.04, max_steps=9000), 120, "straight", 4, 0.8),
+    ("scenario3_chaff_mixed", "nvn", None, base_config("scenario3", 4, 6, missile=6, lat_gap=0.05, max_steps=9000), 100, "smooth", 4, 0.6),
 ]
+
+# np.random.rand() of the chaff test (reference envs/JSBSim/envs/env_base.py:153), by case and call index.  Every other
+# case keeps the constant 0.5 (always below 0.85: the first chaff in range decoys the missile).
+CHAFF_DRAWS = {
+    "scenario2_chaff_mixed": lambda k: 0.5 if (k % 41) == 40 else 0.85 + 0.1 * ((k * 7) % 10) / 10.0,    # mostly >= 0.85, 0.85 itself included
+    "scenario3_chaff_mixed": lambda k: 0.2 if (k % 13) == 12 else 0.95,
+}
 
 
 def run_case(mods, name, kind, task_cls, cfg, T, mode, shoot_dim, shoot_p=0.3, seed=7):
@@ -367,7 +378,13 @@ def run_case(mods, name, kind, task_cls, cfg, T, mode, shoot_dim, shoot_p=0.3, s
     env = cls("golden")
     keyed = _KeyedRandom(seed, 0)
     env.np_random = keyed
-    np.random.rand = lambda *a: 0.5          # chaff draw (env_base.py:153): always below 0.85; the oracle test pins u01 likewise
+    draws = []
+
+    def chaff_draw(*a):        # chaff draw (env_base.py:153); the consumed sequence is stored, the oracle test replays it
+        v = CHAFF_DRAWS[name](len(draws)) if name in CHAFF_DRAWS else 0.5
+        draws.append(v)
+        return v
+    np.random.rand = chaff_draw
     A = len(cfg["aircraft_configs"])
     rng = np.random.default_rng(seed)
     pilot = None
@@ -413,14 +430,14 @@ def run_case(mods, name, kind, task_cls, cfg, T, mode, shoot_dim, shoot_p=0.3, s
             break
     out = {"config": json.dumps(cfg), "kind": kind, "seed": seed, "actions": acts[:steps_done], "obs": np.stack(obs),
            "rewards": np.stack(rews), "dones": np.stack(dones), "status": np.array(status), "bloods": np.array(bloods),
-           "n_missiles": np.array(missiles), "n_chaffs": np.array(chaffs)}
+           "n_missiles": np.array(missiles), "n_chaffs": np.array(chaffs), "chaff_draws": np.array(draws, dtype=np.float64)}
     if share:
         out["share_obs"] = np.stack(share)
     if kind == "control":
         out["turn_counts"] = np.array(env.heading_turn_counts)
     GOLDEN.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(GOLDEN / f"env_{name}.npz", **out)
-    ev = f"steps={steps_done} missiles={max(missiles) if missiles else 0} chaffs={max(chaffs) if chaffs else 0} status={sorted(set(np.array(status).ravel().tolist()))} " \
+    ev = f"steps={steps_done} missiles={max(missiles) if missiles else 0} chaffs={max(chaffs) if chaffs else 0} draws={len(draws)} (>=0.85: {sum(d >= 0.85 for d in draws)}) status={sorted(set(np.array(status).ravel().tolist()))} " \
          f"min_blood={np.min(bloods):.1f} done={bool(np.all(dones[-1]))} sum_rew={np.sum(rews):.3f}"
     print(f"[golden] {name}: {ev}")
 
