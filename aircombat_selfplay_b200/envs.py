@@ -130,6 +130,9 @@ class BatchedEnv:
         """Per-aircraft initial conditions used by the following resets (reference reset_simulators /
         reset_simulators_curriculum, E/envs/singlecombat_env.py:45-122)."""
         self.batch.set_init_states(init_states)
+        for k, row in enumerate(init_states):        # keep the host copy of the config in step (state_dict reads it)
+            for j in range(12):
+                self.batch.cfg.init_state[k][j] = float(row[j])
         self._graph = None
         self._epoch += 1
 
@@ -160,12 +163,18 @@ class BatchedEnv:
             sd.update({"opp:step": self.opponents.step.clone(), "opp:init_heading": self.opponents.init_heading.clone(),
                        "opp:has_init": self.opponents.has_init.clone()})
         sd["seed"] = self.seed_value
+        # what the NEXT auto-resets start from: the per-aircraft initial conditions in force (set_init_states / curriculum stage)
+        sd["init_states"] = torch.tensor([[float(x) for x in self.batch.cfg.init_state[k]] for k in range(self.n_agents)], dtype=torch.float64)
+        sd["curriculum_angle"] = int(self.curriculum_angle)
         return sd
 
     def load_state_dict(self, sd):
         from .capi import ARENAS
         if int(sd["seed"]) != self.seed_value:
             self.seed(int(sd["seed"]))            # NB: seed() restarts the episode counters; the arenas restore them below
+        if "init_states" in sd:                   # rebuilds the reset template before the arenas are restored
+            self.set_init_states(sd["init_states"].cpu().numpy())
+            self.curriculum_angle = int(sd.get("curriculum_angle", 0))
         for k in ARENAS:
             self.batch.set_arena(k, sd[f"arena:{k}"].to(self.device).contiguous())
         self.batch.out_buf.copy_(sd["out_buf"])
@@ -259,27 +268,37 @@ class BatchedEnv:
             return self._graph_out
 
 
+def info_dict(info, heading: bool) -> dict:
+    """One env's ``info`` dict from its [A, ACS_INFO_DIM] int rows.  Keys as the reference: ``current_step`` always
+    (envs/JSBSim/envs/env_base.py:132), ``done_condition`` when an agent terminated this step, ``heading_turn_counts`` only
+    when UnreachHeading is what terminated it (termination_conditions/unreach_heading.py:60-62) -- the runner appends that
+    key whenever it is present (runner/jsbsim_runner.py:55-57), so it must not appear on ordinary steps."""
+    d = {"current_step": int(info[0, 2])}
+    causes = [int(c) for c in info[:, 0]]
+    if any(c >= 0 for c in causes):
+        d["done_condition"] = [DONE_CONDITIONS.get(c, "") for c in causes]
+    if heading and causes[0] == ts.T_UNREACH_HEADING:
+        d["heading_turn_counts"] = int(info[0, 3])
+    return d
+
+
 class LazyInfo(dict):
-    """``infos[i]`` of the VecEnv contract: a dict view over the step's info arrays, materialised on access, so that
-    building ``n_envs`` Python dicts is not on the step path.  Keys as the reference: ``current_step`` always,
-    ``done_condition`` when an agent terminated this step, ``heading_turn_counts`` for the heading task
-    (reference envs/JSBSim/envs/env_base.py:132, termination_conditions/*.py, unreach_heading.py:62)."""
+    """``infos[i]`` of the VecEnv contract: a dict VIEW over the step's info arrays, materialised on access, so that
+    building ``n_envs`` Python dicts is not on the step path.  It subclasses ``dict`` (the reference's tests assert
+    ``isinstance(infos[0], dict)``) but keeps no items of its own: every reader -- ``[]``, ``in``, ``get``, iteration,
+    ``keys / items / values``, ``len``, ``==``, ``copy()``, pickling -- goes through ``info_dict``.  Because ``__iter__``
+    is overridden, CPython's ``dict(info)``, ``{**info}`` and ``f(**info)`` take the generic mapping path (``keys()`` +
+    ``[]``) instead of copying the empty storage, and ``json.dumps(info)`` calls ``items()``: all of them see the content."""
     __slots__ = ("_src", "_i")
 
     def __init__(self, src, i):
-        super().__init__()
+        # one placeholder item in the C-level storage: json's C encoder writes "{}" for a dict whose storage is empty
+        # before it ever asks for items(); with a non-empty storage it calls the overridden items()
+        super().__init__(current_step=None)
         self._src, self._i = src, i
 
     def _materialise(self):
-        s, i = self._src, self._i
-        info = s["info"][i]
-        d = {"current_step": int(info[0, 2])}
-        causes = [int(c) for c in info[:, 0]]
-        if any(c >= 0 for c in causes):
-            d["done_condition"] = [DONE_CONDITIONS.get(c, "") for c in causes]
-        if s["heading"]:
-            d["heading_turn_counts"] = int(info[0, 3])
-        return d
+        return info_dict(self._src["info"][self._i], self._src["heading"])
 
     def __getitem__(self, k):
         return self._materialise()[k]
@@ -305,11 +324,25 @@ class LazyInfo(dict):
     def __len__(self):
         return len(self._materialise())
 
+    def __bool__(self):
+        return True
+
+    def copy(self):
+        return self._materialise()
+
+    def __reduce__(self):
+        return (dict, (self._materialise(),))
+
     def __repr__(self):
         return repr(self._materialise())
 
     def __eq__(self, other):
         return self._materialise() == other
+
+    def __ne__(self, other):
+        return self._materialise() != other
+
+    __hash__ = None
 
 
 class AircraftView:
@@ -446,14 +479,7 @@ class _SingleEnvBase:
         return torch.from_numpy(arr).to(self.core.device).unsqueeze(0)
 
     def _info(self, info_t):
-        info = info_t[0].cpu().numpy()
-        d = {"current_step": int(info[0, 2])}
-        causes = [int(c) for c in info[:, 0]]
-        if any(c >= 0 for c in causes):
-            d["done_condition"] = [DONE_CONDITIONS.get(c, "") for c in causes]
-        if self.core.spec.obs_kind == ts.OBS_HEADING:
-            d["heading_turn_counts"] = int(info[0, 3])
-        return d
+        return info_dict(info_t[0].cpu().numpy(), self.core.spec.obs_kind == ts.OBS_HEADING)
 
 
 class _PlainEnv(_SingleEnvBase):

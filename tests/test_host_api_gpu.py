@@ -32,7 +32,8 @@ class TestSingleControlEnv:
             actions = np.array(_sample(env))
             obs, reward, done, info = env.step(actions)
             assert obs.shape == obs_shape and reward.shape == (1, 1) and done.shape == (1, 1)
-            assert info["current_step"] == env.current_step and "heading_turn_counts" in info
+            assert info["current_step"] == env.current_step
+            assert ("heading_turn_counts" in info) == (bool(done) and info["done_condition"][0] == "unreach_heading")
             act_buf.append(actions); obs_buf.append(obs); rew_buf.append(reward); done_buf.append(done)
             if done:
                 assert env.current_step <= env.max_steps
@@ -388,3 +389,61 @@ def test_render_vs_pursue_style_episode():
                 break
         assert steps <= 60
     env.close()
+
+
+def test_device_rollout_matches_the_numpy_runner_path():
+    """collect -> step -> insert on CUDA tensors (rollout.DeviceRollout) fills the same buffer as the reference runner's numpy
+    path (runner/share_jsbsim_runner.py:157-223 + algorithms/utils/buffer.py:312-350, restated here in numpy over the
+    VecEnv API): same observations, rewards, masks, active masks and recurrent-state resets, episode ends included."""
+    import aircombat_selfplay_b200.envs as envs_mod
+    from aircombat_selfplay_b200.rollout import DeviceRollout
+    orig = envs_mod.load_spec
+
+    def short(*args, **kw):
+        spec = orig(*args, **kw)
+        spec.max_steps = 5
+        return spec
+    import pytest as _pt
+    mp = _pt.MonkeyPatch()
+    mp.setattr(envs_mod, "load_spec", short)
+    try:
+        n, T, cfg = 64, 12, "2v2/NoWeapon/Selfplay"
+        env = BatchedEnv(cfg, n, seed=3)
+        ve = ShareBatchedVecEnv(cfg, n, seed=3)
+    finally:
+        mp.undo()
+    A, D = env.n_agents, env.spec.obs_dim
+
+    def policy(share, obs, ha, hc, masks):                     # deterministic toy actor-critic with a recurrent state; element-wise
+        x = obs.to(torch.float32)                              # IEEE ops only, so the CPU and the GPU evaluation agree bit for bit
+        acts = torch.stack([(x[:, 9 + k].abs() * 997.0).long() % m for k, m in enumerate((41, 41, 41, 30))], dim=-1)
+        ha2 = ha * masks.view(-1, 1, 1) + x[:, :1].unsqueeze(-1)
+        return x[:, :1], acts, -x[:, 1:2], ha2, hc + 1
+    roll = DeviceRollout(env, T)
+    roll.warmup()
+    done_steps = roll.run(policy)
+    assert done_steps == T * n * A
+    b = roll.buffer
+    # ---- the reference path in numpy
+    obs, share = ve.reset()
+    Bo = np.zeros((T + 1, n, A, D), np.float32); Bs = np.zeros((T + 1, n, A, A * D), np.float32)
+    Br = np.zeros((T, n, A, 1), np.float32); Bm = np.ones((T + 1, n, A, 1), np.float32); Bam = np.ones((T + 1, n, A, 1), np.float32)
+    Bha = np.zeros((T + 1, n, A, 1, 128), np.float32); Bact = np.zeros((T, n, A, 4), np.float32)
+    Bo[0], Bs[0] = obs, share
+    for t in range(T):
+        v, acts, lp, ha, hc = policy(torch.from_numpy(np.concatenate(Bs[t])), torch.from_numpy(np.concatenate(Bo[t])),
+                                     torch.from_numpy(np.concatenate(Bha[t])), torch.zeros(n * A, 1, 128), torch.from_numpy(np.concatenate(Bm[t])))
+        actions = np.array(np.split(acts.numpy(), n))
+        ha = np.array(np.split(ha.numpy(), n))
+        obs, share, rewards, dones, infos = ve.step(actions)
+        d = dones.squeeze(axis=-1)
+        de = np.all(d, axis=-1)
+        ha[de] = 0
+        masks = np.ones((n, A, 1), np.float32); masks[de] = 0
+        am = np.ones((n, A, 1), np.float32); am[d] = 0; am[de] = 1
+        Bo[t + 1], Bs[t + 1], Br[t], Bm[t + 1], Bam[t + 1], Bha[t + 1], Bact[t] = obs, share, rewards, masks, am, ha, actions
+    assert (Bm == 0).any() and (Bam == 0).any()               # episodes ended inside the window
+    for name, ref, got in (("obs", Bo, b.obs), ("share_obs", Bs, b.share_obs), ("rewards", Br, b.rewards), ("masks", Bm, b.masks),
+                           ("active_masks", Bam, b.active_masks), ("rnn_states_actor", Bha, b.rnn_states_actor), ("actions", Bact, b.actions)):
+        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=1e-6, err_msg=name)
+    env.close(); ve.close()

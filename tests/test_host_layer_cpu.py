@@ -100,6 +100,20 @@ def test_lazy_info_is_a_dict_view():
     assert infos[1]["current_step"] == 7 and "done_condition" in infos[1] and infos[1]["done_condition"][0] == "low_altitude"
     assert "done_condition" not in infos[0] and "heading_turn_counts" not in infos[0]
     assert dict(infos[1].items())["current_step"] == 7
+    # copies and serialisation see the content (a dict subclass with empty storage would yield {})
+    import json
+    import pickle
+    full = {"current_step": 7, "done_condition": ["low_altitude", ""]}
+    assert dict(infos[1]) == full and infos[1].copy() == full and {**infos[1]} == full and (lambda **kw: kw)(**infos[1]) == full
+    assert json.loads(json.dumps(infos[1])) == full and pickle.loads(pickle.dumps(infos[1])) == full and len(infos[1]) == 2
+    # heading task: the key the runner collects appears only when UnreachHeading ended the episode (unreach_heading.py:60-62)
+    hsrc = {"info": info, "heading": True}
+    info[2, 0, 3] = 4
+    assert "heading_turn_counts" not in LazyInfo(hsrc, 2)
+    info[2, 0, 0] = ts.T_UNREACH_HEADING
+    assert LazyInfo(hsrc, 2)["heading_turn_counts"] == 4
+    info[2, 0, 0] = ts.T_TIMEOUT
+    assert "heading_turn_counts" not in LazyInfo(hsrc, 2)
 
 
 def test_shipped_configs_match_the_reference_yamls():
