@@ -42,7 +42,8 @@ class AcsTaskConfig(ctypes.Structure):
                 ("num_missiles", ctypes.c_int32 * MAX_AGENTS), ("n_missile_slots", ctypes.c_int32),
                 ("init_state", (ctypes.c_double * 12) * MAX_AGENTS), ("heading_increments", ctypes.c_double * 3),
                 ("check_interval", ctypes.c_double), ("seed", ctypes.c_uint64), ("env_offset", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("reserved", ctypes.c_int32), ("curriculum_rule", ctypes.c_int32), ("curriculum_window", ctypes.c_int32),
+                ("curriculum_threshold", ctypes.c_double)]
 
 
 class AcsError(RuntimeError):
@@ -75,6 +76,7 @@ def lib():
         L.acs_env_destroy.argtypes = [vp]
         L.acs_env_set_init_states.argtypes = [vp, vp]
         L.acs_env_set_seed.argtypes = [vp, ctypes.c_uint64, vp]
+        L.acs_env_set_stage_init_states.argtypes = [vp, i, vp]
         L.acs_env_reset.argtypes = [vp, vp, vp, vp, vp]
         L.acs_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, vp]
         L.acs_env_arena_info.argtypes = [vp, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]
@@ -209,6 +211,8 @@ def task_config(spec, n_envs: int, seed: int = 0, env_offset: int = 0) -> AcsTas
     c.n_missile_slots = spec.n_missile_slots
     c.check_interval = spec.check_interval
     c.seed, c.env_offset = seed, env_offset
+    c.curriculum_rule, c.curriculum_window = int(getattr(spec, "curriculum_rule", 0)), int(getattr(spec, "curriculum_window", 0))
+    c.curriculum_threshold = float(getattr(spec, "curriculum_threshold", 0.0))
     return c
 
 
@@ -264,6 +268,14 @@ class EnvBatch:
         arr = np.ascontiguousarray(init_states, dtype=np.float64)
         assert arr.shape == (self.n_agents, 12)
         _check(lib().acs_env_set_init_states(self._h, arr.ctypes.data_as(ctypes.c_void_p)))
+
+    def set_stage_init_states(self, stage: int, init_states):
+        """Initial conditions of curriculum stage ``stage`` (acs.h acs_env_set_stage_init_states); envs reset from the stage in
+        their "stage" field of the ``env_i`` arena."""
+        import numpy as np
+        arr = np.ascontiguousarray(init_states, dtype=np.float64)
+        assert arr.shape == (self.n_agents, 12)
+        _check(lib().acs_env_set_stage_init_states(self._h, int(stage), arr.ctypes.data_as(ctypes.c_void_p)))
 
     @property
     def share_obs(self):

@@ -290,6 +290,8 @@ struct AcsEnv {
   int G, lg;   // lanes per env (1, 2, 4 or 8) and its log2
   ResetTpl tpl;                  // reset template (tpl.t.fdm == nullptr: none, e.g. the heading task)
   char* tpl_block = nullptr;     // the one allocation behind the template
+  char* stage_block = nullptr;   // values of curriculum stages 1 .. ACS_MAX_STAGES-1 (acs_env_set_stage_init_states), allocated on first use
+  size_t n64max = 0, n32max = 0;
   double* tpl_obs = nullptr;     // [A][obs_dim]
   int tpl_mode = 2;              // 0 none, 1 FDM reload only, 2 whole reset (ACS_RESET_TEMPLATE)
   bool fused_reset = true;       // auto-reset inside k_env_post (needs the template)
@@ -305,7 +307,8 @@ struct AcsEnv {
   size_t ev_used = 0;
 };
 
-static int build_reset_template(AcsEnv* e);
+static constexpr int ACS_MAX_STAGES = 256;
+static int build_reset_template(AcsEnv* e, int stage = 0);
 // which substep kernel acs_env_step launches: 0 one thread, 1 two warps, 2 three warps per aircraft
 static int frame_split_effective(const AcsEnv* e) {
   if (e->frame_split >= 0) return e->frame_split;
@@ -403,6 +406,7 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
     // one contiguous block (256-byte aligned pieces): arenas of one env, reset observation, field lists
     const size_t n64max = (size_t)(N_STATE + FDM_N_OUT + N_AD) * A + (size_t)N_MD * A * v.S + N_ED;
     const size_t n32max = (size_t)N_AI * A + (size_t)N_MI * A * v.S + N_EI;
+    e->n64max = n64max; e->n32max = n32max;
     const size_t sz[13] = {sizeof(double) * N_STATE * A, sizeof(double) * FDM_N_OUT * A, sizeof(double) * N_AD * A, sizeof(int) * N_AI * A,
                            sizeof(double) * N_ED, sizeof(int) * N_EI, sizeof(double) * N_MD * A * v.S, sizeof(int) * N_MI * A * v.S,
                            sizeof(double) * A * cfg->obs_dim, sizeof(double) * n64max, sizeof(int) * n64max, sizeof(int) * n32max,
@@ -450,11 +454,11 @@ int acs_env_set_option(AcsEnv* e, const char* name, int value) {
 // reset() of one env on the template arenas (legacy stream, synchronous: called at create / when the initial conditions
 // change, never on the step path).  Run twice over two different fill patterns: a word that comes out the same both
 // times is one reset() writes (and its value does not depend on what was there); the others it leaves alone.
-static int build_reset_template(AcsEnv* e) {
+static int build_reset_template(AcsEnv* e, int stage) {
   ResetTpl& tp = e->tpl;
   EnvView& t = tp.t;
   if (t.fdm == nullptr) return 0;
-  tp.full = 0; tp.n64 = tp.n32 = 0;
+  if (stage == 0) { tp.full = 0; tp.n64 = tp.n32 = 0; tp.n_stages = 1; }     // new stage-0 conditions drop the registered stages
   const int A = t.A, S = t.S, D = e->cfg.obs_dim;
   struct Arena { void* p; int nf, per; size_t elt; };
   const Arena ar[8] = {{t.fdm, N_STATE, A, 8}, {t.out, FDM_N_OUT, A, 8}, {t.ad, N_AD, A, 8}, {t.ai, N_AI, A, 4},
@@ -462,13 +466,15 @@ static int build_reset_template(AcsEnv* e) {
   std::vector<unsigned char> snap[2][8];
   ResetTpl none;
   std::memset(&none, 0, sizeof(none));
+  // a stage's reset observation goes straight to its slot (the template arenas are scratch in whole-reset mode)
+  double* obs_dst = stage == 0 ? e->tpl_obs : (double*)(e->stage_block + (size_t)stage * tp.stage_stride);
   CUDA_TRY(cudaDeviceSynchronize());
   for (int pass = 0; pass < 2; pass++) {
     for (int k = 0; k < 8; k++) CUDA_TRY(cudaMemset(ar[k].p, pass ? 0x55 : 0x00, ar[k].elt * ar[k].nf * ar[k].per));
-    CUDA_TRY(cudaMemset(e->tpl_obs, 0, sizeof(double) * A * D));
+    CUDA_TRY(cudaMemset(obs_dst, 0, sizeof(double) * A * D));
     k_env_reset_fdm<<<1, FDM_BLOCK>>>(t, e->cfg, e->lg, nullptr);
     CUDA_TRY(cudaGetLastError());
-    k_env_reset_task<<<1, 128>>>(t, e->cfg, e->lg, nullptr, e->tpl_obs, nullptr, none);
+    k_env_reset_task<<<1, 128>>>(t, e->cfg, e->lg, nullptr, obs_dst, nullptr, none);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
     for (int k = 0; k < 8; k++) {
@@ -476,7 +482,7 @@ static int build_reset_template(AcsEnv* e) {
       CUDA_TRY(cudaMemcpy(snap[pass][k].data(), ar[k].p, snap[pass][k].size(), cudaMemcpyDeviceToHost));
     }
   }
-  if (e->tpl_mode < 2) return 0;
+  if (e->tpl_mode < 2) return stage == 0 ? 0 : fail("curriculum stages need the whole-reset template (ACS_RESET_TEMPLATE=2)");
   std::vector<double> v64; std::vector<int> d64, v32, d32;
   for (int k = 0; k < 8; k++) {
     for (int f = 0; f < ar[k].nf; f++) {
@@ -508,6 +514,20 @@ static int build_reset_template(AcsEnv* e) {
     }
   }
   if (ar[6].per >= 4096 || N_STATE >= 4096) return 0;
+  if (stage > 0) {
+    // same words as stage 0 (which words reset() writes does not depend on the initial conditions), other values
+    if (!tp.full) return fail("acs_env_set_stage_init_states: the task has no whole-reset template");
+    std::vector<int> h64(tp.n64), h32(tp.n32);
+    CUDA_TRY(cudaMemcpy(h64.data(), tp.d64, sizeof(int) * tp.n64, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(h32.data(), tp.d32, sizeof(int) * tp.n32, cudaMemcpyDeviceToHost));
+    if ((int)d64.size() != tp.n64 || (int)d32.size() != tp.n32 || h64 != d64 || h32 != d32)
+      return fail("acs_env_set_stage_init_states: reset() of this stage writes a different set of words than stage 0");
+    char* sb = e->stage_block + (size_t)stage * tp.stage_stride;
+    CUDA_TRY(cudaMemcpy(sb + tp.stage_off64, v64.data(), sizeof(double) * v64.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(sb + tp.stage_off32, v32.data(), sizeof(int) * v32.size(), cudaMemcpyHostToDevice));
+    if (stage + 1 > tp.n_stages) tp.n_stages = stage + 1;
+    return 0;
+  }
   CUDA_TRY(cudaMemcpy((void*)tp.v64, v64.data(), sizeof(double) * v64.size(), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy((void*)tp.d64, d64.data(), sizeof(int) * d64.size(), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy((void*)tp.v32, v32.data(), sizeof(int) * v32.size(), cudaMemcpyHostToDevice));
@@ -542,6 +562,7 @@ int acs_env_destroy(AcsEnv* e) {
   cudaFree(e->v.ad); cudaFree(e->v.ai); cudaFree(e->v.ed); cudaFree(e->v.ei); cudaFree(e->v.md); cudaFree(e->v.mi);
   if (e->v.traj) cudaFree(e->v.traj);
   if (e->tpl_block) cudaFree(e->tpl_block);
+  if (e->stage_block) cudaFree(e->stage_block);
   for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
   acs_destroy(e->fdm);
   delete e;
@@ -552,6 +573,30 @@ int acs_env_set_init_states(AcsEnv* e, const double* init_host) {
   if (!e || !init_host) return fail("acs_env_set_init_states: null argument");
   std::memcpy(e->cfg.init_state, init_host, sizeof(double) * 12 * e->v.A);
   return build_reset_template(e);
+}
+
+int acs_env_set_stage_init_states(AcsEnv* e, int stage, const double* init_host) {
+  if (!e || !init_host) return fail("acs_env_set_stage_init_states: null argument");
+  if (stage < 0 || stage >= ACS_MAX_STAGES) return fail("acs_env_set_stage_init_states: stage must be in [0, 256)");
+  if (stage == 0) return acs_env_set_init_states(e, init_host);
+  if (e->tpl.t.fdm == nullptr || !e->tpl.full) return fail("acs_env_set_stage_init_states: the task has no whole-reset template");
+  ResetTpl& tp = e->tpl;
+  const int A = e->v.A, D = e->cfg.obs_dim;
+  if (e->stage_block == nullptr) {
+    const size_t o64 = ((sizeof(double) * A * D + 255) / 256) * 256;
+    const size_t o32 = o64 + ((sizeof(double) * e->n64max + 255) / 256) * 256;
+    const size_t stride = o32 + ((sizeof(int) * e->n32max + 255) / 256) * 256;
+    CUDA_TRY(cudaMalloc(&e->stage_block, stride * ACS_MAX_STAGES));
+    CUDA_TRY(cudaMemset(e->stage_block, 0, stride * ACS_MAX_STAGES));
+    tp.stage_base = e->stage_block; tp.stage_stride = (int)stride; tp.stage_off64 = (int)o64; tp.stage_off32 = (int)o32;
+  }
+  // the stage's reset() is evaluated on the template arenas with its own initial conditions; the handle's stay as they are
+  double saved[ACS_MAX_AGENTS][12];
+  std::memcpy(saved, e->cfg.init_state, sizeof(saved));
+  std::memcpy(e->cfg.init_state, init_host, sizeof(double) * 12 * A);
+  const int rc = build_reset_template(e, stage);
+  std::memcpy(e->cfg.init_state, saved, sizeof(saved));
+  return rc;
 }
 
 AcsHandle* acs_env_fdm(AcsEnv* e) { return e ? e->fdm : nullptr; }

@@ -36,7 +36,7 @@ enum {
 };
 // per env ints
 enum { EI_CURRENT_STEP, EI_EPISODE, EI_SUBSTEP_COUNT, EI_TURN_COUNTS, EI_PMV_REF, EI_CG_VALID, EI_TT_VALID, EI_WD_VALID,
-       EI_ORDER_SEQ, EI_BORN_SEQ, EI_FAULTS, EI_DEFERRED, N_EI };
+       EI_ORDER_SEQ, EI_BORN_SEQ, EI_FAULTS, EI_DEFERRED, EI_STAGE, EI_CUR_BITS, EI_CUR_COUNT, N_EI };
 // per missile slot doubles / ints
 enum { MD_POS_N, MD_POS_E, MD_POS_U, MD_VEL_N, MD_VEL_E, MD_VEL_U, MD_THETA, MD_PHI, MD_ALT, MD_T, MD_M, MD_DTHETA,
        MD_DPHI, MD_D_PREV, MD_SIN_THETA, MD_COS_THETA, N_MD };
@@ -53,7 +53,7 @@ static const char* const ED_NAMES[] = {"tgt_heading_deg", "tgt_altitude_ft", "tg
   "cg_prev_ta", "tt_prev0", "tt_prev1", "tt_prev2", "tt_prev3", "tt_prev4", "tt_prev5", "tt_prev6", "tt_prev7", "wd_prev0",
   "wd_prev1", "wd_prev2", "wd_prev3", "wd_prev4", "wd_prev5", "wd_prev6", "wd_prev7"};
 static const char* const EI_NAMES[] = {"current_step", "episode", "substep_count", "turn_counts", "pmv_ref", "cg_valid", "tt_valid",
-  "wd_valid", "order_seq", "born_seq", "faults", "deferred"};
+  "wd_valid", "order_seq", "born_seq", "faults", "deferred", "stage", "curriculum_record", "curriculum_count"};
 static const char* const MD_NAMES[] = {"pos_n", "pos_e", "pos_u", "vel_n", "vel_e", "vel_u", "theta", "phi", "alt", "t", "m",
   "dtheta", "dphi", "d_prev", "sin_theta", "cos_theta"};
 static const char* const MI_NAMES[] = {"status", "kind", "target", "consec", "order", "born", "keyn", "detached"};
@@ -92,6 +92,9 @@ struct ResetTpl {
   int full;
   const char* base;     // the template is one contiguous block [base, base + bytes)
   int bytes;
+  // curriculum stages (acs_env_set_stage_init_states): stage s > 0 keeps its own values -- reset observation, v64, v32 -- at
+  // stage_base + s * stage_stride (+ 0, stage_off64, stage_off32); the word lists d64 / d32 are those of stage 0
+  const char* stage_base; int stage_stride, stage_off64, stage_off32, n_stages;
 };
 // The template is a few KB read by the few warps that reset an env, i.e. cold; a warp asks for all of its lines at once.
 __device__ __forceinline__ void tpl_prefetch(const ResetTpl& tp) {

@@ -1736,6 +1736,9 @@ __global__ void __launch_bounds__(256) k_env_post(const __grid_constant__ EnvVie
     }
   }
   if (L.valid) sDone[L.tid] = cause >= 0;
+  // win of this agent as the reference's `success` flag survives the termination loop: ended ALIVE through SafeReturn
+  const bool won = L.valid && L.lane < cfg.n_ego && cause == ACS_T_SAFE_RETURN && sP[L.tid].status == ST_ALIVE;
+  const bool env_won = (__ballot_sync(L.gmask, won) & L.gmask) != 0;
   __syncwarp(L.gmask);
   if (obs_split) __syncthreads();     // the observation warps are done (share_obs and the reset below read / replace obs)
   if (L.valid) {
@@ -1759,8 +1762,21 @@ __global__ void __launch_bounds__(256) k_env_post(const __grid_constant__ EnvVie
       for (int j = 0; j < A; j++) all = all && sDone[L.gbase + j];
       if (env_done) env_done[L.env] = all;
       EI(v, EI_CURRENT_STEP, L.env) = cs;
+      if (all && cfg.curriculum_window > 0) {
+        // the episode's outcome joins the env's record (last `window` episodes); the stage rule runs here, i.e. before the
+        // reset below, as task.reset applies it before reset_simulators_curriculum (E/tasks/scenario2_task.py:183-187)
+        const int W = min(cfg.curriculum_window, 31);
+        unsigned bits = ((unsigned)EI(v, EI_CUR_BITS, L.env) << 1 | (env_won ? 1u : 0u)) & ((1u << W) - 1u);
+        int cnt = min(EI(v, EI_CUR_COUNT, L.env) + 1, W);
+        const double rate = (double)__popc(bits) / (double)cnt;
+        // rule 1 is the reference's: len(record) > window can never hold (the record is capped at `window`)
+        const bool adv = rate >= cfg.curriculum_threshold && (cfg.curriculum_rule == 2 ? cnt >= W : (cfg.curriculum_rule == 1 ? cnt > W : false));
+        if (adv) { EI(v, EI_STAGE, L.env) = EI(v, EI_STAGE, L.env) + 1; bits = 0; cnt = 0; }
+        EI(v, EI_CUR_BITS, L.env) = (int)bits; EI(v, EI_CUR_COUNT, L.env) = cnt;
+      }
     }
   }
+  __syncwarp();      // the stage written by lane 0 is read by the whole warp in the reset below
   if (fuse_reset) {
     bool all = L.valid;
     for (int j = 0; j < A; j++) all = all && sDone[L.gbase + j];
@@ -1834,10 +1850,19 @@ ENV_DEV void reset_copy_warp(const EnvView& v, const AcsTaskConfig& cfg, const L
     leaders &= leaders - 1;
     const int env = __shfl_sync(0xffffffffu, L.env, src);
     const size_t row0 = (size_t)env * A;
+    // the env's curriculum stage picks the value set (same words, other initial conditions)
+    const double* v64 = tp.v64; const int* v32 = tp.v32; const double* tobs = tp.obs;
+    if (tp.n_stages > 1) {
+      const int stage = min(max(EI(v, EI_STAGE, env), 0), tp.n_stages - 1);
+      if (stage > 0) {
+        const char* sb = tp.stage_base + (size_t)stage * tp.stage_stride;
+        tobs = (const double*)sb; v64 = (const double*)(sb + tp.stage_off64); v32 = (const int*)(sb + tp.stage_off32);
+      }
+    }
 #pragma unroll 2
     for (int w = wl; w < tp.n64; w += 32) {
       const int d = __ldg(tp.d64 + w);
-      const double x = __ldg(tp.v64 + w);
+      const double x = __ldg(v64 + w);
       const int k = d >> 24, f = (d >> 12) & 0xfff, j = d & 0xfff;
       double* b = k == 0 ? v.fdm : (k == 1 ? v.out : (k == 2 ? v.ad : (k == 6 ? v.md : v.ed)));
       const size_t stride = k == 6 ? (size_t)v.rows * S : (k == 4 ? (size_t)v.B : (size_t)v.rows);
@@ -1847,7 +1872,7 @@ ENV_DEV void reset_copy_warp(const EnvView& v, const AcsTaskConfig& cfg, const L
 #pragma unroll 2
     for (int w = wl; w < tp.n32; w += 32) {
       const int d = __ldg(tp.d32 + w);
-      const int x = __ldg(tp.v32 + w);
+      const int x = __ldg(v32 + w);
       const int k = d >> 24, f = (d >> 12) & 0xfff, j = d & 0xfff;
       int* b = k == 3 ? v.ai : (k == 7 ? v.mi : v.ei);
       const size_t stride = k == 7 ? (size_t)v.rows * S : (k == 5 ? (size_t)v.B : (size_t)v.rows);
@@ -1856,7 +1881,7 @@ ENV_DEV void reset_copy_warp(const EnvView& v, const AcsTaskConfig& cfg, const L
     }
     if (wl == 0) EI(v, EI_EPISODE, env) = EI(v, EI_EPISODE, env) + 1;     // the one read-modify-write of reset()
     for (int w = wl; w < AD_; w += 32) {
-      const double x = __ldg(tp.obs + w);
+      const double x = __ldg(tobs + w);
       obs[row0 * cfg.obs_dim + w] = x;
       if (share_obs) for (int a = 0; a < A; a++) share_obs[(row0 + a) * (size_t)AD_ + w] = x;
     }

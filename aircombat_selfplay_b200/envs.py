@@ -54,7 +54,9 @@ class BatchedEnv:
 
     def __init__(self, config_name: str, n_envs: int, device: int = 0, seed: int = 0, env_offset: int = 0,
                  config_dir: Optional[str] = None, substeps: Optional[int] = None, controller_path: Optional[str] = None,
-                 auto_reset: bool = True, use_cuda_graph: Optional[bool] = None, allow_random_controller: bool = False):
+                 auto_reset: bool = True, use_cuda_graph: Optional[bool] = None, allow_random_controller: bool = False,
+                 curriculum_rule: Optional[int] = None, curriculum_threshold: Optional[float] = None,
+                 curriculum_window: Optional[int] = None):
         if not torch.cuda.is_available():
             raise AcsError("CUDA is not available; the simulator has no CPU fallback")
         self.config_name = config_name
@@ -62,6 +64,9 @@ class BatchedEnv:
         self.spec = load_spec(config_name, config_dir, substeps)
         self.task_name = self.spec.name
         self.task_desc = TASKS[self.task_name]
+        for k, x in (("curriculum_rule", curriculum_rule), ("curriculum_threshold", curriculum_threshold), ("curriculum_window", curriculum_window)):
+            if x is not None:          # overrides of the per-env win-rate record / stage rule (set_curriculum_stages)
+                setattr(self.spec, k, type(getattr(self.spec, k))(x))
         if self.spec.use_baseline and not self.task_desc["hier"]:
             raise NotImplementedError("use_baseline is wired for the hierarchical task families this fork ships (scenario1/2/3, "
                                       "wvr, maneuver_curriculum); the LAG-style SingleCombatTask path calls "
@@ -147,6 +152,41 @@ class BatchedEnv:
         self.curriculum_angle = int(angle)
         self.set_init_states(curriculum_init_states(self.spec.env_kind, self.spec.yaml_init_states, self.curriculum_angle))
 
+    def set_curriculum_stages(self, angles):
+        """Per-env curriculum, as the reference keeps it per env process (``curriculum_angle``, ``record``, ``winning_rate`` of
+        Scenario*_curriculum / WVRTask, E/tasks/scenario2_task.py:172-223): stage ``k`` resets through
+        ``reset_simulators_curriculum(angles[k])``.  Every env carries its own stage and its own record of the last
+        ``window`` episode outcomes in the ``env_i`` arena ("stage", "curriculum_record", "curriculum_count"); the device
+        updates the record when an episode ends and applies the rule before the auto-reset that follows.
+        The rule is a constructor argument (``curriculum_rule``): 1 = the reference's rule verbatim (``rate >= threshold and
+        len(record) > 20`` -- never true, the record is capped at 20 entries, so the reference's stage never moves), 2 =
+        advance when the record is full, 0 = record only; default: the task's (1).  Stages can also be written directly
+        (``set_env_stages``)."""
+        from .tasks import curriculum_init_states
+        if not self.spec.curriculum:
+            raise AcsError(f"task {self.task_name!r} has no curriculum reset")
+        angles = [int(a) for a in angles]
+        self.curriculum_angles = angles
+        self.curriculum_angle = angles[0]
+        self.set_init_states(curriculum_init_states(self.spec.env_kind, self.spec.yaml_init_states, angles[0]))
+        for k, a in enumerate(angles[1:], start=1):
+            self.batch.set_stage_init_states(k, curriculum_init_states(self.spec.env_kind, self.spec.yaml_init_states, a))
+
+    def set_env_stages(self, stages: torch.Tensor):
+        """Writes every env's curriculum stage (int tensor [n_envs]); it takes effect at the env's next reset."""
+        names, ei = self.batch.arena("env_i")
+        ei[names.index("stage")] = stages.to(device=self.device, dtype=torch.int32)
+        self.batch.set_arena("env_i", ei)
+
+    def curriculum_state(self):
+        """(stage, wins in the record, episodes in the record) per env, as device tensors."""
+        names, ei = self.batch.arena("env_i")
+        bits = ei[names.index("curriculum_record")]
+        wins = torch.zeros_like(bits)
+        for k in range(31):
+            wins += (bits >> k) & 1
+        return ei[names.index("stage")], wins, ei[names.index("curriculum_count")]
+
     def close(self):
         self.batch.close()
 
@@ -166,14 +206,18 @@ class BatchedEnv:
         # what the NEXT auto-resets start from: the per-aircraft initial conditions in force (set_init_states / curriculum stage)
         sd["init_states"] = torch.tensor([[float(x) for x in self.batch.cfg.init_state[k]] for k in range(self.n_agents)], dtype=torch.float64)
         sd["curriculum_angle"] = int(self.curriculum_angle)
+        sd["curriculum_angles"] = list(getattr(self, "curriculum_angles", []))     # per-env stages: the stage templates to rebuild
         return sd
 
     def load_state_dict(self, sd):
         from .capi import ARENAS
         if int(sd["seed"]) != self.seed_value:
             self.seed(int(sd["seed"]))            # NB: seed() restarts the episode counters; the arenas restore them below
-        if "init_states" in sd:                   # rebuilds the reset template before the arenas are restored
-            self.set_init_states(sd["init_states"].cpu().numpy())
+        if "init_states" in sd:                   # rebuilds the reset template(s) before the arenas are restored
+            if sd.get("curriculum_angles"):
+                self.set_curriculum_stages(sd["curriculum_angles"])
+            else:
+                self.set_init_states(sd["init_states"].cpu().numpy())
             self.curriculum_angle = int(sd.get("curriculum_angle", 0))
         for k in ARENAS:
             self.batch.set_arena(k, sd[f"arena:{k}"].to(self.device).contiguous())

@@ -217,6 +217,9 @@ def build_spec(cfg: dict, substeps_override=None) -> TaskSpec:
     sp.env_kind, sp.curriculum = t["env"], bool(t.get("curriculum"))
     if sp.curriculum:       # every reset of these tasks goes through reset_simulators_curriculum(curriculum_angle), stage 0 first
         sp.init_states = curriculum_init_states(t["env"], sp.yaml_init_states, 0)
+        # the win-rate record of Scenario*_curriculum / WVRTask / Maneuver_curriculum, with the reference's (inert) stage rule
+        sp.curriculum_rule, sp.curriculum_window = 1, 20
+        sp.curriculum_threshold = 0.9 if t["env"] == "1v1" else 0.6
     if t["env"] == "control":
         sp.terminations = list(t.get("terms", _TERMS_HEADING))
         sp.dones_before_rewards, sp.team_mean, sp.share_obs, sp.reward_gate = True, False, False, ts.G_NONE

@@ -104,6 +104,13 @@ class TaskSpec:
     env_kind: str = "control"
     curriculum: bool = False
     yaml_init_states: List[List[float]] = field(default_factory=list)
+    # per-env win-rate record + stage rule, evaluated on the device when an episode ends (include/acs.h AcsTaskConfig):
+    # window 20 episodes; threshold 0.9 for the 1v1 curriculum tasks (scenario1_task.py:169, WVR_task.py:42), 0.6 for the
+    # N-v-N ones (scenario2_task.py:184); rule 1 = the reference's `len(record) > 20`, which never fires (the record is
+    # capped at 20), 2 = advance when the record is full, 0 = record only
+    curriculum_rule: int = 0
+    curriculum_window: int = 0
+    curriculum_threshold: float = 0.0
 
     @property
     def n_agents(self):

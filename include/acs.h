@@ -116,6 +116,15 @@ typedef struct AcsTaskConfig {
   uint64_t seed;                    /* keyed counter RNG seed (replaces np.random / gymnasium np_random draws) */
   int32_t env_offset;               /* global index of this handle's first env (multi-GPU sharding keeps RNG streams per env) */
   int32_t reserved;
+  /* Curriculum tasks (E/tasks/scenario2_task.py:172-223, scenario1_task.py:164-194, WVR_task.py:38-64): every env keeps a
+   * record of its last `curriculum_window` episode outcomes (win = an ego aircraft ended alive through SafeReturn) and a
+   * stage; when an episode ends the record is updated and the stage rule is applied BEFORE the auto-reset, so the reset
+   * that follows already starts from the new stage (acs_env_set_stage_init_states).  curriculum_rule: 0 = stages only
+   * change when the caller writes them (acs_env_set_arena on "stage"); 1 = the reference's rule verbatim -- advance when
+   * rate >= threshold and len(record) > window, which can never hold because the record is capped at `window` entries
+   * (the reference's stage therefore never advances by itself); 2 = advance when the record is full (len == window). */
+  int32_t curriculum_rule, curriculum_window;
+  double curriculum_threshold;
 } AcsTaskConfig;
 
 typedef struct AcsEnv AcsEnv;
@@ -125,6 +134,13 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out);
 int acs_env_destroy(AcsEnv* e);
 /* replaces: env.reload-time changes of init_state (reset_simulators / curriculum resets, E/envs/singlecombat_env.py:45-122) */
 int acs_env_set_init_states(AcsEnv* e, const double* init_host /* [n_agents][12], HOST memory */);
+
+/* replaces: reset_simulators_curriculum(angle) per env process (E/envs/singlecombat_env.py:87-122, multiplecombat_env.py:185-248).
+ * Registers the initial conditions of curriculum stage `stage` (0 <= stage < 256; stage 0 = the handle's own init_state /
+ * acs_env_set_init_states).  Every env resets from the stage in its "stage" field (arena 5, per-env ints), which the
+ * curriculum rule above advances on the device and acs_env_set_arena can write.  Needs the whole-reset template (every
+ * task but the heading task).  init_host [n_agents][12], HOST memory. */
+int acs_env_set_stage_init_states(AcsEnv* e, int stage, const double* init_host);
 
 /* replaces: env.seed(seed) (E/envs/env_base.py:251-266): re-keys the counter RNG and restarts the per-env episode counters, so
  * seed(s); reset(); ... replays the same draws (the reference's determinism test, R/tests/test_jsbsim.py:55-64). */

@@ -447,3 +447,54 @@ def test_device_rollout_matches_the_numpy_runner_path():
                            ("active_masks", Bam, b.active_masks), ("rnn_states_actor", Bha, b.rnn_states_actor), ("actions", Bact, b.actions)):
         np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=1e-6, err_msg=name)
     env.close(); ve.close()
+
+
+def _poke_status(env, rows_mask, value):
+    names, ai = env.batch.arena("ac_i")
+    st = ai[names.index("status")].view(env.n_envs, env.n_agents)
+    st[rows_mask] = value
+    env.batch.set_arena("ac_i", ai)
+
+
+@pytest.mark.parametrize("rule", [2, 1])
+def test_per_env_curriculum_stages_and_win_rate_record(rule):
+    """Every env keeps its own curriculum stage and win-rate record on the device (reference: per env process,
+    envs/JSBSim/tasks/scenario2_task.py:172-223).  Stage k resets exactly like reset_simulators_curriculum(angles[k]); the
+    record is updated when an episode ends and the rule runs before the auto-reset that follows.  rule 2 advances a full
+    record above the threshold; rule 1 is the reference's `len(record) > window`, which never fires."""
+    cfg, n, angles = "scenario2/scenario2_curriculum", 24, [0, 60, 120]
+    env = BatchedEnv(cfg, n, seed=1, curriculum_rule=rule, curriculum_window=3, curriculum_threshold=0.6)
+    env.set_curriculum_stages(angles)
+    stages = torch.arange(n, device="cuda") % 3
+    env.set_env_stages(stages)
+    obs = env.reset()[0].clone()
+    ref_obs = []
+    for a in angles:                                   # the batch-wide stage API gives the reference reset of that angle
+        r = BatchedEnv(cfg, 1, seed=1)
+        r.set_curriculum_angle(a)
+        ref_obs.append(r.reset()[0][0].clone())
+        r.close()
+    for k in range(3):
+        assert torch.equal(obs[stages == k], ref_obs[k].unsqueeze(0).expand(int((stages == k).sum()), -1, -1)), k
+    assert not torch.equal(ref_obs[0], ref_obs[1])
+    # episodes: envs 0..7 win (both enemies down -> the ego team ends alive through SafeReturn), 8..15 lose, the rest fly on
+    env.set_env_stages(torch.zeros(n, dtype=torch.int32, device="cuda"))
+    env.reset()
+    act = torch.zeros((n, 4, 7), dtype=torch.int32, device="cuda")
+    act[..., 0:3] = 1
+    win = torch.zeros((n, 4), dtype=torch.bool, device="cuda"); win[0:8, 2:] = True
+    lose = torch.zeros((n, 4), dtype=torch.bool, device="cuda"); lose[8:16, :2] = True
+    for episode in range(1, 5):
+        _poke_status(env, win | lose, 2)
+        obs, _, rew, done, info = env.step(act)
+        assert bool(env.batch.env_done[:16].all()) and not bool(env.batch.env_done[16:].any()), episode
+        stage, wins, count = env.curriculum_state()
+        if rule == 2 and episode >= 3:                 # third win: record full, rate 1.0 >= 0.6 -> stage 1, record cleared
+            assert stage[:8].tolist() == [1] * 8 and count[:8].tolist() == [episode - 3] * 8
+            if episode == 3:                           # the reset inside that very step already used the new stage
+                assert torch.equal(obs[:8], ref_obs[1].unsqueeze(0).expand(8, -1, -1))
+        else:
+            assert stage[:8].tolist() == [0] * 8 and wins[:8].tolist() == [min(episode, 3)] * 8
+        assert stage[8:16].tolist() == [0] * 8 and wins[8:16].tolist() == [0] * 8 and count[8:16].tolist() == [min(episode, 3)] * 8
+        assert stage[16:].tolist() == [0] * 8 and count[16:].tolist() == [0] * 8
+    env.close()
