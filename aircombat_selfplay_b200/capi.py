@@ -324,10 +324,10 @@ class EnvBatch:
         _check(lib().acs_env_set_timing(self._h, int(on)))
 
     def get_timing(self, reset: bool = True):
-        """({'substeps': ms, 'post': ms, 'reset': ms}, n_steps) of the recorded steps (synchronises)."""
-        ms, n = (ctypes.c_double * 3)(), ctypes.c_int()
+        """({'substeps': ms, 'post': ms, 'reset': ms, 'missiles': ms}, n_steps) of the recorded steps (synchronises)."""
+        ms, n = (ctypes.c_double * 4)(), ctypes.c_int()
         _check(lib().acs_env_get_timing(self._h, ms, ctypes.byref(n), int(reset)))
-        return {"substeps": ms[0], "post": ms[1], "reset": ms[2]}, n.value
+        return {"substeps": ms[0], "post": ms[1], "reset": ms[2], "missiles": ms[3]}, n.value
 
     # ---- introspection (parity tests, rendering)
     def arena(self, name: str):

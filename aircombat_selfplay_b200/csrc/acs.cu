@@ -298,12 +298,11 @@ struct AcsEnv {
   bool post_split = true;        // get_obs on its own warps in k_env_post where that is legal (ACS_POST_SPLIT)
   PostKernel post = nullptr;     // k_env_post instantiation of this task's family (post_kernel_for)
   int post_family = -1;          // its index in ACS_POST_FAMILIES, -1 = the generic kernel
-  bool defer_missiles = true;    // one-thread frame: missiles of decoupled envs run in k_env_missiles (ACS_DEFER_MISSILES)
   int frame_split = -1;          // substep kernel: 0 one thread per aircraft, 1 two-warp frame, -1 by batch size
   int split_max_threads = 0;     // auto: use the two-warp frame up to this many aircraft lanes
   int n_sms = 0;
   bool timing = false;
-  std::vector<cudaEvent_t> ev;   // 4 events per timed step: before substeps, after substeps, after post, after reset
+  std::vector<cudaEvent_t> ev;   // 5 events per timed step: before substeps, after substeps, after missiles, after post, after reset
   size_t ev_used = 0;
 };
 
@@ -392,17 +391,19 @@ int acs_env_create(const AcsTaskConfig* cfg, int device, AcsEnv** out) {
   if (const char* s = std::getenv("ACS_RESET_TEMPLATE")) e->tpl_mode = std::atoi(s);
   if (const char* s = std::getenv("ACS_FUSED_RESET")) e->fused_reset = std::atoi(s) != 0;
   if (const char* s = std::getenv("ACS_POST_SPLIT")) e->post_split = std::atoi(s) != 0;
-  if (const char* s = std::getenv("ACS_DEFER_MISSILES")) e->defer_missiles = std::atoi(s) != 0;
   e->post = post_kernel_for(e->cfg, &e->post_family);
   if (const char* s = std::getenv("ACS_POST_GENERIC")) if (std::atoi(s) != 0) { e->post = k_env_post<PostGeneric>; e->post_family = -1; }
-  v.traj = nullptr;
+  v.traj = nullptr; v.snap = nullptr;
   if (cfg->launch_kind != ACS_L_NONE && cfg->launch_kind != ACS_L_AUTO_GUN) {     // tasks that fly missiles
     CUDA_TRY(cudaMalloc(&v.traj, sizeof(double) * 6 * (size_t)cfg->substeps * rows));
     CUDA_TRY(cudaMemset(v.traj, 0, sizeof(double) * 6 * (size_t)cfg->substeps * rows));
+    // state per substep of the aircraft a missile may hit within the step (7.6 KB per aircraft at K = 12; touched rarely)
+    CUDA_TRY(cudaMalloc(&v.snap, sizeof(double) * N_SNAP * (size_t)cfg->substeps * rows));
+    CUDA_TRY(cudaMemset(v.snap, 0, sizeof(double) * N_SNAP * (size_t)cfg->substeps * rows));
   }
   if (cfg->obs_kind != ACS_OBS_HEADING && e->tpl_mode > 0) {
     EnvView& t = e->tpl.t;
-    t.B = 1; t.A = A; t.S = v.S; t.rows = A; t.traj = nullptr;
+    t.B = 1; t.A = A; t.S = v.S; t.rows = A; t.traj = nullptr; t.snap = nullptr;
     // one contiguous block (256-byte aligned pieces): arenas of one env, reset observation, field lists
     const size_t n64max = (size_t)(N_STATE + FDM_N_OUT + N_AD) * A + (size_t)N_MD * A * v.S + N_ED;
     const size_t n32max = (size_t)N_AI * A + (size_t)N_MI * A * v.S + N_EI;
@@ -550,7 +551,7 @@ int acs_env_get_option(const AcsEnv* e, const char* name, int* value) {
   if (!std::strcmp(name, "reset_template")) { *value = e->tpl.t.fdm == nullptr ? 0 : (e->tpl.full ? 2 : 1); return 0; }
   if (!std::strcmp(name, "launches_per_step")) {       // kernels one auto-resetting acs_env_step launches
     *value = (e->tpl.t.fdm != nullptr && e->tpl.full && e->fused_reset) ? 2 : ((e->tpl.t.fdm != nullptr) ? 3 : 4);
-    if (frame_split_effective(e) == 0 && e->defer_missiles && e->v.traj != nullptr) *value += 1;     // k_env_missiles
+    if (frame_split_effective(e) == 0 && e->v.traj != nullptr) *value += 1;     // k_env_missiles
     return 0;
   }
   return fail(std::string("acs_env_get_option: unknown option ") + name);
@@ -561,6 +562,7 @@ int acs_env_destroy(AcsEnv* e) {
   cudaSetDevice(e->fdm->device);
   cudaFree(e->v.ad); cudaFree(e->v.ai); cudaFree(e->v.ed); cudaFree(e->v.ei); cudaFree(e->v.md); cudaFree(e->v.mi);
   if (e->v.traj) cudaFree(e->v.traj);
+  if (e->v.snap) cudaFree(e->v.snap);
   if (e->tpl_block) cudaFree(e->tpl_block);
   if (e->stage_block) cudaFree(e->stage_block);
   for (cudaEvent_t x : e->ev) cudaEventDestroy(x);
@@ -633,12 +635,14 @@ int acs_env_step(AcsEnv* e, const int32_t* actions_dev, double* obs_dev, double*
   else if (split == 2) k_env_substeps_split3<<<(threads + S3 - 1) / S3, 3 * S3, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   else if (split == 1) k_env_substeps_split<<<(threads + SPLIT_SLOTS - 1) / SPLIT_SLOTS, 2 * SPLIT_SLOTS, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
   else {
-    const int defer = (e->defer_missiles && e->v.traj != nullptr) ? 1 : 0;
-    k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev, defer);
+    // the one-thread frame carries no missile code: k_env_missiles does the missile / chaff work of the step
+    k_env_substeps<<<(threads + FDM_BLOCK - 1) / FDM_BLOCK, FDM_BLOCK, 0, st>>>(e->v, e->cfg, e->lg, actions_dev);
     CUDA_TRY(cudaGetLastError());
-    if (defer) k_env_missiles<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg);
+    if (e->timing) timing_event(e, st);
+    if (e->v.traj != nullptr) k_env_missiles<<<(threads + 127) / 128, 128, 0, st>>>(e->v, e->cfg, e->lg);
   }
   CUDA_TRY(cudaGetLastError());
+  if (e->timing && split != 0) timing_event(e, st);     // (the multi-warp frames carry their missile phase: interval 0)
   if (e->timing) timing_event(e, st);
   const int fuse = (auto_reset && e->tpl.t.fdm != nullptr && e->tpl.full && e->fused_reset) ? 1 : 0;
   const int obs_split = (e->post_split && e->cfg.launch_kind == ACS_L_NONE && !e->cfg.use_artillery &&
@@ -660,16 +664,17 @@ int acs_env_set_timing(AcsEnv* e, int on) {
   return 0;
 }
 
-int acs_env_get_timing(AcsEnv* e, double ms[3], int* n_steps, int reset) {
+int acs_env_get_timing(AcsEnv* e, double ms[4], int* n_steps, int reset) {
   if (!e || !ms || !n_steps) return fail("acs_env_get_timing: null argument");
-  ms[0] = ms[1] = ms[2] = 0.0;
-  const size_t n = e->ev_used / 4;
+  ms[0] = ms[1] = ms[2] = ms[3] = 0.0;
+  const size_t n = e->ev_used / 5;
+  // intervals in stream order: substeps, missiles, post, reset -> ms[0], ms[3], ms[1], ms[2]
   for (size_t k = 0; k < n; k++) {
-    CUDA_TRY(cudaEventSynchronize(e->ev[4 * k + 3]));
-    for (int j = 0; j < 3; j++) {
+    CUDA_TRY(cudaEventSynchronize(e->ev[5 * k + 4]));
+    for (int j = 0; j < 4; j++) {
       float t = 0.f;
-      CUDA_TRY(cudaEventElapsedTime(&t, e->ev[4 * k + j], e->ev[4 * k + j + 1]));
-      ms[j] += t;
+      CUDA_TRY(cudaEventElapsedTime(&t, e->ev[5 * k + j], e->ev[5 * k + j + 1]));
+      ms[j == 0 ? 0 : (j == 1 ? 3 : j - 1)] += t;
     }
   }
   *n_steps = (int)n;

@@ -78,6 +78,8 @@ struct EnvView {
   int B, A, S, rows;
   double* traj;  // [K][6][rows] position / velocity every aircraft published after each substep of the current step, for
                  // the envs whose missiles are integrated by k_env_missiles (nullptr: the task has no missiles)
+  double* snap;  // [K][N_STATE + 4][rows] FDM state (+ the frame's kept scalars) after each substep, written only for aircraft a
+                 // missile may hit within the step: the hit restores the state of the substep it happened in
 };
 // Reset template of a handle (acs.cu, build_reset_template).  Every task but the heading task resets an env to the same
 // state each time (fixed per-lane initial conditions, no random draw), so reset() is run once on a one-env arena `t`.

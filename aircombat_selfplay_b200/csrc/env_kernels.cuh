@@ -262,57 +262,71 @@ struct EomLane {
   double v_mps, w_mps, vc_mps;
   int status, sc0;
   bool has_ms, was_alive;
-  bool deferred;               // the env's missiles are integrated after the K loop by k_env_missiles (this kernel only records
-                               // every aircraft's position / velocity per substep in v.traj)
+  bool deferred;               // the env's missiles / chaff run after the K loop in k_env_missiles (this kernel only records every
+                               // aircraft's position / velocity per substep in v.traj)
+  bool snap;                   // a missile may reach this aircraft within the step: record its state after every substep
   unsigned long long live;     // slots of this aircraft whose missile still runs (live_missiles)
   AcOut o;
 };
-// Can a missile of this aircraft reach its target's fuze radius within this interaction step?  Conservative bound on the
-// closing distance over K substeps: the missile's speed now + the most its motor can add (753 m/s^2 for the AIM-120B
-// numbers, simulatior.py:700-712) + 1500 m/s for the target (an F-16 stays below half of that), plus a margin.
-ENV_DEV bool missile_threatens(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const unsigned long long live) {
+// Which aircraft of the env can a missile of this lane reach (fuze radius) within this interaction step?  Conservative
+// bound on the separation over the T = K dt seconds of the step from the radial closing rate r' = d . v_rel / |d| now:
+// |d(t)| >= d(0)/|d(0)| . d(t) >= |d0| + r' t - a_max t^2 / 2, concave in t, so its minimum over [0, T] is at an end point.
+// a_max = 1500 m/s^2 covers the missile (753 m/s^2 of thrust for the AIM-120B numbers of simulatior.py:700-712, at most
+// 50 g = 490 m/s^2 of commanded lateral acceleration, drag, gravity) plus 15 g for the target; 20 m of margin.  The
+// fuze is only tested at the substep instants, so the continuous-time bound covers it.  Returns a bit per target lane.
+ENV_DEV unsigned missile_threatens(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, const unsigned long long live) {
   const double T = cfg.substeps * cfg.sim_dt;
+  unsigned mask = 0;
   for (unsigned long long m = live; m; m &= m - 1) {
     const int mid = L.row * v.S + (__ffsll((long long)m) - 1);
     if (MI(v, MI_STATUS, mid) != MS_LAUNCHED) continue;          // HIT / MISS missiles never score again
-    const int trow = L.env * v.A + MI(v, MI_TARGET, mid);
+    const int target = MI(v, MI_TARGET, mid);
+    const int trow = L.env * v.A + target;
     const double dx = MD(v, MD_POS_N, mid) - AD(v, AD_POS_N, trow), dy = MD(v, MD_POS_E, mid) - AD(v, AD_POS_E, trow),
                  dz = MD(v, MD_POS_U, mid) - AD(v, AD_POS_U, trow);
-    const double vn = MD(v, MD_VEL_N, mid), ve = MD(v, MD_VEL_E, mid), vu = MD(v, MD_VEL_U, mid);
-    const double reach = missile_params(MI(v, MI_KIND, mid)).Rc + (sqrt(vn * vn + ve * ve + vu * vu) + 800.0 * T + 1500.0) * T + 50.0;
-    if (dx * dx + dy * dy + dz * dz < reach * reach) return true;
+    const double wx = MD(v, MD_VEL_N, mid) - AD(v, AD_VEL_N, trow), wy = MD(v, MD_VEL_E, mid) - AD(v, AD_VEL_E, trow),
+                 wz = MD(v, MD_VEL_U, mid) + AD(v, AD_VEL_D, trow);         // the aircraft publishes v_down
+    const double d0 = sqrt(dx * dx + dy * dy + dz * dz);
+    const double rate = d0 > 0.0 ? (dx * wx + dy * wy + dz * wz) / d0 : -sqrt(wx * wx + wy * wy + wz * wz);
+    const double at_end = d0 + rate * T - 0.5 * 1500.0 * T * T;
+    if (fmin(d0, at_end) < missile_params(MI(v, MI_KIND, mid)).Rc + 20.0) mask |= 1u << target;
   }
-  return false;
+  return mask;
 }
-// allow_defer: this launch is followed by k_env_missiles.  An env is COUPLED when something in its missile phase can feed
-// back into the aircraft or needs the per-substep lockstep of its lanes: a missile close enough to score within this
-// step (the hit stops the target's integration at that substep), or an effective chaff cloud (timers, decoy draws).
-// Every other env with live missiles is DEFERRED: no hit can happen, so aircraft statuses are constant over the step, the
-// missiles are independent of each other and of everything but their target's trajectory -- this kernel integrates the
-// aircraft without stopping and records their position / velocity per substep, k_env_missiles then integrates each
-// missile over the K substeps with its state in registers (same expressions, same per-missile order).
+// allow_defer (the one-thread kernel): the launch is followed by k_env_missiles, which then does ALL missile and chaff work
+// of the step (allocated only for tasks that fly missiles: v.traj; otherwise there is no such work).  The substep
+// kernel integrates the aircraft without stopping and records, for the envs that have missiles or chaff in the air, every
+// aircraft's position / velocity per substep (v.traj).  The one feedback from missiles to aircraft -- a hit freezes the
+// target from the next substep on (simulatior.py:520-533, :210-229) -- is handled by recording the FDM state after every
+// substep for the aircraft a missile can reach within the step (missile_threatens; v.snap): k_env_missiles restores the
+// state of the substep in which the hit happened.  EI_DEFERRED tells k_env_missiles what the env needs: 0 nothing,
+// 1 no missile can score this step (statuses are constant, the missiles are independent: each is integrated over the K
+// substeps in registers), 2 the per-substep lockstep of the env's lanes (fuze arbitration in dict order).
 ENV_DEV void eom_begin(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L, EomLane& E, const bool allow_defer) {
   E.v_mps = E.w_mps = E.vc_mps = 0;
-  E.status = ST_CRASH; E.has_ms = false; E.live = 0; E.deferred = false;
+  E.status = ST_CRASH; E.has_ms = false; E.live = 0; E.deferred = false; E.snap = false;
   E.me.status = ST_CRASH; E.me.bloods = 0; E.me.h = 0; E.me.u_mps = 0;
   E.me.f.n = E.me.f.e = E.me.f.u = E.me.f.vn = E.me.f.ve = E.me.f.vd = 0;
-  bool chaff = false, threat = false;
+  bool chaff = false;
+  unsigned threat = 0;
+  const bool ext = allow_defer && v.traj != nullptr;
   if (L.valid) {
     load_pub(v, L.row, E.me);
     E.status = E.me.status;
     E.live = live_missiles(v, L);
     chaff = AI(v, AI_CH_STATE, L.row) == CH_ACTIVE;
-    if (allow_defer && v.traj != nullptr) threat = missile_threatens(v, cfg, L, E.live);
+    if (ext) threat = missile_threatens(v, cfg, L, E.live);
   }
   const bool any_live = (__ballot_sync(L.gmask, E.live != 0) & L.gmask) != 0;
   const bool any_chaff = (__ballot_sync(L.gmask, chaff) & L.gmask) != 0;
-  const bool any_threat = (__ballot_sync(L.gmask, threat) & L.gmask) != 0;
-  E.deferred = allow_defer && v.traj != nullptr && any_live && !any_chaff && !any_threat;
-  // an env needs the per-substep exchange only while it has missiles that still run or an effective chaff cloud
-  E.has_ms = !E.deferred && (any_live || any_chaff);
+  threat = __reduce_or_sync(L.gmask, threat);
+  E.deferred = ext && (any_live || any_chaff);
+  E.snap = E.deferred && L.valid && ((threat >> L.lane) & 1u);
+  // in-kernel missile phase (no k_env_missiles): per-substep exchange while missiles run or a chaff cloud is effective
+  E.has_ms = !ext && (any_live || any_chaff);
   E.was_alive = L.valid && E.status == ST_ALIVE;
   E.sc0 = (L.env < v.B) ? EI(v, EI_SUBSTEP_COUNT, L.env) : 0;
-  if (L.valid && L.lane == 0) EI(v, EI_DEFERRED, L.env) = E.deferred;
+  if (L.valid && L.lane == 0) EI(v, EI_DEFERRED, L.env) = E.deferred ? (threat ? 2 : 1) : 0;
 }
 // the record k_env_missiles reads: what the aircraft of `row` published after substep k
 ENV_DEV void traj_store(const EnvView& v, const int k, const int row, const Feat& f) {
@@ -377,16 +391,30 @@ ENV_DEV void eom_propulsion(AcCore& a, const Props& p, Frame& f, const double* _
   a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
 }
 
-#ifndef ACS_LEAN_FRAME
-#define ACS_LEAN_FRAME 1
-#endif
+constexpr int N_SNAP = FDM_N_CORE + F16_N_CARRIED + 4;     // the FDM state + FrameKeep
+// state of the aircraft after substep k, for k_env_missiles (a hit in substep k leaves the aircraft in exactly this state)
+ENV_DEV void snap_store(const EnvView& v, const int k, const int row, const AcCore& a, const Props& p, const FcsState& s, const FrameKeep& keep) {
+  double* b = v.snap + (size_t)k * N_SNAP * v.rows;
+  store_state(b, v.rows, row, a, p, s);
+  double* q = b + (size_t)(FDM_N_CORE + F16_N_CARRIED) * v.rows + row;
+  q[0] = keep.pilot_nx; q[(size_t)v.rows] = keep.vcas; q[(size_t)2 * v.rows] = keep.beta; q[(size_t)3 * v.rows] = keep.thrust;
+}
+ENV_DEV void snap_load(const EnvView& v, const int k, const int row, AcCore& a, Props& p, FcsState& s, FrameKeep& keep) {
+  const double* b = v.snap + (size_t)k * N_SNAP * v.rows;
+  f16_props_init(p, s);
+  load_state(b, v.rows, row, a, p, s);
+  const double* q = b + (size_t)(FDM_N_CORE + F16_N_CARRIED) * v.rows + row;
+  keep.pilot_nx = q[0]; keep.vcas = q[(size_t)v.rows]; keep.beta = q[(size_t)2 * v.rows]; keep.thrust = q[(size_t)3 * v.rows];
+}
+
+// The throughput kernel: one thread per aircraft, lean frame (fdm_core.cuh): nothing of a frame's scratch outlives it; the
+// property read-back (_update_properties, simulatior.py:238-257) is materialised once, from the state the aircraft's
+// last frame left, after the K loop.  No missile or chaff code in here at all: k_env_missiles follows (eom_begin);
+// aircraft of envs with missiles or chaff in the air publish their trajectory and, when a missile can reach them, their
+// state per substep to global memory.
 __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
-                                                           const int32_t* __restrict__ actions, const int allow_defer) {
+                                                           const int32_t* __restrict__ actions) {
   __shared__ double sT[F16_NTAB];
-  __shared__ PubAc sP[FDM_BLOCK];
-  __shared__ int sWin[FDM_BLOCK];
-  __shared__ int sShot[FDM_BLOCK];
-  __shared__ PubChaff sCh[FDM_BLOCK];
   stage_tables(sT);
   const Lane L = lane_setup(v, lg);
   const int K = cfg.substeps;
@@ -394,47 +422,27 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
   AcCore a; Props p; FcsState s;
   EomLane E;
-#if ACS_LEAN_FRAME
-  eom_begin(v, cfg, L, E, allow_defer != 0);
-#else
-  eom_begin(v, cfg, L, E, false);
-#endif
+  eom_begin(v, cfg, L, E, true);
   if (L.valid) load_commanded(v, cfg, L, actions, E.status == ST_ALIVE, a, p, s);
-#if ACS_LEAN_FRAME
-  // Lean frame (fdm_core.cuh): nothing of a frame's scratch outlives it.  The publication the other lanes' missiles read is
-  // written to shared memory from inside the frame (the previous substep's readers are behind the __syncwarp that ended
-  // their missile phase); the property read-back (_update_properties, simulatior.py:238-257) is materialised once, from
-  // the state the aircraft's last frame left, after the K loop.
   FrameKeep keep;
   keep.pilot_nx = keep.vcas = keep.beta = keep.thrust = 0.0;
-  const bool has_ms = E.has_ms, deferred = E.deferred;
+  const bool deferred = E.deferred, snap = E.snap;
   const double bloods = E.me.bloods;
   int status = E.status;
-  if (has_ms) sP[L.tid] = E.me;          // dead aircraft stay where the arena has them
   for (int k = 0; k < K; k++) {
     const bool ran = L.valid && status == ST_ALIVE;
     if (ran) {
       if (bloods <= 0) status = ST_SHOTDOWN;     // AircraftSimulator.run's gate (simulatior.py:220-226): still integrates this frame
       fdm_frame_lean(a, p, s, keep, sT, g_atmo, dt, fcs_dt, [&](const Frame& f) {
-        if (has_ms) { PubAc pub; publish_from_frame(f, org, pub); sP[L.tid].f = pub.f; sP[L.tid].h = pub.h; sP[L.tid].u_mps = pub.u_mps; }
         if (deferred) { PubAc pub; publish_from_frame(f, org, pub); traj_store(v, k, L.row, pub.f); }
       });
+      if (snap) snap_store(v, k, L.row, a, p, s, keep);
     } else if (deferred && L.valid) {
       // an aircraft that does not run this substep stays where it stopped: the arena's position before its first frame of
-      // the step, its own last record afterwards (only a gun kill -- bloods <= 0 -- stops an aircraft of a deferred env)
+      // the step, its own last record afterwards (only a gun kill -- bloods <= 0 -- stops an aircraft in this kernel)
       Feat f = E.me.f;
       if (k > 0) traj_load(v, k - 1, L.row, f);
       traj_store(v, k, L.row, f);
-    }
-    if (has_ms) {
-      sP[L.tid].status = status;
-      sWin[L.tid] = 0x7fffffff;
-      sShot[L.tid] = 0;
-      __syncwarp(L.gmask);
-      missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, E.sc0 + k, E.live);
-      __syncwarp(L.gmask);
-      if (sShot[L.tid] && status == ST_ALIVE) status = ST_SHOTDOWN;   // target_aircraft.shotdown() (simulatior.py:527)
-      __syncwarp(L.gmask);
     }
   }
   E.status = status;
@@ -444,32 +452,117 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
     fdm_outputs(a, f, E.o);
     derive_aircraft(E.o, org, E.me, E.v_mps, E.w_mps, E.vc_mps);
   }
-#else
-  Frame f;
-  for (int k = 0; k < K; k++) {
-    const bool ran = eom_runs(L, E);
-    if (ran) fdm_frame(a, p, s, f, sT, g_atmo, dt, fcs_dt, false);
-    eom_after_frame(v, cfg, L, org, E, a, f, ran, k, K, sP, sWin, sShot, sCh);
-  }
-#endif
   eom_end<true>(v, L, E, a, p, s, K);
 }
 
-// ---------------------------------------------------------------------------------------------- deferred missiles
-// The missiles of the envs k_env_substeps marked DEFERRED (eom_begin): no missile of the env can score within this step, so
-// target statuses are constant, nothing feeds back into the aircraft and the missiles do not interact.  One thread per
-// shooter walks its live slots; each missile is loaded once, run() K times against the target's recorded trajectory with
-// its state in registers, and stored once -- instead of K x (load, run, store) between the frames of a 255-register
-// thread.  Same expressions as missile_phase.  A fuze condition met here would mean the reach bound of
-// missile_threatens was wrong: it is counted in the env's fault counter (asserted zero by every parity test).
+// ---------------------------------------------------------------------------------------------- missiles after the K loop
+// All missile and chaff work of a step whose aircraft were integrated by k_env_substeps<true>, one thread per shooter, the
+// lanes of an env adjacent as everywhere.  Per env (EI_DEFERRED, decided in eom_begin from the state at the start of
+// the step):
+//   1  no missile can score within this step.  Target statuses are constant, nothing feeds back into the aircraft, the
+//      missiles do not interact: each missile is loaded once, run() K times against the target's recorded trajectory
+//      with its state in registers, and stored once -- instead of K x (load, run, store) between the frames of a
+//      255-register thread.  Chaff (E/core/simulatior.py:377-381, E/envs/env_base.py:146-154): a cloud is a fixed position
+//      with a timer, so its state at substep k follows from its state at the start of the step; every lane publishes
+//      its cloud once, each missile tests the clouds still effective at that substep (same keyed draws), the owner
+//      lane advances its timer by the same K additions.  A fuze condition met here would mean the reach bound of
+//      missile_threatens was wrong: it is counted in the env's fault counter (asserted zero by every parity test).
+//   2  some missile may score: the env's lanes run the K missile phases in lockstep (missile_phase: dict-order fuze
+//      arbitration, chaff), reading the aircraft's recorded positions; a HIT marks the target SHOTDOWN from that substep
+//      on and -- because k_env_substeps integrated it to the end of the step -- its lane restores the state it had after
+//      the substep of the hit (v.snap) and re-derives the outputs from it, which is exactly where the reference leaves
+//      an aircraft that stops running (simulatior.py:210-229,520-533).
+// Same expressions as the in-kernel missile phase of the multi-warp frames.
 __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg) {
+  __shared__ PubAc sP[128];
+  __shared__ int sWin[128];
+  __shared__ int sShot[128];
+  __shared__ PubChaff sCh[128];
+  __shared__ int sChEnd[128];          // mode 1: first substep at which the lane's cloud is no longer effective (0: none)
   const Lane L = lane_setup(v, lg);
-  if (!L.valid || !EI(v, EI_DEFERRED, L.env)) return;
   const int K = cfg.substeps;
   const double dt = cfg.sim_dt;
-  const int maxlen = (int)(5.0 / dt);
+  const int mode = L.valid ? EI(v, EI_DEFERRED, L.env) : 0;
+  if (!__any_sync(0xffffffffu, mode != 0)) return;
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
+  const int sc0 = L.valid ? EI(v, EI_SUBSTEP_COUNT, L.env) - K : 0;          // k_env_substeps advanced the counter
+
+  // ================================================================ mode 2: lockstep phases, hits, state restore
+  if (__any_sync(0xffffffffu, mode == 2)) {
+    const bool on = mode == 2;
+    unsigned long long live = 0;
+    PubAc me;
+    me.status = ST_CRASH; me.bloods = 0; me.h = 0; me.u_mps = 0; me.f.n = me.f.e = me.f.u = me.f.vn = me.f.ve = me.f.vd = 0;
+    if (on) {
+      live = live_missiles(v, L);
+      me.status = AI(v, AI_STATUS, L.row);       // as k_env_substeps left it: constant over the step unless a missile scores
+    }
+    int hit_k = K;
+    for (int k = 0; k < K; k++) {
+      if (on && hit_k == K) traj_load(v, k, L.row, me.f);       // a shot-down aircraft stays where it was hit
+      sP[L.tid] = me;
+      sWin[L.tid] = 0x7fffffff;
+      sShot[L.tid] = 0;
+      __syncwarp(L.gmask);
+      if ((__ballot_sync(L.gmask, on) & L.gmask) != 0) missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, sc0 + k, live);
+      __syncwarp(L.gmask);
+      if (on && sShot[L.tid] && me.status == ST_ALIVE) { me.status = ST_SHOTDOWN; hit_k = k; }   // target_aircraft.shotdown() (simulatior.py:527)
+      __syncwarp(L.gmask);
+    }
+    if (on && hit_k < K) {
+      AI(v, AI_STATUS, L.row) = ST_SHOTDOWN;
+      if (hit_k < K - 1) {
+        // k_env_substeps ran K frames; the aircraft stopped after frame hit_k
+        AcCore a; Props p; FcsState s; FrameKeep keep;
+        snap_load(v, hit_k, L.row, a, p, s, keep);
+        // the record must be this step's: its clock is (K - 1 - hit_k) frames behind the one k_env_substeps stored
+        const double t_end = v.fdm[(size_t)F_SIM_TIME * v.rows + L.row];
+        if (fabs(a.sim_time - (t_end - (K - 1 - hit_k) * dt)) > 0.25 * dt) atomicAdd(&EI(v, EI_FAULTS, L.env), 1);   // hit on an unrecorded aircraft
+        store_state(v.fdm, v.rows, L.row, a, p, s);
+        Frame f; AcOut o; PubAc pub; double v_mps, w_mps, vc_mps;
+        fdm_refresh(a, p, keep, f);
+        fdm_outputs(a, f, o);
+        derive_aircraft(o, org, pub, v_mps, w_mps, vc_mps);
+        store_out(v.out, v.rows, L.row, o);
+        store_derived(v, L.row, pub, v_mps, w_mps, vc_mps);
+      }
+    }
+  }
+  if (!__any_sync(0xffffffffu, mode == 1)) return;
+
+  // ================================================================ mode 1: every missile on its own
+  const bool on = mode == 1;
+  // ---- chaff run() of the whole step for this lane's cloud, and its publication
+  {
+    PubChaff c;
+    c.state = CH_NONE; c.count = 0; c.n = c.e = c.u = 0.0;
+    int end = 0;
+    if (on) {
+      c.state = AI(v, AI_CH_STATE, L.row);
+      if (c.state != CH_NONE) {
+        double t = AD(v, AD_CH_T, L.row);
+        int st = c.state;
+        end = st == CH_ACTIVE ? K : 0;
+        for (int k = 0; k < K; k++) {
+          t += dt;
+          if (t > 20.0) { if (st == CH_ACTIVE) end = k; st = CH_DONE; }      // run() precedes the test of the same substep
+        }
+        AD(v, AD_CH_T, L.row) = t;
+        AI(v, AI_CH_STATE, L.row) = st;
+        c.count = AI(v, AI_CH_COUNT, L.row);
+        c.n = AD(v, AD_CH_N, L.row); c.e = AD(v, AD_CH_E, L.row); c.u = AD(v, AD_CH_U, L.row);
+      }
+    }
+    sCh[L.tid] = c;
+    sChEnd[L.tid] = end;
+  }
+  __syncwarp(L.gmask);
+  if (!on) return;
+  bool any_chaff = false;
+  for (int j = 0; j < v.A; j++) any_chaff = any_chaff || sChEnd[L.gbase + j] > 0;
+  const int maxlen = (int)(5.0 / dt);
   const int nl = AI(v, AI_N_LAUNCHED, L.row);
+  const int64_t when0 = ((int64_t)EI(v, EI_EPISODE, L.env) << 20) + sc0;
   for (int slot = 0; slot < nl; slot++) {
     const int mid = L.row * v.S + slot;
     if (MI(v, MI_DETACHED, mid) || missile_inert(v, mid, L.env)) continue;
@@ -477,7 +570,8 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
     missile_load(v, mid, m);
     const MissileParams pr = missile_params(m.kind);
     const int trow = L.env * v.A + m.target;
-    const bool target_alive = AI(v, AI_STATUS, trow) == ST_ALIVE;     // constant over the step in a deferred env
+    const bool target_alive = AI(v, AI_STATUS, trow) == ST_ALIVE;     // constant over the step in this mode
+    const int keyn = MI(v, MI_KEYN, mid);
     Feat tg;
     traj_load(v, 0, trow, tg);
     for (int k = 0; k < K; k++) {
@@ -498,6 +592,19 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
         if (inert) break;             // every later run() is the same no-op (missile_inert)
       } else {
         missile_state_trans(m, pr, org, ny, nz, dt);
+      }
+      if (any_chaff && m.status == MS_LAUNCHED) {
+        bool missed = false;
+        for (int j = 0; j < v.A; j++) {
+          if (k >= sChEnd[L.gbase + j]) continue;                     // no cloud, or done by this substep
+          const PubChaff& c = sCh[L.gbase + j];
+          const double dx = c.n - m.pn, dy = c.e - m.pe, dz = c.u - m.pu;
+          if (sqrt(dx * dx + dy * dy + dz * dz) <= 300.0) {
+            for (int q = 0; q < c.count; q++)
+              if (env_u01(cfg.seed, cfg.env_offset + L.env, RNG_CHAFF, when0 + k, L.lane * 64 + keyn, j * 64 + q) < 0.85) missed = true;
+          }
+        }
+        if (missed) m.status = MS_MISS;
       }
       tg = nxt;
     }

@@ -188,10 +188,10 @@ int acs_env_get_option(const AcsEnv* e, const char* name, int* value);
 /* Measurement (no reference counterpart): with timing on, acs_env_step brackets each of its kernels with CUDA events on the
  * caller's stream (event-record nodes when the stream is being captured into a CUDA graph, so the intervals contain no
  * launch gaps); acs_env_get_timing synchronises those events and returns the accumulated milliseconds per kernel --
- * ms[0] k_env_substeps, ms[1] k_env_post, ms[2] the two reset kernels -- and the number of steps covered.  reset != 0
+ * ms[0] k_env_substeps*, ms[1] k_env_post, ms[2] the two reset kernels, ms[3] k_env_missiles -- and the number of steps covered.  reset != 0
  * forgets the recorded steps; reset == 0 keeps them (a replayed graph re-records the same events every launch). */
 int acs_env_set_timing(AcsEnv* e, int on);
-int acs_env_get_timing(AcsEnv* e, double ms[3], int* n_steps, int reset);
+int acs_env_get_timing(AcsEnv* e, double ms[4], int* n_steps, int reset);
 
 /* Measurement helper (no reference counterpart): runs a dependent-free fp64 FMA loop on every SM and returns the
  * achieved FLOP/s in *flops_out; used by bench.py to put an fp64-pipe roof beside the HBM roof. */

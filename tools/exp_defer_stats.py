@@ -20,10 +20,11 @@ for cfg, n in (("scenario3/scenario3", 4096), ("2v2/ShootMissile/HierarchySelfpl
             ni, ei = b.arena("env_i"); mn, mi = b.arena("ms_i"); an, ai = b.arena("ac_i")
             st = mi[mn.index("status")].view(n, A, -1)
             launched = (st == 0).sum(-1).float()
-            acc.append((float(ei[ni.index("deferred")].float().mean()), float((launched.sum(1) > 0).float().mean()), float(launched.mean()),
+            mode = ei[ni.index("deferred")]
+            acc.append((float((mode == 1).float().mean()), float((launched.sum(1) > 0).float().mean()), float(launched.mean()),
                         float(launched.max()), float((ai[an.index("chaff_state")] == 1).view(n, A).any(1).float().mean()),
-                        float((ai[an.index("n_launched")]).float().mean())))
+                        float((ai[an.index("n_launched")]).float().mean()), float((mode == 2).float().mean())))
     m = np.mean(acc, axis=0)
-    print(f"{cfg} x{n}: deferred envs {m[0]:.3f}  envs with LAUNCHED missiles {m[1]:.3f}  LAUNCHED per aircraft mean {m[2]:.3f} max {m[3]:.0f}  "
+    print(f"{cfg} x{n}: envs on the fast missile path {m[0]:.3f}, on the lockstep path {m[6]:.4f}  envs with LAUNCHED missiles {m[1]:.3f}  LAUNCHED per aircraft mean {m[2]:.3f} max {m[3]:.0f}  "
           f"envs with active chaff {m[4]:.3f}  launched slots per aircraft {m[5]:.2f}", flush=True)
     b.close()

@@ -39,11 +39,12 @@ def child(case: str, n_envs: int, split: int, steps: int, warm: int) -> None:
     torch.cuda.synchronize()
     b.set_timing(True)
     for t in range(steps):
-        flush.fill_(t & 0xff)          # cold L2, as bench.py times it
+        if not os.environ.get("EXP_NO_FLUSH"):
+            flush.fill_(t & 0xff)      # cold L2, as bench.py times it
         b.step(acts[warm + t], auto_reset=True)
     ms, k = b.get_timing()
     b.close()
-    print(json.dumps({"sub": ms["substeps"] / k, "post": ms["post"] / k, "reset": ms["reset"] / k, "A": A}))
+    print(json.dumps({"sub": ms["substeps"] / k, "mis": ms.get("missiles", 0.0) / k, "post": ms["post"] / k, "reset": ms["reset"] / k, "A": A}))
 
 
 def main() -> None:
@@ -86,8 +87,8 @@ def main() -> None:
         if "error" in d:
             print(f"{case:>10} x{n:<6} split={split:>2} {lib:<28} ERROR {d['error']}")
             continue
-        tot = d["sub"] + d["post"] + d["reset"]
-        print(f"{case:>10} x{n:<6} split={split:>2} {lib:<28} sub {d['sub']:.4f} post {d['post']:.4f} reset {d['reset']:.4f} ms"
+        tot = d["sub"] + d.get("mis", 0.0) + d["post"] + d["reset"]
+        print(f"{case:>10} x{n:<6} split={split:>2} {lib:<28} sub {d['sub']:.4f} missiles {d.get('mis', 0.0):.4f} post {d['post']:.4f} reset {d['reset']:.4f} ms"
               f" -> {n * d['A'] / tot / 1e3:7.1f} M agent-steps/s", flush=True)
 
 
