@@ -209,6 +209,16 @@ __device__ __noinline__ void missile_phase(const EnvView& v, const AcsTaskConfig
   live_io = live;
 }
 
+// OR over the lanes of an env.  Not __reduce_or_sync(L.gmask, x): with a partial mask that compiles to WARPSYNC.EXCLUSIVE +
+// REDUX, which splits the warp into its 32 / G groups, and the groups reconverge only much later (ncu of the three-warp
+// frame: the state load executed 16 times per warp with 2 active lanes, Propagate 2.25 times with 14: +23 % warp
+// instructions).  A butterfly of full-warp shuffles leaves the warp converged; every call site is warp-uniform.
+ENV_DEV unsigned group_or(const Lane& L, unsigned x) {
+  const int G = __popc(L.gmask);
+  for (int o = 1; o < G; o <<= 1) x |= __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
 // ---------------------------------------------------------------------------------------------- shared by the substep kernels
 // lane of an aircraft slot (the multi-warp frames give several threads the same slot)
 ENV_DEV Lane lane_of_slot(const EnvView& v, const int lg, const int slot, const int gid) {
@@ -317,9 +327,11 @@ ENV_DEV void eom_begin(const EnvView& v, const AcsTaskConfig& cfg, const Lane& L
     chaff = AI(v, AI_CH_STATE, L.row) == CH_ACTIVE;
     if (ext) threat = missile_threatens(v, cfg, L, E.live);
   }
-  const bool any_live = (__ballot_sync(L.gmask, E.live != 0) & L.gmask) != 0;
-  const bool any_chaff = (__ballot_sync(L.gmask, chaff) & L.gmask) != 0;
-  threat = __reduce_or_sync(L.gmask, threat);
+  // full-warp votes (every call site of eom_begin is warp-uniform): a vote on the group's own mask can compile to
+  // WARPSYNC.EXCLUSIVE, which leaves the warp split into its groups (see group_or)
+  const bool any_live = (__ballot_sync(0xffffffffu, E.live != 0) & L.gmask) != 0;
+  const bool any_chaff = (__ballot_sync(0xffffffffu, chaff) & L.gmask) != 0;
+  threat = group_or(L, threat);
   E.deferred = ext && (any_live || any_chaff);
   E.snap = E.deferred && L.valid && ((threat >> L.lane) & 1u);
   // in-kernel missile phase (no k_env_missiles): per-substep exchange while missiles run or a chaff cloud is effective
@@ -504,7 +516,7 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
       sWin[L.tid] = 0x7fffffff;
       sShot[L.tid] = 0;
       __syncwarp(L.gmask);
-      if ((__ballot_sync(L.gmask, on) & L.gmask) != 0) missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, sc0 + k, live);
+      if ((__ballot_sync(0xffffffffu, on) & L.gmask) != 0) missile_phase(v, cfg, L, org, sP, sWin, sShot, sCh, sc0 + k, live);
       __syncwarp(L.gmask);
       if (on && sShot[L.tid] && me.status == ST_ALIVE) { me.status = ST_SHOTDOWN; hit_k = k; }   // target_aircraft.shotdown() (simulatior.py:527)
       __syncwarp(L.gmask);
@@ -1663,7 +1675,7 @@ ENV_DEV double env_rewards(const StepCtx& c, bool valid) {
     for (int ri = 0; ri < nr; ri++) if (reward_is_order_dependent(c, c.cfg.rewards[ri].kind)) serial |= 1u << ri;
     if (!gated) n = enemy_geometry(c, L.lane, geo);
   }
-  serial = __reduce_or_sync(L.gmask, serial);
+  serial = group_or(L, serial);
   // pass 0: every lane evaluates the classes without cross-agent state; passes 1 .. A (only when some class is
   // order-dependent this step): lane pass-1 evaluates those -- one call site of the reward code
   const int passes = serial ? c.v.A + 1 : 1;
@@ -1845,7 +1857,7 @@ __global__ void __launch_bounds__(256) k_env_post(const __grid_constant__ EnvVie
   if (L.valid) sDone[L.tid] = cause >= 0;
   // win of this agent as the reference's `success` flag survives the termination loop: ended ALIVE through SafeReturn
   const bool won = L.valid && L.lane < cfg.n_ego && cause == ACS_T_SAFE_RETURN && sP[L.tid].status == ST_ALIVE;
-  const bool env_won = (__ballot_sync(L.gmask, won) & L.gmask) != 0;
+  const bool env_won = (__ballot_sync(0xffffffffu, won) & L.gmask) != 0;
   __syncwarp(L.gmask);
   if (obs_split) __syncthreads();     // the observation warps are done (share_obs and the reset below read / replace obs)
   if (L.valid) {

@@ -81,3 +81,30 @@ for k, v in stall.most_common(10):
     lines.append(f"{k:28s} {100 * v / max(tots, 1):5.1f}%")
 open(out, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
+
+# ---- hottest CUDA source lines (stall samples aggregated per line), appended to the summary
+try:
+    src = page("source", ["--print-source", "cuda"])
+    hot = []
+    cur = ""
+    for r in src:
+        if len(r) == 1 and r[0].strip():
+            cur = r[0].strip()
+        if not r or "Source" in r and "# Samples" in r:
+            hh = {c: i for i, c in enumerate(r)}
+            continue
+        try:
+            s = int(r[hh["# Samples"]] or 0)
+            n = int(r[hh["Instructions Executed"]] or 0)
+        except Exception:
+            continue
+        if s:
+            hot.append((s, n, cur.split("/")[-1][:40], r[hh["Source"]].strip()[:150]))
+    hot.sort(reverse=True)
+    tot_s = sum(x[0] for x in hot) or 1
+    extra = ["", "hottest CUDA source lines (share of samples, warp instructions, file, line)"]
+    for s, n, f, t in hot[:60]:
+        extra.append(f"{100 * s / tot_s:5.1f}%  {n:10d}  {f:24s} {t}")
+    open(out, "a").write("\n".join(extra) + "\n")
+except Exception as e:  # the summary above is the product; this section is best effort
+    open(out, "a").write(f"\n(hot source lines unavailable: {e})\n")
