@@ -219,6 +219,7 @@ int acs_create(const AcsConfig* cfg, int device, AcsHandle** out) {
   host_atmo(ac);
   CUDA_TRY(cudaMemcpyToSymbol(g_atmo, &ac, sizeof(ac)));
   CUDA_TRY(cudaMemcpyToSymbol(g_f16_tab, F16_TAB_HOST, sizeof(double) * F16_NTAB));
+  CUDA_TRY(cudaMemcpyToSymbol(g_f16_kc, F16_TAB_HOST, sizeof(double) * F16_NTAB));
   *out = h;
   return 0;
 }

@@ -403,6 +403,9 @@ ENV_DEV void eom_propulsion(AcCore& a, const Props& p, Frame& f, const double* _
   a.engflags = (double)((starved_next ? 1 : 0) | (augmentation ? 2 : 0));
 }
 
+#ifndef ACS_FRAME_SYNC
+#define ACS_FRAME_SYNC 0      // tuning builds: block barrier at the top of every frame of k_env_substeps (measured: no effect once the spills were gone)
+#endif
 constexpr int N_SNAP = FDM_N_CORE + F16_N_CARRIED + 4;     // the FDM state + FrameKeep
 // state of the aircraft after substep k, for k_env_missiles (a hit in substep k leaves the aircraft in exactly this state)
 ENV_DEV void snap_store(const EnvView& v, const int k, const int row, const AcCore& a, const Props& p, const FcsState& s, const FrameKeep& keep) {
@@ -427,6 +430,10 @@ ENV_DEV void snap_load(const EnvView& v, const int k, const int row, AcCore& a, 
 __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg,
                                                            const int32_t* __restrict__ actions) {
   __shared__ double sT[F16_NTAB];
+#ifdef ACS_PAD_NOPS      // tuning builds: shift the code that follows by 16 bytes per NOP (code-placement sensitivity)
+#pragma unroll
+  for (int i = 0; i < ACS_PAD_NOPS; i++) asm volatile("nanosleep.u32 0;");
+#endif
   stage_tables(sT);
   const Lane L = lane_setup(v, lg);
   const int K = cfg.substeps;
@@ -442,6 +449,7 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
   const double bloods = E.me.bloods;
   int status = E.status;
   for (int k = 0; k < K; k++) {
+    if (ACS_FRAME_SYNC) __syncthreads();
     const bool ran = L.valid && status == ST_ALIVE;
     if (ran) {
       if (bloods <= 0) status = ST_SHOTDOWN;     // AircraftSimulator.run's gate (simulatior.py:220-226): still integrates this frame

@@ -86,25 +86,38 @@ FDM_DEV double f16_constrain(double lo, double v, double hi) { return v < lo ? l
 // call site, the loop unrolls into independent shared-memory loads).  The model compiler stores the reciprocal
 // breakpoint spacings behind the keys (k[n + r] = 1 / (k[r] - k[r-1])), so the interpolation factor is a multiply.
 struct Bracket { int r; double f; bool above; };
-FDM_HELPER Bracket f16_bracket(const double* __restrict__ k, const int n, const double key) {
+// The whole table array once more in constant memory.  Every breakpoint the search compares against sits at an address
+// known at compile time (the table offset and the loop index are literals), so it is a constant-bank operand of the
+// comparison itself -- no load instruction, no shared-memory latency on the search (ncu: the counting loop was the
+// hottest source line of the frame, LDS + DSETP + add per breakpoint, ~58 breakpoints per frame).  What is indexed by the
+// search RESULT (per-lane addresses) stays in shared memory: the constant cache serialises divergent addresses.
+constexpr int F16_KC_MAX = 2048;
+__constant__ double g_f16_kc[F16_KC_MAX];
+FDM_HELPER Bracket f16_bracket(const double* __restrict__ T, const int off, const int n, const double key) {
+  const double* __restrict__ k = T + off;
   Bracket b;
   int r = 1;
 #pragma unroll
+#ifdef ACS_BRACKET_SMEM      // tuning builds: the search reads shared memory as it did before
   for (int i = 1; i < n - 1; i++) r += (k[i] < key) ? 1 : 0;
+#else
+  for (int i = 1; i < n - 1; i++) r += (g_f16_kc[off + i] < key) ? 1 : 0;
+#endif
   double f = (key - k[r - 1]) * k[n + r];
-  b.r = r; b.f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f); b.above = key >= k[n - 1];
+  b.r = r; b.f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f); b.above = key >= g_f16_kc[off + n - 1];
   return b;
 }
 // Uniformly spaced breakpoints (the alpha, beta and elevator grids): the row comes from one multiply, then one exact
 // fix-up step against the stored breakpoints reproduces the search rule bit for bit (the candidate is off by <= 1).
-FDM_DEV Bracket f16_bracket_u(const double* __restrict__ k, const int n, const double key, const double k0, const double inv_step) {
+FDM_DEV Bracket f16_bracket_u(const double* __restrict__ T, const int off, const int n, const double key, const double k0, const double inv_step) {
+  const double* __restrict__ k = T + off;
   Bracket b;
   const double t0 = (key - k0) * inv_step, t = t0 < 0.0 ? 0.0 : (t0 > (double)(n - 2) ? (double)(n - 2) : t0);
   int r = 1 + (int)t;
   if (r > 1 && k[r - 1] >= key) r--;
   else if (r < n - 1 && k[r] < key) r++;
   const double f = (key - k[r - 1]) * k[n + r];
-  b.r = r; b.f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f); b.above = key >= k[n - 1];
+  b.r = r; b.f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f); b.above = key >= g_f16_kc[off + n - 1];
   return b;
 }
 // 1-D: clamp, no extrapolation.  Below the first key r = 1 and f = 0, which already yields v[0] exactly.
@@ -182,6 +195,7 @@ FDM_HELPER double f16_kinemat2(const double d0, const double d1, const double t1
 FDM_HELPER double f16_powpos(const double x, const double y) { return exp(y * log(x)); }
 
 #include "gen/f16_gen.cuh"
+static_assert(F16_NTAB <= F16_KC_MAX, "g_f16_kc holds the whole table array");
 
 // ------------------------------------------------------------------ ISA-1976 (J/models/atmosphere/FGStandardAtmosphere.cpp)
 // Layer constants are computed on the host exactly as the constructor does (:130-150, :405-462) and passed in.

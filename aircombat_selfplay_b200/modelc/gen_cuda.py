@@ -205,9 +205,9 @@ class CudaGen:
             step = (k[-1] - k[0]) / (len(k) - 1)
             uniform = len(k) >= 12 and all(abs(k[i] - (k[0] + i * step)) <= 0.25 * step for i in range(len(k)))
             if uniform:
-                call = f"f16_bracket_u(T + {off}, {len(k)}, {self.pexpr(var)}, {lit(k[0])}, {lit((len(k) - 1) / (k[-1] - k[0]))})"
+                call = f"f16_bracket_u(T, {off}, {len(k)}, {self.pexpr(var)}, {lit(k[0])}, {lit((len(k) - 1) / (k[-1] - k[0]))})"
             else:
-                call = f"f16_bracket(T + {off}, {len(k)}, {self.pexpr(var)})"
+                call = f"f16_bracket(T, {off}, {len(k)}, {self.pexpr(var)})"
             scope.setdefault("decls", []).append(f"  const Bracket {name} = {call};")
         return scope["brackets"][key]
 
