@@ -499,11 +499,13 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
   __shared__ int sShot[128];
   __shared__ PubChaff sCh[128];
   __shared__ int sChEnd[128];          // mode 1: first substep at which the lane's cloud is no longer effective (0: none)
+  __shared__ int sList[128];           // mode 1: this round's missiles of the block, compacted: (shooter tid << 8) | slot
+  __shared__ int sWarpN[4];
   const Lane L = lane_setup(v, lg);
   const int K = cfg.substeps;
   const double dt = cfg.sim_dt;
   const int mode = L.valid ? EI(v, EI_DEFERRED, L.env) : 0;
-  if (!__any_sync(0xffffffffu, mode != 0)) return;
+  if (!__syncthreads_or(mode != 0)) return;
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
   const int sc0 = L.valid ? EI(v, EI_SUBSTEP_COUNT, L.env) - K : 0;          // k_env_substeps advanced the counter
 
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
       }
     }
   }
-  if (!__any_sync(0xffffffffu, mode == 1)) return;
+  if (!__syncthreads_or(mode == 1)) return;
 
   // ================================================================ mode 1: every missile on its own
   const bool on = mode == 1;
@@ -576,59 +578,87 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
     sCh[L.tid] = c;
     sChEnd[L.tid] = end;
   }
-  __syncwarp(L.gmask);
-  if (!on) return;
-  bool any_chaff = false;
-  for (int j = 0; j < v.A; j++) any_chaff = any_chaff || sChEnd[L.gbase + j] > 0;
+  // ---- the missiles, compacted over the block.  A lane owns the missiles its aircraft launched, but most lanes have none
+  // in the air and a few have two (ncu, 4v4: 12 of 32 lanes active when every lane walked its own slots).  Each round
+  // takes the next live slot of every lane, packs those (shooter, slot) pairs into a dense list and hands entry i to
+  // thread i: whole warps either work or skip, and a missile's K substeps run on whichever thread drew it (everything it
+  // touches -- its own state, the target's recorded trajectory, the env's chaff clouds -- is addressed by the pair).
+  // (Measured: 2.5 x fewer warp instructions on this path for 4v4; the kernel's TIME is set by the lockstep path above.)
   const int maxlen = (int)(5.0 / dt);
-  const int nl = AI(v, AI_N_LAUNCHED, L.row);
-  const int64_t when0 = ((int64_t)EI(v, EI_EPISODE, L.env) << 20) + sc0;
-  for (int slot = 0; slot < nl; slot++) {
-    const int mid = L.row * v.S + slot;
-    if (MI(v, MI_DETACHED, mid) || missile_inert(v, mid, L.env)) continue;
-    Missile m;
-    missile_load(v, mid, m);
-    const MissileParams pr = missile_params(m.kind);
-    const int trow = L.env * v.A + m.target;
-    const bool target_alive = AI(v, AI_STATUS, trow) == ST_ALIVE;     // constant over the step in this mode
-    const int keyn = MI(v, MI_KEYN, mid);
-    Feat tg;
-    traj_load(v, 0, trow, tg);
-    for (int k = 0; k < K; k++) {
-      Feat nxt = tg;
-      if (k + 1 < K) traj_load(v, k + 1, trow, nxt);                  // in flight while this substep computes
-      m.t += dt;
-      double ny, nz, dist;
-      missile_guidance(m, pr, tg, ny, nz, dist);
-      m.consec = (dist > m.d_prev) ? m.consec + 1 : 0;
-      m.d_prev = dist;
-      const double speed = sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
-      if (dist < pr.Rc && target_alive && m.status != MS_MISS) {
-        atomicAdd(&EI(v, EI_FAULTS, L.env), 1);                       // cannot happen (missile_threatens)
-        m.status = MS_HIT;
-      } else if (m.t > pr.t_max || speed < pr.v_min || m.consec >= maxlen || !target_alive) {
-        const bool inert = m.status == MS_MISS && (m.t > pr.t_max || !target_alive || speed < pr.v_min);
-        m.status = MS_MISS;
-        if (inert) break;             // every later run() is the same no-op (missile_inert)
-      } else {
-        missile_state_trans(m, pr, org, ny, nz, dt);
-      }
-      if (any_chaff && m.status == MS_LAUNCHED) {
-        bool missed = false;
-        for (int j = 0; j < v.A; j++) {
-          if (k >= sChEnd[L.gbase + j]) continue;                     // no cloud, or done by this substep
-          const PubChaff& c = sCh[L.gbase + j];
-          const double dx = c.n - m.pn, dy = c.e - m.pe, dz = c.u - m.pu;
-          if (sqrt(dx * dx + dy * dy + dz * dz) <= 300.0) {
-            for (int q = 0; q < c.count; q++)
-              if (env_u01(cfg.seed, cfg.env_offset + L.env, RNG_CHAFF, when0 + k, L.lane * 64 + keyn, j * 64 + q) < 0.85) missed = true;
-          }
-        }
-        if (missed) m.status = MS_MISS;
-      }
-      tg = nxt;
+  const int nl = on ? AI(v, AI_N_LAUNCHED, L.row) : 0;
+  const int G = 1 << lg;
+  int cursor = 0;
+  for (;;) {
+    int slot = -1;
+    for (; cursor < nl; cursor++) {
+      const int mid = L.row * v.S + cursor;
+      if (MI(v, MI_DETACHED, mid) || missile_inert(v, mid, L.env)) continue;
+      slot = cursor++;
+      break;
     }
-    missile_store(v, mid, m);
+    const unsigned have = __ballot_sync(0xffffffffu, slot >= 0);
+    const int wid = threadIdx.x >> 5, wl = threadIdx.x & 31;
+    if (wl == 0) sWarpN[wid] = __popc(have);
+    __syncthreads();                                   // also orders sCh / sChEnd (first round) and the list reuse (later rounds)
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) { const int n = sWarpN[w]; if (w < wid) base += n; total += n; }
+    if (total == 0) break;                             // block-uniform
+    if (slot >= 0) sList[base + __popc(have & ((1u << wl) - 1u))] = (L.tid << 8) | slot;
+    __syncthreads();
+    if ((int)threadIdx.x < total) {
+      const int ent = sList[threadIdx.x];
+      const int stid = ent >> 8, mslot = ent & 255;
+      const int gid = blockIdx.x * blockDim.x + stid;
+      const int env = gid >> lg, lane = gid & (G - 1), row = env * v.A + lane, gbase = stid - lane;
+      const int mid = row * v.S + mslot;
+      bool any_chaff = false;
+      for (int j = 0; j < v.A; j++) any_chaff = any_chaff || sChEnd[gbase + j] > 0;
+      const int64_t when0 = ((int64_t)EI(v, EI_EPISODE, env) << 20) + (EI(v, EI_SUBSTEP_COUNT, env) - K);
+      Missile m;
+      missile_load(v, mid, m);
+      const MissileParams pr = missile_params(m.kind);
+      const int trow = env * v.A + m.target;
+      const bool target_alive = AI(v, AI_STATUS, trow) == ST_ALIVE;     // constant over the step in this mode
+      const int keyn = MI(v, MI_KEYN, mid);
+      Feat tg;
+      traj_load(v, 0, trow, tg);
+      for (int k = 0; k < K; k++) {
+        Feat nxt = tg;
+        if (k + 1 < K) traj_load(v, k + 1, trow, nxt);                  // in flight while this substep computes
+        m.t += dt;
+        double ny, nz, dist;
+        missile_guidance(m, pr, tg, ny, nz, dist);
+        m.consec = (dist > m.d_prev) ? m.consec + 1 : 0;
+        m.d_prev = dist;
+        const double speed = sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
+        if (dist < pr.Rc && target_alive && m.status != MS_MISS) {
+          atomicAdd(&EI(v, EI_FAULTS, env), 1);                         // cannot happen (missile_threatens)
+          m.status = MS_HIT;
+        } else if (m.t > pr.t_max || speed < pr.v_min || m.consec >= maxlen || !target_alive) {
+          const bool inert = m.status == MS_MISS && (m.t > pr.t_max || !target_alive || speed < pr.v_min);
+          m.status = MS_MISS;
+          if (inert) break;             // every later run() is the same no-op (missile_inert)
+        } else {
+          missile_state_trans(m, pr, org, ny, nz, dt);
+        }
+        if (any_chaff && m.status == MS_LAUNCHED) {
+          bool missed = false;
+          for (int j = 0; j < v.A; j++) {
+            if (k >= sChEnd[gbase + j]) continue;                       // no cloud, or done by this substep
+            const PubChaff& c = sCh[gbase + j];
+            const double dx = c.n - m.pn, dy = c.e - m.pe, dz = c.u - m.pu;
+            if (sqrt(dx * dx + dy * dy + dz * dz) <= 300.0) {
+              for (int q = 0; q < c.count; q++)
+                if (env_u01(cfg.seed, cfg.env_offset + env, RNG_CHAFF, when0 + k, lane * 64 + keyn, j * 64 + q) < 0.85) missed = true;
+            }
+          }
+          if (missed) m.status = MS_MISS;
+        }
+        tg = nxt;
+      }
+      missile_store(v, mid, m);
+    }
   }
 }
 
