@@ -60,14 +60,17 @@ class LowLevelController(nn.Module):
 
     @torch.no_grad()
     def forward(self, obs12: torch.Tensor, h: torch.Tensor):
-        """obs12 [N, 12] float32, h [N, 128] float32 -> (actions [N, 4] int32, h' [N, 128])."""
+        """obs12 [N, 12] float32, h [N, 128] float32 -> (actions [N, 4] int32, a transposed view of a [4, N] tensor; h' [N, 128])."""
         x = self.ln1(F.relu_(self.fc1(obs12)))
         x = self.ln2(F.relu_(self.fc2(x)))
         h = self.gru(x, h)
         wp, bp = self._padded_heads()
-        logits = torch.addmm(bp, self.norm(h), wp.t())               # same dot products as the four logits_net layers
+        # logits^T = Wp hn^T + bp: the same dot products as the four logits_net layers, laid out [4 * 41, N] so that the
+        # arg-max reduces over a strided dimension with N contiguous (coalesced; the [N, 4, 41] layout reduced 41 adjacent
+        # floats per thread group: 55 us of a 0.56 ms controller call at 32 768 rows)
+        logits_t = torch.addmm(bp.unsqueeze(1), wp, self.norm(h).t())
         # Categorical(logits).probs.argmax == logits.argmax (first maximum on ties, as torch.argmax)
-        return logits.view(-1, len(HEAD_DIMS), max(HEAD_DIMS)).argmax(dim=-1).to(torch.int32), h
+        return logits_t.view(len(HEAD_DIMS), max(HEAD_DIMS), -1).argmax(dim=1).to(torch.int32).t(), h
 
     def load_reference_state_dict(self, sd: dict):
         """Maps ``BaselineActor.state_dict()`` keys (reference envs/JSBSim/model/baseline_actor.py) onto this module."""

@@ -730,6 +730,15 @@ int acs_debug_split_profile(long long* out16) {
 }
 #endif
 
+#ifdef ACS_MISSILE_PROFILE
+int acs_debug_missile_profile(long long* out8, int reset) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(out8, g_missile_prof, sizeof(long long) * 8));
+  if (reset) { long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; CUDA_TRY(cudaMemcpyToSymbol(g_missile_prof, z, sizeof(z))); }
+  return 0;
+}
+#endif
+
 #ifdef ACS_FRAME_PROFILE
 int acs_debug_frame_profile(long long* out16) {
   CUDA_TRY(cudaMemcpyFromSymbol(out16, g_frame_prof, sizeof(long long) * 16));

@@ -493,6 +493,20 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
 //      the substep of the hit (v.snap) and re-derives the outputs from it, which is exactly where the reference leaves
 //      an aircraft that stops running (simulatior.py:210-229,520-533).
 // Same expressions as the in-kernel missile phase of the multi-warp frames.
+#ifdef ACS_MISSILE_PROFILE
+// tuning builds only: cycles of the lockstep section (warps that ran it) and of the rest of the kernel, per warp: sum, max, count
+__device__ unsigned long long g_missile_prof[8];
+#define MPROF_T0 const long long mp0_ = clock64(); long long mp1_ = mp0_; const bool mp_m2_ = __any_sync(0xffffffffu, mode == 2);
+#define MPROF_T1 mp1_ = clock64();
+#define MPROF_OUT if ((threadIdx.x & 31) == 0) { const long long e_ = clock64(); \
+    if (mp_m2_) { atomicAdd(&g_missile_prof[0], (unsigned long long)(mp1_ - mp0_)); atomicMax(&g_missile_prof[1], (unsigned long long)(mp1_ - mp0_)); atomicAdd(&g_missile_prof[2], 1ull); } \
+    atomicAdd(&g_missile_prof[3], (unsigned long long)(e_ - mp1_)); atomicMax(&g_missile_prof[4], (unsigned long long)(e_ - mp1_)); atomicAdd(&g_missile_prof[5], 1ull); \
+    atomicMax(&g_missile_prof[6], (unsigned long long)(e_ - mp0_)); }
+#else
+#define MPROF_T0
+#define MPROF_T1
+#define MPROF_OUT
+#endif
 __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg) {
   __shared__ PubAc sP[128];
   __shared__ int sWin[128];
@@ -510,6 +524,7 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
   const int sc0 = L.valid ? EI(v, EI_SUBSTEP_COUNT, L.env) - K : 0;          // k_env_substeps advanced the counter
 
   // ================================================================ mode 2: lockstep phases, hits, state restore
+  MPROF_T0
   if (__any_sync(0xffffffffu, mode == 2)) {
     const bool on = mode == 2;
     unsigned long long live = 0;
@@ -550,7 +565,8 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
       }
     }
   }
-  if (!__syncthreads_or(mode == 1)) return;
+  MPROF_T1
+  if (!__syncthreads_or(mode == 1)) { MPROF_OUT return; }
 
   // ================================================================ mode 1: every missile on its own
   const bool on = mode == 1;
@@ -660,6 +676,7 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
       missile_store(v, mid, m);
     }
   }
+  MPROF_OUT
 }
 
 // ---------------------------------------------------------------------------------------------- two-warp frame

@@ -254,7 +254,7 @@ class BatchedEnv:
             x.view(B, A, 12)[:, self.spec.n_ego:] = self.opponents.inputs()
         low, h = self.controller(x, self.rnn)
         self.rnn.copy_(h)                                  # in place: the buffer is captured by the CUDA graph
-        self._low[..., :4] = low.view(B, A, 4)
+        self._low.view(B * A, -1)[:, :4].copy_(low)        # one strided copy: `low` is a transposed view
         if self.spec.shoot_dim:
             self._low[..., 4:] = actions[..., 3:].to(torch.int32)
             if self.opponents is not None:  # scripted aircraft shoot everything when use_artillery, else nothing (scenario2_task.py:52-57)

@@ -82,29 +82,27 @@ for k, v in stall.most_common(10):
 open(out, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
 
-# ---- hottest CUDA source lines (stall samples aggregated per line), appended to the summary
+# ---- hottest CUDA source lines (per-line totals of the `cuda,sass` source page), appended to the summary
 try:
-    src = page("source", ["--print-source", "cuda"])
-    hot = []
-    cur = ""
-    for r in src:
-        if len(r) == 1 and r[0].strip():
-            cur = r[0].strip()
-        if not r or "Source" in r and "# Samples" in r:
-            hh = {c: i for i, c in enumerate(r)}
-            continue
-        try:
-            s = int(r[hh["# Samples"]] or 0)
-            n = int(r[hh["Instructions Executed"]] or 0)
-        except Exception:
-            continue
-        if s:
-            hot.append((s, n, cur.split("/")[-1][:40], r[hh["Source"]].strip()[:150]))
-    hot.sort(reverse=True)
-    tot_s = sum(x[0] for x in hot) or 1
-    extra = ["", "hottest CUDA source lines (share of samples, warp instructions, file, line)"]
-    for s, n, f, t in hot[:60]:
-        extra.append(f"{100 * s / tot_s:5.1f}%  {n:10d}  {f:24s} {t}")
+    cur, hot, i_s, i_n = "", [], None, None
+    for r in page("source", ["--print-source", "cuda,sass"]):
+        if len(r) == 2 and r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+        elif r and r[0] == "Line No":
+            i_s, i_n = r.index("# Samples"), r.index("Instructions Executed")
+        elif i_s is not None and r and r[0].strip().isdigit():
+            try:
+                hot.append((int(r[i_s] or 0), int(r[i_n] or 0), cur, int(r[0]), r[1].strip()[:130]))
+            except ValueError:
+                pass
+    tot_s, tot_n = sum(x[0] for x in hot) or 1, sum(x[1] for x in hot) or 1
+    by_file = collections.Counter()
+    for x in hot:
+        by_file[x[2]] += x[1]
+    extra = ["", "warp instructions by source file: " + ", ".join(f"{k} {100 * v / tot_n:.1f}%" for k, v in by_file.most_common(6)),
+             "", "hottest CUDA source lines (share of stall samples, share of warp instructions, file:line, text)"]
+    for sm, n, f, ln, t in sorted(hot, reverse=True)[:40]:
+        extra.append(f"{100 * sm / tot_s:5.2f}% {100 * n / tot_n:5.2f}%  {f}:{ln}  {t}")
     open(out, "a").write("\n".join(extra) + "\n")
 except Exception as e:  # the summary above is the product; this section is best effort
     open(out, "a").write(f"\n(hot source lines unavailable: {e})\n")
