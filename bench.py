@@ -4,8 +4,12 @@
 Contract: `python bench.py --gpus N --steps K --warmup W` (under torchrun for N > 1) prints ONE JSON line on rank 0.
   value         whole-job agent-steps/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
   e2e           the same metric through the reference-facing VecEnv API: HOST numpy actions in, host obs / rewards /
-                dones out, both copies inside the timed region
-  roofline      the dominant kernel (k_env_substeps_split or k_env_substeps, by batch size) against the measured HBM peak, plus the fp64-pipe view
+                dones out, both copies inside the timed region (default copy=True API; `views`: copy=False;
+                `device_rollout`: the zero-copy runner loop on CUDA tensors, no PCIe)
+  roofline      the dominant kernel (k_env_substeps / _split / _split3, by batch size) against the fp64 peak measured live
+                (primary: the kernel is fp64-pipe / issue bound), with the measured-HBM-peak view under `hbm`
+  workloads     short samples of the other BASELINE.json configs (65 536-env 1v1, 1v1 ShootMissile, 2v2 ShootMissile =
+                north-star config, 4v4) with their per-kernel times and roofline fractions
   cpu_baseline  the CPU oracle port of the same workload on the host cores (rank 0, N=1 only; bounded sample)
 `--impl reference` times the reference-shaped CPU path instead: the restated Python env layer over the restated C++
 FDM, one worker process per host core -- DESIGN.md section 3 explains why the real JSBSim cannot run here.
@@ -332,6 +336,31 @@ def measure(config, n_envs, steps, warmup, seed, world, rank, local, dev, flush,
         e2e["views"], _ = run_e2e(ve)
         e2e["views"]["api"] = "copy=False: the returned arrays are views of the pinned D2H buffer, valid until the next step"
         ve.copy = True
+
+    # ---- the zero-copy runner path (rollout.DeviceRollout: collect -> BatchedEnv.step -> insert on CUDA tensors, a torch replay
+    # buffer, nothing crosses PCIe; reference runner/share_jsbsim_runner.py:157-223).  The policy is a stub that hands out
+    # the same synthetic action rows (no network: the learner side is out of scope), so this is the env + buffer cost.
+    if e2e_views:
+        from aircombat_selfplay_b200.rollout import DeviceRollout
+        ro = DeviceRollout(core, T=32)
+        ro.warmup()
+        cursor = [0]
+        zeros1 = torch.zeros(n_envs * A, 1, device=dev)
+
+        def stub_policy(share, obs, ha, hc, masks):
+            a = acts_dev[cursor[0] % total].view(n_envs * A, -1)
+            cursor[0] += 1
+            return zeros1, a, zeros1, ha, hc
+        ro.run(stub_policy, warmup)
+        torch.cuda.synchronize(); _barrier(world)
+        t0 = time.perf_counter()
+        ro.run(stub_policy, steps)
+        torch.cuda.synchronize(); _barrier(world)
+        s_ = _max_over_ranks(time.perf_counter() - t0, world, dev)
+        e2e["device_rollout"] = {"value": world * n_envs * A * steps / s_, "unit": UNIT, "ms_per_step": s_ / steps * 1e3,
+                                 "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                 "api": "rollout.DeviceRollout.run: collect (stub policy) -> BatchedEnv.step -> DeviceRolloutBuffer.insert, "
+                                        "all on CUDA tensors; wall clock around the loop, L2 not flushed"}
 
     # ---- rooflines of the dominant kernel (k_env_substeps*): DESIGN.md section 5
     peak, peak_src = _peaks()
