@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(FDM_BLOCK, ACS_FDM_MIN_BLOCKS) k_env_substeps(
 #ifdef ACS_MISSILE_PROFILE
 // tuning builds only: cycles of the lockstep section (warps that ran it) and of the rest of the kernel, per warp: sum, max, count
 __device__ unsigned long long g_missile_prof[8];
-#define MPROF_T0 const long long mp0_ = clock64(); long long mp1_ = mp0_; const bool mp_m2_ = __any_sync(0xffffffffu, mode == 2);
+#define MPROF_T0 const long long mp0_ = clock64(); long long mp1_ = mp0_; const bool mp_m2_ = warp_m2;
 #define MPROF_T1 mp1_ = clock64();
 #define MPROF_OUT if ((threadIdx.x & 31) == 0) { const long long e_ = clock64(); \
     if (mp_m2_) { atomicAdd(&g_missile_prof[0], (unsigned long long)(mp1_ - mp0_)); atomicMax(&g_missile_prof[1], (unsigned long long)(mp1_ - mp0_)); atomicAdd(&g_missile_prof[2], 1ull); } \
@@ -507,14 +507,74 @@ __device__ unsigned long long g_missile_prof[8];
 #define MPROF_T1
 #define MPROF_OUT
 #endif
-__global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg) {
+// One independent missile (mode 1) for the K substeps of the step, state in registers: `stid` = block-local thread of the
+// shooter's lane, `mslot` = its slot.  Everything it touches is addressed by that pair.
+ENV_DEV void missile_run_independent(const EnvView& v, const AcsTaskConfig& cfg, const GeoOrigin& org, const int lg, const int stid,
+                                     const int mslot, const PubChaff* sCh, const int* sChEnd) {
+  const int K = cfg.substeps, G = 1 << lg;
+  const double dt = cfg.sim_dt;
+  const int maxlen = (int)(5.0 / dt);
+  const int gid = blockIdx.x * blockDim.x + stid;
+  const int env = gid >> lg, lane = gid & (G - 1), row = env * v.A + lane, gbase = stid - lane;
+  const int mid = row * v.S + mslot;
+  bool any_chaff = false;
+  for (int j = 0; j < v.A; j++) any_chaff = any_chaff || sChEnd[gbase + j] > 0;
+  const int64_t when0 = ((int64_t)EI(v, EI_EPISODE, env) << 20) + (EI(v, EI_SUBSTEP_COUNT, env) - K);   // k_env_substeps advanced the counter
+  Missile m;
+  missile_load(v, mid, m);
+  const MissileParams pr = missile_params(m.kind);
+  const int trow = env * v.A + m.target;
+  const bool target_alive = AI(v, AI_STATUS, trow) == ST_ALIVE;     // constant over the step in this mode
+  const int keyn = MI(v, MI_KEYN, mid);
+  Feat tg;
+  traj_load(v, 0, trow, tg);
+  for (int k = 0; k < K; k++) {
+    Feat nxt = tg;
+    if (k + 1 < K) traj_load(v, k + 1, trow, nxt);                  // in flight while this substep computes
+    m.t += dt;
+    double ny, nz, dist;
+    missile_guidance(m, pr, tg, ny, nz, dist);
+    m.consec = (dist > m.d_prev) ? m.consec + 1 : 0;
+    m.d_prev = dist;
+    const double speed = sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
+    if (dist < pr.Rc && target_alive && m.status != MS_MISS) {
+      atomicAdd(&EI(v, EI_FAULTS, env), 1);                         // cannot happen (missile_threatens)
+      m.status = MS_HIT;
+    } else if (m.t > pr.t_max || speed < pr.v_min || m.consec >= maxlen || !target_alive) {
+      const bool inert = m.status == MS_MISS && (m.t > pr.t_max || !target_alive || speed < pr.v_min);
+      m.status = MS_MISS;
+      if (inert) break;             // every later run() is the same no-op (missile_inert)
+    } else {
+      missile_state_trans(m, pr, org, ny, nz, dt);
+    }
+    if (any_chaff && m.status == MS_LAUNCHED) {
+      bool missed = false;
+      for (int j = 0; j < v.A; j++) {
+        if (k >= sChEnd[gbase + j]) continue;                       // no cloud, or done by this substep
+        const PubChaff& c = sCh[gbase + j];
+        const double dx = c.n - m.pn, dy = c.e - m.pe, dz = c.u - m.pu;
+        if (sqrt(dx * dx + dy * dy + dz * dz) <= 300.0) {
+          for (int q = 0; q < c.count; q++)
+            if (env_u01(cfg.seed, cfg.env_offset + env, RNG_CHAFF, when0 + k, lane * 64 + keyn, j * 64 + q) < 0.85) missed = true;
+        }
+      }
+      if (missed) m.status = MS_MISS;
+    }
+    tg = nxt;
+  }
+  missile_store(v, mid, m);
+}
+
+constexpr int MISSILE_LIST_CAP = 512;      // independent missiles of one block handed out through the list; a lane whose slots
+                                           // do not fit (more than 4 live missiles per lane on average) walks the rest itself
+__global__ void __launch_bounds__(128, 2) k_env_missiles(const EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg) {
   __shared__ PubAc sP[128];
   __shared__ int sWin[128];
   __shared__ int sShot[128];
   __shared__ PubChaff sCh[128];
   __shared__ int sChEnd[128];          // mode 1: first substep at which the lane's cloud is no longer effective (0: none)
-  __shared__ int sList[128];           // mode 1: this round's missiles of the block, compacted: (shooter tid << 8) | slot
-  __shared__ int sWarpN[4];
+  __shared__ int sList[MISSILE_LIST_CAP];   // mode 1: the block's independent missiles, compacted: (shooter tid << 8) | slot
+  __shared__ int sWarpN[4], sWarpM2[4];
   const Lane L = lane_setup(v, lg);
   const int K = cfg.substeps;
   const double dt = cfg.sim_dt;
@@ -522,9 +582,71 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
   if (!__syncthreads_or(mode != 0)) return;
   const GeoOrigin org = geo_origin(cfg.center[0], cfg.center[1], cfg.center[2]);
   const int sc0 = L.valid ? EI(v, EI_SUBSTEP_COUNT, L.env) - K : 0;          // k_env_substeps advanced the counter
+  const int wid = threadIdx.x >> 5, wl = threadIdx.x & 31;
+  const bool warp_m2 = __any_sync(0xffffffffu, mode == 2);
+  MPROF_T0
+
+  // ================================================================ mode 1, part 1: chaff of the step, the block's missile list
+  // ---- chaff run() of the whole step for this lane's cloud, and its publication
+  const bool on1 = mode == 1;
+  {
+    PubChaff c;
+    c.state = CH_NONE; c.count = 0; c.n = c.e = c.u = 0.0;
+    int end = 0;
+    if (on1) {
+      c.state = AI(v, AI_CH_STATE, L.row);
+      if (c.state != CH_NONE) {
+        double t = AD(v, AD_CH_T, L.row);
+        int st = c.state;
+        end = st == CH_ACTIVE ? K : 0;
+        for (int k = 0; k < K; k++) {
+          t += dt;
+          if (t > 20.0) { if (st == CH_ACTIVE) end = k; st = CH_DONE; }      // run() precedes the test of the same substep
+        }
+        AD(v, AD_CH_T, L.row) = t;
+        AI(v, AI_CH_STATE, L.row) = st;
+        c.count = AI(v, AI_CH_COUNT, L.row);
+        c.n = AD(v, AD_CH_N, L.row); c.e = AD(v, AD_CH_E, L.row); c.u = AD(v, AD_CH_U, L.row);
+      }
+    }
+    sCh[L.tid] = c;
+    sChEnd[L.tid] = end;
+  }
+  // ---- the independent missiles, compacted over the block.  A lane owns the missiles its aircraft launched, but most lanes
+  // have none in the air and a few have two (ncu, 4v4: 12 of 32 lanes active when every lane walked its own slots).  The
+  // live (shooter, slot) pairs of the whole block go into one dense list; a missile's K substeps run on whichever thread
+  // draws its entry.  The list is consumed by the warps that have NO threatened env: the lockstep section below is the
+  // longest chain of the kernel (~120-200 k cycles per warp against ~100 k for an independent missile), and with the two
+  // running side by side a block costs the longer of them instead of their sum.
+  const int nl = on1 ? AI(v, AI_N_LAUNCHED, L.row) : 0;
+  unsigned long long mine = 0;                       // live slots of this lane (slots >= 64 cannot exist: acs_env_create caps S)
+  for (int sl = 0; sl < nl; sl++) {
+    const int mid = L.row * v.S + sl;
+    if (MI(v, MI_DETACHED, mid) || missile_inert(v, mid, L.env)) continue;
+    mine |= 1ull << sl;
+  }
+  const int cnt = __popcll(mine);
+  int incl = cnt;                                    // inclusive warp scan
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (wl >= o) incl += y; }
+  if (wl == 31) { sWarpN[wid] = incl; sWarpM2[wid] = warp_m2 ? 1 : 0; }
+  __syncthreads();
+  int base = incl - cnt, total = 0, nfree = 0, frank = 0;
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    const int n = sWarpN[w];
+    if (w < wid) { base += n; frank += sWarpM2[w] ? 0 : 1; }
+    total += n; nfree += sWarpM2[w] ? 0 : 1;
+  }
+  unsigned long long rest = mine;                    // what does not fit into the list stays with its lane
+  for (int i = base; rest && i < MISSILE_LIST_CAP; i++) {
+    sList[i] = (L.tid << 8) | (__ffsll((long long)rest) - 1);
+    rest &= rest - 1;
+  }
+  __syncthreads();                                   // the list, sCh and sChEnd are complete: the last block-wide barrier
+  const int listed = min(total, MISSILE_LIST_CAP);
 
   // ================================================================ mode 2: lockstep phases, hits, state restore
-  MPROF_T0
   if (__any_sync(0xffffffffu, mode == 2)) {
     const bool on = mode == 2;
     unsigned long long live = 0;
@@ -566,116 +688,16 @@ __global__ void __launch_bounds__(128) k_env_missiles(const EnvView v, const __g
     }
   }
   MPROF_T1
-  if (!__syncthreads_or(mode == 1)) { MPROF_OUT return; }
 
-  // ================================================================ mode 1: every missile on its own
-  const bool on = mode == 1;
-  // ---- chaff run() of the whole step for this lane's cloud, and its publication
-  {
-    PubChaff c;
-    c.state = CH_NONE; c.count = 0; c.n = c.e = c.u = 0.0;
-    int end = 0;
-    if (on) {
-      c.state = AI(v, AI_CH_STATE, L.row);
-      if (c.state != CH_NONE) {
-        double t = AD(v, AD_CH_T, L.row);
-        int st = c.state;
-        end = st == CH_ACTIVE ? K : 0;
-        for (int k = 0; k < K; k++) {
-          t += dt;
-          if (t > 20.0) { if (st == CH_ACTIVE) end = k; st = CH_DONE; }      // run() precedes the test of the same substep
-        }
-        AD(v, AD_CH_T, L.row) = t;
-        AI(v, AI_CH_STATE, L.row) = st;
-        c.count = AI(v, AI_CH_COUNT, L.row);
-        c.n = AD(v, AD_CH_N, L.row); c.e = AD(v, AD_CH_E, L.row); c.u = AD(v, AD_CH_U, L.row);
-      }
-    }
-    sCh[L.tid] = c;
-    sChEnd[L.tid] = end;
-  }
-  // ---- the missiles, compacted over the block.  A lane owns the missiles its aircraft launched, but most lanes have none
-  // in the air and a few have two (ncu, 4v4: 12 of 32 lanes active when every lane walked its own slots).  Each round
-  // takes the next live slot of every lane, packs those (shooter, slot) pairs into a dense list and hands entry i to
-  // thread i: whole warps either work or skip, and a missile's K substeps run on whichever thread drew it (everything it
-  // touches -- its own state, the target's recorded trajectory, the env's chaff clouds -- is addressed by the pair).
-  // (Measured: 2.5 x fewer warp instructions on this path for 4v4; the kernel's TIME is set by the lockstep path above.)
-  const int maxlen = (int)(5.0 / dt);
-  const int nl = on ? AI(v, AI_N_LAUNCHED, L.row) : 0;
-  const int G = 1 << lg;
-  int cursor = 0;
-  for (;;) {
-    int slot = -1;
-    for (; cursor < nl; cursor++) {
-      const int mid = L.row * v.S + cursor;
-      if (MI(v, MI_DETACHED, mid) || missile_inert(v, mid, L.env)) continue;
-      slot = cursor++;
-      break;
-    }
-    const unsigned have = __ballot_sync(0xffffffffu, slot >= 0);
-    const int wid = threadIdx.x >> 5, wl = threadIdx.x & 31;
-    if (wl == 0) sWarpN[wid] = __popc(have);
-    __syncthreads();                                   // also orders sCh / sChEnd (first round) and the list reuse (later rounds)
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < 4; w++) { const int n = sWarpN[w]; if (w < wid) base += n; total += n; }
-    if (total == 0) break;                             // block-uniform
-    if (slot >= 0) sList[base + __popc(have & ((1u << wl) - 1u))] = (L.tid << 8) | slot;
-    __syncthreads();
-    if ((int)threadIdx.x < total) {
-      const int ent = sList[threadIdx.x];
-      const int stid = ent >> 8, mslot = ent & 255;
-      const int gid = blockIdx.x * blockDim.x + stid;
-      const int env = gid >> lg, lane = gid & (G - 1), row = env * v.A + lane, gbase = stid - lane;
-      const int mid = row * v.S + mslot;
-      bool any_chaff = false;
-      for (int j = 0; j < v.A; j++) any_chaff = any_chaff || sChEnd[gbase + j] > 0;
-      const int64_t when0 = ((int64_t)EI(v, EI_EPISODE, env) << 20) + (EI(v, EI_SUBSTEP_COUNT, env) - K);
-      Missile m;
-      missile_load(v, mid, m);
-      const MissileParams pr = missile_params(m.kind);
-      const int trow = env * v.A + m.target;
-      const bool target_alive = AI(v, AI_STATUS, trow) == ST_ALIVE;     // constant over the step in this mode
-      const int keyn = MI(v, MI_KEYN, mid);
-      Feat tg;
-      traj_load(v, 0, trow, tg);
-      for (int k = 0; k < K; k++) {
-        Feat nxt = tg;
-        if (k + 1 < K) traj_load(v, k + 1, trow, nxt);                  // in flight while this substep computes
-        m.t += dt;
-        double ny, nz, dist;
-        missile_guidance(m, pr, tg, ny, nz, dist);
-        m.consec = (dist > m.d_prev) ? m.consec + 1 : 0;
-        m.d_prev = dist;
-        const double speed = sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
-        if (dist < pr.Rc && target_alive && m.status != MS_MISS) {
-          atomicAdd(&EI(v, EI_FAULTS, env), 1);                         // cannot happen (missile_threatens)
-          m.status = MS_HIT;
-        } else if (m.t > pr.t_max || speed < pr.v_min || m.consec >= maxlen || !target_alive) {
-          const bool inert = m.status == MS_MISS && (m.t > pr.t_max || !target_alive || speed < pr.v_min);
-          m.status = MS_MISS;
-          if (inert) break;             // every later run() is the same no-op (missile_inert)
-        } else {
-          missile_state_trans(m, pr, org, ny, nz, dt);
-        }
-        if (any_chaff && m.status == MS_LAUNCHED) {
-          bool missed = false;
-          for (int j = 0; j < v.A; j++) {
-            if (k >= sChEnd[gbase + j]) continue;                       // no cloud, or done by this substep
-            const PubChaff& c = sCh[gbase + j];
-            const double dx = c.n - m.pn, dy = c.e - m.pe, dz = c.u - m.pu;
-            if (sqrt(dx * dx + dy * dy + dz * dz) <= 300.0) {
-              for (int q = 0; q < c.count; q++)
-                if (env_u01(cfg.seed, cfg.env_offset + env, RNG_CHAFF, when0 + k, lane * 64 + keyn, j * 64 + q) < 0.85) missed = true;
-            }
-          }
-          if (missed) m.status = MS_MISS;
-        }
-        tg = nxt;
-      }
-      missile_store(v, mid, m);
+  // ================================================================ mode 1, part 2: the list, then what did not fit
+  if (!warp_m2 || nfree == 0) {
+    const int rank = nfree ? frank : wid, nw = nfree ? nfree : 4;
+    for (int i = rank * 32 + wl; i < listed; i += nw * 32) {
+      const int ent = sList[i];
+      missile_run_independent(v, cfg, org, lg, ent >> 8, ent & 255, sCh, sChEnd);
     }
   }
+  for (; rest; rest &= rest - 1) missile_run_independent(v, cfg, org, lg, L.tid, __ffsll((long long)rest) - 1, sCh, sChEnd);
   MPROF_OUT
 }
 
@@ -1830,7 +1852,7 @@ ENV_DEV void reset_copy_warp(const EnvView& v, const AcsTaskConfig& cfg, const L
 // heading task (UnreachHeading re-targets what the observation shows); get_obs precedes terminations and rewards in the
 // reference (E/envs/env_base.py:155-171), and here it reads its own copy of the pre-termination aircraft state.
 template <class S>
-__global__ void __launch_bounds__(256) k_env_post(const __grid_constant__ EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg, double* __restrict__ obs,
+__global__ void __launch_bounds__(256, 2) k_env_post(const __grid_constant__ EnvView v, const __grid_constant__ AcsTaskConfig cfg, const int lg, double* __restrict__ obs,
                                                   double* __restrict__ share_obs, double* __restrict__ rewards,
                                                   uint8_t* __restrict__ dones, int32_t* __restrict__ info, uint8_t* __restrict__ env_done,
                                                   const int fuse_reset, const __grid_constant__ ResetTpl tpl, const int obs_split) {
