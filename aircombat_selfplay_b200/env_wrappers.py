@@ -87,40 +87,97 @@ class BatchedVecEnv(VecEnv):
             VecEnv.__init__(self, num_envs, self.core.observation_space, self.core.action_space)
         self.num_agents = self.core.num_agents
         self.copy = copy
-        b = self.core.batch
         with torch.cuda.device(self.core.device):
-            self._host = torch.empty(b.out_buf.shape, dtype=torch.uint8).pin_memory()
-            self._views = b.host_views(self._host)
             self._act_host = torch.empty((num_envs, self.num_agents, self.core.act_dim), dtype=torch.int32).pin_memory()
             self._act_np = self._act_host.numpy()
             self._act_dev = self.core._act_in          # the step graph's static input buffer: H2D lands directly in it
-        src = {"info": self._views["info"], "heading": self.core.spec.obs_kind == ts.OBS_HEADING}
-        self._infos = np.empty(num_envs, dtype=object)
-        for i in range(num_envs):
-            self._infos[i] = LazyInfo(src, i)
+        # Output slots.  A step lands its packed outputs in a pinned host buffer with ONE D2H copy and returns numpy views of
+        # it.  ``copy=True`` (the default) promises what the reference gives: arrays that stay valid for as long as the caller
+        # holds them.  Instead of copying every array out of a single buffer (three host copies per step, a quarter of the
+        # end-to-end step at 4096 envs), the wrapper keeps a small pool of pinned buffers and never writes into one whose
+        # arrays are still referenced from outside (CPython reference counts of the arrays it handed out, and of the views
+        # the caller derived from them -- a derived view keeps its parent alive).  A runner that drops last step's arrays when
+        # it takes the next ones cycles through two slots.  Past ``MAX_SLOTS`` live buffers the arrays are copied out instead.
+        # ``copy=False``: always slot 0, valid until the next step.
+        self._slots = []
+        self._cur, self._copy_out = self._new_slot(), False
+        self._new_slot()                               # a caller that holds last step's arrays across a step alternates between two
         self._pending = False
         # the whole host-facing step -- pinned H2D of the actions, (controller +) env kernels, D2H of the packed outputs --
-        # replays as ONE CUDA graph: one launch per step instead of a copy, four kernels and a copy
+        # replays as ONE CUDA graph (one per output slot): one launch per step instead of a copy, four kernels and a copy
         self.use_cuda_graph = True
-        self._g, self._g_epoch = None, -1
         self.h2d_bytes_per_step = self._act_host.numel() * 4
-        self.d2h_bytes_per_step = self._host.numel()
+        self.d2h_bytes_per_step = self._cur["host"].numel()
+
+    MAX_SLOTS = 8
+
+    # ------------------------------------------------------------------ output slots
+    def _build_slot(self):
+        b, N, A = self.core.batch, self.num_envs, self.num_agents
+        with torch.cuda.device(self.core.device):
+            host = torch.empty(b.out_buf.shape, dtype=torch.uint8).pin_memory()
+        views = b.host_views(host)
+        src = {"info": views["info"], "heading": self.core.spec.obs_kind == ts.OBS_HEADING}
+        infos = np.empty(N, dtype=object)
+        for i in range(N):
+            infos[i] = LazyInfo(src, i)
+        obs = views["obs"]
+        out = {"obs": obs, "rewards": views["rewards"].reshape(N, A, 1),
+               "dones": views["dones"].view(np.bool_).reshape(N, A, 1),      # the kernel writes 0 / 1: a view, not a conversion
+               "infos": infos}
+        if self.share:
+            # share_obs [N, A, A*D]: every agent's row is the concatenation of all agents' observations (reference
+            # envs/JSBSim/envs/env_base.py:183-189), a read-only stride-0 view of ``obs`` -- never copied over PCIe or
+            # materialised; the runner's buffer insert makes the one copy it needs
+            D = obs.shape[-1]
+            out["share"] = np.broadcast_to(obs.reshape(N, 1, A * D), (N, A, A * D))
+        # every array a caller can end up holding, directly or as the parent of a view it derived
+        return {"host": host, "views": views, "out": out, "graph": None, "epoch": -1, "watched": list(views.values()) + list(out.values())}
+
+    @staticmethod
+    def _refcounts(slot):
+        import sys
+        return [sys.getrefcount(x) for x in slot["watched"]]
+
+    def _new_slot(self):
+        slot = self._build_slot()                      # (its locals are gone: only the slot references the arrays now)
+        slot["baseline"] = self._refcounts(slot)
+        self._slots.append(slot)
+        return slot
+
+    @classmethod
+    def _slot_free(cls, slot):
+        return cls._refcounts(slot) == slot["baseline"]
+
+    def _pick_slot(self):
+        """The buffer this step writes: slot 0 for ``copy=False``; otherwise one whose arrays nobody outside holds."""
+        if not self.copy:
+            return self._slots[0], False
+        for slot in self._slots:
+            if self._slot_free(slot):
+                return slot, False
+        if len(self._slots) < self.MAX_SLOTS:
+            return self._new_slot(), False
+        if getattr(self, "_scratch", None) is None:       # every slot is held by the caller: land in a buffer that is never
+            self._scratch = self._build_slot()            # handed out, and copy the arrays out of it
+        return self._scratch, True
+
+    @property
+    def _views(self):
+        return self._cur["views"]
+
+    @property
+    def _host(self):
+        return self._cur["host"]
+
+    @property
+    def _infos(self):
+        return self._cur["out"]["infos"]
 
     # ------------------------------------------------------------------ helpers
     def _fetch(self):
-        self._host.copy_(self.core.batch.out_buf, non_blocking=True)
+        self._cur["host"].copy_(self.core.batch.out_buf, non_blocking=True)
         torch.cuda.current_stream(self.core.device).synchronize()
-
-    def _arr(self, name):
-        a = self._views[name]
-        return a.copy() if self.copy else a
-
-    def _share(self, obs):
-        """share_obs [N, A, A*D]: every agent's row is the concatenation of all agents' observations (reference
-        envs/JSBSim/envs/env_base.py:183-189), returned as a read-only stride-0 view of ``obs`` -- it is never copied
-        over PCIe or materialised; the runner's buffer insert makes the one copy it needs."""
-        N, A, D = obs.shape
-        return np.broadcast_to(obs.reshape(N, 1, A * D), (N, A, A * D))
 
     def _put_actions(self, actions, h2d=True):
         a = self._act_np
@@ -135,34 +192,46 @@ class BatchedVecEnv(VecEnv):
         if h2d:
             self._act_dev.copy_(self._act_host, non_blocking=True)
 
+    def _outputs(self, keys):
+        o = self._cur["out"]
+        if self._copy_out:      # pool exhausted: the reference's semantics by copying (infos stay views of slot 0)
+            c = {k: (o[k].copy() if k in ("obs", "rewards", "dones") else o[k]) for k in keys}
+            if "share" in keys:
+                N, A, D = c["obs"].shape
+                c["share"] = np.broadcast_to(c["obs"].reshape(N, 1, A * D), (N, A, A * D))
+            return tuple(c[k] for k in keys)
+        return tuple(o[k] for k in keys)
+
     # ------------------------------------------------------------------ VecEnv
     def reset(self):
+        self._cur, self._copy_out = self._pick_slot()
         with torch.cuda.device(self.core.device):
             self.core.reset()
             self._fetch()
-        obs = self._arr("obs")
-        return (obs, self._share(obs)) if self.share else obs
+        return self._outputs(("obs", "share")) if self.share else self._outputs(("obs",))[0]
 
-    def _capture(self):
+    def _capture(self, slot):
         core = self.core
         core._warm_for_capture()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._act_dev.copy_(self._act_host, non_blocking=True)
             core._step_body(self._act_dev)
-            self._host.copy_(core.batch.out_buf, non_blocking=True)
-        self._g, self._g_epoch = g, core._epoch
+            slot["host"].copy_(core.batch.out_buf, non_blocking=True)
+        slot["graph"], slot["epoch"] = g, core._epoch
 
     def step_async(self, actions):
         core = self.core
+        self._cur, self._copy_out = self._pick_slot()
+        slot = self._cur
         with torch.cuda.device(core.device):
             if self.use_cuda_graph and not core._timing:
                 if not core._was_reset:
                     raise AcsError("step() called before reset()")
                 self._put_actions(actions, h2d=False)
-                if self._g is None or self._g_epoch != core._epoch:
-                    self._capture()
-                self._g.replay()
+                if slot["graph"] is None or slot["epoch"] != core._epoch:
+                    self._capture(slot)
+                slot["graph"].replay()
                 self._graphed = True
             else:
                 self._put_actions(actions)
@@ -178,15 +247,7 @@ class BatchedVecEnv(VecEnv):
             else:
                 self._fetch()
         self._pending = False
-        N, A = self.num_envs, self.num_agents
-        obs = self._arr("obs")
-        rewards = self._arr("rewards").reshape(N, A, 1)
-        dones = self._views["dones"].view(np.bool_).reshape(N, A, 1)     # the kernel writes 0 / 1: a view, not a conversion
-        if self.copy:
-            dones = dones.copy()
-        if self.share:
-            return obs, self._share(obs), rewards, dones, self._infos
-        return obs, rewards, dones, self._infos
+        return self._outputs(("obs", "share", "rewards", "dones", "infos") if self.share else ("obs", "rewards", "dones", "infos"))
 
     def render(self, mode, filepath):
         """reference DummyVecEnv.render (envs/env_wrappers.py:170-172): the TacView text log of env 0."""

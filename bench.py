@@ -316,25 +316,25 @@ def measure(config, n_envs, steps, warmup, seed, world, rank, local, dev, flush,
 
     # ---- end to end through the VecEnv contract (host numpy in / out, the default API: fresh arrays every step)
     def run_e2e(v):
-        v.reset()
+        out = v.reset()
         for t in range(warmup):
-            v.step(acts_host[t])
+            out = v.step(acts_host[t])       # held across the next call, as a runner does: the output-slot pool reaches its steady state
         torch.cuda.synchronize(); _barrier(world)
         done = 0
         t0 = time.perf_counter()
         for k in range(steps):
             out = v.step(acts_host[warmup + k])
-            done += int(out[-2].all(axis=1).sum())
+            done += int(np.count_nonzero(out[-2]))        # finished AGENT episodes (a reduction over [N, A, 1] per axis costs 70 us of host time)
         _barrier(world)
         s_ = _max_over_ranks(time.perf_counter() - t0, world, dev)
         return {"value": world * n_envs * A * steps / s_, "unit": UNIT, "h2d_bytes_per_step": v.h2d_bytes_per_step,
                 "d2h_bytes_per_step": v.d2h_bytes_per_step, "ms_per_step": s_ / steps * 1e3}, done
     e2e, done_envs = run_e2e(ve)
-    e2e["api"] = "VecEnv.step(numpy) with the default copy=True: obs / rewards / dones are fresh host arrays every step"
+    e2e["api"] = "VecEnv.step(numpy) with the default copy=True: obs / rewards / dones stay valid for as long as the caller holds them (views of a pool of pinned output slots; a slot is rewritten only when nothing references its arrays)"
     if e2e_views:
         ve.copy = False
         e2e["views"], _ = run_e2e(ve)
-        e2e["views"]["api"] = "copy=False: the returned arrays are views of the pinned D2H buffer, valid until the next step"
+        e2e["views"]["api"] = "copy=False: one pinned D2H buffer, the returned views are valid until the next step"
         ve.copy = True
 
     # ---- the zero-copy runner path (rollout.DeviceRollout: collect -> BatchedEnv.step -> insert on CUDA tensors, a torch replay
@@ -385,7 +385,7 @@ def measure(config, n_envs, steps, warmup, seed, world, rank, local, dev, flush,
                     "missile_live_fraction": live_frac,
                     "note": "secondary view: fusing the K substeps leaves the kernel fp64-pipe / issue bound, not HBM bound"}}
     res = {"value": value, "ms_per_step": ms / steps, "e2e": e2e, "roofline": roof, "clocks": clocks, "A": A, "hier": bool(core.hier),
-           "gpu_launches": batch.get_option("launches_per_step") * steps, "episodes_finished_in_e2e": done_envs,
+           "gpu_launches": batch.get_option("launches_per_step") * steps, "agent_episodes_finished_in_e2e": done_envs,
            "missile_live_fraction": live_frac}
     ve.close()
     return res
@@ -414,7 +414,7 @@ def run_b200(args):
             "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(desc, config, n_envs, m["A"], m["hier"]),
             "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"], "roofline": m["roofline"],
-            "episodes_finished_in_e2e": m["episodes_finished_in_e2e"],
+            "agent_episodes_finished_in_e2e": m["agent_episodes_finished_in_e2e"],
             "parity": "FDM parity is against the restated CPU oracle (unpinned: no runnable JSBSim here); the env layer is pinned "
                       "by golden trajectories of the reference's own Python (DESIGN.md section 3)"}
     # ---- the other BASELINE.json configurations, short samples of the same measurement (headline stays configs[1])

@@ -188,6 +188,55 @@ def test_vecenv_matches_device_api_and_auto_resets():
     ve.close(); ref.close()
 
 
+def test_step_outputs_stay_valid_while_held_without_host_copies():
+    """copy=True (default): the arrays a step returns are views of a pinned output slot that is never rewritten while the
+    caller (or a view it derived) holds them -- the reference's "fresh arrays" contract without copying them out; a slot
+    whose arrays were dropped is reused; with every slot held the arrays are copied out instead; copy=False keeps one
+    buffer that the next step overwrites."""
+    n = 8
+    ve = ShareBatchedVecEnv("2v2/NoWeapon/Selfplay", n, seed=2)
+    ref = BatchedEnv("2v2/NoWeapon/Selfplay", n, seed=2)
+    rng = np.random.default_rng(0)
+    acts = [rng.integers(0, 30, (n, ve.num_agents, 4)) for _ in range(14)]
+    truth = []                                              # what each step returned, from the device API
+    ref.reset()
+    for a in acts:
+        o, _, r, d, _ = ref.step(torch.tensor(a, dtype=torch.int32, device="cuda"))
+        truth.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().astype(bool)))
+    ve.reset()
+    held = []
+    for t, a in enumerate(acts[:6]):                        # hold everything: each step must land in its own buffer
+        held.append(ve.step(a))
+    assert len(ve._slots) >= 6
+    for t, (obs, share, rew, done, infos) in enumerate(held):
+        assert np.array_equal(obs, truth[t][0]) and np.array_equal(rew[..., 0], truth[t][1]) and np.array_equal(done[..., 0], truth[t][2])
+        assert np.array_equal(share[:, 1], obs.reshape(n, -1)) and infos[0]["current_step"] == t + 1
+        assert not obs.flags.owndata                        # a view of the pinned slot, not a host copy
+    row = held[2][0][3]                                     # a derived view alone keeps its slot alive
+    keep_t2 = truth[2][0][3].copy()
+    held = None
+    n_slots = len(ve._slots)
+    for t in range(6, 10):                                  # outputs dropped every step: the pool does not grow
+        out = ve.step(acts[t])
+        assert np.array_equal(out[0], truth[t][0])
+        out = None
+    assert len(ve._slots) == n_slots and np.array_equal(row, keep_t2)
+    ve.MAX_SLOTS = len(ve._slots)                           # exhaust the pool: copies, still correct and independent
+    held = [ve.step(acts[t]) for t in range(10, 14)] + [row]
+    extra = [sl["out"]["obs"] for sl in ve._slots]          # every slot referenced from outside
+    o1 = ve.step(acts[0])[0]
+    assert o1.flags.owndata and len(ve._slots) == ve.MAX_SLOTS
+    for t in range(10, 14):
+        assert np.array_equal(held[t - 10][0], truth[t][0])
+    del extra, held, o1
+    ve.copy = False                                         # one buffer, overwritten by the next step
+    a0 = ve.step(acts[1])[0]
+    before = a0.copy()
+    a1 = ve.step(acts[2])[0]
+    assert a1 is a0 and not np.array_equal(before, a1)
+    ve.close(); ref.close()
+
+
 @pytest.mark.parametrize("config", ["1v1/NoWeapon/Selfplay", "scenario2/scenario2"])
 def test_whole_step_graph_equals_eager_launches(config, monkeypatch):
     """VecEnv.step replays one CUDA graph (pinned H2D of the actions, controller + env kernels, D2H of the packed outputs);
@@ -217,7 +266,7 @@ def test_whole_step_graph_equals_eager_launches(config, monkeypatch):
         for x, y in zip(oa[:-1], ob[:-1]):
             assert np.array_equal(np.asarray(x), np.asarray(y)), t
         assert oa[-1][0]["current_step"] == ob[-1][0]["current_step"] == t % 6 + 1
-    assert a._g is not None and b._g is None
+    assert a._cur["graph"] is not None and all(sl["graph"] is None for sl in b._slots)
     a.close(); b.close()
 
 

@@ -6,7 +6,7 @@ import numpy as np, torch
 from aircombat_selfplay_b200.capi import EnvBatch
 from aircombat_selfplay_b200.tasks import load_spec
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-for cfg, n in (("1v1/NoWeapon/Selfplay", 4096), ("2v2/ShootMissile/HierarchySelfplay", 1024), ("scenario3/scenario3", 512), ("singlecontrol/heading", 2048)):
+for cfg, n in (("1v1/NoWeapon/Selfplay", 4096), ("1v1/ShootMissile/Selfplay", 2048), ("2v2/ShootMissile/HierarchySelfplay", 1024), ("scenario3/scenario3", 512), ("singlecontrol/heading", 2048)):
     spec = load_spec(cfg, substeps_override=12)
     A = spec.n_agents
     stats = []
