@@ -10,6 +10,30 @@
 
 #define ENV_DEV __device__ __forceinline__
 
+// The missile / chaff path takes its quotients, roots and elementary functions from fmath.cuh (guard-free Newton
+// sequences, coefficient tables in constant memory) like the FDM frame; -DACS_IEEE_MATH_MISSILE (or -DACS_IEEE_MATH)
+// restores `/`, sqrt() and libdevice on this path alone (tuning builds).
+#include "fmath.cuh"
+#if defined(ACS_IEEE_MATH_MISSILE) && !defined(ACS_IEEE_MATH)
+ENV_DEV double em_div(double a, double b) { return a / b; }
+ENV_DEV double em_rcp(double b) { return 1.0 / b; }
+ENV_DEV double em_sqrt(double x) { return sqrt(x); }
+ENV_DEV double em_sqrt0(double x) { return sqrt(x); }
+ENV_DEV double em_rsqrt(double x) { return 1.0 / sqrt(x); }
+ENV_DEV double em_sin(double x) { return sin(x); }
+ENV_DEV double em_exp(double x) { return exp(x); }
+ENV_DEV void em_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+#else
+ENV_DEV double em_div(double a, double b) { return fm_div(a, b); }
+ENV_DEV double em_rcp(double b) { return fm_rcp(b); }
+ENV_DEV double em_sqrt(double x) { return fm_sqrt(x); }
+ENV_DEV double em_sqrt0(double x) { return fm_sqrt0(x); }
+ENV_DEV double em_rsqrt(double x) { return fm_rsqrt(x); }
+ENV_DEV double em_sin(double x) { return fm_sin(x); }
+ENV_DEV double em_exp(double x) { return fm_exp(x); }
+ENV_DEV void em_sincos(double x, double* s, double* c) { fm_sincos(x, s, c); }
+#endif
+
 // ----------------------------------------------------------------------------- arenas (structure of arrays)
 // per aircraft doubles
 enum {
@@ -181,16 +205,16 @@ ENV_DEV double neu2alt(const GeoOrigin& o, double n, double e, double u) {
   const double vv = o.slo * t + o.clo * e;
   const double x = o.x0 + uu, y = o.y0 + vv, z = o.z0 + w;
   const double a = WGS84_A, ec = WGS84_B / WGS84_A, ec2 = ec * ec, e2 = 1.0 - ec2, c = a * e2;
-  const double rxy = sqrt(x * x + y * y);
+  const double rxy = em_sqrt(x * x + y * y);      // (never on the polar axis: fmath.cuh, operands > 0)
   const double s0 = fabs(z), zc = ec * s0, c0 = ec * rxy, c02 = c0 * c0, s02 = s0 * s0, a02 = c02 + s02;
-  const double a0 = sqrt(a02), a03 = a02 * a0;
+  const double a0 = em_sqrt(a02), a03 = a02 * a0;
   double s1 = zc * a03 + c * s02 * s0;
   const double c1 = rxy * a03 - c * c02 * c0, cs0c0 = c * c0 * s0;
   const double b0 = 1.5 * cs0c0 * ((rxy * s0 - zc * c0) * a0 - cs0c0);
   s1 = s1 * a03 - b0 * s0;
   const double cc = ec * (c1 * a03 - b0 * c0);
   const double s12 = s1 * s1, cc2 = cc * cc;
-  return (rxy * cc + s0 * s1 - a * sqrt(ec2 * s12 + cc2)) / sqrt(s12 + cc2);
+  return (rxy * cc + s0 * s1 - a * em_sqrt(ec2 * s12 + cc2)) * em_rsqrt(s12 + cc2);
 }
 
 // ----------------------------------------------------------------------------- AO / TA / R (E/utils/utils.py:58-103)
@@ -222,13 +246,13 @@ ENV_DEV AoTaR get_ao_ta_r(const Feat& ego, const Feat& enm, bool two_d) {
 }
 
 // ----------------------------------------------------------------------------- missile (E/core/simulatior.py:393-608)
-struct MissileParams { double g, t_max, t_thrust, Isp, Length, Diameter, cD, m0, dm, K, nyz_max, Rc, v_min; };
+struct MissileParams { double g, t_max, t_thrust, Isp, Length, Diameter, cD, m0, dm, K, nyz_max, Rc, v_min, inv_t_max; };
 // kind 0: base class numbers (AIM-9L, :420-433); kind 1: AIM_9M / AIM_120B subclasses, both AIM-120B numbers (:663-712)
 ENV_DEV MissileParams missile_params(int kind) {
   MissileParams p;
   p.g = 9.81; p.dm = 6.0; p.v_min = 150.0;
-  if (kind == 0) { p.t_max = 60.0; p.t_thrust = 3.0; p.Isp = 120.0; p.Length = 2.87; p.Diameter = 0.127; p.cD = 0.4; p.m0 = 84.0; p.K = 3.0; p.nyz_max = 30.0; p.Rc = 300.0; }
-  else { p.t_max = 27.22; p.t_thrust = 1.4; p.Isp = 1837.0; p.Length = 3.66; p.Diameter = 0.18; p.cD = 0.02; p.m0 = 152.0; p.K = 5.0; p.nyz_max = 50.0; p.Rc = 5.0; }
+  if (kind == 0) { p.t_max = 60.0; p.inv_t_max = 1.0 / 60.0; p.t_thrust = 3.0; p.Isp = 120.0; p.Length = 2.87; p.Diameter = 0.127; p.cD = 0.4; p.m0 = 84.0; p.K = 3.0; p.nyz_max = 30.0; p.Rc = 300.0; }
+  else { p.t_max = 27.22; p.inv_t_max = 1.0 / 27.22; p.t_thrust = 1.4; p.Isp = 1837.0; p.Length = 3.66; p.Diameter = 0.18; p.cD = 0.02; p.m0 = 152.0; p.K = 5.0; p.nyz_max = 50.0; p.Rc = 5.0; }
   return p;
 }
 struct Missile {
@@ -254,50 +278,54 @@ ENV_DEV void missile_store(const EnvView& v, int mid, const Missile& m) {
 // distance to the target: the R returned by _guidance (:563)
 ENV_DEV double missile_distance(const Missile& m, const Feat& tg) {
   const double ax = m.pn - tg.n, ay = m.pe - tg.e, az = tg.u - m.pu;
-  return sqrt(ax * ax + ay * ay + az * az);
+  return em_sqrt0(ax * ax + ay * ay + az * az);
 }
 // _guidance (:556-576): proportional navigation; returns clipped (ny, nz) and the distance
 ENV_DEV void missile_guidance(const Missile& m, const MissileParams& pr, const Feat& tg, double& ny, double& nz, double& dist) {
-  const double v_m = sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
+  // divisions by constants are multiplications by their reciprocals, quotients and roots the guard-free sequences of
+  // fmath.cuh (<= 1 ulp from the reference's operations each)
+  const double v_m = em_sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
   // theta_m = arcsin(dz/v) enters only through its cosine (:569-570): cos(arcsin(x)) = |v_xy| / |v|
   const double ex = m.pn - tg.n, ey = m.pe - tg.e;
-  const double Rxy = sqrt(ex * ex + ey * ey);
+  const double Rxy = em_sqrt(ex * ex + ey * ey);
   const double ez = tg.u - m.pu;
-  const double Rxyz = sqrt(ex * ex + ey * ey + ez * ez);
+  const double Rxyz = em_sqrt(ex * ex + ey * ey + ez * ez);
   const double dxt = tg.n - m.pn, dyt = tg.e - m.pe, dzt = tg.u - m.pu;
   const double dvx = tg.vn - m.vn, dvy = tg.ve - m.ve, dvz = tg.vd - m.vu;
-  const double dbeta = (dvy * dxt - dvx * dyt) / (Rxy * Rxy);
-  const double deps = (dvz * (Rxy * Rxy) - dzt * (dxt * dvx + dyt * dvy)) / ((Rxyz * Rxyz) * Rxy);
-  const double K = fmax(pr.K * (pr.t_max - m.t) / pr.t_max, 0.0);
-  const double ct = sqrt(m.vn * m.vn + m.ve * m.ve) / v_m;
-  ny = env_clip(K * v_m / pr.g * ct * dbeta, -pr.nyz_max, pr.nyz_max);
-  nz = env_clip(K * v_m / pr.g * deps + ct, -pr.nyz_max, pr.nyz_max);
+  const double dbeta = em_div(dvy * dxt - dvx * dyt, Rxy * Rxy);
+  const double deps = em_div(dvz * (Rxy * Rxy) - dzt * (dxt * dvx + dyt * dvy), (Rxyz * Rxyz) * Rxy);
+  const double K0 = pr.K * (pr.t_max - m.t) * pr.inv_t_max, K = K0 > 0.0 ? K0 : 0.0;
+  const double ct = em_div(em_sqrt0(m.vn * m.vn + m.ve * m.ve), v_m);
+  const double Kvg = K * v_m * (1.0 / 9.81);       // pr.g is 9.81 for every missile kind
+  ny = env_clip(Kvg * ct * dbeta, -pr.nyz_max, pr.nyz_max);
+  nz = env_clip(Kvg * deps + ct, -pr.nyz_max, pr.nyz_max);
   dist = Rxyz;
 }
 // _state_trans (:578-608)
 ENV_DEV void missile_state_trans(Missile& m, const MissileParams& pr, const GeoOrigin& org, double ny, double nz, double dt) {
   m.pn = m.pn + dt * m.vn; m.pe = m.pe + dt * m.ve; m.pu = m.pu + dt * m.vu;
   m.alt = neu2alt(org, m.pn, m.pe, m.pu);
-  double v = sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
+  double v = em_sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
   double theta = m.theta, phi = m.phi;
   const double Isp = m.t < pr.t_thrust ? pr.Isp : 0.0;
   const double T = pr.g * Isp * pr.dm;
   double S0 = 3.14159265358979323846 * ((pr.Diameter / 2) * (pr.Diameter / 2));
-  const double sdt = sin(m.dtheta), sdp = sin(m.dphi);
-  S0 += sqrt(sdt * sdt + sdp * sdp) * pr.Diameter * pr.Length;
-  const double rho = 1.225 * exp(-m.alt / 9300.0);
+  const double sdt = em_sin(m.dtheta), sdp = em_sin(m.dphi);
+  S0 += em_sqrt0(sdt * sdt + sdp * sdp) * pr.Diameter * pr.Length;
+  const double rho = 1.225 * em_exp(m.alt * (-1.0 / 9300.0));
   const double D = 0.5 * pr.cD * S0 * rho * (v * v);
-  const double nx = (T - D) / (m.m * pr.g);
+  const double nx = em_div(T - D, m.m * pr.g);
   double st = m.st, ct = m.ct;                 // sin/cos of the current pitch angle, kept from the previous update
   const double dv = pr.g * (nx - st);
-  m.dphi = pr.g / v * (ny / ct);
-  m.dtheta = pr.g / v * (nz - ct);
+  const double gv = pr.g * em_rcp(v);
+  m.dphi = gv * em_div(ny, ct);
+  m.dtheta = gv * (nz - ct);
   v += dt * dv;
   phi += dt * m.dphi;
   theta += dt * m.dtheta;
   double sp, cp;
-  sincos(theta, &st, &ct);
-  sincos(phi, &sp, &cp);
+  em_sincos(theta, &st, &ct);
+  em_sincos(phi, &sp, &cp);
   m.vn = v * ct * cp; m.ve = v * ct * sp; m.vu = v * st;
   m.theta = theta; m.phi = phi; m.st = st; m.ct = ct;
   if (m.t < pr.t_thrust) m.m = m.m - dt * pr.dm;

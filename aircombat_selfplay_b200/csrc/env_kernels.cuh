@@ -68,7 +68,8 @@ ENV_DEV void derive_aircraft(const AcOut& o, const GeoOrigin& org, PubAc& p, dou
 // it: the geodetic sines and cosines are already there (Fukushima), so no inverse trigonometry and no sincos.
 ENV_DEV void publish_from_frame(const Frame& f, const GeoOrigin& org, PubAc& p) {
   p.h = env_clip(f.h_asl * 0.3048, -500.0, 26000.0);
-  const double n = (WGS84_A * WGS84_A) / hypot(WGS84_A * f.cosLatGd, WGS84_B * f.sinLatGd);
+  const double ac = WGS84_A * f.cosLatGd, bs = WGS84_B * f.sinLatGd;
+  const double n = (WGS84_A * WGS84_A) * em_rsqrt(ac * ac + bs * bs);      // a^2 / hypot(a cos, b sin); no overflow at 6e6 m
   const double x = (n + p.h) * f.cosLatGd * f.cosLon, y = (n + p.h) * f.cosLatGd * f.sinLon;
   const double z = (n * ((WGS84_B / WGS84_A) * (WGS84_B / WGS84_A)) + p.h) * f.sinLatGd;
   const double u = x - org.x0, v = y - org.y0, w = z - org.z0;
@@ -106,7 +107,7 @@ ENV_DEV bool missile_inert(const EnvView& v, const int mid, const int env) {
   if (AI(v, AI_STATUS, env * v.A + MI(v, MI_TARGET, mid)) != ST_ALIVE) return true;
   if (MD(v, MD_T, mid) > pr.t_max) return true;
   const double vn = MD(v, MD_VEL_N, mid), ve = MD(v, MD_VEL_E, mid), vu = MD(v, MD_VEL_U, mid);
-  return sqrt(vn * vn + ve * ve + vu * vu) < pr.v_min;
+  return em_sqrt(vn * vn + ve * ve + vu * vu) < pr.v_min;
 }
 // bit s = slot s of this aircraft holds a missile that still runs (slots >= 64 cannot exist: acs_env_create caps S)
 ENV_DEV unsigned long long live_missiles(const EnvView& v, const Lane& L) {
@@ -141,7 +142,7 @@ __device__ __noinline__ void missile_phase(const EnvView& v, const AcsTaskConfig
     const int target = MI(v, MI_TARGET, mid);
     const Feat& tg = sP[L.gbase + target].f;
     const double ax = MD(v, MD_POS_N, mid) - tg.n, ay = MD(v, MD_POS_E, mid) - tg.e, az = tg.u - MD(v, MD_POS_U, mid);
-    const double d = sqrt(ax * ax + ay * ay + az * az);
+    const double d = em_sqrt0(ax * ax + ay * ay + az * az);
     if (d < missile_params(MI(v, MI_KIND, mid)).Rc && MI(v, MI_STATUS, mid) != MS_MISS) atomicMin(&sWin[L.gbase + target], MI(v, MI_ORDER, mid));
   }
   // ---- chaff run() (:377-381) and publication
@@ -181,9 +182,9 @@ __device__ __noinline__ void missile_phase(const EnvView& v, const AcsTaskConfig
     if (dist < pr.Rc && target_alive && m.status != MS_MISS) {
       m.status = MS_HIT;
       sShot[L.gbase + m.target] = 1;
-    } else if (m.t > pr.t_max || sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu) < pr.v_min || m.consec >= maxlen || !target_alive) {
+    } else if (m.t > pr.t_max || em_sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu) < pr.v_min || m.consec >= maxlen || !target_alive) {
       // inert from here on (see missile_inert); `consec >= maxlen` alone is not permanent
-      if (m.status == MS_MISS && (m.t > pr.t_max || !target_alive || sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu) < pr.v_min)) live &= ~(1ull << slot);
+      if (m.status == MS_MISS && (m.t > pr.t_max || !target_alive || em_sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu) < pr.v_min)) live &= ~(1ull << slot);
       m.status = MS_MISS;
     } else {
       missile_state_trans(m, pr, org, ny, nz, dt);
@@ -197,7 +198,7 @@ __device__ __noinline__ void missile_phase(const EnvView& v, const AcsTaskConfig
         const PubChaff& c = sCh[L.gbase + j];
         if (c.state != CH_ACTIVE) continue;
         const double dx = c.n - m.pn, dy = c.e - m.pe, dz = c.u - m.pu;
-        if (sqrt(dx * dx + dy * dy + dz * dz) <= 300.0) {
+        if (em_sqrt0(dx * dx + dy * dy + dz * dz) <= 300.0) {
           for (int q = 0; q < c.count; q++)
             if (env_u01(cfg.seed, cfg.env_offset + L.env, RNG_CHAFF, when, L.lane * 64 + keyn, j * 64 + q) < 0.85) missed = true;
         }
@@ -536,7 +537,7 @@ ENV_DEV void missile_run_independent(const EnvView& v, const AcsTaskConfig& cfg,
     missile_guidance(m, pr, tg, ny, nz, dist);
     m.consec = (dist > m.d_prev) ? m.consec + 1 : 0;
     m.d_prev = dist;
-    const double speed = sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
+    const double speed = em_sqrt(m.vn * m.vn + m.ve * m.ve + m.vu * m.vu);
     if (dist < pr.Rc && target_alive && m.status != MS_MISS) {
       atomicAdd(&EI(v, EI_FAULTS, env), 1);                         // cannot happen (missile_threatens)
       m.status = MS_HIT;
@@ -553,7 +554,7 @@ ENV_DEV void missile_run_independent(const EnvView& v, const AcsTaskConfig& cfg,
         if (k >= sChEnd[gbase + j]) continue;                       // no cloud, or done by this substep
         const PubChaff& c = sCh[gbase + j];
         const double dx = c.n - m.pn, dy = c.e - m.pe, dz = c.u - m.pu;
-        if (sqrt(dx * dx + dy * dy + dz * dz) <= 300.0) {
+        if (em_sqrt0(dx * dx + dy * dy + dz * dz) <= 300.0) {
           for (int q = 0; q < c.count; q++)
             if (env_u01(cfg.seed, cfg.env_offset + env, RNG_CHAFF, when0 + k, lane * 64 + keyn, j * 64 + q) < 0.85) missed = true;
         }

@@ -11,6 +11,7 @@
 // (gen/f16_gen.cuh); the 43 lookup tables are read from shared memory (pointer T).
 #pragma once
 #include <cmath>
+#include "fmath.cuh"
 
 #define FDM_DEV __device__ __forceinline__
 // helpers instantiated many times per frame; ACS_NOINLINE_HELPERS trades call overhead for instruction-cache footprint
@@ -139,7 +140,7 @@ FDM_DEV double f16_tab2(const double* __restrict__ v, const int nc, const Bracke
 FDM_DEV double f16_pid(double Input, double test, double kp, double ki, double kd, int int_type, double dt,
                        double& prev, double& prev2, double& itot) {
   double I_out_delta = 0.0;
-  const double Dval = (Input - prev) / dt;   // dt is a kernel-uniform value: one reciprocal, hoisted by the compiler
+  const double Dval = (Input - prev) * fm_rcp(dt);   // dt is kernel-uniform: the reciprocal is loop-invariant (<= 1 ulp from the quotient)
   if (fabs(test) < 0.000001) {
     switch (int_type) {
       case 1: I_out_delta = Input; break;
@@ -157,7 +158,10 @@ FDM_DEV double f16_pid(double Input, double test, double kp, double ki, double k
   return Output;
 }
 FDM_DEV bool f16_equal_to_roundoff(double a, double b) {
-  return fabs(a - b) <= (2.0 * 2.220446049250313e-16) * fmax(fabs(a), fabs(b));
+  // d <= eps * max(|a|, |b|)  <=>  d <= eps |a| or d <= eps |b| (a positive factor is monotonic under rounding): no fmax,
+  // which sm_100a expands into compare + selects + NaN handling (this test sits on every actuator, ~10 per frame)
+  const double d = fabs(a - b), e = 2.0 * 2.220446049250313e-16;
+  return d <= e * fabs(a) || d <= e * fabs(b);
 }
 // J/models/flight_control/FGKinemat.cpp:99-157.  Input already scaled by the last detent.
 FDM_DEV double f16_kinemat(const double* __restrict__ det, const double* __restrict__ tim, int n, double Input, double Output, double dt) {
@@ -167,9 +171,9 @@ FDM_DEV double f16_kinemat(const double* __restrict__ det, const double* __restr
     int ind = 1;
     while (ind < n - 1 && ((Input < Output) ? det[ind] < Output : det[ind] <= Output)) ++ind;
     if (tim[ind] <= 0.0) { Output = Input; break; }
-    const double Rate = (det[ind] - det[ind - 1]) / tim[ind];
+    const double Rate = fm_div(det[ind] - det[ind - 1], tim[ind]);      // tim[ind] > 0 here, detents ascend: Rate > 0
     const double ThisInput = f16_constrain(det[ind - 1], Input, det[ind]);
-    double ThisDt = fabs((ThisInput - Output) / Rate);
+    double ThisDt = fabs(fm_div(ThisInput - Output, Rate));
     if (dt0 < ThisDt) { ThisDt = dt0; if (Output < Input) Output += ThisDt * Rate; else Output -= ThisDt * Rate; }
     else Output = ThisInput;
     dt0 -= ThisDt;
@@ -192,7 +196,7 @@ FDM_HELPER double f16_kinemat2(const double d0, const double d1, const double t1
   return Output;
 }
 // x^y for x > 0 as exp(y ln x): 2-3 ulp instead of pow()'s < 1 ulp at a quarter of its instruction count
-FDM_HELPER double f16_powpos(const double x, const double y) { return exp(y * log(x)); }
+FDM_HELPER double f16_powpos(const double x, const double y) { return fm_powpos(x, y); }
 
 #include "gen/f16_gen.cuh"
 static_assert(F16_NTAB <= F16_KC_MAX, "g_f16_kc holds the whole table array");
@@ -207,7 +211,7 @@ struct AtmoConst {
   double invdH[9], Pexp[8], Piso[8], invSLdensity;
 };
 struct Atmo { double T, P, rho, a, density_altitude; };
-FDM_DEV double atmo_geopot(const AtmoConst& c, double h) { return (h * c.EarthRadius) / (c.EarthRadius + h); }
+FDM_DEV double atmo_geopot(const AtmoConst& c, double h) { return fm_div(h * c.EarthRadius, c.EarthRadius + h); }
 FDM_DEV double atmo_geomet(const AtmoConst& c, double H) { return (H * c.EarthRadius) / (c.EarthRadius - H); }
 FDM_DEV void atmosphere_calculate(const AtmoConst& c, double altitude, Atmo& o) {
   const double G = atmo_geopot(c, altitude);
@@ -230,10 +234,10 @@ FDM_DEV void atmosphere_calculate(const AtmoConst& c, double altitude, Atmo& o) 
   for (; b < 7; ++b) { const double testAlt = c.H[b + 1]; if (G < testAlt) break; BaseAlt = testAlt; }
   const double Tmb = c.Tmb[b], deltaH = G - BaseAlt, Lmb = c.Lapse[b];
   double Pm;
-  if (Lmb != 0.0) Pm = c.PB[b] * f16_powpos(Tmb / (Tmb + Lmb * deltaH), c.Pexp[b]);
+  if (Lmb != 0.0) Pm = c.PB[b] * fm_pow_ratio(Tmb, Tmb + Lmb * deltaH, c.Pexp[b]);   // (T_base / T)^(g0 / (R L))
   else Pm = c.PB[b] * exp(c.Piso[b] * deltaH);
-  o.T = Tm; o.P = Pm; o.rho = Pm / (c.Reng * Tm);
-  o.a = sqrt(1.4 * c.Reng * Tm);
+  o.T = Tm; o.P = Pm; o.rho = fm_div(Pm, c.Reng * Tm);
+  o.a = fm_sqrt(1.4 * c.Reng * Tm);
   // CalculateDensityAltitude :464-492.  On a standard day (the reference never biases temperature or pressure) the
   // density altitude IS the geometric altitude: the reference's power-law inversion returns it to 6e-13 relative
   // (tests/test_oracle_fdm.py::test_density_altitude_is_identity_on_a_standard_day), so the inversion is skipped.
@@ -253,19 +257,19 @@ FDM_DEV void atmosphere_calculate(const AtmoConst& c, double altitude, Atmo& o) 
 // J/FGJSBBase.cpp:245-296
 FDM_DEV double pitot_total_pressure(double mach, double p) {
   if (mach < 0) return p;
-  if (mach < 1) { const double t = 1 + 0.2 * mach * mach; return p * ((t * t) * t * sqrt(t)); }       // t^3.5
+  if (mach < 1) { const double t = 1 + 0.2 * mach * mach; return p * ((t * t) * t * fm_sqrt(t)); }    // t^3.5
   const double m2 = mach * mach, m7 = (m2 * m2) * (m2 * mach), x = 7 * m2 - 1;
-  return p * 166.92158009316827 * m7 / ((x * x) * sqrt(x));                                          // M^7 / x^2.5
+  return fm_div(p * 166.92158009316827 * m7, (x * x) * fm_sqrt(x));                                  // M^7 / x^2.5
 }
 FDM_DEV double mach_from_impact_pressure(double qc, double p) {
-  const double A = qc / p + 1;
+  const double A = fm_div(qc, p) + 1;
   // A^(1/3.5) = A^(2/7): fp32 seed, two Newton steps on y^7 = A^2 (relative error 1e-6 -> 3e-12 -> < 1 ulp)
   double y = (double)exp2f(0.2857142857142857f * log2f((float)A));
 #pragma unroll
-  for (int i = 0; i < 2; i++) { const double y2 = y * y, y3 = y2 * y, y6 = y3 * y3; y -= (y6 * y - A * A) / (7.0 * y6); }
-  double M = sqrt(5.0 * (y - 1));
+  for (int i = 0; i < 2; i++) { const double y2 = y * y, y3 = y2 * y, y6 = y3 * y3; y -= fm_div(y6 * y - A * A, 7.0 * y6); }
+  double M = fm_sqrt0(5.0 * (y - 1));
   if (M > 1.0)
-    for (int i = 0; i < 10; i++) { const double y = 1 - 1.0 / (7.0 * M * M); M = 0.8812848543473311 * sqrt(A * ((y * y) * sqrt(y))); }
+    for (int i = 0; i < 10; i++) { const double y = 1 - fm_rcp(7.0 * M * M); M = 0.8812848543473311 * fm_sqrt(A * ((y * y) * fm_sqrt(y))); }
   return M;
 }
 
@@ -386,27 +390,27 @@ FDM_DEV void add_pointmass_inertia(M33& J, const V3& cg, double mass_sl, double 
 FDM_DEV void location_derived(Frame& f, M33& Tec2l) {
   const double x = f.ecef.x, y = f.ecef.y, z = f.ecef.z;
   const double rxy2 = x * x + y * y;
-  f.radius = sqrt(rxy2 + z * z);
-  const double rxy = sqrt(rxy2);
+  f.radius = fm_sqrt(rxy2 + z * z);
+  const double rxy = fm_sqrt0(rxy2);
   f.rxy = rxy;
   double sinLon, cosLon;
-  if (rxy == 0.0) { sinLon = 0.0; cosLon = 1.0; } else { const double ir = 1.0 / rxy; sinLon = y * ir; cosLon = x * ir; }
+  if (rxy == 0.0) { sinLon = 0.0; cosLon = 1.0; } else { const double ir = fm_rcp(rxy); sinLon = y * ir; cosLon = x * ir; }
   f.sinLon = sinLon; f.cosLon = cosLon;
   // geocentric latitude only enters through its sine and cosine (J2 gravity, sea-level radius): z/r and rxy/r
-  f.cosLatGc = rxy / f.radius;
+  f.cosLatGc = fm_div(rxy, f.radius);
   const double ec = EARTH_B / EARTH_A, ec2 = ec * ec, e2 = 1.0 - ec2, c = EARTH_A * e2;
   const double s0 = fabs(z), zc = ec * s0, c0 = ec * rxy, c02 = c0 * c0, s02 = s0 * s0, a02 = c02 + s02;
-  const double a0 = sqrt(a02), a03 = a02 * a0;
+  const double a0 = fm_sqrt(a02), a03 = a02 * a0;
   double s1 = zc * a03 + c * s02 * s0;
   const double c1 = rxy * a03 - c * c02 * c0, cs0c0 = c * c0 * s0;
   const double b0 = 1.5 * cs0c0 * ((rxy * s0 - zc * c0) * a0 - cs0c0);
   s1 = s1 * a03 - b0 * s0;
   const double cc = ec * (c1 * a03 - b0 * c0);
-  const double s12 = s1 * s1, cc2 = cc * cc, inorm = 1.0 / sqrt(s12 + cc2);
+  const double s12 = s1 * s1, cc2 = cc * cc, inorm = fm_rsqrt(s12 + cc2);
   const double sgn = z < 0.0 ? -1.0 : 1.0;
   const double cosLat = cc * inorm, sinLat = sgn * s1 * inorm;
   f.cosLatGd = cosLat; f.sinLatGd = sinLat; f.gd_s1 = s1; f.gd_cc = cc;
-  f.geodAlt = (rxy * cc + s0 * s1 - EARTH_A * sqrt(ec2 * s12 + cc2)) * inorm;
+  f.geodAlt = (rxy * cc + s0 * s1 - EARTH_A * fm_sqrt(ec2 * s12 + cc2)) * inorm;
   Tec2l.m[0][0] = -cosLon * sinLat; Tec2l.m[0][1] = -sinLon * sinLat; Tec2l.m[0][2] = cosLat;
   Tec2l.m[1][0] = -sinLon; Tec2l.m[1][1] = cosLon; Tec2l.m[1][2] = 0.0;
   Tec2l.m[2][0] = -cosLon * cosLat; Tec2l.m[2][1] = -sinLon * cosLat; Tec2l.m[2][2] = -sinLat;
@@ -434,11 +438,12 @@ FDM_DEV void fdm_propagate_rot(AcCore& a, const double dt, V3& vi_before) {   //
       const double qd2 = 0.5 * (a.q3 * a.wi.x + a.q0 * a.wi.y - a.q1 * a.wi.z);
       const double qd3 = 0.5 * (-a.q2 * a.wi.x + a.q1 * a.wi.y + a.q0 * a.wi.z);
       a.q0 += dt * qd0; a.q1 += dt * qd1; a.q2 += dt * qd2; a.q3 += dt * qd3;
-      const double n = sqrt(a.q0 * a.q0 + a.q1 * a.q1 + a.q2 * a.q2 + a.q3 * a.q3);
+      // |q| and 1 / |q| from one inverse-square-root chain (the reference divides by sqrt: <= 1 ulp apart)
+      const double qq = a.q0 * a.q0 + a.q1 * a.q1 + a.q2 * a.q2 + a.q3 * a.q3, iq = fm_rsqrt(qq), n = qq * iq;
       // Select, not branch: about half of the aircraft renormalise in a given frame, and with a branch here ptxas has put
       // the reconvergence point behind the rest of Propagate (ncu: ~700 instructions per frame executed 2.25 times with 14
       // active lanes, +23 % warp instructions in the multi-warp frames).  x * 1.0 is exact, so the bits are the same.
-      const double rn = (n == 0.0 || fabs(n - 1.000) < 1e-10) ? 1.0 : 1.0 / n;
+      const double rn = (qq == 0.0 || fabs(n - 1.000) < 1e-10) ? 1.0 : iq;
       a.q0 *= rn; a.q1 *= rn; a.q2 *= rn; a.q3 *= rn;
     }
     a.wi = a.wi + dt * a.pqridot;                                                        // eRectEuler
@@ -456,7 +461,7 @@ FDM_DEV void fdm_propagate_pos(AcCore& a, Frame& f, const V3& v0, const double d
     a.dqv1 = a.dqv0; a.dqv0 = v0;
   }
   a.epa += EARTH_OMEGA * dt;
-  sincos(a.epa, &f.sin_epa, &f.cos_epa);
+  fm_sincos_small(a.epa, &f.sin_epa, &f.cos_epa);
   // vLocation = Ti2ec * vInertialPosition
   f.ecef = v3(f.cos_epa * a.ri.x + f.sin_epa * a.ri.y, -f.sin_epa * a.ri.x + f.cos_epa * a.ri.y, a.ri.z);
   M33 Tec2l;
@@ -492,7 +497,7 @@ FDM_DEV void fdm_stage_propagate(AcCore& a, Props& p, Frame& f, const double dt)
 FDM_DEV void fdm_stage_gravity(Frame& f) {
   // ---------------- Inertial: J2 gravity in ECEF (J/models/FGInertial.cpp:193-211)
   {
-    const double ir = 1.0 / f.radius, sinLat = f.ecef.z * ir, adivr = EARTH_A * ir, preCommon = 1.5 * EARTH_J2 * adivr * adivr;
+    const double ir = fm_rcp(f.radius), sinLat = f.ecef.z * ir, adivr = EARTH_A * ir, preCommon = 1.5 * EARTH_J2 * adivr * adivr;
     const double xy = 1.0 - 5.0 * (sinLat * sinLat), z = 3.0 - 5.0 * (sinLat * sinLat), GMOverr2 = EARTH_GM * (ir * ir);
     f.grav.x = -GMOverr2 * ((1.0 + (preCommon * xy)) * f.ecef.x * ir);
     f.grav.y = -GMOverr2 * ((1.0 + (preCommon * xy)) * f.ecef.y * ir);
@@ -503,7 +508,7 @@ FDM_DEV void fdm_stage_gravity(Frame& f) {
 FDM_DEV void fdm_stage_atmosphere(Props& p, Frame& f, const AtmoConst& ac) {
   // ---------------- Atmosphere at h = |r| - sea-level radius (J/models/FGPropagate.cpp:573-576, FGLocation.cpp:273-279)
   const double ecr = EARTH_B / EARTH_A;
-  const double slr = EARTH_A * ecr / sqrt(1.0 - (1.0 - ecr * ecr) * f.cosLatGc * f.cosLatGc);
+  const double slr = (EARTH_A * ecr) * fm_rsqrt(1.0 - (1.0 - ecr * ecr) * f.cosLatGc * f.cosLatGc);
   f.h_asl = f.radius - slr;
   atmosphere_calculate(ac, f.h_asl, f.atm);
   p.atmosphere_density_altitude = f.atm.density_altitude;
@@ -535,7 +540,7 @@ FDM_DEV void fdm_stage_massbalance(AcCore& a, Frame& f) {
     pm = pm + K_PM0_W * v3(K_PM0_X, K_PM0_Y, K_PM0_Z);
     pm = pm + K_PM1_W * v3(K_PM1_X, K_PM1_Y, K_PM1_Z);
     const V3 num = (K_emptywt * v3(K_CG_X, K_CG_Y, K_CG_Z) + pm) + tm;
-    const double rw = 1.0 / Weight;
+    const double rw = fm_rcp(Weight);
     f.cg = v3(num.x * rw, num.y * rw, num.z * rw);
     a.cg = f.cg;
     M33 J;
@@ -561,7 +566,7 @@ FDM_DEV void fdm_stage_massbalance(AcCore& a, Frame& f) {
     f.J = J;
     const double Ixx = J.m[0][0], Iyy = J.m[1][1], Izz = J.m[2][2], Ixy = -J.m[0][1], Ixz = -J.m[0][2], Iyz = -J.m[1][2];
     double k1 = (Iyy * Izz - Iyz * Iyz), k2 = (Iyz * Ixz + Ixy * Izz), k3 = (Ixy * Iyz + Iyy * Ixz);
-    const double denom = 1.0 / (Ixx * k1 - Ixy * k2 - Ixz * k3);
+    const double denom = fm_rcp(Ixx * k1 - Ixy * k2 - Ixz * k3);
     k1 = k1 * denom; k2 = k2 * denom; k3 = k3 * denom;
     const double k4 = (Izz * Ixx - Ixz * Ixz) * denom, k5 = (Ixy * Ixz + Iyz * Ixx) * denom, k6 = (Ixx * Iyy - Ixy * Ixy) * denom;
     f.Jinv.m[0][0] = k1; f.Jinv.m[0][1] = k2; f.Jinv.m[0][2] = k3;
@@ -577,7 +582,7 @@ FDM_DEV double fdm_airspeed(Frame& f) {   // Vt^2 and Vt from the body velocitie
   const double U = f.uvw.x, V = f.uvw.y, W = f.uvw.z;
   const double AeroU2 = U * U, AeroV2 = V * V, AeroW2 = W * W, mUW = AeroU2 + AeroW2;
   f.Vt2 = mUW + AeroV2;
-  f.Vt = sqrt(f.Vt2);
+  f.Vt = fm_sqrt0(f.Vt2);
   return mUW;
 }
 FDM_DEV void fdm_stage_aux_kin(const AcCore& a, Props& p, Frame& f, WindAxes& w) {
@@ -589,11 +594,12 @@ FDM_DEV void fdm_stage_aux_kin(const AcCore& a, Props& p, Frame& f, WindAxes& w)
   sa = 0.0; ca = 1.0; sb = 0.0; cb = 1.0;
   if (f.Vt > 0.001) {
     // the wind->body matrix needs only sines and cosines of alpha and beta: ratios of the velocity components
-    const double sUW = sqrt(mUW), iVt = 1.0 / f.Vt;
-    f.beta = atan2(V, sUW); sb = V * iVt; cb = sUW * iVt;
-    if (mUW >= 1E-6) { const double iUW = 1.0 / sUW; f.alpha = atan2(W, U); sa = W * iUW; ca = U * iUW; }
+    const double sUW = fm_sqrt0(mUW), iVt = fm_rcp(f.Vt);
+    // beta = atan2(V, sUW) and alpha = atan2(W, U) from the sines and cosines the wind axes need anyway (fmath.cuh)
+    sb = V * iVt; cb = sUW * iVt; f.beta = fm_angle_sc(sb, cb, V, sUW);
+    if (mUW >= 1E-6) { const double iUW = fm_rcp(sUW); sa = W * iUW; ca = U * iUW; f.alpha = fm_angle_sc(sa, ca, W, U); }
   }
-  const double Vground = sqrt(f.vel.x * f.vel.x + f.vel.y * f.vel.y);
+  const double Vground = fm_sqrt0(f.vel.x * f.vel.x + f.vel.y * f.vel.y);
   const V3 eye = structural_to_body(f.cg, K_EYEPOINT_X, K_EYEPOINT_Y, K_EYEPOINT_Z);
   V3 pa = a.bodyaccel + cross(a.pqridot, eye);
   pa = pa + cross(a.wi, cross(a.wi, eye));
@@ -609,7 +615,7 @@ FDM_DEV void fdm_stage_aux_kin(const AcCore& a, Props& p, Frame& f, WindAxes& w)
 }
 FDM_DEV void fdm_stage_aux_air(Props& p, Frame& f, const AtmoConst& ac) {   // needs f.Vt2, f.Vt, f.atm
   f.qbar = (0.5 * f.atm.rho) * f.Vt2;
-  f.mach = f.Vt / f.atm.a;
+  f.mach = fm_div(f.Vt, f.atm.a);
   if (fabs(f.mach) > 0.0) {
     const double qc = pitot_total_pressure(f.mach, f.atm.P) - f.atm.P;
     f.vcas = ac.StdDaySLsoundspeed * mach_from_impact_pressure(qc, ac.StdDaySLpressure);
@@ -650,17 +656,17 @@ FDM_DEV double fdm_stage_engine(AcCore& a, const Props& p, const Atmo& atm, cons
   } else {  // tpRun (:196-272)
     const double idlethrust = K_ENG_milthrust * idleT, milthrust = (K_ENG_milthrust - idlethrust) * milT;
     const double sigma = atm.rho * ac.invSLdensity;
-    const double n = fmin(1.0, a.N2norm + 0.1);
+    const double n0 = a.N2norm + 0.1, n = n0 < 1.0 ? n0 : 1.0;   // fmin without its NaN handling
     const double sden = (1 + 3 * (1 - n) * (1 - n) * (1 - n) + (1 - sigma));
     const double dbase = 90.0 / (K_ENG_bypassratio + 3.0);
-    const double rden = 1.0 / sden;   // one reciprocal for the three spool rates
+    const double rden = fm_rcp(sden);   // one reciprocal for the three spool rates
     const double up = (1.0 * dbase) * rden, dn2 = (3.0 * dbase) * rden, dn1 = (2.4 * dbase) * rden;
     a.N2 = seek(a.N2, K_ENG_idlen2 + ThrottlePos * N2_factor, up, dn2);
     a.N1 = seek(a.N1, K_ENG_idlen1 + ThrottlePos * N1_factor, up, dn1);
     a.N2norm = (a.N2 - K_ENG_idlen2) * (1.0 / N2_factor);
     thrust = idlethrust + (milthrust * a.N2norm * a.N2norm);
     if (!augmentation) {
-      const double tsfc = K_ENG_tsfc * sqrt(atm.T * (1.0 / 389.7)) * (0.84 + (1 - a.N2norm) * (1 - a.N2norm));
+      const double tsfc = K_ENG_tsfc * fm_sqrt(atm.T * (1.0 / 389.7)) * (0.84 + (1 - a.N2norm) * (1 - a.N2norm));
       a.FF = seek(a.FF, thrust * tsfc, 1000.0, 10000.0);
       if (a.FF < K_ENG_idleff) a.FF = K_ENG_idleff;
     }
@@ -710,7 +716,7 @@ FDM_DEV void fdm_stage_accelerations(AcCore& a, Frame& f, const WindAxes& w, con
   const V3 F = Fa + Fp, M = Ma + Mp;
   // Accelerations (J/models/FGAccelerations.cpp:138-207)
   a.pqridot = mul(f.Jinv, M - cross(a.wi, mul(f.J, a.wi)));
-  const double rm = 1.0 / f.Mass;
+  const double rm = fm_rcp(f.Mass);
   a.bodyaccel = v3(F.x * rm, F.y * rm, F.z * rm);
   // vUVWidot = Tb2i * vBodyAccel + Tec2i * vGravAccel
   const V3 gi = v3(f.cos_epa * f.grav.x - f.sin_epa * f.grav.y, f.sin_epa * f.grav.x + f.cos_epa * f.grav.y, f.grav.z);
@@ -799,7 +805,7 @@ FDM_DEV void fdm_mass_cg(const AcCore& a, double& Mass, V3& cg) {
   pm = pm + K_PM0_W * v3(K_PM0_X, K_PM0_Y, K_PM0_Z);
   pm = pm + K_PM1_W * v3(K_PM1_X, K_PM1_Y, K_PM1_Z);
   const V3 num = (K_emptywt * v3(K_CG_X, K_CG_Y, K_CG_Z) + pm) + tm;
-  const double rw = 1.0 / Weight;
+  const double rw = fm_rcp(Weight);
   cg = v3(num.x * rw, num.y * rw, num.z * rw);
 }
 // MassBalance, second half: inertia tensor about the cg and its inverse.  tanks = the contents MassBalance saw (before this
@@ -837,7 +843,7 @@ FDM_DEV void fdm_inertia(const double t0, const double t1, const double t2, cons
   Jout = J;
   const double Ixx = J.m[0][0], Iyy = J.m[1][1], Izz = J.m[2][2], Ixy = -J.m[0][1], Ixz = -J.m[0][2], Iyz = -J.m[1][2];
   double k1 = (Iyy * Izz - Iyz * Iyz), k2 = (Iyz * Ixz + Ixy * Izz), k3 = (Ixy * Iyz + Iyy * Ixz);
-  const double denom = 1.0 / (Ixx * k1 - Ixy * k2 - Ixz * k3);
+  const double denom = fm_rcp(Ixx * k1 - Ixy * k2 - Ixz * k3);
   k1 = k1 * denom; k2 = k2 * denom; k3 = k3 * denom;
   const double k4 = (Izz * Ixx - Ixz * Ixz) * denom, k5 = (Ixy * Ixz + Iyz * Ixx) * denom, k6 = (Ixx * Iyy - Ixy * Ixy) * denom;
   Jinv.m[0][0] = k1; Jinv.m[0][1] = k2; Jinv.m[0][2] = k3;
@@ -900,7 +906,7 @@ FDM_DEV void fdm_frame_lean(AcCore& a, Props& p, FcsState& s, FrameKeep& keep, c
     M33 J, Jinv;
     fdm_inertia(tk0, tk1, tk2, tk3, cg_prev, cg, J, Jinv);
     a.pqridot = mul(Jinv, M - cross(a.wi, mul(J, a.wi)));
-    const double rm = 1.0 / Mass;
+    const double rm = fm_rcp(Mass);
     a.bodyaccel = v3(F.x * rm, F.y * rm, F.z * rm);
     const M33 Ti2b = quat_T(opaque(a.q0), opaque(a.q1), opaque(a.q2), opaque(a.q3));
     a.uvwidot = mulT(Ti2b, a.bodyaccel) + gi;
@@ -915,7 +921,7 @@ FDM_DEV void fdm_refresh(const AcCore& a, const Props& p, const FrameKeep& keep,
   fdm_propagate_pos(t, f, t.vi, 0.0);
   fdm_propagate_combine(t, pp, f, t.ri.x, t.ri.y);
   const double ecr = EARTH_B / EARTH_A;
-  const double slr = EARTH_A * ecr / sqrt(1.0 - (1.0 - ecr * ecr) * f.cosLatGc * f.cosLatGc);
+  const double slr = (EARTH_A * ecr) * fm_rsqrt(1.0 - (1.0 - ecr * ecr) * f.cosLatGc * f.cosLatGc);
   f.h_asl = f.radius - slr;
   f.vcas = keep.vcas; f.pilotN = v3(keep.pilot_nx, p.accelerations_n_pilot_y_norm, p.accelerations_n_pilot_z_norm);
   f.alpha = p.aero_alpha_rad; f.beta = keep.beta; f.mach = p.velocities_mach; f.thrust = keep.thrust;
@@ -1053,7 +1059,7 @@ FDM_DEV void fdm_reset(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
     bool steady = false, pAug = false;
     double pN1 = -1.0, pN2 = -1.0, pFF = -1.0;
     while (!steady && j < 6000) {
-      const double n = fmin(1.0, a.N2norm + 0.1);
+      const double n0 = a.N2norm + 0.1, n = n0 < 1.0 ? n0 : 1.0;   // fmin without its NaN handling
       const double sden = (1 + 3 * (1 - n) * (1 - n) * (1 - n) + (1 - sigma));
       const double up = (1.0 * dbase) / sden, dn2 = (3.0 * dbase) / sden, dn1 = (2.4 * dbase) / sden;
       a.N2 = seek(a.N2, K_ENG_idlen2 + ThrottlePos * N2_factor, up, dn2);

@@ -336,7 +336,7 @@ class CudaGen:
         for f in self.ir["aero_pre"]:
             code.append(f"  p.{cid(f['name'])} = {self.product(f['factors'], scope)};")
         code.append("  // FGAerodynamics::Run: bi2vel/ci2vel after the pre-functions (J/models/FGAerodynamics.cpp:152-158)")
-        code.append("  if (twovel != 0) { const double r2v = 1.0 / twovel; p.aero_bi2vel = K_bw * r2v; p.aero_ci2vel = K_cbarw * r2v; }")
+        code.append("  if (twovel != 0) { const double r2v = fm_rcp(twovel); p.aero_bi2vel = K_bw * r2v; p.aero_ci2vel = K_cbarw * r2v; }")
         for ax in self.ir["aero_axes"]:
             i = AXES.index(ax["axis"])
             code.append(f"  // axis {ax['axis']}")

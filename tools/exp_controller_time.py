@@ -42,6 +42,18 @@ for name, fn in (("F.layer_norm", lambda: F.layer_norm(x, (128,), w, b)), ("var_
                  ("native_layer_norm [N/8, 8, 128]", lambda: F.layer_norm(x.view(-1, 8, 128), (128,), w, b))):
     fn(); print("  %-34s %.1f us" % (name, 1e3 * timed(fn, 100)))
 print("  max |F.layer_norm - manual| = %.2e" % float((F.layer_norm(x, (128,), w, b) - ln_manual(x)).abs().max()))
+xt = x.t().contiguous(); wc = w[:, None].contiguous(); bc = b[:, None].contiguous(); ones = torch.full((128, 1), 1.0 / 128, device="cuda")
+def ln_t(xt):           # transposed layout [128, N]: the statistics reduce over the strided dimension, N stays contiguous
+    var, mean = torch.var_mean(xt, dim=0, correction=0, keepdim=True)
+    return torch.addcmul(bc, (xt - mean) * torch.rsqrt(var + 1e-5), wc)
+def ln_gemv(x):         # moments through two matrix-vector products
+    m = x @ ones; d = x - m; v = (d * d) @ ones
+    return torch.addcmul(b, d * torch.rsqrt(v + 1e-5), w)
+for name, fn in (("transposed var_mean + addcmul", lambda: ln_t(xt)), ("var_mean over dim 0 alone", lambda: torch.var_mean(xt, dim=0, correction=0, keepdim=True)),
+                 ("moments by gemv", lambda: ln_gemv(x)), ("x @ ones alone", lambda: x @ ones)):
+    fn(); print("  %-34s %.1f us" % (name, 1e3 * timed(fn, 100)))
+print("  max |F.layer_norm - transposed| = %.2e, gemv %.2e" % (float((F.layer_norm(x, (128,), w, b) - ln_t(xt).t()).abs().max()),
+                                                              float((F.layer_norm(x, (128,), w, b) - ln_gemv(x)).abs().max())))
 x12 = torch.randn(N, 12, device="cuda"); w1 = torch.randn(128, 12, device="cuda"); b1 = torch.randn(128, device="cuda")
 x16 = F.pad(x12, (0, 4)); w16 = F.pad(w1, (0, 4))
 for name, fn in (("linear K=12", lambda: F.linear(x12, w1, b1)), ("linear K=16 (padded)", lambda: F.linear(x16, w16, b1)),
