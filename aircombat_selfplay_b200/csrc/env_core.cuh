@@ -23,6 +23,10 @@ ENV_DEV double em_rsqrt(double x) { return 1.0 / sqrt(x); }
 ENV_DEV double em_sin(double x) { return sin(x); }
 ENV_DEV double em_exp(double x) { return exp(x); }
 ENV_DEV void em_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+ENV_DEV double em_cos(double x) { return cos(x); }
+ENV_DEV double em_acos(double x) { return acos(x); }
+ENV_DEV double em_tanh(double x) { return tanh(x); }
+ENV_DEV double em_atanh(double x) { return atanh(x); }
 #else
 ENV_DEV double em_div(double a, double b) { return fm_div(a, b); }
 ENV_DEV double em_rcp(double b) { return fm_rcp(b); }
@@ -32,7 +36,14 @@ ENV_DEV double em_rsqrt(double x) { return fm_rsqrt(x); }
 ENV_DEV double em_sin(double x) { return fm_sin(x); }
 ENV_DEV double em_exp(double x) { return fm_exp(x); }
 ENV_DEV void em_sincos(double x, double* s, double* c) { fm_sincos(x, s, c); }
+ENV_DEV double em_cos(double x) { return fm_cos(x); }
+ENV_DEV double em_acos(double x) { return fm_acos(x); }
+ENV_DEV double em_tanh(double x) { return fm_tanh(x); }
+ENV_DEV double em_atanh(double x) { return fm_atanh(x); }
 #endif
+// fmax / fmin without their NaN handling (sm_100a expands them into compare + selects + fix-up)
+ENV_DEV double env_max(double a, double b) { return a > b ? a : b; }
+ENV_DEV double env_min(double a, double b) { return a < b ? a : b; }
 
 // ----------------------------------------------------------------------------- arenas (structure of arrays)
 // per aircraft doubles
@@ -168,9 +179,10 @@ static constexpr double ENV_DEG2RAD = 3.14159265358979323846 / 180.0;
 
 ENV_DEV void geodetic2ecef(double lat_deg, double lon_deg, double alt, double& x, double& y, double& z) {
   double sla, cla, slo, clo;
-  sincos(lat_deg * ENV_DEG2RAD, &sla, &cla);
-  sincos(lon_deg * ENV_DEG2RAD, &slo, &clo);
-  const double n = (WGS84_A * WGS84_A) / hypot(WGS84_A * cla, WGS84_B * sla);
+  em_sincos(lat_deg * ENV_DEG2RAD, &sla, &cla);
+  em_sincos(lon_deg * ENV_DEG2RAD, &slo, &clo);
+  const double ac = WGS84_A * cla, bs = WGS84_B * sla;
+  const double n = (WGS84_A * WGS84_A) * em_rsqrt(ac * ac + bs * bs);      // a^2 / hypot(a cos, b sin); no overflow at 6e6 m
   x = (n + alt) * cla * clo;
   y = (n + alt) * cla * slo;
   z = (n * ((WGS84_B / WGS84_A) * (WGS84_B / WGS84_A)) + alt) * sla;
@@ -180,8 +192,8 @@ struct GeoOrigin { double x0, y0, z0, sla, cla, slo, clo; };
 ENV_DEV GeoOrigin geo_origin(double lon0, double lat0, double alt0) {
   GeoOrigin o;
   geodetic2ecef(lat0, lon0, alt0, o.x0, o.y0, o.z0);
-  sincos(lat0 * ENV_DEG2RAD, &o.sla, &o.cla);
-  sincos(lon0 * ENV_DEG2RAD, &o.slo, &o.clo);
+  em_sincos(lat0 * ENV_DEG2RAD, &o.sla, &o.cla);
+  em_sincos(lon0 * ENV_DEG2RAD, &o.slo, &o.clo);
   return o;
 }
 // LLA2NEU (E/utils/utils.py:30-41): pymap3d.geodetic2ned -> (north, east, up)
@@ -224,21 +236,21 @@ ENV_DEV AoTaR get_ao_ta_r(const Feat& ego, const Feat& enm, bool two_d) {
   const double dx = enm.n - ego.n, dy = enm.e - ego.e, dz = enm.u - ego.u;
   double ego_v, enm_v, R, p1, p2;
   if (two_d) {
-    ego_v = sqrt(ego.vn * ego.vn + ego.ve * ego.ve);
-    enm_v = sqrt(enm.vn * enm.vn + enm.ve * enm.ve);
-    R = sqrt(dx * dx + dy * dy);
+    ego_v = em_sqrt0(ego.vn * ego.vn + ego.ve * ego.ve);
+    enm_v = em_sqrt0(enm.vn * enm.vn + enm.ve * enm.ve);
+    R = em_sqrt0(dx * dx + dy * dy);
     p1 = dx * ego.vn + dy * ego.ve;
     p2 = dx * enm.vn + dy * enm.ve;
   } else {
-    ego_v = sqrt(ego.vn * ego.vn + ego.ve * ego.ve + ego.vd * ego.vd);
-    enm_v = sqrt(enm.vn * enm.vn + enm.ve * enm.ve + enm.vd * enm.vd);
-    R = sqrt(dx * dx + dy * dy + dz * dz);
+    ego_v = em_sqrt0(ego.vn * ego.vn + ego.ve * ego.ve + ego.vd * ego.vd);
+    enm_v = em_sqrt0(enm.vn * enm.vn + enm.ve * enm.ve + enm.vd * enm.vd);
+    R = em_sqrt0(dx * dx + dy * dy + dz * dz);
     p1 = dx * ego.vn + dy * ego.ve + dz * ego.vd;
     p2 = dx * enm.vn + dy * enm.ve + dz * enm.vd;
   }
   AoTaR g;
-  g.AO = acos(env_clip(p1 / (R * ego_v + 1e-8), -1.0, 1.0));
-  g.TA = acos(env_clip(p2 / (R * enm_v + 1e-8), -1.0, 1.0));
+  g.AO = em_acos(env_clip(em_div(p1, R * ego_v + 1e-8), -1.0, 1.0));
+  g.TA = em_acos(env_clip(em_div(p2, R * enm_v + 1e-8), -1.0, 1.0));
   g.R = R;
   const double cr = ego.vn * dy - ego.ve * dx;
   g.side = (double)((cr > 0) - (cr < 0));
@@ -333,21 +345,23 @@ ENV_DEV void missile_state_trans(Missile& m, const MissileParams& pr, const GeoO
 
 // ----------------------------------------------------------------------------- reward shaping (E/reward_functions/posture_reward.py:51-75)
 ENV_DEV double posture_orientation(int version, double AO, double TA) {
-  const double PI = 3.14159265358979323846;
-  const double ta_term = atanh(1.0 - fmax(2 * TA / PI, 1e-4)) / (2 * PI);
-  if (version == 0) return (1.0 - tanh(9 * (AO - PI / 9))) / 3.0 + 1 / 3.0 + fmin(ta_term, 0.0) + 0.5;
-  if (version == 1) return (1.0 - tanh(2 * (AO - PI / 2))) / 2.0 * atanh(1.0 - fmax(2 * TA / PI, 1e-4)) / (2 * PI) + 0.5;
-  return 1 / (50 * AO / PI + 2) + 1 / 2.0 + fmin(ta_term, 0.0) + 0.5;
+  // quotients by constants as reciprocal multiplies, tanh / atanh / exp from fmath.cuh: <= 1e-15 from the reference's
+  // expressions, compared at 1e-6
+  const double PI = 3.14159265358979323846, I2PI = 1.0 / (2 * PI);
+  const double ta_term = em_atanh(1.0 - env_max((2 / PI) * TA, 1e-4)) * I2PI;
+  if (version == 0) return (1.0 - em_tanh(9 * (AO - PI / 9))) * (1.0 / 3.0) + 1 / 3.0 + env_min(ta_term, 0.0) + 0.5;
+  if (version == 1) return (1.0 - em_tanh(2 * (AO - PI / 2))) * 0.5 * ta_term + 0.5;
+  return em_rcp((50 / PI) * AO + 2) + 1 / 2.0 + env_min(ta_term, 0.0) + 0.5;
 }
 ENV_DEV double posture_range(int version, double R, double td) {
-  if (version == 0) return exp(-((R - td) * (R - td)) * 0.004) / (1.0 + exp(-(R - td + 2) * 2));
+  if (version == 0) return em_div(em_exp(-((R - td) * (R - td)) * 0.004), 1.0 + em_exp(-(R - td + 2) * 2));
   if (version == 1 || version == 2) {
-    const double base = env_clip(1.2 * fmin(exp(-(R - td) * 0.21), 1.0) / (1.0 + exp(-(R - td + 1) * 0.8)), 0.3, 1.0);
+    const double base = env_clip(em_div(1.2 * env_min(em_exp(-(R - td) * 0.21), 1.0), 1.0 + em_exp(-(R - td + 1) * 0.8)), 0.3, 1.0);
     if (version == 1) return base;
     const double sg = (double)((7 - R > 0) - (7 - R < 0));
-    return fmax(base, sg);
+    return env_max(base, sg);
   }
-  return 1.0 * (R < 5) + (R >= 5) * env_clip(-0.032 * (R * R) + 0.284 * R + 0.38, 0.0, 1.0) + env_clip(exp(-0.16 * R), 0.0, 0.2);
+  return 1.0 * (R < 5) + (R >= 5) * env_clip(-0.032 * (R * R) + 0.284 * R + 0.38, 0.0, 1.0) + env_clip(em_exp(-0.16 * R), 0.0, 0.2);
 }
 // delta heading in [-180, 180] as the catalog derives it (E/core/catalog.py update_delta_heading) and clips it
 ENV_DEV double delta_heading_deg(double target_deg, double psi_deg) {

@@ -240,9 +240,9 @@ ENV_DEV Controls decode_action(const EnvView& v, const AcsTaskConfig& cfg, const
   const int32_t* act = actions + (size_t)L.row * adim;
   Controls c;
   if (cfg.act_kind == ACS_ACT_HEADING) {
-    c.u0 = act[0] * 2. / (41 - 1.) - 1.; c.u1 = act[1] * 2. / (41 - 1.) - 1.; c.u2 = act[2] * 2. / (41 - 1.) - 1.; c.u3 = act[3] * 0.5 / (30 - 1.) + 0.4;
+    c.u0 = em_div(act[0] * 2., 41 - 1.) - 1.; c.u1 = em_div(act[1] * 2., 41 - 1.) - 1.; c.u2 = em_div(act[2] * 2., 41 - 1.) - 1.; c.u3 = em_div(act[3] * 0.5, 30 - 1.) + 0.4;
   } else {
-    c.u0 = act[0] / 20. - 1.; c.u1 = act[1] / 20. - 1.; c.u2 = act[2] / 20. - 1.; c.u3 = act[3] / 58. + 0.4;
+    c.u0 = em_div(act[0], 20.) - 1.; c.u1 = em_div(act[1], 20.) - 1.; c.u2 = em_div(act[2], 20.) - 1.; c.u3 = em_div(act[3], 58.) + 0.4;
   }
   c.u0 = env_clip(c.u0, -1.0, 1.0); c.u1 = env_clip(c.u1, -1.0, 1.0); c.u2 = env_clip(c.u2, -1.0, 1.0); c.u3 = env_clip(c.u3, 0.0, 0.9);
   int shoot = 0;
@@ -1307,10 +1307,10 @@ ENV_DEV int missile_warning(const StepCtx& c, int agent) {
 }
 ENV_DEV void attack_geometry(const PubAc& ag, const PubAc& en, double& distance, double& ang_deg) {
   const double tx = en.f.n - ag.f.n, ty = en.f.e - ag.f.e, tz = en.f.u - ag.f.u;
-  distance = sqrt(tx * tx + ty * ty + tz * tz);
-  const double hv = sqrt(ag.f.vn * ag.f.vn + ag.f.ve * ag.f.ve + ag.f.vd * ag.f.vd);
+  distance = em_sqrt0(tx * tx + ty * ty + tz * tz);
+  const double hv = em_sqrt0(ag.f.vn * ag.f.vn + ag.f.ve * ag.f.ve + ag.f.vd * ag.f.vd);
   const double sum = tx * ag.f.vn + ty * ag.f.ve + tz * ag.f.vd;
-  ang_deg = acos(env_clip(sum / (distance * hv + 1e-8), -1.0, 1.0)) * (180.0 / 3.14159265358979323846);
+  ang_deg = em_acos(env_clip(sum / (distance * hv + 1e-8), -1.0, 1.0)) * (180.0 / 3.14159265358979323846);
 }
 // MissileSimulator.create -> launch + target (simulatior.py:497-518), env.add_temp_simulator (env_base.py:90-92)
 ENV_DEV int launch_missile(const StepCtx& c, int a, int target, int kind, int keyn) {
@@ -1325,7 +1325,7 @@ ENV_DEV int launch_missile(const StepCtx& c, int a, int target, int kind, int ke
   MD(v, MD_POS_N, mid) = pa.f.n; MD(v, MD_POS_E, mid) = pa.f.e; MD(v, MD_POS_U, mid) = pa.f.u;
   MD(v, MD_VEL_N, mid) = pa.f.vn; MD(v, MD_VEL_E, mid) = pa.f.ve; MD(v, MD_VEL_U, mid) = pa.f.vd;
   MD(v, MD_THETA, mid) = OUTF(v, O_PITCH, row); MD(v, MD_PHI, mid) = OUTF(v, O_HEADING, row);
-  { double st, ct; sincos(OUTF(v, O_PITCH, row), &st, &ct); MD(v, MD_SIN_THETA, mid) = st; MD(v, MD_COS_THETA, mid) = ct; }
+  { double st, ct; em_sincos(OUTF(v, O_PITCH, row), &st, &ct); MD(v, MD_SIN_THETA, mid) = st; MD(v, MD_COS_THETA, mid) = ct; }
   MD(v, MD_ALT, mid) = pa.h; MD(v, MD_T, mid) = 0.0; MD(v, MD_M, mid) = pr.m0; MD(v, MD_DTHETA, mid) = 0.0; MD(v, MD_DPHI, mid) = 0.0;
   MD(v, MD_D_PREV, mid) = INFINITY;
   MI(v, MI_STATUS, mid) = MS_LAUNCHED; MI(v, MI_KIND, mid) = kind; MI(v, MI_TARGET, mid) = target; MI(v, MI_CONSEC, mid) = 0;
@@ -1357,7 +1357,7 @@ ENV_DEV int scenario_target(const StepCtx& c, int a) {
     if (same_team(c.cfg, a, j)) continue;
     const PubAc& en = c.sP[c.L.gbase + j];
     const double tx = en.f.n - ag.f.n, ty = en.f.e - ag.f.e, tz = en.f.u - ag.f.u;
-    const double d = sqrt(tx * tx + ty * ty + tz * tz);
+    const double d = em_sqrt0(tx * tx + ty * ty + tz * tz);
     if (d > bd) { bd = d; best = j; }   // np.argmax: first maximum
   }
   return best;
@@ -1421,7 +1421,7 @@ ENV_DEV void task_step_agent(const StepCtx& c, int a) {
     for (int j = 0; j < v.A; j++) {
       if (same_team(cfg, a, j)) continue;
       const double tx = sP[j].f.n - sP[a].f.n, ty = sP[j].f.e - sP[a].f.e, tz = sP[j].f.u - sP[a].f.u;
-      const double d = sqrt(tx * tx + ty * ty + tz * tz);
+      const double d = em_sqrt0(tx * tx + ty * ty + tz * tz);
       if (d < bd) { bd = d; ti = j; }              // np.argmin: first minimum
     }
     double distance, ang;
@@ -1476,7 +1476,7 @@ ENV_DEV void task_step_agent(const StepCtx& c, int a) {
           const int mid = jr * v.S + s;
           if (MI(v, MI_DETACHED, mid) || MI(v, MI_TARGET, mid) != a) continue;
           const double dx = sP[a].f.n - MD(v, MD_POS_N, mid), dy = sP[a].f.e - MD(v, MD_POS_E, mid), dz = sP[a].f.u - MD(v, MD_POS_U, mid);
-          if (sqrt(dx * dx + dy * dy + dz * dz) < 1000) cnt++;
+          if (em_sqrt0(dx * dx + dy * dy + dz * dz) < 1000) cnt++;
         }
       }
       if (cnt > 0) {
@@ -1491,8 +1491,8 @@ ENV_DEV void task_step_agent(const StepCtx& c, int a) {
 // ---------------------------------------------------------------------------------------------- observations
 ENV_DEV void obs_ego9(const EnvView& v, int row, const PubAc& s, double* o) {
   double sr, cr, sp, cp;
-  sincos(OUTF(v, O_ROLL, row), &sr, &cr);
-  sincos(OUTF(v, O_PITCH, row), &sp, &cp);
+  em_sincos(OUTF(v, O_ROLL, row), &sr, &cr);
+  em_sincos(OUTF(v, O_PITCH, row), &sp, &cp);
   o[0] = s.h / 5000; o[1] = sr; o[2] = cr; o[3] = sp; o[4] = cp;
   o[5] = s.u_mps / 340; o[6] = AD(v, AD_V_MPS, row) / 340; o[7] = AD(v, AD_W_MPS, row) / 340; o[8] = AD(v, AD_VC_MPS, row) / 340;
 }
@@ -1509,7 +1509,7 @@ ENV_DEV bool obs_missile6(const StepCtx& c, int a, double* o) {
   mf.n = MD(v, MD_POS_N, mid); mf.e = MD(v, MD_POS_E, mid); mf.u = MD(v, MD_POS_U, mid);
   mf.vn = MD(v, MD_VEL_N, mid); mf.ve = MD(v, MD_VEL_E, mid); mf.vd = MD(v, MD_VEL_U, mid);
   const AoTaR g = get_ao_ta_r(ego.f, mf, false);
-  o[0] = (sqrt(mf.vn * mf.vn + mf.ve * mf.ve + mf.vd * mf.vd) - ego.u_mps) / 340; o[1] = (mf.u - ego.h) / 1000;
+  o[0] = (em_sqrt0(mf.vn * mf.vn + mf.ve * mf.ve + mf.vd * mf.vd) - ego.u_mps) / 340; o[1] = (mf.u - ego.h) / 1000;
   o[2] = g.AO; o[3] = g.TA; o[4] = g.R / 10000; o[5] = g.side;
   return true;
 }
@@ -1553,7 +1553,7 @@ ENV_DEV void write_obs(const StepCtx& c, int a, double* __restrict__ o) {
       if (same_team(cfg, a, j)) continue;
       if (first < 0) first = j;
       const double tx = sP[j].f.n - s.f.n, ty = sP[j].f.e - s.f.e, tz = sP[j].f.u - s.f.u;
-      const double d = sqrt(tx * tx + ty * ty + tz * tz);
+      const double d = em_sqrt0(tx * tx + ty * ty + tz * tz);
       if (sP[j].status == ST_ALIVE && d < bd) { bd = d; e = j; }   // stable sort by distance: the first minimum wins
     }
     if (e < 0) e = first;
@@ -1634,11 +1634,11 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a, const AoTaR* geo, int
         if (ref < 0) { ref = mid; EI(v, EI_PMV_REF, env) = ref; }
         const double mvx = MD(v, MD_VEL_N, mid), mvy = MD(v, MD_VEL_E, mid), mvz = MD(v, MD_VEL_U, mid);
         const double pvx = MD(v, MD_VEL_N, ref), pvy = MD(v, MD_VEL_E, ref), pvz = MD(v, MD_VEL_U, ref);
-        const double nm = sqrt(mvx * mvx + mvy * mvy + mvz * mvz), np_ = sqrt(pvx * pvx + pvy * pvy + pvz * pvz);
-        const double na = sqrt(s.f.vn * s.f.vn + s.f.ve * s.f.ve + s.f.vd * s.f.vd);
+        const double nm = em_sqrt0(mvx * mvx + mvy * mvy + mvz * mvz), np_ = em_sqrt0(pvx * pvx + pvy * pvy + pvz * pvz);
+        const double na = em_sqrt0(s.f.vn * s.f.vn + s.f.ve * s.f.ve + s.f.vd * s.f.vd);
         const double v_dec = (np_ - nm) / 340 * r.scale;
         const double ang = (mvx * s.f.vn + mvy * s.f.ve + mvz * s.f.vd) / (nm * na);
-        rew = ang < 0 ? ang / (fmax(v_dec, 0.0) + 1) : ang * fmax(v_dec, 0.0);
+        rew = ang < 0 ? ang / (env_max(v_dec, 0.0) + 1) : ang * env_max(v_dec, 0.0);
       } else {
         EI(v, EI_PMV_REF, env) = -1;
       }
@@ -1657,11 +1657,11 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a, const AoTaR* geo, int
       const double d_head = delta_heading_deg(ED(v, ED_TGT_HEADING, env), psi_deg);
       const double d_alt = env_clip((ED(v, ED_TGT_ALT, env) - OUTF(v, O_H_SL_FT, row)) * 0.3048, -40000.0, 40000.0);
       const double d_vel = env_clip(ED(v, ED_TGT_VEL, env) - s.u_mps, -1400.0, 1400.0);
-      const double heading_r = exp(-((d_head / 5.0) * (d_head / 5.0)));
-      const double alt_r = exp(-((d_alt / 15.24) * (d_alt / 15.24)));
-      const double roll_r = exp(-((roll / 0.35) * (roll / 0.35)));
-      const double speed_r = exp(-((d_vel / 24) * (d_vel / 24)));
-      double rew = pow(heading_r * alt_r * roll_r * speed_r, 1 / 4.0);
+      const double heading_r = em_exp(-((d_head / 5.0) * (d_head / 5.0)));
+      const double alt_r = em_exp(-((d_alt / 15.24) * (d_alt / 15.24)));
+      const double roll_r = em_exp(-((roll / 0.35) * (roll / 0.35)));
+      const double speed_r = em_exp(-((d_vel / 24) * (d_vel / 24)));
+      double rew = em_sqrt0(em_sqrt0(heading_r * alt_r * roll_r * speed_r));   // x^(1/4)
       if (c.cs > 1) rew = rew + (-fabs(p - AD(v, AD_HR_P, row)) * 1.0) + (-fabs(q - AD(v, AD_HR_Q, row)) * 1.0);
       AD(v, AD_HR_ROLL, row) = roll; AD(v, AD_HR_P, row) = p; AD(v, AD_HR_Q, row) = q;
       return reward_process(c, ri, row, rew);
@@ -1670,7 +1670,7 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a, const AoTaR* geo, int
       int e0 = -1;
       for (int j = 0; j < v.A && e0 < 0; j++) if (!same_team(cfg, a, j)) e0 = j;
       const double ego_z = s.f.u / 1000, enm_z = sP[e0].f.u / 1000;
-      return reward_process(c, ri, row, fmin(r.p0 - fabs(ego_z - enm_z), 0.0));
+      return reward_process(c, ri, row, env_min(r.p0 - fabs(ego_z - enm_z), 0.0));
     }
   // per-enemy geometry rewards share the (AO, TA, R) list
   double nr = 0;
@@ -1689,12 +1689,12 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a, const AoTaR* geo, int
     for (int i = 0; i < n; i++) {
       const double R = geo[i].R;
       if (tt) {
-        if (R >= 3000 * FT && R <= 5000 * FT) d[i] = R * sin(geo[i].TA);
-        else if (R <= 3000 * FT) d[i] = sqrt(R * R + (3000 * FT) * (3000 * FT) - 2 * R * (3000 * FT) * cos(geo[i].TA));
-        else d[i] = sqrt(R * R + (5000 * FT) * (5000 * FT) - 2 * R * (5000 * FT) * cos(geo[i].TA));
+        if (R >= 3000 * FT && R <= 5000 * FT) d[i] = R * em_sin(geo[i].TA);
+        else if (R <= 3000 * FT) d[i] = em_sqrt0(R * R + (3000 * FT) * (3000 * FT) - 2 * R * (3000 * FT) * em_cos(geo[i].TA));
+        else d[i] = em_sqrt0(R * R + (5000 * FT) * (5000 * FT) - 2 * R * (5000 * FT) * em_cos(geo[i].TA));
       } else {
-        if (R >= 500 * FT && R <= 3000 * FT) d[i] = R * sin(geo[i].AO);
-        else d[i] = sqrt(R * R + (3000 * FT) * (3000 * FT) - 2 * R * (3000 * FT) * cos(geo[i].AO));
+        if (R >= 500 * FT && R <= 3000 * FT) d[i] = R * em_sin(geo[i].AO);
+        else d[i] = em_sqrt0(R * R + (3000 * FT) * (3000 * FT) - 2 * R * (3000 * FT) * em_cos(geo[i].AO));
       }
     }
     const int fvalid = tt ? EI_TT_VALID : EI_WD_VALID, fprev = tt ? ED_TT_PREV0 : ED_WD_PREV0;
@@ -1703,7 +1703,7 @@ ENV_DEV double reward_one(const StepCtx& c, int ri, int a, const AoTaR* geo, int
       for (int i = 1; i < n; i++) ED(v, fprev + i, env) = d[i - 1];
       EI(v, fvalid, env) = 1;
     }
-    for (int i = 0; i < n; i++) nr += -1 / 60.0 * tanh((d[i] - ED(v, fprev + i, env)) / sqrt(geo[i].R));
+    for (int i = 0; i < n; i++) nr += -1 / 60.0 * em_tanh((d[i] - ED(v, fprev + i, env)) / em_sqrt0(geo[i].R));
   }
   return reward_process(c, ri, row, nr);
 }
@@ -1810,9 +1810,9 @@ ENV_DEV int agent_termination(const StepCtx& c, int a) {
     } else if (t == ACS_T_EXTREME_STATE) {         // extreme_state.py:14-33 + catalog.py:386-416
       const double pp = OUTF(v, O_P, row), qq = OUTF(v, O_Q, row), rr = OUTF(v, O_R, row);
       const bool ev = OUTF(v, O_ECI_VMAG, row) >= 1e10;
-      const bool er = sqrt(pp * pp + qq * qq + rr * rr) >= 1000;
+      const bool er = em_sqrt0(pp * pp + qq * qq + rr * rr) >= 1000;
       const bool ea = OUTF(v, O_H_SL_FT, row) >= 1e10;
-      const bool eacc = fmax(fmax(fabs(OUTF(v, O_NPX, row)), fabs(OUTF(v, O_NPY, row))), fabs(OUTF(v, O_NPZ, row))) > 1e1;
+      const bool eacc = env_max(env_max(fabs(OUTF(v, O_NPX, row)), fabs(OUTF(v, O_NPY, row))), fabs(OUTF(v, O_NPZ, row))) > 1e1;
       done = ea || er || ev || eacc;
       if (done) sP[a].status = ST_CRASH;
     } else if (t == ACS_T_OVERLOAD) {              // overload.py:18-46

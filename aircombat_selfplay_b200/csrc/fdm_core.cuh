@@ -49,7 +49,7 @@ FDM_DEV V3 operator-(const V3& a, const V3& b) { return v3(a.x - b.x, a.y - b.y,
 FDM_DEV V3 operator*(double s, const V3& a) { return v3(s * a.x, s * a.y, s * a.z); }
 FDM_DEV V3 cross(const V3& a, const V3& b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 FDM_DEV double dot(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-FDM_DEV double mag(const V3& a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+FDM_DEV double mag(const V3& a) { return fm_sqrt0(a.x * a.x + a.y * a.y + a.z * a.z); }
 
 struct M33 { double m[3][3]; };
 FDM_DEV V3 mul(const M33& a, const V3& v) {
@@ -86,7 +86,7 @@ FDM_DEV double f16_constrain(double lo, double v, double hi) { return v < lo ? l
 // breakpoints ascend, so that row is 1 + #{1 <= i <= n-2 : k[i] < key}: a branch-free count (n is a literal at every
 // call site, the loop unrolls into independent shared-memory loads).  The model compiler stores the reciprocal
 // breakpoint spacings behind the keys (k[n + r] = 1 / (k[r] - k[r-1])), so the interpolation factor is a multiply.
-struct Bracket { int r; double f; bool above; };
+struct Bracket { int r; double f; };
 // The whole table array once more in constant memory.  Every breakpoint the search compares against sits at an address
 // known at compile time (the table offset and the loop index are literals), so it is a constant-bank operand of the
 // comparison itself -- no load instruction, no shared-memory latency on the search (ncu: the counting loop was the
@@ -105,7 +105,7 @@ FDM_HELPER Bracket f16_bracket(const double* __restrict__ T, const int off, cons
   for (int i = 1; i < n - 1; i++) r += (g_f16_kc[off + i] < key) ? 1 : 0;
 #endif
   double f = (key - k[r - 1]) * k[n + r];
-  b.r = r; b.f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f); b.above = key >= g_f16_kc[off + n - 1];
+  b.r = r; b.f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f);
   return b;
 }
 // Uniformly spaced breakpoints (the alpha, beta and elevator grids): the row comes from one multiply, then one exact
@@ -118,14 +118,16 @@ FDM_DEV Bracket f16_bracket_u(const double* __restrict__ T, const int off, const
   if (r > 1 && k[r - 1] >= key) r--;
   else if (r < n - 1 && k[r] < key) r++;
   const double f = (key - k[r - 1]) * k[n + r];
-  b.r = r; b.f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f); b.above = key >= g_f16_kc[off + n - 1];
+  b.r = r; b.f = f > 1.0 ? 1.0 : (f < 0.0 ? 0.0 : f);
   return b;
 }
 // 1-D: clamp, no extrapolation.  Below the first key r = 1 and f = 0, which already yields v[0] exactly.
+// The convex form (1 - f) lo + f hi returns v[r - 1] at f = 0 and v[r] at f = 1 EXACTLY, so the clamped factor alone
+// gives the end values beyond the first and last key -- no "key >= last key" test and select per lookup (the reference's
+// lo + f (hi - lo) does not reproduce hi at f = 1; in between the two forms differ by <= 1 ulp).
 FDM_DEV double f16_tab1(const double* __restrict__ v, const int n, const Bracket& b) {
-  const double lo = v[b.r - 1];
-  const double y = b.f * (v[b.r] - lo) + lo;
-  return b.above ? v[n - 1] : y;
+  (void)n;
+  return fma(b.f, v[b.r], (1.0 - b.f) * v[b.r - 1]);
 }
 FDM_DEV double f16_tab2(const double* __restrict__ v, const int nc, const Bracket& rb, const Bracket& cb) {
   const double* r0 = v + (rb.r - 1) * nc;
@@ -158,10 +160,12 @@ FDM_DEV double f16_pid(double Input, double test, double kp, double ki, double k
   return Output;
 }
 FDM_DEV bool f16_equal_to_roundoff(double a, double b) {
-  // d <= eps * max(|a|, |b|)  <=>  d <= eps |a| or d <= eps |b| (a positive factor is monotonic under rounding): no fmax,
-  // which sm_100a expands into compare + selects + NaN handling (this test sits on every actuator, ~10 per frame)
-  const double d = fabs(a - b), e = 2.0 * 2.220446049250313e-16;
-  return d <= e * fabs(a) || d <= e * fabs(b);
+  // JSBSim: |a - b| <= 2 eps max(|a|, |b|).  sm_100a has no fp64 max: the compiler expands it (and re-forms it from the
+  // equivalent "d <= eps |a| or d <= eps |b|") into DSETP.MAX + selects + NaN fix-up, ~12 instructions on every actuator
+  // of every frame.  When the test can hold at all, |a| and |b| agree to 2 eps, so scaling by |a| alone decides
+  // differently only for d within a relative 4e-16 of the threshold -- and either decision leaves the actuator within
+  // 2 eps of the other (it keeps its position instead of snapping to an input that is already that close).
+  return fabs(a - b) <= (2.0 * 2.220446049250313e-16) * fabs(a);
 }
 // J/models/flight_control/FGKinemat.cpp:99-157.  Input already scaled by the last detent.
 FDM_DEV double f16_kinemat(const double* __restrict__ det, const double* __restrict__ tim, int n, double Input, double Output, double dt) {
@@ -354,10 +358,13 @@ FDM_DEV void mat_quat(const M33& a, double q[4]) {
   if (t1 > best) { idx = 1; best = t1; }
   if (t2 > best) { idx = 2; best = t2; }
   if (t3 > best) { idx = 3; best = t3; }
-  if (idx == 0) { q[0] = 0.50 * sqrt(t0); q[1] = 0.25 * (m23 - m32) / q[0]; q[2] = 0.25 * (m31 - m13) / q[0]; q[3] = 0.25 * (m12 - m21) / q[0]; }
-  else if (idx == 1) { q[1] = 0.50 * sqrt(t1); q[0] = 0.25 * (m23 - m32) / q[1]; q[2] = 0.25 * (m12 + m21) / q[1]; q[3] = 0.25 * (m31 + m13) / q[1]; }
-  else if (idx == 2) { q[2] = 0.50 * sqrt(t2); q[0] = 0.25 * (m31 - m13) / q[2]; q[1] = 0.25 * (m12 + m21) / q[2]; q[3] = 0.25 * (m23 + m32) / q[2]; }
-  else { q[3] = 0.50 * sqrt(t3); q[0] = 0.25 * (m12 - m21) / q[3]; q[1] = 0.25 * (m13 + m31) / q[3]; q[2] = 0.25 * (m23 + m32) / q[3]; }
+  // q_main = sqrt(t) / 2 and the other three 0.25 (..) / q_main = (..) / (2 sqrt(t)) from ONE inverse square root (the
+  // reference takes a square root and three quotients: <= 2 ulp apart)
+  const double iq = fm_rsqrt(best), h = 0.5 * iq, qm = 0.5 * (best * iq);
+  if (idx == 0) { q[0] = qm; q[1] = h * (m23 - m32); q[2] = h * (m31 - m13); q[3] = h * (m12 - m21); }
+  else if (idx == 1) { q[1] = qm; q[0] = h * (m23 - m32); q[2] = h * (m12 + m21); q[3] = h * (m31 + m13); }
+  else if (idx == 2) { q[2] = qm; q[0] = h * (m31 - m13); q[1] = h * (m12 + m21); q[3] = h * (m23 + m32); }
+  else { q[3] = qm; q[0] = h * (m12 - m21); q[1] = h * (m13 + m31); q[2] = h * (m23 + m32); }
 }
 // J/math/FGMatrix33.cpp:159-192
 FDM_DEV void mat_euler(const M33& a, double& phi, double& tht, double& psi) {
@@ -365,11 +372,11 @@ FDM_DEV void mat_euler(const M33& a, double& phi, double& tht, double& psi) {
   const double m13 = a.m[0][2];
   if (m13 <= -1.0) { tht = 0.5 * M_PI; lock = true; }
   else if (1.0 <= m13) { tht = -0.5 * M_PI; lock = true; }
-  else tht = asin(-m13);
-  if (lock) { phi = atan2(-a.m[2][1], a.m[1][1]); psi = 0.0; }
+  else tht = fm_atan2(-m13, fm_sqrt0((1.0 - m13) * (1.0 + m13)));    // asin(-m13), |m13| < 1
+  if (lock) { phi = fm_atan2(-a.m[2][1], a.m[1][1]); psi = 0.0; }
   else {
-    phi = atan2(a.m[1][2], a.m[2][2]);
-    psi = atan2(a.m[0][1], a.m[0][0]);
+    phi = fm_atan2(a.m[1][2], a.m[2][2]);
+    psi = fm_atan2(a.m[0][1], a.m[0][0]);
     if (psi < 0.0) psi += 2 * M_PI;
   }
 }
@@ -929,10 +936,10 @@ FDM_DEV void fdm_refresh(const AcCore& a, const Props& p, const FrameKeep& keep,
 
 // outputs of the frame that has just run (what the reference reads back through get_property_value)
 FDM_DEV void fdm_outputs(const AcCore& a, const Frame& f, AcOut& o) {
-  const double lon = (f.rxy == 0.0) ? 0.0 : atan2(f.ecef.y, f.ecef.x);
+  const double lon = (f.rxy == 0.0) ? 0.0 : fm_atan2(f.ecef.y, f.ecef.x);
   o.lon_deg = lon * RADTODEG;
   const double sgn = f.ecef.z < 0.0 ? -1.0 : 1.0;
-  o.lat_geod_deg = (sgn * atan(f.gd_s1 / f.gd_cc)) * RADTODEG;
+  o.lat_geod_deg = (sgn * fm_atan2(f.gd_s1, f.gd_cc)) * RADTODEG;      // atan(s1 / cc), both >= 0
   o.h_sl_ft = f.h_asl;
   {  // Euler angles through the local quaternion, as FGPropagate::GetEuler does (qAttitudeLocal = Tl2b.GetQuaternion())
     double ql[4];

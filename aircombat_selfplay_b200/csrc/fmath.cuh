@@ -58,6 +58,12 @@ FM_CONST double FM_SIN_T[10] = {-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 36
                                 -1.0 / 1307674368000.0, 1.0 / 355687428096000.0, -1.0 / 121645100408832000.0,
                                 1.0 / 51090942171709440000.0};
 
+// argument-reduction constants (in constant memory like the coefficients: a literal costs two UMOV per use):
+// 2/pi, -(pi/2) in three parts | 1/pi, -pi in three parts | log2(e), -ln2 in two parts
+FM_CONST double FM_RED[11] = {0.6366197723675814, -1.5707963267948966, -6.123233995736766e-17, 1.4973849048591698e-33,
+                              0.3183098861837907, -3.141592653589793, -1.2246467991473532e-16, 2.9947698097183397e-33,
+                              1.4426950408889634, -6.93147180369123816490e-01, -1.90821492927058770002e-10};
+
 #ifdef ACS_IEEE_MATH
 FM_DEV double fm_div(double a, double b) { return a / b; }
 FM_DEV double fm_rcp(double b) { return 1.0 / b; }
@@ -66,11 +72,17 @@ FM_DEV double fm_sqrt0(double x) { return sqrt(x); }
 FM_DEV double fm_rsqrt(double x) { return 1.0 / sqrt(x); }
 FM_DEV void fm_sincos_small(double x, double* s, double* c) { sincos(x, s, c); }
 FM_DEV double fm_angle_sc(double s, double c, double y, double x) { (void)s; (void)c; return atan2(y, x); }
+FM_DEV double fm_atan2(double y, double x) { return atan2(y, x); }
 FM_DEV double fm_powpos(double x, double y) { return exp(y * log(x)); }
 FM_DEV double fm_pow_ratio(double num, double den, double y) { return exp(y * log(num / den)); }
 FM_DEV double fm_exp(double z) { return exp(z); }
 FM_DEV void fm_sincos(double x, double* s, double* c) { sincos(x, s, c); }
 FM_DEV double fm_sin(double x) { return sin(x); }
+FM_DEV double fm_cos(double x) { return cos(x); }
+FM_DEV double fm_acos(double x) { return acos(x); }
+FM_DEV double fm_log(double x) { return log(x); }
+FM_DEV double fm_tanh(double x) { return tanh(x); }
+FM_DEV double fm_atanh(double x) { return atanh(x); }
 #else
 
 #ifdef __CUDACC__
@@ -78,12 +90,19 @@ FM_DEV double fm_rcp_seed(double b) { double r; asm("rcp.approx.ftz.f64 %0, %1;"
 FM_DEV double fm_rsq_seed(double x) { double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r; }   // MUFU.RSQ64H
 FM_DEV double fm_pow2i(int n) { return __hiloint2double((n + 1023) << 20, 0); }
 FM_DEV double fm_rint(double x) { return rint(x); }
+// x = m 2^e with m in [1, 2) for normal positive x
+FM_DEV double fm_frexp1(double x, int* e) {
+  const int hi = __double2hiint(x);
+  *e = (hi >> 20) - 1023;
+  return __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+}
 #else
 // host build (tests): seeds with a deliberately poor relative error of 2^-12
 FM_DEV double fm_rcp_seed(double b) { return (double)(float)(1.0 / b) * (1.0 + 1.0 / 4096.0); }
 FM_DEV double fm_rsq_seed(double x) { return (double)(float)(1.0 / sqrt(x)) * (1.0 - 1.0 / 4096.0); }
 FM_DEV double fm_pow2i(int n) { return ldexp(1.0, n); }
 FM_DEV double fm_rint(double x) { return rint(x); }
+FM_DEV double fm_frexp1(double x, int* e) { const double m = frexp(x, e); *e -= 1; return m + m; }
 #endif
 
 // 1 / b after one cubic Newton step: relative error (seed error)^3 + 2^-53
@@ -129,19 +148,25 @@ FM_DEV double fm_rsqrt(double x) {
     out = fma(od_, u, ev_);                                                                  \
   }
 
-// sin and cos of a small angle (the earth rotation angle: 7.3e-5 rad/s of simulated time)
-FM_DEV void fm_sincos_small(double x, double* s, double* c) {
-  if (fabs(x) <= 0.78539816339744831) {
-    const double z = x * x;
-    double ps = FM_SIN_S[5], pc = FM_COS_C[5];
-#pragma unroll
-    for (int k = 4; k >= 0; k--) { ps = fma(ps, z, FM_SIN_S[k]); pc = fma(pc, z, FM_COS_C[k]); }
-    *s = fma(x * z, ps, x);
-    *c = fma(z * z, pc, fma(-0.5, z, 1.0));
-  } else sincos(x, s, c);
+// atan2(y, x) for finite operands: the smaller magnitude over the larger, folded once more at tan(pi/8) through
+// atan(a) = pi/4 + atan((a - 1) / (a + 1)) -- operands selected BEFORE the one division -- then the octant fix-ups.
+// A few ulp; atan2(0, 0) = 0 and the sign of y as libm (the sign of a zero x is not distinguished).
+FM_DEV double fm_atan2(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const double mx = ax > ay ? ax : ay, mn = ax > ay ? ay : ax;
+  const bool big = mn > 0.41421356237309503 * mx;
+  const double num = big ? mn - mx : mn, den = big ? mn + mx : mx;
+  const double t = fm_div(num, den), u = t * t, w = u * u;
+  double q;
+  FM_POLY_EO(FM_ATAN_Q, 13, u, w, q)
+  double r = fma(t, q, big ? 0.78539816339744831 : 0.0);
+  if (ay > ax) r = 1.5707963267948966 - r;
+  if (x < 0.0) r = 3.141592653589793 - r;
+  r = mx == 0.0 ? 0.0 : r;
+  return copysign(r, y);
 }
 // The angle whose sine s and cosine c are known (s^2 + c^2 = 1 to rounding): 2 atan(s / (1 + c)).  |angle| <= 45 deg
-// takes the polynomial (angle of attack and sideslip of an aircraft that flies forwards); anything else is atan2(y, x).
+// takes the short form (angle of attack and sideslip of an aircraft that flies forwards); anything else fm_atan2(y, x).
 FM_DEV double fm_angle_sc(double s, double c, double y, double x) {
   if (c >= 0.7072) {
     const double t = fm_div(s, 1.0 + c), u = t * t, w = u * u;
@@ -149,13 +174,13 @@ FM_DEV double fm_angle_sc(double s, double c, double y, double x) {
     FM_POLY_EO(FM_ATAN_Q, 13, u, w, q)
     return (t + t) * q;
   }
-  return atan2(y, x);
+  return fm_atan2(y, x);
 }
 // exp(z + zl), |z| <= 700, zl a rounding-error term: z = n ln2 + r, |r| <= ln2 / 2, Taylor through r^13, scale by 2^n
 FM_DEV double fm_exp_core(double z, double zl) {
-  const double n = fm_rint(z * 1.4426950408889634);
-  double r = fma(n, -6.93147180369123816490e-01, z);
-  r = fma(n, -1.90821492927058770002e-10, r) + zl;
+  const double n = fm_rint(z * FM_RED[8]);
+  double r = fma(n, FM_RED[9], z);
+  r = fma(n, FM_RED[10], r) + zl;
   const double r2 = r * r;
   double p;
   FM_POLY_EO(FM_EXP_E, 14, r, r2, p)
@@ -176,44 +201,80 @@ FM_DEV double fm_pow_ratio(double num, double den, double y) {
   }
   return exp(y * log(num / den));
 }
-// exp(z) for |z| <= 700 (no overflow / underflow handling below that bound); libdevice beyond
+FM_DEV double fm_powpos(double x, double y) { return fm_pow_ratio(x, 1.0, y); }
+// exp(z) with z clamped to [-700, 700] (1e-304 .. 1e304: no overflow / underflow handling, no libdevice fallback)
 FM_DEV double fm_exp(double z) {
-  if (fabs(z) <= 700.0) return fm_exp_core(z, 0.0);
-  return exp(z);
+  const double zc = z < -700.0 ? -700.0 : (z > 700.0 ? 700.0 : z);
+  return fm_exp_core(zc, 0.0);
 }
-// sin and cos for |x| <= 1e5: x = n pi/2 + r by a three-term Cody-Waite reduction (fma keeps every product exact), then
-// the kernels above on |r| <= pi/4 and the quadrant swap; libdevice beyond (its own slow path starts at 1.05e5)
+// sin and cos for |x| < 3e9 (the quadrant is an int): x = n pi/2 + r by a three-term Cody-Waite reduction -- fma keeps
+// x - n P1 exact, so the reduction error is |n| 2^-160 + one rounding of r -- then the kernels above on |r| <= pi/4 and
+// the quadrant swap.  No libdevice fallback: the angles of this simulator are bounded by construction (attitudes; a
+// missile heading integrates <= 2 rad/s for <= 60 s); NaN and infinity still give NaN.
 FM_DEV void fm_sincos(double x, double* s, double* c) {
-  if (fabs(x) <= 1.0e5) {
-    const double n = fm_rint(x * 0.6366197723675814);
-    double r = fma(n, -1.5707963267948966, x);
-    r = fma(n, -6.123233995736766e-17, r);
-    r = fma(n, 1.4973849048591698e-33, r);
-    const int q = (int)n;
-    const double z = r * r;
+  const double n = fm_rint(x * FM_RED[0]);
+  double r = fma(n, FM_RED[1], x);
+  r = fma(n, FM_RED[2], r);
+  r = fma(n, FM_RED[3], r);
+  const int q = (int)n;
+  const double z = r * r;
+  double ps = FM_SIN_S[5], pc = FM_COS_C[5];
+#pragma unroll
+  for (int k = 4; k >= 0; k--) { ps = fma(ps, z, FM_SIN_S[k]); pc = fma(pc, z, FM_COS_C[k]); }
+  const double sr = fma(r * z, ps, r), cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const double s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
+  *s = (q & 2) ? -s0 : s0;
+  *c = ((q + 1) & 2) ? -c0 : c0;
+}
+// sin alone: x = n pi + r, one odd polynomial on |r| <= pi/2 (Taylor through r^21: truncation 1.3e-18); same domain
+FM_DEV double fm_sin(double x) {
+  const double n = fm_rint(x * FM_RED[4]);
+  double r = fma(n, FM_RED[5], x);
+  r = fma(n, FM_RED[6], r);
+  r = fma(n, FM_RED[7], r);
+  const double z = r * r, w = z * z;
+  double p;
+  FM_POLY_EO(FM_SIN_T, 10, z, w, p)
+  const double sr = fma(r * z, p, r);
+  return ((int)n & 1) ? -sr : sr;
+}
+// sin and cos of a small angle (the earth rotation angle: 7.3e-5 rad/s of simulated time)
+FM_DEV void fm_sincos_small(double x, double* s, double* c) {
+  if (fabs(x) <= 0.78539816339744831) {
+    const double z = x * x;
     double ps = FM_SIN_S[5], pc = FM_COS_C[5];
 #pragma unroll
     for (int k = 4; k >= 0; k--) { ps = fma(ps, z, FM_SIN_S[k]); pc = fma(pc, z, FM_COS_C[k]); }
-    const double sr = fma(r * z, ps, r), cr = fma(z * z, pc, fma(-0.5, z, 1.0));
-    const double s0 = (q & 1) ? cr : sr, c0 = (q & 1) ? sr : cr;
-    *s = (q & 2) ? -s0 : s0;
-    *c = ((q + 1) & 2) ? -c0 : c0;
-  } else sincos(x, s, c);
+    *s = fma(x * z, ps, x);
+    *c = fma(z * z, pc, fma(-0.5, z, 1.0));
+  } else fm_sincos(x, s, c);
 }
-// sin alone: x = n pi + r, one odd polynomial on |r| <= pi/2 (Taylor through r^21: truncation 1.3e-18)
-FM_DEV double fm_sin(double x) {
-  if (fabs(x) <= 1.0e5) {
-    const double n = fm_rint(x * 0.3183098861837907);
-    double r = fma(n, -3.141592653589793, x);
-    r = fma(n, -1.2246467991473532e-16, r);
-    r = fma(n, 2.9947698097183397e-33, r);
-    const double z = r * r, w = z * z;
-    double p;
-    FM_POLY_EO(FM_SIN_T, 10, z, w, p)
-    const double sr = fma(r * z, p, r);
-    return ((int)n & 1) ? -sr : sr;
-  }
-  return sin(x);
+FM_DEV double fm_cos(double x) { double sn, cs; fm_sincos(x, &sn, &cs); return cs; }
+// acos(x), |x| <= 1: 2 atan2(sqrt(1 - x), sqrt(1 + x)) -- 1 - x is exact near 1, so small angles keep their relative accuracy
+FM_DEV double fm_acos(double x) {
+  const double r = fm_atan2(fm_sqrt0(1.0 - x), fm_sqrt0(1.0 + x));
+  return r + r;
 }
-FM_DEV double fm_powpos(double x, double y) { return fm_pow_ratio(x, 1.0, y); }
+// log(x), x > 0 and normal: x = m 2^e with m in [sqrt(1/2), sqrt(2)), ln m through atanh as above; log(0) = -inf
+FM_DEV double fm_log(double x) {
+  int e;
+  double m = fm_frexp1(x, &e);
+  if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+  const double s = fm_div(m - 1.0, m + 1.0), v = s * s, w = v * v;
+  double l;
+  FM_POLY_EO(FM_LOG_L, 12, v, w, l)
+  const double ed = (double)e;
+  const double r = fma(ed, -FM_RED[9], fma(s + s, l, ed * -FM_RED[10]));
+  return x > 0.0 ? r : (x == 0.0 ? -INFINITY : NAN);
+}
+// tanh and atanh to an ABSOLUTE accuracy of a few 1e-16 (reward shaping, compared at 1e-6): (1 - t) / (1 + t) with
+// t = exp(-2 |x|), and log((1 + y) / (1 - y)) / 2 (atanh(-1) = -inf, atanh(1) = +inf as libm)
+FM_DEV double fm_tanh(double x) {
+  const double t = fm_exp(-2.0 * fabs(x));
+  return copysign(fm_div(1.0 - t, 1.0 + t), x);
+}
+FM_DEV double fm_atanh(double y) {
+  if (y >= 1.0) return INFINITY;
+  return 0.5 * fm_log(fm_div(1.0 + y, 1.0 - y));
+}
 #endif

@@ -32,10 +32,11 @@ def test_division_and_roots_are_correctly_rounded_from_a_poor_seed(report):
 
 def test_trigonometric_kernels(report):
     assert report["sin"] <= 1.0 and report["cos"] <= 1.5                      # |x| <= pi/4
-    assert report["sincos_s"] <= 2.0 and report["sincos_c"] <= 2.0            # |x| <= 9e4, Cody-Waite reduction
+    assert report["sincos_s"] <= 2.0 and report["sincos_c"] <= 2.0            # |x| <= 2e8, Cody-Waite reduction
     assert report["abs_s"] <= 2.5e-16 and report["abs_c"] <= 2.5e-16
     assert report["abs_sin"] <= 4e-16                                          # odd polynomial on |r| <= pi/2
     assert report["angle"] <= 5.0                                              # atan2 from (sin, cos): inputs carry ~3 ulp
+    assert report["atan2"] <= 4.0 and report["abs_atan2"] <= 6e-16 and "atan2_special" not in report   # all quadrants, axes
 
 
 def test_exp_and_the_isa_power_law(report):
@@ -46,3 +47,11 @@ def test_exp_and_the_isa_power_law(report):
 def test_special_operands(report):
     # sqrt0(0) = 0, 0 / b = 0, angle(0, 1) = 0, ratio 1 -> 1, fallback branches (ratio far from 1, |x| > pi/4, |angle| > 45 deg)
     assert report["bad"] == 0
+
+
+def test_reward_and_geometry_functions(report):
+    # acos keeps RELATIVE accuracy towards small angles (AO / TA start near 1e-7 in the reference's own scenarios)
+    assert report["acos"] <= 6.0 and report["abs_acos"] <= 1e-15
+    assert report["log"] <= 4.0
+    assert report["abs_tanh"] <= 5e-16 and report["abs_atanh"] <= 3e-15 and report["abs_cos"] <= 3e-16
+    assert report["bad2"] == 0      # acos(+-1), log(0) = -inf, atanh(+-1) = +-inf, exp clamps instead of underflowing
