@@ -129,10 +129,11 @@ FM_DEV double fm_sqrt(double x) {
   const double y = fm_rsqrt1(x), g = x * y;
   return fma(fma(-g, g, x), 0.5 * y, g);
 }
-// the same for operands that can be exactly zero (a seed of +inf would give NaN)
+// the same for operands that can be zero or subnormal (the seed flushes subnormals: +inf, then NaN): 0 below the
+// smallest normal number -- also for negative operands, where sqrt() gives NaN; NaN stays NaN
 FM_DEV double fm_sqrt0(double x) {
   const double g = fm_sqrt(x);
-  return x == 0.0 ? 0.0 : g;
+  return x < 2.2250738585072014e-308 ? 0.0 : g;
 }
 FM_DEV double fm_rsqrt(double x) {
   const double y = fm_rsqrt1(x), g = x * y;

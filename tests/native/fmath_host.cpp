@@ -88,7 +88,7 @@ int main() {
          a_acos, r_acos, r_log, a_tanh, a_atanh, r_cos, bad2);
   // special values
   int bad = 0;
-  if (fm_sqrt0(0.0) != 0.0) bad |= 1;
+  if (fm_sqrt0(0.0) != 0.0 || fm_sqrt0(1e-310) != 0.0 || fm_sqrt0(4.0) != 2.0 || !(fm_sqrt0(NAN) != fm_sqrt0(NAN))) bad |= 1;
   if (fm_div(0.0, 3.0) != 0.0) bad |= 2;
   if (fm_angle_sc(0.0, 1.0, 0.0, 5.0) != 0.0) bad |= 4;
   if (fm_pow_ratio(300.0, 300.0, -5.2) != 1.0) bad |= 8;
