@@ -240,9 +240,9 @@ ENV_DEV Controls decode_action(const EnvView& v, const AcsTaskConfig& cfg, const
   const int32_t* act = actions + (size_t)L.row * adim;
   Controls c;
   if (cfg.act_kind == ACS_ACT_HEADING) {
-    c.u0 = em_div(act[0] * 2., 41 - 1.) - 1.; c.u1 = em_div(act[1] * 2., 41 - 1.) - 1.; c.u2 = em_div(act[2] * 2., 41 - 1.) - 1.; c.u3 = em_div(act[3] * 0.5, 30 - 1.) + 0.4;
+    c.u0 = act[0] * 2. / (41 - 1.) - 1.; c.u1 = act[1] * 2. / (41 - 1.) - 1.; c.u2 = act[2] * 2. / (41 - 1.) - 1.; c.u3 = act[3] * 0.5 / (30 - 1.) + 0.4;
   } else {
-    c.u0 = em_div(act[0], 20.) - 1.; c.u1 = em_div(act[1], 20.) - 1.; c.u2 = em_div(act[2], 20.) - 1.; c.u3 = em_div(act[3], 58.) + 0.4;
+    c.u0 = act[0] / 20. - 1.; c.u1 = act[1] / 20. - 1.; c.u2 = act[2] / 20. - 1.; c.u3 = act[3] / 58. + 0.4;
   }
   c.u0 = env_clip(c.u0, -1.0, 1.0); c.u1 = env_clip(c.u1, -1.0, 1.0); c.u2 = env_clip(c.u2, -1.0, 1.0); c.u3 = env_clip(c.u3, 0.0, 0.9);
   int shoot = 0;
@@ -1493,12 +1493,12 @@ ENV_DEV void obs_ego9(const EnvView& v, int row, const PubAc& s, double* o) {
   double sr, cr, sp, cp;
   em_sincos(OUTF(v, O_ROLL, row), &sr, &cr);
   em_sincos(OUTF(v, O_PITCH, row), &sp, &cp);
-  o[0] = em_div(s.h, 5000); o[1] = sr; o[2] = cr; o[3] = sp; o[4] = cp;
-  o[5] = em_div(s.u_mps, 340); o[6] = em_div(AD(v, AD_V_MPS, row), 340); o[7] = em_div(AD(v, AD_W_MPS, row), 340); o[8] = em_div(AD(v, AD_VC_MPS, row), 340);
+  o[0] = s.h / 5000; o[1] = sr; o[2] = cr; o[3] = sp; o[4] = cp;
+  o[5] = s.u_mps / 340; o[6] = AD(v, AD_V_MPS, row) / 340; o[7] = AD(v, AD_W_MPS, row) / 340; o[8] = AD(v, AD_VC_MPS, row) / 340;
 }
 ENV_DEV void obs_rel6(const PubAc& ego, const PubAc& other, bool two_d, double* o) {
   const AoTaR g = get_ao_ta_r(ego.f, other.f, two_d);
-  o[0] = em_div(other.u_mps - ego.u_mps, 340); o[1] = em_div(other.h - ego.h, 1000); o[2] = g.AO; o[3] = g.TA; o[4] = em_div(g.R, 10000); o[5] = g.side;
+  o[0] = (other.u_mps - ego.u_mps) / 340; o[1] = (other.h - ego.h) / 1000; o[2] = g.AO; o[3] = g.TA; o[4] = g.R / 10000; o[5] = g.side;
 }
 ENV_DEV bool obs_missile6(const StepCtx& c, int a, double* o) {
   const int mid = missile_warning(c, a);
@@ -1509,8 +1509,8 @@ ENV_DEV bool obs_missile6(const StepCtx& c, int a, double* o) {
   mf.n = MD(v, MD_POS_N, mid); mf.e = MD(v, MD_POS_E, mid); mf.u = MD(v, MD_POS_U, mid);
   mf.vn = MD(v, MD_VEL_N, mid); mf.ve = MD(v, MD_VEL_E, mid); mf.vd = MD(v, MD_VEL_U, mid);
   const AoTaR g = get_ao_ta_r(ego.f, mf, false);
-  o[0] = em_div(em_sqrt0(mf.vn * mf.vn + mf.ve * mf.ve + mf.vd * mf.vd) - ego.u_mps, 340); o[1] = em_div(mf.u - ego.h, 1000);
-  o[2] = g.AO; o[3] = g.TA; o[4] = em_div(g.R, 10000); o[5] = g.side;
+  o[0] = (em_sqrt0(mf.vn * mf.vn + mf.ve * mf.ve + mf.vd * mf.vd) - ego.u_mps) / 340; o[1] = (mf.u - ego.h) / 1000;
+  o[2] = g.AO; o[3] = g.TA; o[4] = g.R / 10000; o[5] = g.side;
   return true;
 }
 // get_obs for agent a into o[obs_dim] (global memory); citations per branch in taskspec.py
@@ -1529,7 +1529,7 @@ ENV_DEV void write_obs(const StepCtx& c, int a, double* __restrict__ o) {
     const double d_alt = env_clip((ED(v, ED_TGT_ALT, c.L.env) - OUTF(v, O_H_SL_FT, row)) * 0.3048, -40000.0, 40000.0);
     const double d_head = delta_heading_deg(ED(v, ED_TGT_HEADING, c.L.env), psi_deg);
     const double d_vel = env_clip(ED(v, ED_TGT_VEL, c.L.env) - s.u_mps, -1400.0, 1400.0);
-    o[0] = em_div(d_alt, 1000); o[1] = em_div(d_head, 180) * 3.14159265358979323846; o[2] = em_div(d_vel, 340);
+    o[0] = d_alt / 1000; o[1] = d_head / 180 * 3.14159265358979323846; o[2] = d_vel / 340;
     obs_ego9(v, row, s, t);
     for (int i = 0; i < 9; i++) o[3 + i] = t[i];
     for (int i = 0; i < 12; i++) o[i] = env_clip(o[i], -10.0, 10.0);
