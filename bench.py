@@ -252,10 +252,12 @@ def cpu_env_baseline(config: str, rounds: int, warm_rounds: int = 2, budget_s: f
 
 # ----------------------------------------------------------------------------- B200 arm
 KERNELS = ("k_env_substeps", "k_env_substeps_split", "k_env_substeps_split3", "k_env_substeps_split4")
-# Algorithmic fp64 work of one aircraft substep: 2*DFMA + DMUL + DADD thread instructions of the FDM frame in the committed
-# ncu capture (profiles/r1_k_env_substeps_split3_4096envs_final.txt: 24 770 per aircraft per 12-substep step).  It is a
-# property of the physics, kept fixed across kernel versions; missile / chaff arithmetic is NOT counted (conservative).
-FLOPS_PER_SUBSTEP = 2064.0
+# fp64 work of one aircraft substep: 2*DFMA + DMUL + DADD thread instructions the substep kernel EXECUTES per aircraft, from
+# the committed ncu capture of the kernels as they are now (profiles/r2b_k_env_substeps_65536envs.txt: 23 487 per aircraft per
+# 12-substep step; it was 24 770 / 25 081 before the guard-free division / sqrt sequences of csrc/fmath.cuh removed Newton
+# steps).  Re-counted whenever the frame's arithmetic changes, so that `achieved` never credits work the kernel no longer
+# does; missile / chaff arithmetic is NOT counted (conservative).
+FLOPS_PER_SUBSTEP = 1957.0
 MISSILE_SLOT_BYTES = 2 * 16 * 8 + 8 * 4 + 2 * 4     # 16 doubles read + written, 8 ints read, 2 ints written per live slot
 
 
@@ -375,7 +377,7 @@ def measure(config, n_envs, steps, warmup, seed, world, rank, local, dev, flush,
     roof = {"bound": "fp64", "kernel": kname, "achieved": ach_tf, "peak": (fp64_peak or 0.0) / 1e12, "unit": "TFLOP/s",
             "frac": (ach_tf / (fp64_peak / 1e12)) if fp64_peak else None,
             "peak_source": "measured live (acs_bench_fp64_peak: dependent-free DFMA loop on every SM; MEASURED_PEAKS.json has no fp64 figure)",
-            "flops_per_agent_step": flops, "flops_note": "algorithmic FDM flops only (2*DFMA + DMUL + DADD of one frame x 12); missile arithmetic not counted",
+            "flops_per_agent_step": flops, "flops_note": "fp64 flops the substep kernel executes for the FDM (ncu: 2*DFMA + DMUL + DADD of one frame x 12, current kernels); missile arithmetic not counted",
             "traffic": _ncu_traffic(kname, config, n_envs), "kernel_ms": k_ms,
             "kernel_share_of_step": kms["substeps"] / max(sum(kms.values()), 1e-12),
             "missiles_ms": kms.get("missiles", 0.0) / max(ksteps, 1), "post_ms": kms["post"] / max(ksteps, 1),
