@@ -92,6 +92,7 @@ def lib():
         L.acs_env_set_timing.argtypes = [vp, i]
         L.acs_env_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i), i]
         L.acs_bench_fp64_peak.argtypes = [i, ctypes.POINTER(ctypes.c_double)]
+        L.acs_debug_fmath.argtypes = [i, vp, vp, vp, vp, i, vp]
         _LIB = L
     return _LIB
 
@@ -365,3 +366,20 @@ def fp64_peak_flops(device: int = 0) -> float:
     out = ctypes.c_double()
     _check(lib().acs_bench_fp64_peak(device, ctypes.byref(out)))
     return out.value
+
+
+FMATH_OPS = ("div", "rcp", "sqrt", "rsqrt", "sincos", "sin", "exp", "log", "atan2", "acos", "tanh", "pow_ratio", "angle_sc",
+             "sincos_small")
+
+
+def fmath_probe(op: str, a: torch.Tensor, b=None):
+    """One function of csrc/fmath.cuh over device arrays (include/acs.h: acs_debug_fmath) -> (out, out2).  Test helper."""
+    assert a.is_cuda and a.dtype == torch.float64 and a.is_contiguous()
+    out, out2 = torch.empty_like(a), torch.empty_like(a)
+    bp = None
+    if b is not None:
+        assert b.is_cuda and b.dtype == torch.float64 and b.is_contiguous() and b.numel() == a.numel()
+        bp = ctypes.c_void_p(b.data_ptr())
+    _check(lib().acs_debug_fmath(FMATH_OPS.index(op), ctypes.c_void_p(a.data_ptr()), bp, ctypes.c_void_p(out.data_ptr()),
+                                 ctypes.c_void_p(out2.data_ptr()), a.numel(), _stream()))
+    return out, out2

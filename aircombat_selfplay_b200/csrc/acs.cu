@@ -342,6 +342,38 @@ static int env_arena(const AcsEnv* e, int which, void** ptr, int* nf, int* per, 
   return fail("unknown arena id");
 }
 
+// one fmath.cuh function per launch over arrays (acs_debug_fmath: the DEVICE build of the guard-free sequences, with the real
+// MUFU seeds, against libm in tests/test_fmath_gpu.py)
+__global__ void k_fmath_probe(const int op, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
+                              double* __restrict__ out2, const int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = a[i], y = b ? b[i] : 0.0;
+  double r = 0.0, r2 = 0.0;
+  switch (op) {
+    case ACS_FMATH_DIV: r = fm_div(x, y); break;
+    case ACS_FMATH_RCP: r = fm_rcp(x); break;
+    case ACS_FMATH_SQRT: r = fm_sqrt(x); r2 = fm_sqrt0(x); break;
+    case ACS_FMATH_RSQRT: r = fm_rsqrt(x); break;
+    case ACS_FMATH_SINCOS: fm_sincos(x, &r, &r2); break;
+    case ACS_FMATH_SIN: r = fm_sin(x); r2 = fm_cos(x); break;
+    case ACS_FMATH_EXP: r = fm_exp(x); break;
+    case ACS_FMATH_LOG: r = fm_log(x); break;
+    case ACS_FMATH_ATAN2: r = fm_atan2(x, y); break;
+    case ACS_FMATH_ACOS: r = fm_acos(x); break;
+    case ACS_FMATH_TANH: r = fm_tanh(x); r2 = fm_atanh(x); break;
+    case ACS_FMATH_POW_RATIO: r = fm_pow_ratio(x, y, -5.255876113278518); r2 = fm_pow_ratio(x, y, 34.16319474407325); break;
+    case ACS_FMATH_ANGLE_SC: {   // (x, y) = (component across, component along): the sine / cosine pair as Auxiliary forms it
+      const double ih = fm_rcp(fm_sqrt(x * x + y * y));
+      r = fm_angle_sc(x * ih, y * ih, x, y);
+      break;
+    }
+    case ACS_FMATH_SINCOS_SMALL: fm_sincos_small(x, &r, &r2); break;
+  }
+  out[i] = r;
+  if (out2) out2[i] = r2;
+}
+
 __global__ void k_fp64_peak(double* out, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 1.0000001, c = 1e-9;
@@ -745,6 +777,17 @@ int acs_debug_frame_profile(long long* out16) {
   return 0;
 }
 #endif
+
+int acs_debug_fmath(int op, const double* a_dev, const double* b_dev, double* out_dev, double* out2_dev, int n, void* stream) {
+  if (!a_dev || !out_dev || n < 0) return fail("acs_debug_fmath: null argument");
+  if (op < 0 || op >= ACS_FMATH_N_OPS) return fail("acs_debug_fmath: unknown op");
+  if ((op == ACS_FMATH_DIV || op == ACS_FMATH_ATAN2 || op == ACS_FMATH_POW_RATIO || op == ACS_FMATH_ANGLE_SC) && !b_dev)
+    return fail("acs_debug_fmath: this op takes two operands");
+  if (n == 0) return 0;
+  k_fmath_probe<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(op, a_dev, b_dev, out_dev, out2_dev, n);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
 
 int acs_bench_fp64_peak(int device, double* flops_out) {
   if (!flops_out) return fail("acs_bench_fp64_peak: null argument");

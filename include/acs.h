@@ -193,6 +193,19 @@ int acs_env_get_option(const AcsEnv* e, const char* name, int* value);
 int acs_env_set_timing(AcsEnv* e, int on);
 int acs_env_get_timing(AcsEnv* e, double ms[4], int* n_steps, int reset);
 
+/* Test helper (no reference counterpart): evaluates ONE function of csrc/fmath.cuh -- the guard-free fp64 division /
+ * reciprocal / square-root sequences and the constant-memory polynomial kernels the FDM frame, the missile path and the
+ * per-step logic use instead of `/`, sqrt() and libdevice -- over device arrays, so that the device build (real MUFU
+ * seeds) can be compared with libm (tests/test_fmath_gpu.py).  a_dev, b_dev, out_dev, out2_dev: double[n] on the device;
+ * b_dev may be NULL for one-operand functions, out2_dev may be NULL.  out2 = second result where there is one (SQRT:
+ * fm_sqrt0; SINCOS / SINCOS_SMALL: cosine; SIN: fm_cos; TANH: fm_atanh; POW_RATIO: the second ISA exponent). */
+enum {
+  ACS_FMATH_DIV = 0, ACS_FMATH_RCP, ACS_FMATH_SQRT, ACS_FMATH_RSQRT, ACS_FMATH_SINCOS, ACS_FMATH_SIN, ACS_FMATH_EXP,
+  ACS_FMATH_LOG, ACS_FMATH_ATAN2, ACS_FMATH_ACOS, ACS_FMATH_TANH, ACS_FMATH_POW_RATIO, ACS_FMATH_ANGLE_SC,
+  ACS_FMATH_SINCOS_SMALL, ACS_FMATH_N_OPS
+};
+int acs_debug_fmath(int op, const double* a_dev, const double* b_dev, double* out_dev, double* out2_dev, int n, void* stream);
+
 /* Measurement helper (no reference counterpart): runs a dependent-free fp64 FMA loop on every SM and returns the
  * achieved FLOP/s in *flops_out; used by bench.py to put an fp64-pipe roof beside the HBM roof. */
 int acs_bench_fp64_peak(int device, double* flops_out);
