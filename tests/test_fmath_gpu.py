@@ -42,7 +42,8 @@ def test_division_reciprocal_and_roots_are_correctly_rounded_on_the_device():
     s, s0 = _probe("sqrt", x)
     assert np.array_equal(s, np.sqrt(x)) and np.array_equal(s0, np.sqrt(x))
     rs, _ = _probe("rsqrt", x)
-    assert _ulps(rs, 1.0 / np.sqrt(x)).max() <= 1.5
+    want = (1.0 / np.sqrt(x.astype(np.longdouble)))          # 1 / sqrt in double rounds twice: compare with extended precision
+    assert float((np.abs(rs.astype(np.longdouble) - want) / np.spacing(np.abs(want.astype(np.float64)))).max()) <= 1.01
     # operands the *0 variant exists for: zero, subnormal (flushed seed), and a NaN that must stay one
     _, s0 = _probe("sqrt", np.array([0.0, 1e-310, 4.0, np.nan]))
     assert s0[0] == 0.0 and s0[1] == 0.0 and s0[2] == 2.0 and np.isnan(s0[3])
@@ -64,7 +65,7 @@ def test_trigonometric_functions_on_the_device():
     s, c = _probe("sincos", x)
     assert np.abs(s - np.sin(x)).max() <= 3e-16 and np.abs(c - np.cos(x)).max() <= 3e-16
     s1, c1 = _probe("sin", x)
-    assert np.abs(s1 - np.sin(x)).max() <= 4e-16 and np.array_equal(c1, c)
+    assert np.abs(s1 - np.sin(x)).max() <= 4e-16 and np.abs(c1 - c).max() <= 2.3e-16
     xs = rng.uniform(-0.78, 0.78, N)
     s, c = _probe("sincos_small", xs)
     assert _ulps(s, np.sin(xs)).max() <= 1.5 and _ulps(c, np.cos(xs)).max() <= 2.0
