@@ -417,7 +417,7 @@ def run_b200(args):
             "data": "synthetic", "config": workload_config(desc, config, n_envs, m["A"], m["hier"]),
             "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"], "roofline": m["roofline"],
             "agent_episodes_finished_in_e2e": m["agent_episodes_finished_in_e2e"],
-            "parity": "FDM parity is against the restated CPU oracle (unpinned: no runnable JSBSim here); the env layer is pinned "
+            "parity": "FDM parity is against the restated CPU oracle (unpinned: no runnable JSBSim here; only its atmosphere model is pinned by JSBSim's own reference data); the env layer is pinned "
                       "by golden trajectories of the reference's own Python (DESIGN.md section 3)"}
     # ---- the other BASELINE.json configurations, short samples of the same measurement (headline stays configs[1])
     if not args.no_workloads and args.workload == "1v1_noweapon" and not args.envs:

@@ -3,7 +3,8 @@
 // executed by the product path (aircombat_selfplay_b200/); only tests/, __graft_entry__.smoke()
 // and bench.py's cpu_baseline / --impl reference legs may use it.
 //
-// PARITY UNPINNED: the reference's FDM is the pip wheel jsbsim==1.1.6, which is not installable
+// PARITY UNPINNED (except the atmosphere model, which reproduces the real-JSBSim reference data of
+// envs/JSBSim/data/tests/TestDensityAltitude.py / TestPressureAltitude.py: tests/test_oracle_fdm.py): the reference's FDM is the pip wheel jsbsim==1.1.6, which is not installable
 // here (no network), and the vendored JSBSim sources under /root/reference/envs/JSBSim/data/src
 // ship without headers, so the real FDM cannot be built or run in this container.  This file is a
 // scalar fp64 restatement of exactly the code path the reference exercises for the F-16
@@ -217,6 +218,8 @@ struct StdAtmosphere {
   static const int NR = 9;
   double H[NR], Tt[NR];
   double LapseRates[NR - 1], PressureBreakpoints[NR], StdDensityBreakpoints[NR];
+  double StdLapseRates[NR - 1], StdPressureBreakpoints[NR];   // frozen at construction (:118-135); the inverse functions use these
+  double TemperatureBias;                                     // atmosphere/delta-T (:343-353); the reference never sets it: 0
   double SLdensity, SLpressure, SLtemperature, SLsoundspeed;
   // outputs of Calculate()
   double Temperature, Pressure, Density, Soundspeed, DensityAltitude, PressureAltitude, Viscosity, KinematicViscosity;
@@ -235,20 +238,33 @@ struct StdAtmosphere {
     const double t[NR] = {518.67, 389.97, 389.97, 411.57, 487.17, 487.17, 386.37, 336.5028, 336.5028};
     for (int i = 0; i < NR; i++) { H[i] = h[i]; Tt[i] = t[i]; }
     // CalculateLapseRates (:405-417), TemperatureDeltaGradient = 0
-    for (int b = 0; b < NR - 1; b++) LapseRates[b] = (Tt[b + 1] - Tt[b]) / (H[b + 1] - H[b]) - 0.0;
-    // CalculatePressureBreakpoints (:419-440), TemperatureBias = 0
-    PressureBreakpoints[0] = StdDaySLpressure;
+    TemperatureBias = 0.0;
+    for (int b = 0; b < NR - 1; b++) { LapseRates[b] = (Tt[b + 1] - Tt[b]) / (H[b + 1] - H[b]) - 0.0; StdLapseRates[b] = LapseRates[b]; }
+    CalculatePressureBreakpoints(StdDaySLpressure);
+    for (int i = 0; i < NR; i++) StdPressureBreakpoints[i] = PressureBreakpoints[i];
+    for (int i = 0; i < NR; i++) StdDensityBreakpoints[i] = StdPressureBreakpoints[i] / (Rdry * Tt[i]);  // :457-462
+    SLtemperature = Tt[0]; SLpressure = StdDaySLpressure; SLdensity = SLpressure / (Rdry * SLtemperature);
+    SLsoundspeed = std::sqrt(SHRatio * Rdry * SLtemperature);
+    Calculate(0.0);
+  }
+  // CalculatePressureBreakpoints (:419-440); TemperatureDeltaGradient = 0
+  void CalculatePressureBreakpoints(double SLpress) {
+    PressureBreakpoints[0] = SLpress;
     for (int b = 0; b < NR - 1; b++) {
-      double BaseTemp = Tt[b], deltaH = H[b + 1] - H[b], Tmb = BaseTemp + 0.0 + (H[NR - 1] - H[b]) * 0.0;
+      double BaseTemp = Tt[b], deltaH = H[b + 1] - H[b], Tmb = BaseTemp + TemperatureBias + (H[NR - 1] - H[b]) * 0.0;
       if (LapseRates[b] != 0.00) {
         double Lmb = LapseRates[b], Exp = g0 / (Rdry * Lmb), factor = Tmb / (Tmb + Lmb * deltaH);
         PressureBreakpoints[b + 1] = PressureBreakpoints[b] * std::pow(factor, Exp);
       } else PressureBreakpoints[b + 1] = PressureBreakpoints[b] * std::exp(-g0 * deltaH / (Rdry * Tmb));
     }
-    for (int i = 0; i < NR; i++) StdDensityBreakpoints[i] = PressureBreakpoints[i] / (Rdry * Tt[i]);  // :457-462
-    SLtemperature = Tt[0]; SLpressure = StdDaySLpressure; SLdensity = SLpressure / (Rdry * SLtemperature);
-    SLsoundspeed = std::sqrt(SHRatio * Rdry * SLtemperature);
-    Calculate(0.0);
+  }
+  // SetTemperatureBias(eRankine, t) (:343-353) -- what writing the property atmosphere/delta-T does.  Only the known-answer
+  // tests of JSBSim's own suite use it (tests/test_oracle_fdm.py); the F-16 path keeps the bias at 0.
+  void SetTemperatureBias(double t_R) {
+    TemperatureBias = t_R;
+    CalculatePressureBreakpoints(SLpressure);
+    SLtemperature = GetTemperature(0.0);
+    SLsoundspeed = std::sqrt(SHRatio * Reng * SLtemperature); SLdensity = SLpressure / (Reng * SLtemperature);
   }
   double GeopotentialAltitude(double h) const { return (h * EarthRadius) / (EarthRadius + h); }
   double GeometricAltitude(double H_) const { return (H_ * EarthRadius) / (EarthRadius - H_); }
@@ -260,11 +276,12 @@ struct StdAtmosphere {
     if (span != 0.0) { f = (key - H[r - 1]) / span; if (f > 1.0) f = 1.0; } else f = 1.0;
     return f * (Tt[r] - Tt[r - 1]) + Tt[r - 1];
   }
-  // :244-271 GetTemperature (bias/gradient = 0)
+  // :244-271 GetTemperature (gradient = 0)
   double GetTemperature(double altitude) const {
     double GeoPotAlt = GeopotentialAltitude(altitude), Tm;
     if (GeoPotAlt >= 0.0) Tm = TempTable(GeoPotAlt);
     else Tm = TempTable(0.0) + GeoPotAlt * LapseRates[0];
+    Tm += TemperatureBias;   // :263
     return Tm;
   }
   // :191-227 GetPressure
@@ -284,15 +301,15 @@ struct StdAtmosphere {
   double CalculateDensityAltitude(double density) const {
     int b = 0;
     for (; b < NR - 2; b++) if (density >= StdDensityBreakpoints[b + 1]) break;
-    double Tmb = Tt[b], Hb = H[b], Lmb = LapseRates[b], pb = StdDensityBreakpoints[b], da;
+    double Tmb = Tt[b], Hb = H[b], Lmb = StdLapseRates[b], pb = StdDensityBreakpoints[b], da;
     if (Lmb != 0.0) { double Exp = -1.0 / (1.0 + g0 / (Rdry * Lmb)); da = Hb + (Tmb / Lmb) * (std::pow(density / pb, Exp) - 1); }
     else { double Factor = -Rdry * Tmb / g0; da = Hb + Factor * std::log(density / pb); }
     return GeometricAltitude(da);
   }
   double CalculatePressureAltitude(double pressure) const {
     int b = 0;
-    for (; b < NR - 2; b++) if (pressure >= PressureBreakpoints[b + 1]) break;
-    double Tmb = Tt[b], Hb = H[b], Lmb = LapseRates[b], Pb = PressureBreakpoints[b], pa;
+    for (; b < NR - 2; b++) if (pressure >= StdPressureBreakpoints[b + 1]) break;
+    double Tmb = Tt[b], Hb = H[b], Lmb = StdLapseRates[b], Pb = StdPressureBreakpoints[b], pa;
     if (Lmb != 0.00) { double Exp = -Rdry * Lmb / g0; pa = Hb + (Tmb / Lmb) * (std::pow(pressure / Pb, Exp) - 1); }
     else { double Factor = -Rdry * Tmb / g0; pa = Hb + Factor * std::log(pressure / Pb); }
     return GeometricAltitude(pa);
@@ -1051,6 +1068,7 @@ int orc_fdm_comp_type(int i) { return orc::FCS_COMPS[i].type; }
 // pid state: [n_comps][3]
 void orc_fdm_get_pid(void* h, double* o) { F16* f = (F16*)h; for (int i = 0; i < orc::N_FCS_COMPS; i++) { o[3 * i] = f->pid[i].Input_prev; o[3 * i + 1] = f->pid[i].Input_prev2; o[3 * i + 2] = f->pid[i].I_out_total; } }
 // standalone closed-form helpers (used by the known-answer tests)
+void orc_atmosphere_biased(double h_ft, double delta_T_R, double* out) { orc::StdAtmosphere a; a.SetTemperatureBias(delta_T_R); a.Calculate(h_ft); out[0] = a.Temperature; out[1] = a.Pressure; out[2] = a.Density; out[3] = a.Soundspeed; out[4] = a.DensityAltitude; out[5] = a.PressureAltitude; }
 void orc_atmosphere(double h_ft, double* out) { orc::StdAtmosphere a; a.Calculate(h_ft); out[0] = a.Temperature; out[1] = a.Pressure; out[2] = a.Density; out[3] = a.Soundspeed; out[4] = a.DensityAltitude; out[5] = a.PressureAltitude; }
 double orc_vcas_from_mach(double mach, double p) { orc::StdAtmosphere a; double qc = orc::PitotTotalPressure(mach, p) - p; return a.StdDaySLsoundspeed * orc::MachFromImpactPressure(qc, a.StdDaySLpressure); }
 double orc_kinemat(const double* detents, const double* times, int ndet, int noscale, double input, double output, double dt) {

@@ -48,6 +48,7 @@ def lib():
         L.orc_fdm_comp_type.argtypes = [i]
         L.orc_fdm_get_pid.argtypes = [vp, ctypes.POINTER(d)]
         L.orc_atmosphere.argtypes = [d, ctypes.POINTER(d)]
+        L.orc_atmosphere_biased.argtypes = [d, d, ctypes.POINTER(d)]
         L.orc_vcas_from_mach.restype = d
         L.orc_vcas_from_mach.argtypes = [d, d]
         L.orc_geodetic.argtypes = [d, d, d, ctypes.POINTER(d)]
@@ -132,9 +133,14 @@ class OracleFdm:
         return out
 
 
-def atmosphere(h_ft: float):
+def atmosphere(h_ft: float, delta_T_R: float = None):
+    """ISA-1976 at geometric altitude ``h_ft``; ``delta_T_R`` = the property atmosphere/delta-T (a temperature bias over the
+    whole profile, J/models/atmosphere/FGStandardAtmosphere.cpp:343-353) -- used by the known-answer tests only."""
     out = (ctypes.c_double * 6)()
-    lib().orc_atmosphere(h_ft, out)
+    if delta_T_R is None:
+        lib().orc_atmosphere(h_ft, out)
+    else:
+        lib().orc_atmosphere_biased(h_ft, delta_T_R, out)
     return dict(zip(["T", "P", "rho", "a", "density_altitude", "pressure_altitude"], list(out)))
 
 

@@ -291,3 +291,63 @@ def test_inertia_matrix_known_answer():
         J = J + w * lb2slug * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
     np.testing.assert_allclose(m0["J"], J, rtol=1e-12, atol=1e-9)
     np.testing.assert_allclose(m0["J"] @ m0["Jinv"], np.eye(3), atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------- JSBSim's own golden numbers
+# The two tables below are OUTPUTS OF THE REAL JSBSim, committed in the reference tree as the reference data of its own tests:
+# (geometric altitude ft, atmosphere/delta-T deg R, expected altitude ft).  They pin the layer table, lapse rates, pressure
+# break points (pow / exp per layer), the geopotential conversion and both inverse functions of the restated atmosphere --
+# including the density altitude the F-16's engine tables are indexed with -- through all eight layers.
+JSBSIM_DENSITY_ALTITUDE = [   # envs/JSBSim/data/tests/TestDensityAltitude.py:29-72
+    (0, 0, 0), (0, -27, -1838.3210293), (0, 27, 1724.0715454),
+    (10000, 0, 10000), (10000, -27, 8842.6417730), (10000, 27, 11117.881412),
+    (20000, 0, 20000), (20000, -27, 19524.3027252), (20000, 27, 20511.1447732),
+    (30000, 0, 30000), (30000, -27, 30206.6618955), (30000, 27, 29903.8616766),
+    (40000, 0, 40000), (40000, -27, 40795.49296642545), (40000, 27, 39370.88017359472),
+    (50000, 0, 50000), (50000, -27, 51540.55687445524), (50000, 27, 48722.498495051164),
+    (60000, 0, 60000), (60000, -27, 62286.38628793139), (60000, 27, 58073.53700852329),
+    (100000, 0, 100000), (100000, -27, 105340.83866126923), (100000, 27, 95441.10933931815),
+    (150000, 0, 150000), (150000, -27, 159983.12837740956), (150000, 27, 141847.12260237316),
+    (160000, 0, 160000), (160000, -27, 171305.317547756), (160000, 27, 150762.4482763878),
+    (220000, 0, 220000), (220000, -27, 233395.46205079104), (220000, 27, 207735.4268030979),
+    (260000, 0, 260000), (260000, -27, 274351.9265767301), (260000, 27, 246964.3481013492),
+    (290000, 0, 290000), (290000, -27, 305321.815863847), (290000, 27, 276290.37419984984),
+    (320000, 0, 320000), (320000, -27, 337990.28144264355), (320000, 27, 304417.9280936986),
+]
+JSBSIM_PRESSURE_ALTITUDE = [  # envs/JSBSim/data/tests/TestPressureAltitude.py:29-72
+    (0, 0, 0), (0, -27, 0), (0, 27, 0),
+    (10000, 0, 10000), (10000, -27, 10549.426597202142), (10000, 27, 9504.969939165301),
+    (20000, 0, 20000), (20000, -27, 21099.40877940678), (20000, 27, 19009.488882465),
+    (30000, 0, 30000), (30000, -27, 31649.946590500946), (30000, 27, 28513.556862000503),
+    (40000, 0, 40000), (40000, -27, 42294.25242340247), (40000, 27, 37972.879013500584),
+    (50000, 0, 50000), (50000, -27, 53040.858132036126), (50000, 27, 47323.24573196882),
+    (60000, 0, 60000), (60000, -27, 63788.23024872676), (60000, 27, 56673.032160129085),
+    (100000, 0, 100000), (100000, -27, 107018.51146890492), (100000, 27, 93910.6118895332),
+    (150000, 0, 150000), (150000, -27, 161956.60354430682), (150000, 27, 139810.93668842476),
+    (160000, 0, 160000), (160000, -27, 172582.32995327076), (160000, 27, 148992.4108097521),
+    (220000, 0, 220000), (220000, -27, 233772.88181515134), (220000, 27, 207274.89794422916),
+    (260000, 0, 260000), (260000, -27, 275000.20893894637), (260000, 27, 246263.63421221747),
+    (290000, 0, 290000), (290000, -27, 306867.8082342206), (290000, 27, 275185.69941262825),
+    (320000, 0, 320000), (320000, -27, 339541.05112835445), (320000, 27, 302991.642663158),
+]
+
+
+@pytest.mark.parametrize("h_ft,delta_T,expected", JSBSIM_DENSITY_ALTITUDE)
+def test_density_altitude_matches_jsbsim_reference_data(h_ft, delta_T, expected):
+    """TestDensityAltitude.test_densityaltitude (:75-97): `atmosphere/density-altitude` after ic/h-sl-ft + atmosphere/delta-T,
+    asserted there to 7 places relative; then the standard-day density AT the density altitude equals the density it came from."""
+    got = ofdm.atmosphere(float(h_ft), float(delta_T))
+    if expected < 1e-9:
+        assert got["density_altitude"] == pytest.approx(expected, abs=5e-8)
+    else:
+        assert got["density_altitude"] / expected == pytest.approx(1.0, abs=5e-8)
+    assert ofdm.atmosphere(got["density_altitude"])["rho"] == pytest.approx(got["rho"], abs=5e-8, rel=1e-12)
+
+
+@pytest.mark.parametrize("h_ft,delta_T,expected", JSBSIM_PRESSURE_ALTITUDE)
+def test_pressure_altitude_matches_jsbsim_reference_data(h_ft, delta_T, expected):
+    """TestPressureAltitude.test_pressurealtitude (:75-92): `atmosphere/pressure-altitude`, asserted there with delta = 1e-7 ft
+    (1e-12 relative at 100 000 ft); then the standard-day pressure AT the pressure altitude equals the pressure it came from."""
+    got = ofdm.atmosphere(float(h_ft), float(delta_T))
+    assert got["pressure_altitude"] == pytest.approx(expected, abs=1e-7)
+    assert ofdm.atmosphere(got["pressure_altitude"])["P"] == pytest.approx(got["P"], abs=5e-8, rel=1e-12)
