@@ -109,6 +109,46 @@ def test_turbine_spools_up_with_the_published_rate():
     assert d1["N2"] - d0["N2"] == pytest.approx(rate / 60.0, rel=1e-6)
 
 
+def test_turbine_spool_sequence_known_answer():
+    """TestTurbine.testSpoolUp / runScript (envs/JSBSim/data/tests/TestTurbine.py:25-69,99-105, run there on the F-16 itself):
+    every frame N1 and N2 `seek` their targets idle + ThrottlePos * (max - idle) with the default spool-up rate
+    delay / (1 + 3 (1 - n)^3 + (1 - sigma)), n = min(1, N2norm + 0.1), delay = 90 dt / (BPR + 3); N1 spools DOWN 2.4 times and
+    N2 3.0 times faster.  Throttle up to the stop, then back to idle, as the JSBSim test does."""
+    idle_n1, max_n1, idle_n2, max_n2, bpr = 40.0, 100.0, 53.0, 100.0, 0.4     # data/engine/F100-PW-229.xml:17-23
+    dt = 1.0 / 60.0
+    delay = 90.0 * dt / (bpr + 3.0)
+    rho0 = ofdm.atmosphere(0.0)["rho"]
+
+    def seek(x, target, accel, decel):                                      # TestTurbine.py:25-33
+        if x < target:
+            return min(x + accel, target)
+        if x > target:
+            return max(x - decel, target)
+        return x
+
+    f = ofdm.OracleFdm()
+    f.reset(h_sl_ft=15000.0, u_fps=700.0)
+    went_up = went_down = 0
+    for cmd, frames in ((0.5, 240), (0.0, 420)):      # throttle-pos-norm = 2 cmd (f16.xml:869-873): 1.0, then 0.0
+        f.set_controls(0.0, 0.0, 0.0, cmd)
+        pos = min(1.0, 2.0 * cmd)
+        for _ in range(frames):
+            d0 = f.snapshot_dict()
+            f.run(1)
+            d1 = f.snapshot_dict()
+            sigma = d1["density"] / rho0
+            n = min(1.0, d0["N2norm"] + 0.1)
+            up = delay / (1 + 3 * (1 - n) ** 3 + (1 - sigma))
+            n1 = seek(d0["N1"], idle_n1 + pos * (max_n1 - idle_n1), up, 2.4 * up)
+            n2 = seek(d0["N2"], idle_n2 + pos * (max_n2 - idle_n2), up, 3.0 * up)
+            assert d1["N1"] == pytest.approx(n1, abs=1e-7)          # assertAlmostEqual: 7 places
+            assert d1["N2"] == pytest.approx(n2, abs=1e-7)
+            went_up += d1["N2"] > d0["N2"]
+            went_down += d1["N1"] < d0["N1"]
+    assert went_up > 50 and went_down > 50                          # both branches of both seeks were exercised
+    assert d1["N2"] == pytest.approx(idle_n2, abs=1e-9) and d1["N1"] == pytest.approx(idle_n1, abs=1e-9)
+
+
 def test_level_flight_is_quiescent_and_time_advances():
     f = ofdm.OracleFdm()
     f.reset()
