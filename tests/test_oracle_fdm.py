@@ -43,6 +43,13 @@ def test_isa_atmosphere(h_ft):
     assert got["a"] == pytest.approx(a, rel=2e-6)
 
 
+def test_gas_constant_matches_jsbsim_documentation():
+    """envs/JSBSim/data/doc/spreadsheets/Standard_Atmosphere_constants.ods lists the value JSBSim uses: Reng = 1716.5572
+    ft lbf / slug / R (= R* / M in British units); the oracle's follows from its sea-level state, P = rho Reng T."""
+    a = ofdm.atmosphere(0.0)
+    assert a["P"] / (a["rho"] * a["T"]) == pytest.approx(1716.5572, abs=5e-5)
+
+
 def test_density_altitude_is_identity_on_a_standard_day():
     # CalculateDensityAltitude inverts the density profile (FGStandardAtmosphere.cpp:464-492)
     for h in [0.0, 5000.0, 20000.0, 36000.0, 45000.0]:
