@@ -258,6 +258,51 @@ FDM_DEV void atmosphere_calculate(const AtmoConst& c, double altitude, Atmo& o) 
   o.density_altitude = atmo_geomet(c, da);
 }
 
+// Host side: the layer constants, computed exactly as the reference's constructor does and copied to constant memory by
+// acs_create (tests/native/fdm_host.cpp fills the same struct when it compiles this header for the host).
+static inline void host_atmo(AtmoConst& c) {
+  // FGAtmosphere.h / FGStandardAtmosphere.cpp ctor (reference data/src/models/atmosphere/FGStandardAtmosphere.cpp:60-150)
+  const double Rstar = 8.31432 * KGTOSLUG / (1.8 * (FTTOM * FTTOM));
+  const double Mair = 28.9645 * KGTOSLUG / 1000.0;
+  c.g0 = 9.80665 / FTTOM;
+  c.Reng = Rstar / Mair;
+  c.EarthRadius = 6356766.0 / FTTOM;
+  const double h[9] = {0.0000, 36089.2388, 65616.7979, 104986.8766, 154199.4751, 167322.8346, 232939.6325, 278385.8268, 298556.4304};
+  const double t[9] = {518.67, 389.97, 389.97, 411.57, 487.17, 487.17, 386.37, 336.5028, 336.5028};
+  for (int i = 0; i < 9; i++) { c.H[i] = h[i]; c.Tt[i] = t[i]; }
+  for (int b = 0; b < 8; b++) c.Lapse[b] = (t[b + 1] - t[b]) / (h[b + 1] - h[b]) - 0.0;
+  c.StdDaySLpressure = 2116.228;
+  c.PB[0] = c.StdDaySLpressure;
+  for (int b = 0; b < 8; b++) {
+    const double deltaH = h[b + 1] - h[b], Tmb = t[b];
+    if (c.Lapse[b] != 0.0) { const double L = c.Lapse[b]; c.PB[b + 1] = c.PB[b] * std::pow(Tmb / (Tmb + L * deltaH), c.g0 / (c.Reng * L)); }
+    else c.PB[b + 1] = c.PB[b] * std::exp(-c.g0 * deltaH / (c.Reng * Tmb));
+  }
+  for (int i = 0; i < 9; i++) c.DB[i] = c.PB[i] / (c.Reng * t[i]);
+  c.SLdensity = c.StdDaySLpressure / (c.Reng * t[0]);
+  c.StdDaySLsoundspeed = std::sqrt(1.4 * c.Reng * 518.67);
+  // Tmb[b] = GetTemperature(GeometricAltitude(H[b])): the geometric/geopotential round trip of the base altitude
+  for (int b = 0; b < 8; b++) {
+    const double geomet = (h[b] * c.EarthRadius) / (c.EarthRadius - h[b]);
+    const double G = (geomet * c.EarthRadius) / (c.EarthRadius + geomet);
+    double Tm;
+    if (G >= 0.0) {
+      if (G <= h[0]) Tm = t[0];
+      else if (G >= h[8]) Tm = t[8];
+      else { int r = 1; while (r < 8 && h[r] < G) r++; double f = (G - h[r - 1]) / (h[r] - h[r - 1]); if (f > 1.0) f = 1.0; Tm = f * (t[r] - t[r - 1]) + t[r - 1]; }
+    } else Tm = t[0] + G * c.Lapse[0];
+    c.Tmb[b] = Tm;
+  }
+  // reciprocals / exponents the device code multiplies by (fdm_core.cuh, AtmoConst)
+  c.invdH[0] = 0.0;
+  for (int r = 1; r < 9; r++) c.invdH[r] = 1.0 / (h[r] - h[r - 1]);
+  for (int b = 0; b < 8; b++) {
+    c.Pexp[b] = c.Lapse[b] != 0.0 ? c.g0 / (c.Reng * c.Lapse[b]) : 0.0;
+    c.Piso[b] = -c.g0 / (c.Reng * c.Tmb[b]);
+  }
+  c.invSLdensity = 1.0 / c.SLdensity;
+}
+
 // J/FGJSBBase.cpp:245-296
 FDM_DEV double pitot_total_pressure(double mach, double p) {
   if (mach < 0) return p;
@@ -793,7 +838,11 @@ FDM_DEV void fdm_frame(AcCore& a, Props& p, FcsState& s, Frame& f, const double*
 //   * Ti2b: rebuilt from the quaternion in Accelerations; gravity: rotated to the inertial frame at once (3 doubles
 //     instead of gravity + sin / cos of the earth rotation angle).
 // opaque(): the optimiser must not merge a recomputation with the original (that would re-create the long live range).
+#ifdef __CUDACC__
 FDM_DEV double opaque(double x) { asm volatile("" : "+d"(x)); return x; }
+#else
+FDM_DEV double opaque(double x) { return x; }     // host build of this header (tests/native/fdm_host.cpp)
+#endif
 
 struct FrameKeep { double pilot_nx, vcas, beta, thrust; };
 

@@ -97,9 +97,17 @@ FM_DEV double fm_frexp1(double x, int* e) {
   return __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
 }
 #else
-// host build (tests): seeds with a deliberately poor relative error of 2^-12
-FM_DEV double fm_rcp_seed(double b) { return (double)(float)(1.0 / b) * (1.0 + 1.0 / 4096.0); }
-FM_DEV double fm_rsq_seed(double x) { return (double)(float)(1.0 / sqrt(x)) * (1.0 - 1.0 / 4096.0); }
+// host build (tests): seeds with a deliberately poor relative error of 2^-12 -- a 24-bit significand like a float's, but
+// over the whole double exponent range, as the hardware seeds have (the FDM takes 1 / sqrt of numbers near 1e102)
+FM_DEV double fm_host_seed24(double v) {
+  unsigned long long u;
+  __builtin_memcpy(&u, &v, 8);
+  u &= ~((1ull << 29) - 1ull);
+  __builtin_memcpy(&v, &u, 8);
+  return v;
+}
+FM_DEV double fm_rcp_seed(double b) { return fm_host_seed24(1.0 / b) * (1.0 + 1.0 / 4096.0); }
+FM_DEV double fm_rsq_seed(double x) { return fm_host_seed24(1.0 / sqrt(x)) * (1.0 - 1.0 / 4096.0); }
 FM_DEV double fm_pow2i(int n) { return ldexp(1.0, n); }
 FM_DEV double fm_rint(double x) { return rint(x); }
 FM_DEV double fm_frexp1(double x, int* e) { const double m = frexp(x, e); *e -= 1; return m + m; }
