@@ -96,4 +96,16 @@ void fh_run(void* hv, int n_frames, int lean) {
   }
 }
 void fh_get(void* hv, double* state, double* out) { store(*(HostFdm*)hv, state, out); }
+// what load_state does (csrc/acs.cu): the state arena's words, in STATE_NAMES order, into the registers of one aircraft
+void fh_set_state(void* hv, const double* st) {
+  HostFdm* h = (HostFdm*)hv;
+  AcCore& a = h->a; Props& p = h->p; FcsState& s = h->s;
+  f16_props_init(p, s);
+  int k = 0;
+#define LD(name, expr) expr = st[k++];
+  FDM_CORE_FIELDS(LD)
+  F16_CARRIED_FIELDS(LD)
+#undef LD
+  f16_props_derive(p);
+}
 }

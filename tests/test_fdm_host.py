@@ -35,6 +35,7 @@ def host_lib(tmp_path_factory):
     L.fh_set_controls.argtypes = [vp, pd]
     L.fh_run.argtypes = [vp, i, i]
     L.fh_get.argtypes = [vp, pd, pd]
+    L.fh_set_state.argtypes = [vp, pd]
     L.fh_state_name.restype = ctypes.c_char_p
     L.fh_state_name.argtypes = [i]
     L.fh_out_name.restype = ctypes.c_char_p
@@ -66,6 +67,9 @@ class HostFdm:
 
     def run(self, n):
         self.L.fh_run(self.h, n, self.lean)
+
+    def set_state(self, st):
+        self.L.fh_set_state(self.h, self._p(np.ascontiguousarray(st, dtype=np.float64)))
 
     def get(self):
         st, out = np.zeros(len(self.state_names)), np.zeros(len(self.output_names))
@@ -148,3 +152,52 @@ def test_lean_and_full_frames_agree(host_lib):
         (sa, oa), (sb, ob) = x.get(), y.get()
         np.testing.assert_allclose(sa, sb, rtol=1e-11, atol=1e-11)
         np.testing.assert_allclose(oa, ob, rtol=1e-11, atol=1e-11)
+
+
+def test_single_step_deltas_from_identical_states_over_a_wide_envelope(host_lib):
+    """north_star: single-step state deltas <= 1e-9 from identical states.  The oracle flies aggressive random commands from
+    random attitudes, rates, speeds (sub- and supersonic: the Rayleigh branch of Vcas), altitudes and latitudes; before every
+    12-frame step its state is injected into the host build of the product source (what load_state does), both advance one
+    step, and every state word and output is compared.  Both frames (full / lean)."""
+    rng = np.random.default_rng(2)
+    full, lean = HostFdm(host_lib, False), HostFdm(host_lib, True)
+    names = full.state_names
+    worst, where = 0.0, None
+    mach, alpha, alt = [], [], []
+    for n in range(40):
+        ic = np.zeros(12)
+        ic[0], ic[1], ic[2], ic[3] = rng.uniform(100, 140), rng.uniform(-70, 70), rng.uniform(4000, 45000), rng.uniform(0, 360)
+        ic[4], ic[5], ic[6] = rng.uniform(250, 1800), rng.uniform(-30, 30), rng.uniform(-60, 60)
+        ic[7:10] = rng.uniform(-0.3, 0.3, 3)
+        ic[10], ic[11] = rng.uniform(-180, 180), rng.uniform(-60, 60)
+        f = OracleFdm()
+        f.reset(*ic)
+        for step in range(60):
+            d0 = oracle_named_state(f)
+            st = np.array([d0[nm] for nm in names])
+            if rng.random() < 0.7:
+                u = np.array([rng.integers(0, 41) / 20 - 1, rng.integers(0, 41) / 20 - 1, rng.integers(0, 41) / 20 - 1, rng.integers(0, 30) / 58 + 0.4])
+            else:          # full deflections, idle or full throttle
+                u = np.array([rng.choice([-1.0, 1.0]), rng.choice([-1.0, 1.0]), rng.choice([-1.0, 1.0]), rng.choice([0.0, 0.9])])
+            f.set_controls(*u)
+            f.run(12)
+            d1 = oracle_named_state(f)
+            mach.append(d1["mach"]); alpha.append(d1["alpha_rad"]); alt.append(d1["h_sl_ft"])
+            for h in (full, lean):
+                h.set_state(st)
+                h.set_controls(u)
+                h.run(12)
+                a, o = h.get()
+                for k, nm in enumerate(names):
+                    e = abs(a[k] - d1[nm]) / field_scale(nm, d1[nm])
+                    if e > worst:
+                        worst, where = e, (nm, n, step, h.lean, a[k], d1[nm])
+                for k, nm in enumerate(h.output_names):
+                    if nm in d1:
+                        e = abs(o[k] - d1[nm]) / max(1.0, abs(d1[nm]))
+                        if e > worst:
+                            worst, where = e, ("out:" + nm, n, step, h.lean, o[k], d1[nm])
+            if d1["h_sl_ft"] < 500.0:
+                break
+    assert worst < 1e-9, where
+    assert max(mach) > 1.4 and min(mach) < 0.4 and max(alpha) > 0.25 and min(alpha) < -0.15 and max(alt) > 35000 and min(alt) < 3000
