@@ -101,6 +101,44 @@ def test_reset_reproduces_the_initial_conditions():
     assert d["tank0"] == 3000.0 and d["tank1"] == 3000.0
 
 
+def test_attitude_conventions_known_answer():
+    """The quaternion / matrix arithmetic JSBSim keeps in headers (FGQuaternion, FGMatrix33, FGColumnVector3: not in the
+    reference tree) is pinned by the textbook definitions it implements: for random Euler angles and body velocities the
+    reset state gives the angles back, a unit quaternion, NED velocity = (3-2-1 direction cosine matrix)^T (u, v, w) and
+    |v_ECI| = |v_NED + Omega x r| (FGPropagate::SetInitialState, J/models/FGPropagate.cpp:143-186)."""
+    rng = np.random.default_rng(4)
+    omega = 7.292115e-5
+    for _ in range(50):
+        phi, tht, psi = rng.uniform(-179, 179), rng.uniform(-85, 85), rng.uniform(0.5, 359.5)
+        uvw = np.array([rng.uniform(300, 1200), rng.uniform(-80, 80), rng.uniform(-120, 120)])
+        lat, pqr = rng.uniform(-70, 70), rng.uniform(-0.5, 0.5, 3)
+        f = ofdm.OracleFdm()
+        f.reset(lon_deg=rng.uniform(-179, 179), lat_geod_deg=lat, h_sl_ft=rng.uniform(5000, 40000), psi_deg=psi,
+                u_fps=uvw[0], v_fps=uvw[1], w_fps=uvw[2], p=pqr[0], q=pqr[1], r=pqr[2], phi_deg=phi, theta_deg=tht)
+        d = f.snapshot_dict()
+        assert math.degrees(d["roll_rad"]) == pytest.approx(phi, abs=1e-9)
+        assert math.degrees(d["pitch_rad"]) == pytest.approx(tht, abs=1e-9)
+        assert math.degrees(d["heading_rad"]) == pytest.approx(psi, abs=1e-9)
+        assert d["q0"] ** 2 + d["q1"] ** 2 + d["q2"] ** 2 + d["q3"] ** 2 == pytest.approx(1.0, abs=1e-14)
+        assert [d["u_fps"], d["v_fps"], d["w_fps"]] == pytest.approx(list(uvw), abs=1e-9)
+        assert [d["p_rad_sec"], d["q_rad_sec"], d["r_rad_sec"]] == pytest.approx(list(pqr), abs=1e-12)
+        cf, sf, ct, st, cp, sp = (math.cos(math.radians(phi)), math.sin(math.radians(phi)), math.cos(math.radians(tht)),
+                                  math.sin(math.radians(tht)), math.cos(math.radians(psi)), math.sin(math.radians(psi)))
+        Tl2b = np.array([[ct * cp, ct * sp, -st],                                   # local (NED) -> body, 3-2-1 sequence
+                         [sf * st * cp - cf * sp, sf * st * sp + cf * cp, sf * ct],
+                         [cf * st * cp + sf * sp, cf * st * sp - sf * cp, cf * ct]])
+        ned = Tl2b.T @ uvw
+        assert [d["v_north_fps"], d["v_east_fps"], d["v_down_fps"]] == pytest.approx(list(ned), abs=1e-8)
+        # inertial velocity: the earth's rotation adds Omega x r = Omega * r_xy towards the east
+        a, b = 20925646.32546, 20855486.5951
+        e2, la = 1 - (b / a) ** 2, math.radians(lat)
+        N = a / math.sqrt(1 - e2 * math.sin(la) ** 2)
+        r_xy = (N + d["geod_alt_ft"]) * math.cos(la)
+        # east in NED is exactly the direction of Omega x r; north / down in the geodetic frame are perpendicular to it
+        v_eci = math.sqrt(ned[0] ** 2 + (ned[1] + omega * r_xy) ** 2 + ned[2] ** 2)
+        assert d["eci_velocity_mag_fps"] == pytest.approx(v_eci, rel=1e-10)
+
+
 def test_turbine_spools_up_with_the_published_rate():
     """reference envs/JSBSim/data/tests/TestTurbine.py:36-41,99-105: N2 seeks IdleN2 + throttle*N2_factor at
     delay/(1+3(1-n)^3+(1-sigma)) per second with delay = 90/(BPR+3)."""
