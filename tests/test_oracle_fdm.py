@@ -139,6 +139,74 @@ def test_attitude_conventions_known_answer():
         assert d["eci_velocity_mag_fps"] == pytest.approx(v_eci, rel=1e-10)
 
 
+def test_air_data_and_weight_known_answer():
+    """FGAuxiliary's air data from their definitions (J/models/FGAuxiliary.cpp:134-231: alpha = atan2(w, u), beta = atan2(v,
+    sqrt(u^2 + w^2)), Vt = |uvw| without wind, qbar = rho Vt^2 / 2, Mach = Vt / a), the calibrated airspeed from the isentropic
+    pitot relations (J/FGJSBBase.cpp:245-296: impact pressure at Mach and static pressure, read back at sea-level pressure),
+    and the weight FGMassBalance sums (X/:69-90, 279-288: empty 17 400 lb + pilot 230 lb + 2 x 3000 lb of fuel)."""
+    rng = np.random.default_rng(6)
+    for _ in range(30):
+        h = rng.uniform(3000, 45000)
+        uvw = np.array([rng.uniform(300, 1700), rng.uniform(-60, 60), rng.uniform(-100, 100)])
+        f = ofdm.OracleFdm()
+        f.reset(h_sl_ft=h, u_fps=uvw[0], v_fps=uvw[1], w_fps=uvw[2])
+        d, atm = f.snapshot_dict(), ofdm.atmosphere(h)
+        vt = float(np.linalg.norm(uvw))
+        assert d["alpha_rad"] == pytest.approx(math.atan2(uvw[2], uvw[0]), abs=1e-12)
+        assert d["beta_rad"] == pytest.approx(math.atan2(uvw[1], math.hypot(uvw[0], uvw[2])), abs=1e-12)
+        assert d["vt_fps"] == pytest.approx(vt, rel=1e-12)
+        assert d["density"] == pytest.approx(atm["rho"], rel=1e-9) and d["pressure_psf"] == pytest.approx(atm["P"], rel=1e-9)
+        assert d["qbar"] == pytest.approx(0.5 * atm["rho"] * vt * vt, rel=1e-9)
+        mach = vt / atm["a"]
+        assert d["mach"] == pytest.approx(mach, rel=1e-9)
+        # calibrated airspeed: the same impact pressure measured at sea-level static pressure
+        g, psl, asl = 1.4, 2116.228, ofdm.atmosphere(0.0)["a"]
+        if mach < 1.0:
+            qc = atm["P"] * ((1 + 0.2 * mach * mach) ** 3.5 - 1.0)
+        else:      # Rayleigh pitot formula behind a normal shock
+            qc = atm["P"] * (((g + 1) / 2 * mach * mach) ** (g / (g - 1)) * ((g + 1) / (2 * g * mach * mach - (g - 1))) ** (1 / (g - 1)) - 1.0)
+        mc = math.sqrt(5.0 * ((qc / psl + 1.0) ** (1 / 3.5) - 1.0))
+        if mc > 1.0:                                     # solve Rayleigh for the Mach number that gives qc at psl
+            for _ in range(60):
+                mc = 0.88128485 * math.sqrt((qc / psl + 1.0) * (1.0 - 1.0 / (7.0 * mc * mc)) ** 2.5)
+        assert d["vc_fps"] == pytest.approx(mc * asl, rel=1e-6)
+        assert d["mass_slugs"] == pytest.approx((17400.0 + 230.0 + 6000.0) / 32.174049, rel=1e-12)
+
+
+def test_translational_integrators_known_answer():
+    """FGPropagate integrates with the PREVIOUS frame's derivatives (J/models/FGPropagate.cpp:218-297): inertial position by
+    Adams-Bashforth 3, inertial velocity by Adams-Bashforth 2 (:93-96, :371-470), the derivative history primed with the
+    initial derivative (InitializeDerivatives).  Checked with the textbook coefficients over the first three frames."""
+    dt = 1.0 / 60.0
+    f = ofdm.OracleFdm()
+    f.reset(lat_geod_deg=35.0, h_sl_ft=18000.0, psi_deg=77.0, u_fps=900.0, w_fps=30.0, theta_deg=4.0, phi_deg=20.0)
+    f.set_controls(0.3, -0.4, 0.1, 0.8)
+    S = [f.snapshot_dict()]
+    for _ in range(3):
+        f.run(1)
+        S.append(f.snapshot_dict())
+    r = [np.array([d["ri_x"], d["ri_y"], d["ri_z"]]) for d in S]
+    v = [np.array([d["vi_x"], d["vi_y"], d["vi_z"]]) for d in S]
+    a = [np.array([d["uvwidot_x"], d["uvwidot_y"], d["uvwidot_z"]]) for d in S]      # inertial acceleration a frame leaves behind
+    # frame 1: the history holds the initial derivative three times -> both schemes reduce to rectangular Euler
+    assert r[1] == pytest.approx(r[0] + dt * v[0], rel=1e-15, abs=1e-7)
+    assert v[1] == pytest.approx(v[0] + dt * a[0], rel=1e-14, abs=1e-10)
+    # frame 2: AB2 on (a1, a0); AB3 on (v1, v0, v0)
+    assert v[2] == pytest.approx(v[1] + dt * (1.5 * a[1] - 0.5 * a[0]), rel=1e-14, abs=1e-10)
+    assert r[2] == pytest.approx(r[1] + dt * (23.0 * v[1] - 16.0 * v[0] + 5.0 * v[0]) / 12.0, rel=1e-15, abs=1e-7)
+    # frame 3: the full three-point formula
+    assert v[3] == pytest.approx(v[2] + dt * (1.5 * a[2] - 0.5 * a[1]), rel=1e-14, abs=1e-10)
+    assert r[3] == pytest.approx(r[2] + dt * (23.0 * v[2] - 16.0 * v[1] + 5.0 * v[0]) / 12.0, rel=1e-15, abs=1e-7)
+    # inertial angular rate: rectangular Euler on the newest derivative (:93)
+    w = [np.array([d["wi_x"], d["wi_y"], d["wi_z"]]) for d in S]
+    wd = [np.array([d["pqridot_x"], d["pqridot_y"], d["pqridot_z"]]) for d in S]
+    for k in range(3):
+        assert w[k + 1] == pytest.approx(w[k] + dt * wd[k], rel=1e-14, abs=1e-16)
+        assert sum(S[k + 1][q] ** 2 for q in ("q0", "q1", "q2", "q3")) == pytest.approx(1.0, abs=2.1e-10)   # FGQuaternion::Normalize leaves |q| alone within 1e-10 of 1
+    # the earth rotation angle advances with the sidereal rate, the clock with dt
+    assert S[3]["epa"] == pytest.approx(3 * dt * 7.292115e-5, rel=1e-12) and S[3]["sim_time"] == pytest.approx(3 * dt, abs=1e-15)
+
+
 def test_turbine_spools_up_with_the_published_rate():
     """reference envs/JSBSim/data/tests/TestTurbine.py:36-41,99-105: N2 seeks IdleN2 + throttle*N2_factor at
     delay/(1+3(1-n)^3+(1-sigma)) per second with delay = 90/(BPR+3)."""
