@@ -207,6 +207,38 @@ def test_translational_integrators_known_answer():
     assert S[3]["epa"] == pytest.approx(3 * dt * 7.292115e-5, rel=1e-12) and S[3]["sim_time"] == pytest.approx(3 * dt, abs=1e-15)
 
 
+def test_newton_euler_known_answer():
+    """FGAccelerations (J/models/FGAccelerations.cpp:109-207) from first principles, on the state a few frames of manoeuvring
+    leave behind: body acceleration = F / m, inertial angular acceleration = J^-1 (M - w x J w), inertial acceleration =
+    T_b->i F / m + gravity, with T from the textbook quaternion -> direction-cosine formula, the ECEF position from a rotation
+    by the earth rotation angle, and gravity from the J2 field at that position."""
+    rng = np.random.default_rng(8)
+    for _ in range(10):
+        f = ofdm.OracleFdm()
+        f.reset(lat_geod_deg=rng.uniform(-60, 60), h_sl_ft=rng.uniform(8000, 35000), psi_deg=rng.uniform(0, 360),
+                u_fps=rng.uniform(500, 1100), phi_deg=rng.uniform(-60, 60), theta_deg=rng.uniform(-20, 20))
+        f.set_controls(*(list(rng.uniform(-1, 1, 3)) + [rng.uniform(0.2, 0.9)]))
+        f.run(int(rng.integers(3, 40)))
+        d, mp = f.snapshot_dict(), ofdm.mass_properties(f)
+        F = np.array([d["fx"], d["fy"], d["fz"]]); M = np.array([d["mx"], d["my"], d["mz"]])
+        w = np.array([d["wi_x"], d["wi_y"], d["wi_z"]])
+        assert d["mass_slugs"] == pytest.approx(mp["mass"], rel=1e-14)
+        assert [d["bodyaccel_x"], d["bodyaccel_y"], d["bodyaccel_z"]] == pytest.approx(list(F / mp["mass"]), rel=1e-12, abs=1e-12)
+        assert mp["J"] @ mp["Jinv"] == pytest.approx(np.eye(3), abs=1e-12)
+        wdot = mp["Jinv"] @ (M - np.cross(w, mp["J"] @ w))
+        assert [d["pqridot_x"], d["pqridot_y"], d["pqridot_z"]] == pytest.approx(list(wdot), rel=1e-11, abs=1e-13)
+        q0, q1, q2, q3 = d["q0"], d["q1"], d["q2"], d["q3"]
+        Ti2b = np.array([[q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, 2 * (q1 * q2 + q0 * q3), 2 * (q1 * q3 - q0 * q2)],
+                         [2 * (q1 * q2 - q0 * q3), q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3, 2 * (q2 * q3 + q0 * q1)],
+                         [2 * (q1 * q3 + q0 * q2), 2 * (q2 * q3 - q0 * q1), q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3]])
+        ce, se = math.cos(d["epa"]), math.sin(d["epa"])
+        Ti2ec = np.array([[ce, se, 0.0], [-se, ce, 0.0], [0.0, 0.0, 1.0]])
+        ri = np.array([d["ri_x"], d["ri_y"], d["ri_z"]])
+        g_i = Ti2ec.T @ ofdm.gravity(*(Ti2ec @ ri))
+        a_i = Ti2b.T @ (F / mp["mass"]) + g_i
+        assert [d["uvwidot_x"], d["uvwidot_y"], d["uvwidot_z"]] == pytest.approx(list(a_i), rel=1e-9, abs=1e-9)
+
+
 def test_turbine_spools_up_with_the_published_rate():
     """reference envs/JSBSim/data/tests/TestTurbine.py:36-41,99-105: N2 seeks IdleN2 + throttle*N2_factor at
     delay/(1+3(1-n)^3+(1-sigma)) per second with delay = 90/(BPR+3)."""
