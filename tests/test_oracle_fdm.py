@@ -239,6 +239,30 @@ def test_newton_euler_known_answer():
         assert [d["uvwidot_x"], d["uvwidot_y"], d["uvwidot_z"]] == pytest.approx(list(a_i), rel=1e-9, abs=1e-9)
 
 
+def test_pilot_load_factor_uses_last_frames_accelerations():
+    """FGAuxiliary runs before FGAccelerations in a frame (J/FGFDMExec.cpp:222-236), so the pilot-station load factor the FCS and
+    the Overload termination see is built from the PREVIOUS frame's linear and angular accelerations and this frame's rates:
+    n_pilot = (a_body + wdot x r + w x (w x r)) / g0 with r from the centre of gravity to the eye point (X/:50-54),
+    J/models/FGAuxiliary.cpp:205-222."""
+    g0 = 9.80665 / 0.3048
+    f = ofdm.OracleFdm()
+    f.reset(h_sl_ft=15000.0, u_fps=950.0, phi_deg=35.0)
+    f.set_controls(0.6, -0.7, 0.2, 0.7)
+    f.run(5)
+    for _ in range(20):
+        prev = f.snapshot_dict()
+        f.run(1)
+        d, mp = f.snapshot_dict(), ofdm.mass_properties(f)
+        cg = mp["cg"]
+        r = np.array([(cg[0] - (-336.2)) / 12.0, (0.0 - cg[1]) / 12.0, (cg[2] - 29.5) / 12.0])     # structural (in) -> body (ft)
+        a = np.array([prev["bodyaccel_x"], prev["bodyaccel_y"], prev["bodyaccel_z"]])
+        wd = np.array([prev["pqridot_x"], prev["pqridot_y"], prev["pqridot_z"]])
+        w = np.array([d["wi_x"], d["wi_y"], d["wi_z"]])
+        n = (a + np.cross(wd, r) + np.cross(w, np.cross(w, r))) / g0
+        assert [d["n_pilot_x"], d["n_pilot_y"], d["n_pilot_z"]] == pytest.approx(list(n), rel=1e-10, abs=1e-12)
+    assert abs(d["n_pilot_z"]) > 1.5          # the manoeuvre loads the aircraft: the check is not about a quiescent state
+
+
 def test_turbine_spools_up_with_the_published_rate():
     """reference envs/JSBSim/data/tests/TestTurbine.py:36-41,99-105: N2 seeks IdleN2 + throttle*N2_factor at
     delay/(1+3(1-n)^3+(1-sigma)) per second with delay = 90/(BPR+3)."""
