@@ -345,6 +345,26 @@ def test_fuel_burn_matches_fuel_flow():
     assert burnt < d["FuelFlow_pph"] / 3600.0 * 10.0 * 1.5
 
 
+def test_fuel_is_drawn_equally_from_the_tanks_every_frame():
+    """FGPropulsion::ConsumeFuel (J/models/FGPropulsion.cpp:164-260) after FGTurbine::CalcFuelNeed (propulsion/FGTurbine.cpp:381-387):
+    each frame the engine's fuel flow of THAT frame, pph / 3600 * dt, leaves the two tanks that hold fuel in equal parts --
+    afterburner included (throttle command 0.9 -> throttle position 1.8: augmentation)."""
+    dt = 1.0 / 60.0
+    f = ofdm.OracleFdm()
+    f.reset()
+    f.set_controls(0.0, 0.0, 0.0, 0.9)
+    f.run(150)
+    for _ in range(40):
+        a = f.snapshot_dict()
+        f.run(1)
+        b = f.snapshot_dict()
+        need = b["FuelFlow_pph"] / 3600.0 * dt
+        assert a["tank0"] - b["tank0"] == pytest.approx(need / 2, rel=1e-9)
+        assert a["tank1"] - b["tank1"] == pytest.approx(need / 2, rel=1e-9)
+        assert b["tank2"] == 0.0 and b["tank3"] == 0.0
+    assert int(b["engflags"]) & 2                # the augmentation flag is up: the afterburner branch of FGTurbine::Run was timed
+
+
 def test_same_inputs_same_trajectory():
     a, b = ofdm.OracleFdm(), ofdm.OracleFdm()
     rng = np.random.default_rng(1)
